@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the state-vector gate-application path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N = 1   workload = BASELINE configs[1]: 30-qubit random-unitary circuit, depth 40, complex64, one B200.
+        One "step" = |0..0> -> the whole 1800-gate circuit, submitted through rocsvxApplyCircuit.
+N > 1   (torchrun, one rank per GPU) workload = configs[3]-class circuit on 33 + log2(N) qubits sharded by the
+        top log2(N) index bits (36 qubits at N = 8), global<->local index-bit exchanges over NCCL.
+Prints ONE JSON line (rank 0).  `value` is gates/s normalised to 30 qubits (gates * 2^(n-30) / s), which at
+N = 1 is plain gates/s.  --impl reference times the CPU restatement of the reference's per-gate path
+(oracle/, OpenMP over the host cores) on a bounded sample of the same circuit.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.p = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample(n, gates, prec="c64", repeats=1):
+    """Time the oracle port (one full pass per gate, like the reference's one-kernel-per-gate path) on a few
+    gates of the workload.  Returns (seconds per 1q gate, seconds per 2q gate, cores)."""
+    from oracle import sv_oracle as so
+    from tests import util
+    o = so.Oracle(n, prec)
+    one = [g for g in gates if len(g[1]) == 1][:3]
+    two = [g for g in gates if len(g[1]) == 2][:2]
+    util.run_on_oracle(o, one[:1] + two[:1])          # warm-up: page in the state
+    t1 = t2 = 0.0
+    for _ in range(repeats):
+        t = time.perf_counter(); util.run_on_oracle(o, one); t1 += (time.perf_counter() - t) / len(one)
+        t = time.perf_counter(); util.run_on_oracle(o, two); t2 += (time.perf_counter() - t) / len(two)
+    return t1 / repeats, t2 / repeats, os.cpu_count()
+
+
+def host_ram_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def workload_for(ngpus):
+    from rocquantum_b200 import workloads
+    if ngpus == 1:
+        n = env_int("ROCQ_BENCH_QUBITS", 30)
+        depth = env_int("ROCQ_BENCH_DEPTH", 40)
+        return n, workloads.c2_random_unitary(n, depth, seed=30), f"C2: {n}-qubit random-unitary circuit, depth {depth}, fused sweeps, complex64"
+    m = ngpus.bit_length() - 1
+    n = env_int("ROCQ_BENCH_QUBITS", 33 + m)
+    depth = env_int("ROCQ_BENCH_DEPTH", 20)
+    return n, workloads.c4_global_layers(n, depth, seed=36), (f"C4: {n}-qubit random circuit, depth {depth}, sharded over {ngpus} GPUs by the top "
+                                                             f"{m} qubits, global-qubit swaps via NCCL, complex64")
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the reference's algorithm (one pass over the state per gate, no fusion) on the host cores."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import sv_oracle as so
+    so.build(ref=False)
+    n, gates, wl = workload_for(args.gpus)
+    n_run = n
+    need_gb = (1 << n) * 8 / 1e9 * 1.3
+    while n_run > 20 and need_gb > 0.6 * host_ram_gb():
+        n_run -= 1
+        need_gb /= 2
+    n_run = min(n_run, env_int("ROCQ_REF_MAX_QUBITS", 30))
+    from rocquantum_b200 import workloads
+    sample_gates = workloads.c2_random_unitary(n_run, 1, seed=30) if args.gpus == 1 else workloads.c4_global_layers(n_run, 1, seed=36)
+    from tests import util
+    o = so.Oracle(n_run, "c64")
+    one = [g for g in sample_gates if len(g[1]) == 1][:1]
+    two = [g for g in sample_gates if len(g[1]) == 2][:1]
+    n1 = sum(1 for g in gates if len(g[1]) == 1)
+    n2 = len(gates) - n1
+    times = []
+    for step in range(args.warmup + args.steps):
+        t = time.perf_counter(); util.run_on_oracle(o, one); a = time.perf_counter() - t
+        t = time.perf_counter(); util.run_on_oracle(o, two); b = time.perf_counter() - t
+        if step >= args.warmup:
+            times.append((a, b))
+    t1 = statistics.mean(x[0] for x in times) * 2.0 ** (n - n_run)
+    t2 = statistics.mean(x[1] for x in times) * 2.0 ** (n - n_run)
+    circuit_s = n1 * t1 + n2 * t2
+    value = len(gates) / circuit_s * 2.0 ** (n - 30)
+    sample = (f"1 one-qubit + 1 two-qubit Haar gate of the workload per step at {n_run} qubits"
+              + ("" if n_run == n else f", extrapolated x2^{n - n_run} to {n} qubits") + "; one full pass per gate (no fusion), OpenMP")
+    line = {"impl": "reference", "metric": "gates_per_sec", "value": value, "unit": "gates/s (30-qubit equivalent)", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": circuit_s * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c64", "data": "synthetic", "config": {"workload": wl},
+            "cpu_baseline": {"value": value, "unit": "gates/s (30-qubit equivalent)", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "gates/s (30-qubit equivalent)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    from rocquantum_b200 import capi
+    from rocquantum_b200.statevec import StateVector
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    ngpus = world
+    n, gates, wl = workload_for(ngpus)
+    ngates = len(gates)
+    lib = capi.load("c64")
+    arr, keep = capi.make_ops(gates)
+
+    if ngpus == 1:
+        sv = StateVector(n, "c64")
+        n_local = n
+
+        def step():
+            sv.init()
+            st = lib.rocsvxApplyCircuit(sv.h, sv.d, n, arr, ngates)
+            assert st == 0, st
+    else:
+        from rocquantum_b200 import distributed
+        sv = distributed.DistStateVector(n, "c64")
+        n_local = sv.n_local
+
+        def step():
+            sv.init()
+            sv.apply_ops(arr, ngates)
+
+    def barrier():
+        sv.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sv.stats(reset=True)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        dev_ms += sv.stats().lastSweepMs          # CUDA events on the handle's stream around the step's sweeps
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None
+    st = sv.stats()
+    if world > 1:
+        t = torch.tensor([elapsed, dev_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed, dev_ms = float(t[0]), float(t[1])
+    norm = 2.0 ** (n - 30)
+    value = ngates * args.steps / elapsed * norm
+    sweeps_per_step = st.sweeps / args.steps
+
+    # ---- end to end through the public call: host gate list in, host result out, every step ----------
+    e2e_t, d2h = 0.0, 0
+    sv.stats(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        if ngpus == 1:
+            z = sv.expect_z(0)                      # D2H read of the step's result
+            s = sv.sample(list(range(min(n, 64))), 256)
+            d2h = 8 + s.nbytes
+        else:
+            z = sv.expect_z(0)
+            d2h = 8
+    barrier()
+    e2e_t = time.perf_counter() - t0
+    st_e2e = sv.stats()
+    if world > 1:
+        t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t[0])
+    e2e_value = ngates * args.steps / e2e_t * norm
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    sweep_bytes = 2.0 * (1 << n_local) * 8
+    avg_sweep_ms = dev_ms / max(1, st.sweeps)
+    achieved = sweep_bytes / (avg_sweep_ms * 1e-3) / 1e9 if avg_sweep_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "tile_sweep_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "frac_of_8TBs_spec": achieved / 8000.0, "peak_source": peak_src,
+                "traffic": None, "algorithmic_bytes_per_launch": sweep_bytes, "avg_launch_ms": avg_sweep_ms,
+                "launches_per_step": sweeps_per_step, "gates_per_sweep": ngates / max(1.0, sweeps_per_step)}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("tile_sweep_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = None
+    if ngpus == 1 and not args.no_cpu:
+        try:
+            n_cpu = n
+            while n_cpu > 20 and (1 << n_cpu) * 8 / 1e9 * 1.3 > 0.6 * host_ram_gb():
+                n_cpu -= 1
+            t1, t2, cores = cpu_sample(n_cpu, gates)
+            scale = 2.0 ** (n - n_cpu)
+            n1 = sum(1 for g in gates if len(g[1]) == 1)
+            cpu_val = ngates / ((n1 * t1 + (ngates - n1) * t2) * scale)
+            cpu = {"value": cpu_val, "unit": "gates/s", "cores": cores, "kind": "port",
+                   "sample": f"3 one-qubit + 2 two-qubit Haar gates of the same circuit at {n_cpu} qubits"
+                             + ("" if n_cpu == n else f" (extrapolated x2^{n - n_cpu})") + ", one full pass per gate, OpenMP over all cores; "
+                             "'port' because the reference never defines rocsvApplyMatrix (SURVEY.md section 0.1)"}
+        except Exception as ex:                      # the baseline must not take the bench down
+            cpu = {"value": None, "unit": "gates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+
+    line = {"metric": "gates_per_sec", "value": value, "unit": "gates/s" if n == 30 else "gates/s (30-qubit equivalent: gates*2^(n-30)/s)",
+            "n_gpus": ngpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+            "config": {"workload": wl, "qubits": n, "gates": ngates, "l2": "state (8 * 2^n_local bytes) is far larger than the 126 MB L2",
+                       "timing": "K steps between stream-sync + barrier, max over ranks; per-sweep time from CUDA events on the engine's stream"},
+            "clocks": clk, "device_ms_per_step": dev_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": "gates/s" if n == 30 else "gates/s (30-qubit equivalent)",
+                    "h2d_bytes_per_step": st_e2e.h2dBytes // args.steps, "d2h_bytes_per_step": d2h,
+                    "what": "rocsvInitializeState + rocsvxApplyCircuit(host gate list) + <Z0> and 256 sampled bitstrings read back, every step; "
+                            "the gate list reaches the device as sweep programs in kernel parameters"},
+            "gpu_launches": int(st.kernelLaunches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,227 @@
+/* include/hipStateVec.h -- the drop-in C ABI of the B200-native state-vector engine.
+ *
+ * Source-compatible twin of the reference header
+ *   /root/reference/rocquantum/include/rocquantum/hipStateVec.h   (cited below as REF:<line>)
+ * with the <hip/hip_runtime.h> dependency removed: rocComplex is a plain interleaved (re,im)
+ * pair, layout-identical to hipFloatComplex / hipDoubleComplex (and float2 / double2).
+ * Every rocsv* prototype below has exactly the reference's signature; the 17 entry points the
+ * reference declares but never defines are implemented here from their
+ * documented contract.  Entry points prefixed rocsvx are extensions of this engine.
+ *
+ * Precision is fixed at library build time, like the reference (REF:6-15):
+ *   libhipStateVec.so       rocComplex = complex64   (default)
+ *   libhipStateVec_f64.so   rocComplex = complex128  (built with -DROCQ_PRECISION_DOUBLE)
+ *
+ * Pointers: d_state / matrixDevice / d_matrix / d_fusedMatrix are DEVICE pointers; qubit index
+ * arrays, result pointers and h_* buffers are HOST pointers (REF:147, 435).  d_state == NULL means
+ * "the state owned by the handle" (reference hipStateVec.cpp:80-85).
+ * No function throws; all return rocqStatus_t (REF:22-31).
+ */
+#ifndef HIPSTATEVEC_H
+#define HIPSTATEVEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef ROCQ_PRECISION_DOUBLE                                   /* REF:7-10 */
+typedef struct { double x, y; } rocComplex;
+typedef double real_t;
+static const real_t REAL_EPSILON = 1e-12;
+#else                                                          /* REF:11-15 */
+typedef struct { float x, y; } rocComplex;
+typedef float real_t;
+static const real_t REAL_EPSILON = 1e-6f;
+#endif
+
+struct rocsvInternalHandle;                                    /* REF:18-19 */
+typedef struct rocsvInternalHandle* rocsvHandle_t;
+
+typedef enum {                                                 /* REF:22-31 */
+    ROCQ_STATUS_SUCCESS = 0,
+    ROCQ_STATUS_FAILURE = 1,
+    ROCQ_STATUS_INVALID_VALUE = 2,
+    ROCQ_STATUS_ALLOCATION_FAILED = 3,
+    ROCQ_STATUS_HIP_ERROR = 4,          /* any CUDA runtime / launch failure */
+    ROCQ_STATUS_NOT_IMPLEMENTED = 5,
+    ROCQ_STATUS_RCCL_ERROR = 6          /* any NCCL failure */
+} rocqStatus_t;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- lifecycle and state (REF:43, 51, 61, 69, 79) ---- */
+rocqStatus_t rocsvCreate(rocsvHandle_t* handle);
+rocqStatus_t rocsvDestroy(rocsvHandle_t handle);
+rocqStatus_t rocsvAllocateState(rocsvHandle_t handle, unsigned numQubits, rocComplex** d_state, size_t batchSize);
+rocqStatus_t rocsvFreeState(rocsvHandle_t handle);
+rocqStatus_t rocsvInitializeState(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits);
+
+/* ---- distributed state (REF:92, 104).  One process per GPU: call rocsvxDistInit first; each rank
+ *      then owns the slice global = (rank << numLocalQubits) | local (swap_kernels.hip:10-22). ---- */
+rocqStatus_t rocsvAllocateDistributedState(rocsvHandle_t handle, unsigned totalNumQubits);
+rocqStatus_t rocsvInitializeDistributedState(rocsvHandle_t handle);
+
+/* ---- fused 1-qubit matrix on the handle's state; 2x2 DEVICE, column-major (REF:118-120) ---- */
+rocqStatus_t rocsvApplyFusedSingleQubitMatrix(rocsvHandle_t handle, unsigned targetQubit, const rocComplex* d_fusedMatrix);
+
+/* ---- relabel two qubit positions by physically permuting amplitudes (REF:135-137) ---- */
+rocqStatus_t rocsvSwapIndexBits(rocsvHandle_t handle, unsigned qubit_idx1, unsigned qubit_idx2);
+
+/* ---- arbitrary k-qubit matrix: DEVICE, column-major M[i + j*dim], index bit b <-> qubitIndices[b]
+ *      (REF:151-157; layout spec multi_qubit_kernels.hip:22-30, 91-99) ---- */
+rocqStatus_t rocsvApplyMatrix(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits,
+                              const unsigned* qubitIndices, unsigned numTargetQubits,
+                              const rocComplex* matrixDevice, unsigned matrixDim);
+
+/* ---- measure one qubit, collapse and renormalise (REF:172-177) ---- */
+rocqStatus_t rocsvMeasure(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits,
+                          unsigned qubitToMeasure, int* outcome, double* probability);
+
+/* ---- named gates (REF:184-232) ---- */
+rocqStatus_t rocsvApplyX(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit);
+rocqStatus_t rocsvApplyY(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit);
+rocqStatus_t rocsvApplyZ(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit);
+rocqStatus_t rocsvApplyH(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit);
+rocqStatus_t rocsvApplyS(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit);
+rocqStatus_t rocsvApplyT(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit);
+rocqStatus_t rocsvApplySdg(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit);
+rocqStatus_t rocsvApplyRx(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit, double theta);
+rocqStatus_t rocsvApplyRy(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit, double theta);
+rocqStatus_t rocsvApplyRz(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit, double theta);
+
+/* ---- two-qubit and controlled gates (REF:241-281) ---- */
+rocqStatus_t rocsvApplyCNOT(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned controlQubit, unsigned targetQubit);
+rocqStatus_t rocsvApplyCZ(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned qubit1, unsigned qubit2);
+rocqStatus_t rocsvApplySWAP(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned qubit1, unsigned qubit2);
+rocqStatus_t rocsvApplyCRX(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned controlQubit, unsigned targetQubit, double theta);
+rocqStatus_t rocsvApplyCRY(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned controlQubit, unsigned targetQubit, double theta);
+rocqStatus_t rocsvApplyCRZ(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned controlQubit, unsigned targetQubit, double theta);
+rocqStatus_t rocsvApplyMultiControlledX(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, const unsigned* controlQubits, unsigned numControlQubits, unsigned targetQubit);
+rocqStatus_t rocsvApplyCSWAP(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned controlQubit, unsigned targetQubit1, unsigned targetQubit2);
+
+/* ---- readback (REF:286, 291) ---- */
+rocqStatus_t rocsvGetStateVectorFull(rocsvHandle_t handle, rocComplex* d_state, rocComplex* h_state);
+rocqStatus_t rocsvGetStateVectorSlice(rocsvHandle_t handle, rocComplex* d_state, rocComplex* h_state, unsigned batch_index);
+
+/* ---- handle-owned pinned host staging buffer (REF:307, 316, 324) ---- */
+rocqStatus_t rocsvEnsurePinnedBuffer(rocsvHandle_t handle, size_t minSizeBytes);
+void* rocsvGetPinnedBufferPointer(rocsvHandle_t handle);
+rocqStatus_t rocsvFreePinnedBuffer(rocsvHandle_t handle);
+
+/* ---- expectation values (REF:340-423).  All are NON-destructive here (a superset of the
+ *      reference wording for X/Y, REF:349, 367). ---- */
+rocqStatus_t rocsvGetExpectationValueSinglePauliZ(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit, double* result);
+rocqStatus_t rocsvGetExpectationValueSinglePauliX(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit, double* result);
+rocqStatus_t rocsvGetExpectationValueSinglePauliY(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, unsigned targetQubit, double* result);
+rocqStatus_t rocsvGetExpectationValuePauliProductZ(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, const unsigned* targetQubits, unsigned numTargetPaulis, double* result);
+rocqStatus_t rocsvGetExpectationPauliString(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, const char* pauliString, const unsigned* targetQubits, unsigned numTargetPaulis, double* result);
+
+/* ---- sampling: uint64 per shot, bit j = outcome of measuredQubits[j] (REF:439-445) ---- */
+rocqStatus_t rocsvSample(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, const unsigned* measuredQubits, unsigned numMeasuredQubits, unsigned numShots, uint64_t* h_results);
+
+/* ---- controlled k-qubit matrix (REF:461-468) and matrix + measure (REF:487-494) ---- */
+rocqStatus_t rocsvApplyControlledMatrix(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, const unsigned* controlQubits, unsigned numControls, const unsigned* targetQubits, unsigned numTargets, const rocComplex* d_matrix);
+rocqStatus_t rocsvApplyMatrixAndMeasure(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, const unsigned* targetQubits, unsigned numTargetQubits, const rocComplex* d_matrix, unsigned qubitToMeasure, int* outcome);
+
+/* ======================================================================================
+ * Extensions (not in the reference header).  They exist because the reference leaves the RNG,
+ * state import, circuit-level submission and the multi-process layout unspecified.
+ * ====================================================================================== */
+
+/* sizeof(real_t) of this build: 4 (complex64) or 8 (complex128). */
+unsigned rocsvxGetPrecisionBytes(void);
+
+/* Seed of the Philox4x32-10 stream behind rocsvMeasure / rocsvSample (default 0).  Draw `shot` of the
+ * c-th measuring call on a handle uses counter (shot, c); see DESIGN.md "sampling spec". */
+rocqStatus_t rocsvxSetSeed(rocsvHandle_t handle, uint64_t seed);
+
+/* Host -> device import of batchSize*2^n amplitudes (the reference has no import at all). */
+rocqStatus_t rocsvxSetStateVector(rocsvHandle_t handle, rocComplex* d_state, const rocComplex* h_state);
+
+/* Block until everything enqueued on the handle's stream has finished (flushes deferred gates). */
+rocqStatus_t rocsvxSynchronize(rocsvHandle_t handle);
+
+/* Deferred execution.  With fusion enabled, rocsvApply* calls validate, enqueue and return; the
+ * queue is partitioned into fused HBM sweeps and launched by rocsvxFlush or by any entry point that
+ * reads the state (readback, measure, sample, expectation, free, destroy).  Default: disabled, or
+ * the value of the ROCQ_FUSION environment variable at rocsvCreate. */
+rocqStatus_t rocsvxSetFusion(rocsvHandle_t handle, int enabled);
+rocqStatus_t rocsvxFlush(rocsvHandle_t handle);
+
+/* Circuit-level submission: the whole gate queue in one call (what Circuit.flush() /
+ * GateFusion::processQueue feed one gate at a time in the reference, python/rocq/api.py:74-89,
+ * GateFusion.cpp:89-156).  Always fused, regardless of rocsvxSetFusion. */
+typedef enum {
+    ROCSVX_H = 0, ROCSVX_X, ROCSVX_Y, ROCSVX_Z, ROCSVX_S, ROCSVX_SDG, ROCSVX_T,
+    ROCSVX_RX, ROCSVX_RY, ROCSVX_RZ,                 /* targets[0], theta */
+    ROCSVX_CNOT, ROCSVX_CZ, ROCSVX_SWAP,             /* CNOT: controlMask bit + targets[0]; CZ/SWAP: targets[0..1] */
+    ROCSVX_CRX, ROCSVX_CRY, ROCSVX_CRZ,              /* controlMask (1 bit), targets[0], theta */
+    ROCSVX_MCX,                                      /* controlMask, targets[0] */
+    ROCSVX_CSWAP,                                    /* controlMask (1 bit), targets[0..1] */
+    ROCSVX_MATRIX                                    /* numTargets, targets[], controlMask, matrix (HOST) */
+} rocsvxGateKind;
+
+typedef struct {
+    int32_t kind;              /* rocsvxGateKind */
+    uint32_t numTargets;
+    uint32_t targets[8];
+    uint64_t controlMask;      /* bit q set => qubit q is a control (acts where all controls are 1) */
+    double theta;
+    const double* matrix;      /* ROCSVX_MATRIX only: HOST, column-major 2^k x 2^k, interleaved (re,im) doubles */
+} rocsvxGateOp;
+
+rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits,
+                                const rocsvxGateOp* ops, size_t numOps);
+
+/* ||psi||^2 of batch member 0 (one read sweep). */
+rocqStatus_t rocsvxGetNorm(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, double* result);
+
+/* Batched Pauli-string expectation: numTerms strings in one call.  paulis = concatenated characters,
+ * qubits = concatenated qubit indices, offsets[t]..offsets[t+1] delimit term t (offsets has
+ * numTerms+1 entries).  results[t] = <psi|P_t|psi>. */
+rocqStatus_t rocsvxGetExpectationPauliBatch(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits,
+                                            const char* paulis, const unsigned* qubits, const unsigned* offsets,
+                                            unsigned numTerms, double* results);
+
+/* Counters since rocsvCreate / the last reset: what the engine actually launched. */
+typedef struct {
+    uint64_t kernelLaunches;   /* every kernel of this library */
+    uint64_t sweeps;           /* launches of the fused tile-sweep kernel */
+    uint64_t gatesSubmitted;   /* gates received through rocsvApply* / rocsvxApplyCircuit */
+    uint64_t opsExecuted;      /* tile ops after algebraic fusion */
+    uint64_t h2dBytes;         /* host->device bytes the engine itself moved: sweep programs (kernel parameters), matrices */
+    double   lastSweepMs;      /* device time of the most recent flush (CUDA events), 0 if none */
+} rocsvxStats;
+rocqStatus_t rocsvxGetStats(rocsvHandle_t handle, rocsvxStats* stats, int reset);
+
+/* Device timer on the handle's stream (CUDA events): Start records, Stop records, flushes nothing and
+ * returns the elapsed milliseconds after synchronising on the stop event. */
+rocqStatus_t rocsvxTimerStart(rocsvHandle_t handle);
+rocqStatus_t rocsvxTimerStop(rocsvHandle_t handle, double* milliseconds);
+
+/* Host-only planning (no GPU needed): partition `ops` into sweeps exactly as the engine would and
+ * describe the plan as text into buf (NUL-terminated, truncated to bufSize).  Returns the number of
+ * sweeps through *numSweeps.  tileBits = 0 selects the engine default. */
+rocqStatus_t rocsvxPlanCircuit(unsigned numQubits, unsigned tileBits, const rocsvxGateOp* ops, size_t numOps,
+                               unsigned* numSweeps, char* buf, size_t bufSize);
+
+/* ---- multi-process distribution (one process per GPU).  The 128-byte id is NCCL's unique id: rank 0
+ *      obtains it and the host broadcasts it by any means (torch.distributed in bench.py). ---- */
+rocqStatus_t rocsvxDistGetUniqueId(void* id128);
+rocqStatus_t rocsvxDistInit(rocsvHandle_t handle, int rank, int numRanks, const void* id128);
+rocqStatus_t rocsvxDistGetInfo(rocsvHandle_t handle, int* rank, int* numRanks, unsigned* numLocalQubits, rocComplex** d_localSlice);
+
+/* Host-only plan of a global<->local index-bit exchange: swapping the k = numPairs global bits
+ * globalBits[] with the local bits localBits[] on `rank` of `numRanks`.  Writes up to maxSegs
+ * segments {peer, sendOffset, recvOffset, count} in amplitudes; returns how many through *numSegs. */
+typedef struct { int32_t peer; uint64_t sendOffset; uint64_t recvOffset; uint64_t count; } rocsvxExchangeSeg;
+rocqStatus_t rocsvxDistPlanExchange(unsigned numLocalQubits, int numRanks, int rank,
+                                    const unsigned* localBits, const unsigned* globalBits, unsigned numPairs,
+                                    rocsvxExchangeSeg* segs, size_t maxSegs, size_t* numSegs);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* HIPSTATEVEC_H */

@@ -1,0 +1,821 @@
+// rocquantum_b200/csrc/engine.cu -- host side of the drop-in C ABI (include/hipStateVec.h).
+//
+// Mirrors, entry point by entry point, /root/reference/rocquantum/src/hipStateVec/hipStateVec.cpp
+// (handle :62-68, validation and status codes :100-186, lifecycle :190-272, gates :276-687, readback
+// :691-730) and implements the 17 entry points the reference only declares.  Every gate becomes a
+// HostOp (host_ops.h); eager mode runs it as a one-op sweep, fusion mode queues it and cuts the queue
+// into fused sweeps at the next flush.  There is no CPU fallback: if CUDA is unusable, rocsvCreate
+// fails with ROCQ_STATUS_HIP_ERROR.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hipStateVec.h"
+#include "dist.h"
+#include "host_ops.h"
+#include "sv_internal.h"
+
+using rq::cd;
+using rq::HostOp;
+
+static_assert(sizeof(rocComplex) == sizeof(rq_cplx), "rocComplex layout");
+static_assert(sizeof(rq_program_large) <= 32764, "kernel parameter limit");
+
+struct rocsvInternalHandle {
+    cudaStream_t stream = nullptr;
+    size_t batchSize = 1;
+    unsigned numQubits = 0;
+    rq_cplx* d_state = nullptr;
+    bool ownsState = false;
+    // deferred gate queue (fusion mode)
+    bool fusion = false;
+    std::vector<HostOp> queue;
+    rq_cplx* queue_state = nullptr;
+    unsigned queue_n = 0;
+    // RNG
+    uint64_t seed = 0, draws = 0;
+    // scratch
+    double* d_partials = nullptr;       // RBLOCKS doubles + 8 results
+    uint64_t* d_upartials = nullptr;    // 4*RBLOCKS + 4
+    void* h_scratch = nullptr;          // pinned, 4 KB
+    void* pinned = nullptr;             // user-visible pinned buffer (rocsvEnsurePinnedBuffer)
+    size_t pinnedSize = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
+    // tuning
+    unsigned tileBits = RQ_MAX_TILE_BITS;
+    double budget = 1e30;
+    rocsvxStats stats{};
+    rq::Dist dist;
+};
+
+namespace {
+
+typedef rocsvInternalHandle H;
+
+inline rocqStatus_t cuda_status(int e, const char* what) {
+    if (e == (int)cudaSuccess) return ROCQ_STATUS_SUCCESS;
+    fprintf(stderr, "hipStateVec(B200): %s failed: %s\n", what, cudaGetErrorString((cudaError_t)e));
+    return ROCQ_STATUS_HIP_ERROR;
+}
+#define RQ_CUDA(call, what)                                            \
+    do {                                                               \
+        const rocqStatus_t _s = cuda_status((int)(call), what);        \
+        if (_s != ROCQ_STATUS_SUCCESS) return _s;                      \
+    } while (0)
+
+inline rq_cplx* resolve(H* h, rocComplex* ext) {          // hipStateVec.cpp:80-85
+    if (ext) return reinterpret_cast<rq_cplx*>(ext);
+    return h ? h->d_state : nullptr;
+}
+
+rq::PlanLimits limits_for(const H* h, bool large) {
+    rq::PlanLimits L;
+    L.tile_bits = h->tileBits;
+    L.budget = h->budget;
+    if (large) { L.max_ops = sizeof(rq_program_large::ops) / sizeof(rq_tile_op); L.pool_cplx = sizeof(rq_program_large::pool) / sizeof(rq_cplx); }
+    else { L.max_ops = sizeof(rq_program_small::ops) / sizeof(rq_tile_op); L.pool_cplx = sizeof(rq_program_small::pool) / sizeof(rq_cplx); }
+    if (h->dist.active()) L.never_resident = h->dist.global_mask();
+    return L;
+}
+
+// run ops (already validated) on `state`: dense/diag ops wider than the tile kernel handles go through
+// the gather kernel, everything else through planned sweeps.
+rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>& ops, bool fused) {
+    size_t i = 0;
+    while (i < ops.size()) {
+        // segment of tile-capable ops
+        size_t j = i;
+        while (j < ops.size() && ops[j].targets.size() <= 4) ++j;
+        if (j > i) {
+            std::vector<HostOp> seg(ops.begin() + i, ops.begin() + j);
+            if (fused && seg.size() > 1) seg = rq::fuse_algebraic(seg, n);
+            const bool large = seg.size() > 1;
+            const rq::PlanLimits L = limits_for(h, large);
+            const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(seg, n, L);
+            for (const rq::SweepPlan& sp : plans) {
+                int e;
+                if (large) {
+                    static thread_local rq_program_large P;
+                    if (!rq::build_program(P, sp, seg, n, h->batchSize, h->dist.high_base())) return ROCQ_STATUS_FAILURE;
+                    e = rq_launch_sweep_large(state, &P, h->stream);
+                    h->stats.h2dBytes += sizeof(P);
+                } else {
+                    static thread_local rq_program_small P;
+                    if (!rq::build_program(P, sp, seg, n, h->batchSize, h->dist.high_base())) return ROCQ_STATUS_FAILURE;
+                    e = rq_launch_sweep_small(state, &P, h->stream);
+                    h->stats.h2dBytes += sizeof(P);
+                }
+                RQ_CUDA(e, "tile sweep launch");
+                h->stats.kernelLaunches++;
+                h->stats.sweeps++;
+                h->stats.opsExecuted += sp.ops.size();
+            }
+            i = j;
+        }
+        if (i < ops.size()) {                 // one wide op through the gather kernel
+            const HostOp& o = ops[i];
+            const unsigned k = (unsigned)o.targets.size();
+            if (k > 10) return ROCQ_STATUS_NOT_IMPLEMENTED;
+            const rq_cplx* dm = reinterpret_cast<const rq_cplx*>(o.ext);
+            rq_cplx* tmp = nullptr;
+            if (!dm) {                        // host matrix (or diagonal): upload, stream-ordered
+                const size_t D = (size_t)1 << k;
+                std::vector<rq_cplx> hm(D * D, rq_cplx{0, 0});
+                if (o.kind == HostOp::DIAG) for (size_t d = 0; d < D; ++d) { hm[d + d * D].x = (rq_real)o.data[d].real(); hm[d + d * D].y = (rq_real)o.data[d].imag(); }
+                else for (size_t e = 0; e < D * D; ++e) { hm[e].x = (rq_real)o.data[e].real(); hm[e].y = (rq_real)o.data[e].imag(); }
+                RQ_CUDA(cudaMallocAsync(&tmp, D * D * sizeof(rq_cplx), h->stream), "cudaMallocAsync");
+                RQ_CUDA(cudaMemcpyAsync(tmp, hm.data(), D * D * sizeof(rq_cplx), cudaMemcpyHostToDevice, h->stream), "matrix upload");
+                RQ_CUDA(cudaStreamSynchronize(h->stream), "sync");     // hm goes out of scope
+                h->stats.h2dBytes += D * D * sizeof(rq_cplx);
+                dm = tmp;
+            }
+            RQ_CUDA(rq_launch_gather(state, n, h->batchSize, o.targets.data(), k, o.cmask, dm, h->stream), "gather launch");
+            h->stats.kernelLaunches++;
+            h->stats.opsExecuted++;
+            if (tmp) RQ_CUDA(cudaFreeAsync(tmp, h->stream), "cudaFreeAsync");
+            ++i;
+        }
+    }
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t flush(H* h) {
+    if (h->queue.empty()) return ROCQ_STATUS_SUCCESS;
+    std::vector<HostOp> q;
+    q.swap(h->queue);
+    cudaEventRecord(h->ev0, h->stream);
+    const rocqStatus_t s = run_ops(h, h->queue_state, h->queue_n, q, true);
+    cudaEventRecord(h->ev1, h->stream);
+    h->stats.lastSweepMs = -1.0;         // resolved lazily in rocsvxGetStats
+    return s;
+}
+
+// validate-and-dispatch for one gate: reference order of checks (hipStateVec.cpp:280-282, 108-110)
+rocqStatus_t submit(H* h, rocComplex* d_state, unsigned n, HostOp&& op) {
+    rq_cplx* state = resolve(h, d_state);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    const uint64_t Q = op.qubits();
+    if (n < 64 && (Q >> n) != 0) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->dist.active()) {
+        const rocqStatus_t s = h->dist.localize(h, op);     // may exchange slices; rewrites op to physical positions
+        if (s != ROCQ_STATUS_SUCCESS) return s;
+        n = h->dist.num_local();
+    }
+    h->stats.gatesSubmitted++;
+    if (h->fusion) {
+        if (!h->queue.empty() && (h->queue_state != state || h->queue_n != n)) {
+            const rocqStatus_t s = flush(h);
+            if (s != ROCQ_STATUS_SUCCESS) return s;
+        }
+        h->queue_state = state;
+        h->queue_n = n;
+        h->queue.push_back(std::move(op));
+        return ROCQ_STATUS_SUCCESS;
+    }
+    std::vector<HostOp> one;
+    one.push_back(std::move(op));
+    return run_ops(h, state, n, one, false);
+}
+
+inline bool valid_q(unsigned q, unsigned n) { return q < n; }     // hipStateVec.cpp:96-98
+
+rocqStatus_t single(H* h, rocComplex* d, unsigned n, unsigned t, HostOp&& op) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (!resolve(h, d)) return ROCQ_STATUS_INVALID_VALUE;
+    if (!valid_q(t, n)) return ROCQ_STATUS_INVALID_VALUE;
+    return submit(h, d, n, std::move(op));
+}
+rocqStatus_t two(H* h, rocComplex* d, unsigned n, unsigned a, unsigned b, HostOp&& op) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (!resolve(h, d)) return ROCQ_STATUS_INVALID_VALUE;
+    if (!valid_q(a, n) || !valid_q(b, n) || a == b) return ROCQ_STATUS_INVALID_VALUE;
+    return submit(h, d, n, std::move(op));
+}
+
+const cd I1(0.0, 1.0);
+
+// read back `count` doubles / u64 from device scratch (synchronises the stream)
+rocqStatus_t fetch(H* h, const void* dsrc, void* hdst, size_t bytes) {
+    RQ_CUDA(cudaMemcpyAsync(h->h_scratch, dsrc, bytes, cudaMemcpyDeviceToHost, h->stream), "scratch D2H");
+    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
+    memcpy(hdst, h->h_scratch, bytes);
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t pauli_expect(H* h, rq_cplx* state, unsigned n, uint64_t xm, uint64_t zm, unsigned ny, double* result) {
+    const unsigned nb = rq_reduce_blocks();
+    RQ_CUDA(rq_launch_pauli_expect(state, n, xm, zm, ny, h->d_partials, nb, h->d_partials + nb, h->stream), "expectation launch");
+    h->stats.kernelLaunches += 2;
+    rocqStatus_t s = fetch(h, h->d_partials + nb, result, sizeof(double));
+    if (s == ROCQ_STATUS_SUCCESS && h->dist.active()) s = h->dist.allreduce_sum(h, result, 1);
+    return s;
+}
+
+typedef unsigned __int128 u128;
+inline double u128_to_double(u128 v) { return (double)(uint64_t)(v >> 64) * 0x1p64 + (double)(uint64_t)v; }
+inline u128 mul_u53(u128 S, uint64_t U) {
+    const u128 A = (u128)(uint64_t)S * U, B = (u128)(uint64_t)(S >> 64) * U;
+    return (B << 11) + (A >> 53);
+}
+void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+uint64_t uniform53(uint64_t seed, uint64_t call, uint64_t shot) {
+    const uint32_t ctr[4] = {(uint32_t)shot, (uint32_t)(shot >> 32), (uint32_t)call, (uint32_t)(call >> 32)};
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t x[4];
+    philox4x32_10(ctr, key, x);
+    return (((uint64_t)x[0] << 32) | x[1]) >> 11;
+}
+
+}  // namespace
+
+// needed by dist.cpp
+rocqStatus_t rq_engine_flush(rocsvInternalHandle* h) { return flush(h); }
+cudaStream_t rq_engine_stream(rocsvInternalHandle* h) { return h->stream; }
+rq::Dist& rq_engine_dist(rocsvInternalHandle* h) { return h->dist; }
+rocqStatus_t rq_engine_run(rocsvInternalHandle* h, rq_cplx* state, unsigned n, const std::vector<HostOp>& ops) { return run_ops(h, state, n, ops, false); }
+void rq_engine_count_launch(rocsvInternalHandle* h, unsigned k) { h->stats.kernelLaunches += k; }
+
+extern "C" {
+
+// ---- lifecycle (hipStateVec.cpp:190-251) ---------------------------------------------------------------
+rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
+    if (!handle) return ROCQ_STATUS_INVALID_VALUE;
+    *handle = nullptr;
+    H* h = new H();
+    if (cudaStreamCreate(&h->stream) != cudaSuccess) {
+        fprintf(stderr, "hipStateVec(B200): no usable CUDA device (%s); this engine has no CPU fallback\n",
+                cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return ROCQ_STATUS_HIP_ERROR;
+    }
+    const unsigned nb = rq_reduce_blocks();
+    if (rq_sweep_configure() != 0 || cudaMalloc(&h->d_partials, (nb + 8) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_upartials, (4 * nb + 4) * sizeof(uint64_t)) != cudaSuccess ||
+        cudaHostAlloc(&h->h_scratch, 4096, cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaEventCreate(&h->tm0) != cudaSuccess || cudaEventCreate(&h->tm1) != cudaSuccess) {
+        fprintf(stderr, "hipStateVec(B200): handle setup failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        rocsvDestroy(h);
+        return ROCQ_STATUS_HIP_ERROR;
+    }
+    if (const char* e = getenv("ROCQ_FUSION")) h->fusion = atoi(e) != 0;
+    if (const char* e = getenv("ROCQ_TILE_BITS")) { const int t = atoi(e); if (t >= 6 && t <= RQ_MAX_TILE_BITS) h->tileBits = (unsigned)t; }
+    if (const char* e = getenv("ROCQ_SWEEP_BUDGET")) { const double b = atof(e); if (b > 0) h->budget = b; }
+    *handle = h;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t rocsvDestroy(rocsvHandle_t h) {
+    if (!h) return ROCQ_STATUS_SUCCESS;                   // hipStateVec.cpp:203-210
+    if (h->stream) { flush(h); cudaStreamSynchronize(h->stream); }
+    h->dist.shutdown();
+    rocsvFreeState(h);
+    if (h->d_partials) cudaFree(h->d_partials);
+    if (h->d_upartials) cudaFree(h->d_upartials);
+    if (h->h_scratch) cudaFreeHost(h->h_scratch);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->tm0) cudaEventDestroy(h->tm0);
+    if (h->tm1) cudaEventDestroy(h->tm1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t rocsvAllocateState(rocsvHandle_t h, unsigned numQubits, rocComplex** d_state, size_t batchSize) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (numQubits > 40) return ROCQ_STATUS_ALLOCATION_FAILED;
+    flush(h);
+    cudaStreamSynchronize(h->stream);
+    h->batchSize = batchSize > 0 ? batchSize : 1;
+    h->numQubits = numQubits;
+    if (h->d_state && h->ownsState) { cudaFree(h->d_state); h->d_state = nullptr; h->ownsState = false; }
+    size_t total = h->batchSize * ((size_t)1 << numQubits);
+    if (total * sizeof(rq_cplx) < 16) total = 16 / sizeof(rq_cplx);       // keep bulk copies 16-byte sized
+    rq_cplx* p = nullptr;
+    if (cudaMalloc(&p, total * sizeof(rq_cplx)) != cudaSuccess) { cudaGetLastError(); return ROCQ_STATUS_ALLOCATION_FAILED; }
+    if (d_state) *d_state = reinterpret_cast<rocComplex*>(p);
+    h->d_state = p;
+    h->ownsState = true;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t rocsvFreeState(rocsvHandle_t h) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->stream) { flush(h); cudaStreamSynchronize(h->stream); }
+    if (h->d_state && h->ownsState) cudaFree(h->d_state);
+    h->d_state = nullptr;
+    h->ownsState = false;
+    h->numQubits = 0;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t rocsvInitializeState(rocsvHandle_t h, rocComplex* d_state, unsigned numQubits) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    rq_cplx* state = resolve(h, d_state);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    h->queue.clear();                                      // anything queued is overwritten by the reset
+    const size_t total = h->batchSize * ((size_t)1 << numQubits);
+    RQ_CUDA(rq_launch_init_state(state, total, 1, h->stream), "initialize state");
+    h->stats.kernelLaunches++;
+    h->numQubits = numQubits;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+// ---- named gates (hipStateVec.cpp:276-427) ---------------------------------------------------------------
+rocqStatus_t rocsvApplyH(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) {
+    const double s = 1.0 / std::sqrt(2.0);
+    return single(h, d, n, t, rq::make_dense1(t, s, s, s, -s));
+}
+rocqStatus_t rocsvApplyX(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) { return single(h, d, n, t, rq::make_x(t)); }
+rocqStatus_t rocsvApplyY(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) {
+    return single(h, d, n, t, rq::make_dense1(t, 0.0, -I1, I1, 0.0));
+}
+rocqStatus_t rocsvApplyZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) { return single(h, d, n, t, rq::make_phase(1ull << t, -1.0)); }
+rocqStatus_t rocsvApplyS(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) { return single(h, d, n, t, rq::make_phase(1ull << t, I1)); }
+rocqStatus_t rocsvApplySdg(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) { return single(h, d, n, t, rq::make_phase(1ull << t, -I1)); }
+rocqStatus_t rocsvApplyT(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) {
+    const double ph = 3.14159265358979323846 / 4.0;
+    return single(h, d, n, t, rq::make_phase(1ull << t, cd(std::cos(ph), std::sin(ph))));
+}
+rocqStatus_t rocsvApplyRx(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double theta) {
+    const double c = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
+    return single(h, d, n, t, rq::make_dense1(t, c, cd(0.0, -s), cd(0.0, -s), c));
+}
+rocqStatus_t rocsvApplyRy(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double theta) {
+    const double c = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
+    return single(h, d, n, t, rq::make_dense1(t, c, -s, s, c));
+}
+rocqStatus_t rocsvApplyRz(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double theta) {
+    const double c = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
+    return single(h, d, n, t, rq::make_diag1(t, cd(c, -s), cd(c, s)));
+}
+
+// ---- two-qubit and controlled gates (hipStateVec.cpp:431-687) -----------------------------------------------
+rocqStatus_t rocsvApplyCNOT(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned c, unsigned t) { return two(h, d, n, c, t, rq::make_x(t, 1ull << (c & 63))); }
+rocqStatus_t rocsvApplyCZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned a, unsigned b) { return two(h, d, n, a, b, rq::make_phase((1ull << (a & 63)) | (1ull << (b & 63)), -1.0)); }
+rocqStatus_t rocsvApplySWAP(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned a, unsigned b) { return two(h, d, n, a, b, rq::make_swap(a, b)); }
+rocqStatus_t rocsvApplyCRX(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned c, unsigned t, double theta) {
+    const double co = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
+    return two(h, d, n, c, t, rq::make_dense1(t, co, cd(0.0, -s), cd(0.0, -s), co, 1ull << (c & 63)));
+}
+rocqStatus_t rocsvApplyCRY(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned c, unsigned t, double theta) {
+    const double co = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
+    return two(h, d, n, c, t, rq::make_dense1(t, co, -s, s, co, 1ull << (c & 63)));
+}
+rocqStatus_t rocsvApplyCRZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned c, unsigned t, double theta) {
+    const double co = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
+    return two(h, d, n, c, t, rq::make_diag1(t, cd(co, -s), cd(co, s), 1ull << (c & 63)));
+}
+
+rocqStatus_t rocsvApplyMultiControlledX(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* controls, unsigned nc, unsigned t) {
+    if (!h || !controls || nc == 0) return ROCQ_STATUS_INVALID_VALUE;          // hipStateVec.cpp:605-607
+    if (!resolve(h, d)) return ROCQ_STATUS_INVALID_VALUE;
+    if (!valid_q(t, n)) return ROCQ_STATUS_INVALID_VALUE;
+    if (nc > 63) return ROCQ_STATUS_NOT_IMPLEMENTED;                           // :613-615
+    uint64_t mask = 0;
+    for (unsigned i = 0; i < nc; ++i) {
+        if (!valid_q(controls[i], n) || controls[i] == t) return ROCQ_STATUS_INVALID_VALUE;
+        mask |= 1ull << controls[i];
+    }
+    return submit(h, d, n, rq::make_x(t, mask));
+}
+
+rocqStatus_t rocsvApplyCSWAP(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned c, unsigned a, unsigned b) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (!resolve(h, d)) return ROCQ_STATUS_INVALID_VALUE;
+    if (!valid_q(c, n) || !valid_q(a, n) || !valid_q(b, n) || c == a || c == b || a == b) return ROCQ_STATUS_INVALID_VALUE;
+    return submit(h, d, n, rq::make_swap(a, b, 1ull << c));
+}
+
+// ---- arbitrary matrices (hipStateVec.h:118-120, 151-157, 461-468) -----------------------------------------------
+static rocqStatus_t apply_device_matrix(H* h, rocComplex* d, unsigned n, const unsigned* controls, unsigned nc,
+                                        const unsigned* targets, unsigned k, const rocComplex* d_matrix) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (!resolve(h, d)) return ROCQ_STATUS_INVALID_VALUE;
+    if (!targets || k == 0 || !d_matrix || (nc > 0 && !controls)) return ROCQ_STATUS_INVALID_VALUE;
+    if (k > 10) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    if (nc > 63) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    uint64_t seen = 0, cmask = 0;
+    for (unsigned i = 0; i < k; ++i) {
+        if (!valid_q(targets[i], n) || ((seen >> targets[i]) & 1ull)) return ROCQ_STATUS_INVALID_VALUE;
+        seen |= 1ull << targets[i];
+    }
+    for (unsigned i = 0; i < nc; ++i) {
+        if (!valid_q(controls[i], n) || ((seen >> controls[i]) & 1ull)) return ROCQ_STATUS_INVALID_VALUE;
+        seen |= 1ull << controls[i];
+        cmask |= 1ull << controls[i];
+    }
+    HostOp o;
+    o.targets.assign(targets, targets + k);
+    o.cmask = cmask;
+    if (h->fusion || h->dist.active()) {
+        // deferred: the caller may free/overwrite the matrix before the flush -> take a host copy now
+        const size_t D = (size_t)1 << k;
+        std::vector<rq_cplx> hm(D * D);
+        RQ_CUDA(cudaMemcpy(hm.data(), d_matrix, D * D * sizeof(rq_cplx), cudaMemcpyDeviceToHost), "matrix D2H");
+        std::vector<cd> m(D * D);
+        for (size_t e = 0; e < D * D; ++e) m[e] = cd(hm[e].x, hm[e].y);
+        o = rq::make_matrix(o.targets, cmask, m);
+    } else {
+        o.kind = HostOp::DENSE;
+        o.ext = d_matrix;
+    }
+    return submit(h, d, n, std::move(o));
+}
+
+rocqStatus_t rocsvApplyMatrix(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* qubitIndices, unsigned numTargetQubits,
+                              const rocComplex* matrixDevice, unsigned matrixDim) {
+    if (numTargetQubits < 32 && matrixDim != (1u << numTargetQubits)) return ROCQ_STATUS_INVALID_VALUE;
+    return apply_device_matrix(h, d, n, nullptr, 0, qubitIndices, numTargetQubits, matrixDevice);
+}
+rocqStatus_t rocsvApplyControlledMatrix(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* controls, unsigned nc,
+                                        const unsigned* targets, unsigned nt, const rocComplex* d_matrix) {
+    return apply_device_matrix(h, d, n, controls, nc, targets, nt, d_matrix);
+}
+rocqStatus_t rocsvApplyFusedSingleQubitMatrix(rocsvHandle_t h, unsigned targetQubit, const rocComplex* d_fusedMatrix) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    const unsigned n = h->dist.active() ? h->dist.num_total() : h->numQubits;
+    return apply_device_matrix(h, nullptr, n, nullptr, 0, &targetQubit, 1, d_fusedMatrix);
+}
+
+rocqStatus_t rocsvSwapIndexBits(rocsvHandle_t h, unsigned q1, unsigned q2) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    const unsigned n = h->dist.active() ? h->dist.num_total() : h->numQubits;
+    if (!h->d_state) return ROCQ_STATUS_INVALID_VALUE;
+    if (!valid_q(q1, n) || !valid_q(q2, n)) return ROCQ_STATUS_INVALID_VALUE;
+    if (q1 == q2) return ROCQ_STATUS_SUCCESS;
+    if (h->dist.active()) return h->dist.swap_index_bits(h, q1, q2);
+    return submit(h, nullptr, n, rq::make_swap(q1, q2));
+}
+
+// ---- readback (hipStateVec.cpp:691-730) ---------------------------------------------------------------
+rocqStatus_t rocsvGetStateVectorFull(rocsvHandle_t h, rocComplex* d_state, rocComplex* h_state) {
+    if (!h || !h_state) return ROCQ_STATUS_INVALID_VALUE;
+    rq_cplx* state = resolve(h, d_state);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    rocqStatus_t s = flush(h);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    if (h->dist.active()) { s = h->dist.canonicalize(h); if (s != ROCQ_STATUS_SUCCESS) return s; }
+    const size_t total = h->batchSize * ((size_t)1 << h->numQubits);
+    RQ_CUDA(cudaMemcpyAsync(h_state, state, total * sizeof(rq_cplx), cudaMemcpyDeviceToHost, h->stream), "state D2H");
+    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
+    return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t rocsvGetStateVectorSlice(rocsvHandle_t h, rocComplex* d_state, rocComplex* h_state, unsigned batch_index) {
+    if (!h || !h_state) return ROCQ_STATUS_INVALID_VALUE;
+    rq_cplx* state = resolve(h, d_state);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    if (batch_index >= h->batchSize) return ROCQ_STATUS_INVALID_VALUE;
+    rocqStatus_t s = flush(h);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    if (h->dist.active()) { s = h->dist.canonicalize(h); if (s != ROCQ_STATUS_SUCCESS) return s; }
+    const size_t N = (size_t)1 << h->numQubits;
+    RQ_CUDA(cudaMemcpyAsync(h_state, state + batch_index * N, N * sizeof(rq_cplx), cudaMemcpyDeviceToHost, h->stream), "slice D2H");
+    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
+    return ROCQ_STATUS_SUCCESS;
+}
+
+// ---- pinned buffer (hipStateVec.h:307-324) ---------------------------------------------------------------
+rocqStatus_t rocsvEnsurePinnedBuffer(rocsvHandle_t h, size_t minSizeBytes) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->pinned && h->pinnedSize >= minSizeBytes) return ROCQ_STATUS_SUCCESS;
+    if (h->pinned) { cudaFreeHost(h->pinned); h->pinned = nullptr; h->pinnedSize = 0; }
+    if (minSizeBytes == 0) return ROCQ_STATUS_SUCCESS;
+    if (cudaHostAlloc(&h->pinned, minSizeBytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h->pinned = nullptr; return ROCQ_STATUS_ALLOCATION_FAILED; }
+    h->pinnedSize = minSizeBytes;
+    return ROCQ_STATUS_SUCCESS;
+}
+void* rocsvGetPinnedBufferPointer(rocsvHandle_t h) { return h ? h->pinned : nullptr; }
+rocqStatus_t rocsvFreePinnedBuffer(rocsvHandle_t h) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->pinned) cudaFreeHost(h->pinned);
+    h->pinned = nullptr;
+    h->pinnedSize = 0;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+// ---- expectation values (hipStateVec.h:340-423) ---------------------------------------------------------------
+static rocqStatus_t expect_string(H* h, rocComplex* d, unsigned n, const char* paulis, const unsigned* qubits, unsigned k, double* result) {
+    if (!h || !result) return ROCQ_STATUS_INVALID_VALUE;
+    rq_cplx* state = resolve(h, d);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    if (k > 0 && (!paulis || !qubits)) return ROCQ_STATUS_INVALID_VALUE;
+    uint64_t xm = 0, zm = 0, seen = 0;
+    unsigned ny = 0;
+    for (unsigned j = 0; j < k; ++j) {
+        if (!valid_q(qubits[j], n) || ((seen >> qubits[j]) & 1ull)) return ROCQ_STATUS_INVALID_VALUE;
+        seen |= 1ull << qubits[j];
+        const uint64_t bit = 1ull << qubits[j];
+        switch (paulis[j]) {
+            case 'I': case 'i': break;
+            case 'X': case 'x': xm |= bit; break;
+            case 'Y': case 'y': xm |= bit; zm |= bit; ++ny; break;
+            case 'Z': case 'z': zm |= bit; break;
+            default: return ROCQ_STATUS_INVALID_VALUE;
+        }
+    }
+    rocqStatus_t s = flush(h);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    if (h->dist.active()) return h->dist.pauli_expect(h, xm, zm, ny, result);
+    return pauli_expect(h, state, n, xm, zm, ny, result);
+}
+rocqStatus_t rocsvGetExpectationValueSinglePauliZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double* r) { return expect_string(h, d, n, "Z", &t, 1, r); }
+rocqStatus_t rocsvGetExpectationValueSinglePauliX(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double* r) { return expect_string(h, d, n, "X", &t, 1, r); }
+rocqStatus_t rocsvGetExpectationValueSinglePauliY(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double* r) { return expect_string(h, d, n, "Y", &t, 1, r); }
+rocqStatus_t rocsvGetExpectationValuePauliProductZ(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* qs, unsigned k, double* r) {
+    if (k > 64) return ROCQ_STATUS_INVALID_VALUE;
+    char buf[65];
+    memset(buf, 'Z', sizeof buf);
+    buf[k] = 0;
+    return expect_string(h, d, n, buf, qs, k, r);
+}
+rocqStatus_t rocsvGetExpectationPauliString(rocsvHandle_t h, rocComplex* d, unsigned n, const char* paulis, const unsigned* qs, unsigned k, double* r) {
+    if (paulis && strlen(paulis) != k) return ROCQ_STATUS_INVALID_VALUE;       // hipStateVec.h:413
+    return expect_string(h, d, n, paulis, qs, k, r);
+}
+rocqStatus_t rocsvxGetExpectationPauliBatch(rocsvHandle_t h, rocComplex* d, unsigned n, const char* paulis, const unsigned* qubits,
+                                            const unsigned* offsets, unsigned numTerms, double* results) {
+    if (!h || !results || !offsets) return ROCQ_STATUS_INVALID_VALUE;
+    for (unsigned t = 0; t < numTerms; ++t) {
+        const unsigned b = offsets[t], e = offsets[t + 1];
+        if (e < b) return ROCQ_STATUS_INVALID_VALUE;
+        const rocqStatus_t s = expect_string(h, d, n, paulis + b, qubits + b, e - b, results + t);
+        if (s != ROCQ_STATUS_SUCCESS) return s;
+    }
+    return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t rocsvxGetNorm(rocsvHandle_t h, rocComplex* d, unsigned n, double* r) { return expect_string(h, d, n, "", nullptr, 0, r); }
+
+// ---- measurement (hipStateVec.h:172-177; algorithm measurement_kernels.hip:37-77, MULTI_GPU_GUIDE.md:61-78) ----
+rocqStatus_t rocsvMeasure(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned q, int* outcome, double* probability) {
+    if (!h || !outcome) return ROCQ_STATUS_INVALID_VALUE;
+    rq_cplx* state = resolve(h, d);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    if (!valid_q(q, n)) return ROCQ_STATUS_INVALID_VALUE;
+    rocqStatus_t s = flush(h);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    if (h->dist.active()) return h->dist.measure(h, q, outcome, probability);
+    const unsigned nb = rq_reduce_blocks();
+    RQ_CUDA(rq_launch_fixed_masses(state, n, q, h->d_upartials, nb, h->d_upartials + 4 * nb, h->stream), "mass reduction");
+    h->stats.kernelLaunches += 2;
+    uint64_t m[4];
+    s = fetch(h, h->d_upartials + 4 * nb, m, sizeof m);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    const u128 S0 = ((u128)m[0] << 64) | m[1], S1 = ((u128)m[2] << 64) | m[3];
+    const uint64_t U = uniform53(h->seed, h->draws++, 0);
+    const int out = mul_u53(S0 + S1, U) < S0 ? 0 : 1;
+    const double tot = u128_to_double(S0 + S1), mass = u128_to_double(out ? S1 : S0);
+    if (!(mass > 0.0)) return ROCQ_STATUS_FAILURE;
+    *outcome = out;
+    if (probability) *probability = mass / tot;
+    RQ_CUDA(rq_launch_collapse(state, n, q, out, 1.0 / std::sqrt(mass * 0x1p-88), h->stream), "collapse");
+    h->stats.kernelLaunches++;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t rocsvApplyMatrixAndMeasure(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* targets, unsigned nt,
+                                        const rocComplex* d_matrix, unsigned qubitToMeasure, int* outcome) {
+    const rocqStatus_t s = apply_device_matrix(h, d, n, nullptr, 0, targets, nt, d_matrix);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    double p = 0.0;
+    return rocsvMeasure(h, d, n, qubitToMeasure, outcome, &p);
+}
+
+// ---- sampling (hipStateVec.h:439-445) ---------------------------------------------------------------
+rocqStatus_t rocsvSample(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* measured, unsigned nm, unsigned numShots,
+                         uint64_t* h_results) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    rq_cplx* state = resolve(h, d);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    if (nm > 64 || (nm > 0 && !measured)) return ROCQ_STATUS_INVALID_VALUE;
+    for (unsigned j = 0; j < nm; ++j) if (!valid_q(measured[j], n)) return ROCQ_STATUS_INVALID_VALUE;
+    if (numShots == 0) return ROCQ_STATUS_SUCCESS;
+    if (!h_results) return ROCQ_STATUS_INVALID_VALUE;
+    rocqStatus_t s = flush(h);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    if (h->dist.active()) return h->dist.sample(h, measured, nm, numShots, h_results);
+
+    const unsigned cb = n < 10 ? n : (n > 30 ? n - 20 : 10);              // chunk of 2^cb amplitudes, <= 2^20 chunks
+    const uint64_t nchunks = 1ull << (n - cb);
+    uint64_t *d_hi = nullptr, *d_idx = nullptr;
+    RQ_CUDA(cudaMallocAsync(&d_hi, 2 * nchunks * sizeof(uint64_t), h->stream), "chunk scratch");
+    uint64_t* d_lo = d_hi + nchunks;
+    RQ_CUDA(rq_launch_chunk_masses(state, n, cb, d_hi, d_lo, h->stream), "chunk masses");
+    std::vector<uint64_t> hv(2 * nchunks);
+    RQ_CUDA(cudaMemcpyAsync(hv.data(), d_hi, 2 * nchunks * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream), "chunk D2H");
+    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
+    u128 acc = 0;                                                          // exact inclusive scan
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        acc += ((u128)hv[c] << 64) | hv[nchunks + c];
+        hv[c] = (uint64_t)(acc >> 64);
+        hv[nchunks + c] = (uint64_t)acc;
+    }
+    if (acc == 0) { cudaFreeAsync(d_hi, h->stream); return ROCQ_STATUS_FAILURE; }
+    RQ_CUDA(cudaMemcpyAsync(d_hi, hv.data(), 2 * nchunks * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream), "scan H2D");
+    RQ_CUDA(cudaMallocAsync(&d_idx, (size_t)numShots * sizeof(uint64_t), h->stream), "shot scratch");
+    RQ_CUDA(rq_launch_sample(state, n, cb, d_hi, d_lo, nchunks, (uint64_t)(acc >> 64), (uint64_t)acc, h->seed, h->draws++, numShots, 0,
+                             d_idx, h->stream), "sample");
+    h->stats.kernelLaunches += 2;
+    std::vector<uint64_t> idx(numShots);
+    RQ_CUDA(cudaMemcpyAsync(idx.data(), d_idx, (size_t)numShots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream), "shots D2H");
+    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
+    cudaFreeAsync(d_hi, h->stream);
+    cudaFreeAsync(d_idx, h->stream);
+    for (unsigned sidx = 0; sidx < numShots; ++sidx) {
+        uint64_t bits = 0;
+        for (unsigned j = 0; j < nm; ++j) bits |= ((idx[sidx] >> measured[j]) & 1ull) << j;
+        h_results[sidx] = bits;
+    }
+    return ROCQ_STATUS_SUCCESS;
+}
+
+// ---- extensions ---------------------------------------------------------------
+unsigned rocsvxGetPrecisionBytes(void) { return (unsigned)sizeof(rq_real); }
+rocqStatus_t rocsvxSetSeed(rocsvHandle_t h, uint64_t seed) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    h->seed = seed;
+    h->draws = 0;
+    return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t rocsvxSetStateVector(rocsvHandle_t h, rocComplex* d_state, const rocComplex* h_state) {
+    if (!h || !h_state) return ROCQ_STATUS_INVALID_VALUE;
+    rq_cplx* state = resolve(h, d_state);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    h->queue.clear();
+    const size_t total = h->batchSize * ((size_t)1 << h->numQubits);
+    RQ_CUDA(cudaMemcpyAsync(state, h_state, total * sizeof(rq_cplx), cudaMemcpyHostToDevice, h->stream), "state H2D");
+    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
+    return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t rocsvxSynchronize(rocsvHandle_t h) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    const rocqStatus_t s = flush(h);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
+    return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t rocsvxSetFusion(rocsvHandle_t h, int enabled) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (!enabled) { const rocqStatus_t s = flush(h); if (s != ROCQ_STATUS_SUCCESS) return s; }
+    h->fusion = enabled != 0;
+    return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t rocsvxFlush(rocsvHandle_t h) { return h ? flush(h) : ROCQ_STATUS_INVALID_VALUE; }
+
+static rocqStatus_t convert_ops(unsigned n, const rocsvxGateOp* ops, size_t numOps, std::vector<HostOp>& out) {
+    out.reserve(numOps);
+    for (size_t i = 0; i < numOps; ++i) {
+        const rocsvxGateOp& g = ops[i];
+        const unsigned t0 = g.targets[0], t1 = g.targets[1];
+        const uint64_t cm = g.controlMask;
+        auto okq = [&](unsigned q) { return q < n; };
+        if (n < 64 && (cm >> n)) return ROCQ_STATUS_INVALID_VALUE;
+        const double c = std::cos(g.theta / 2.0), s = std::sin(g.theta / 2.0), r = 1.0 / std::sqrt(2.0);
+        const bool one_ctrl = __builtin_popcountll(cm) == 1;
+        switch (g.kind) {
+            case ROCSVX_H: case ROCSVX_X: case ROCSVX_Y: case ROCSVX_Z: case ROCSVX_S: case ROCSVX_SDG: case ROCSVX_T:
+            case ROCSVX_RX: case ROCSVX_RY: case ROCSVX_RZ:
+                if (!okq(t0) || cm) return ROCQ_STATUS_INVALID_VALUE;
+                break;
+            case ROCSVX_CNOT: case ROCSVX_CRX: case ROCSVX_CRY: case ROCSVX_CRZ:
+                if (!okq(t0) || !one_ctrl || ((cm >> t0) & 1ull)) return ROCQ_STATUS_INVALID_VALUE;
+                break;
+            case ROCSVX_MCX:
+                if (!okq(t0) || cm == 0 || ((cm >> t0) & 1ull)) return ROCQ_STATUS_INVALID_VALUE;
+                break;
+            case ROCSVX_CZ: case ROCSVX_SWAP:
+                if (!okq(t0) || !okq(t1) || t0 == t1 || cm) return ROCQ_STATUS_INVALID_VALUE;
+                break;
+            case ROCSVX_CSWAP:
+                if (!okq(t0) || !okq(t1) || t0 == t1 || !one_ctrl || ((cm >> t0) & 1ull) || ((cm >> t1) & 1ull)) return ROCQ_STATUS_INVALID_VALUE;
+                break;
+            case ROCSVX_MATRIX: break;
+            default: return ROCQ_STATUS_INVALID_VALUE;
+        }
+        switch (g.kind) {
+            case ROCSVX_H: out.push_back(rq::make_dense1(t0, r, r, r, -r)); break;
+            case ROCSVX_X: out.push_back(rq::make_x(t0)); break;
+            case ROCSVX_Y: out.push_back(rq::make_dense1(t0, 0.0, -I1, I1, 0.0)); break;
+            case ROCSVX_Z: out.push_back(rq::make_phase(1ull << t0, -1.0)); break;
+            case ROCSVX_S: out.push_back(rq::make_phase(1ull << t0, I1)); break;
+            case ROCSVX_SDG: out.push_back(rq::make_phase(1ull << t0, -I1)); break;
+            case ROCSVX_T: { const double ph = 3.14159265358979323846 / 4.0; out.push_back(rq::make_phase(1ull << t0, cd(std::cos(ph), std::sin(ph)))); break; }
+            case ROCSVX_RX: out.push_back(rq::make_dense1(t0, c, cd(0, -s), cd(0, -s), c)); break;
+            case ROCSVX_RY: out.push_back(rq::make_dense1(t0, c, -s, s, c)); break;
+            case ROCSVX_RZ: out.push_back(rq::make_diag1(t0, cd(c, -s), cd(c, s))); break;
+            case ROCSVX_CNOT: case ROCSVX_MCX: out.push_back(rq::make_x(t0, cm)); break;
+            case ROCSVX_CZ: out.push_back(rq::make_phase((1ull << t0) | (1ull << t1), -1.0)); break;
+            case ROCSVX_SWAP: out.push_back(rq::make_swap(t0, t1)); break;
+            case ROCSVX_CRX: out.push_back(rq::make_dense1(t0, c, cd(0, -s), cd(0, -s), c, cm)); break;
+            case ROCSVX_CRY: out.push_back(rq::make_dense1(t0, c, -s, s, c, cm)); break;
+            case ROCSVX_CRZ: out.push_back(rq::make_diag1(t0, cd(c, -s), cd(c, s), cm)); break;
+            case ROCSVX_CSWAP: out.push_back(rq::make_swap(t0, t1, cm)); break;
+            case ROCSVX_MATRIX: {
+                const unsigned k = g.numTargets;
+                if (k == 0 || k > 8 || !g.matrix) return ROCQ_STATUS_INVALID_VALUE;
+                uint64_t seen = cm;
+                std::vector<unsigned> ts(g.targets, g.targets + k);
+                for (unsigned q : ts) { if (!okq(q) || ((seen >> q) & 1ull)) return ROCQ_STATUS_INVALID_VALUE; seen |= 1ull << q; }
+                const size_t D = (size_t)1 << k;
+                std::vector<cd> m(D * D);
+                for (size_t e = 0; e < D * D; ++e) m[e] = cd(g.matrix[2 * e], g.matrix[2 * e + 1]);
+                out.push_back(rq::make_matrix(ts, cm, m));
+                break;
+            }
+        }
+    }
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t h, rocComplex* d, unsigned n, const rocsvxGateOp* ops, size_t numOps) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    rq_cplx* state = resolve(h, d);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    if (numOps == 0) return ROCQ_STATUS_SUCCESS;
+    if (!ops) return ROCQ_STATUS_INVALID_VALUE;
+    std::vector<HostOp> hops;
+    rocqStatus_t s = convert_ops(n, ops, numOps, hops);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    s = flush(h);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    h->stats.gatesSubmitted += numOps;
+    if (h->dist.active()) return h->dist.run_circuit(h, hops);
+    cudaEventRecord(h->ev0, h->stream);
+    s = run_ops(h, state, n, hops, true);
+    cudaEventRecord(h->ev1, h->stream);
+    h->stats.lastSweepMs = -1.0;
+    return s;
+}
+
+rocqStatus_t rocsvxTimerStart(rocsvHandle_t h) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    RQ_CUDA(cudaEventRecord(h->tm0, h->stream), "timer start");
+    return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t rocsvxTimerStop(rocsvHandle_t h, double* ms) {
+    if (!h || !ms) return ROCQ_STATUS_INVALID_VALUE;
+    RQ_CUDA(cudaEventRecord(h->tm1, h->stream), "timer stop");
+    RQ_CUDA(cudaEventSynchronize(h->tm1), "timer sync");
+    float f = 0.f;
+    RQ_CUDA(cudaEventElapsedTime(&f, h->tm0, h->tm1), "timer elapsed");
+    *ms = (double)f;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t rocsvxGetStats(rocsvHandle_t h, rocsvxStats* stats, int reset) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->stats.lastSweepMs < 0.0) {
+        float ms = 0.f;
+        cudaEventSynchronize(h->ev1);
+        h->stats.lastSweepMs = cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess ? (double)ms : 0.0;
+    }
+    if (stats) *stats = h->stats;
+    if (reset) h->stats = rocsvxStats{};
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t rocsvxPlanCircuit(unsigned n, unsigned tileBits, const rocsvxGateOp* ops, size_t numOps, unsigned* numSweeps, char* buf,
+                               size_t bufSize) {
+    if (!ops && numOps) return ROCQ_STATUS_INVALID_VALUE;
+    std::vector<HostOp> hops;
+    const rocqStatus_t s = convert_ops(n, ops, numOps, hops);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    for (const HostOp& o : hops) if (o.targets.size() > 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    std::vector<HostOp> fused = hops.size() > 1 ? rq::fuse_algebraic(hops, n) : hops;
+    rq::PlanLimits L;
+    if (tileBits >= 1 && tileBits <= RQ_MAX_TILE_BITS) L.tile_bits = tileBits;
+    L.max_ops = sizeof(rq_program_large::ops) / sizeof(rq_tile_op);
+    L.pool_cplx = sizeof(rq_program_large::pool) / sizeof(rq_cplx);
+    if (const char* e = getenv("ROCQ_SWEEP_BUDGET")) { const double b = atof(e); if (b > 0) L.budget = b; }
+    const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(fused, n, L);
+    // every plan must be emittable
+    static thread_local rq_program_large P;
+    for (const rq::SweepPlan& sp : plans)
+        if (!rq::build_program(P, sp, fused, n, 1, 0)) return ROCQ_STATUS_FAILURE;
+    if (numSweeps) *numSweeps = (unsigned)plans.size();
+    if (buf && bufSize) {
+        const std::string txt = rq::dump_plan(plans, fused);
+        const size_t m = txt.size() < bufSize - 1 ? txt.size() : bufSize - 1;
+        memcpy(buf, txt.data(), m);
+        buf[m] = 0;
+    }
+    return ROCQ_STATUS_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,423 @@
+// rocquantum_b200/csrc/host_ops.h -- host-side gate representation, algebraic fusion and the sweep
+// planner.  Pure C++ (no CUDA): the same code plans on a machine without a GPU (rocsvxPlanCircuit).
+//
+// Role in the reference: this is what sits behind Circuit.flush() (python/rocq/api.py:74-89, "placeholder
+// ... without fusion") and GateFusion::processQueue (rocquantum/src/hipStateVec/GateFusion.cpp:89-156,
+// which only fuses one 1q gate before/after a CNOT).  Here every queue is (1) fused algebraically --
+// runs of 1q gates and neighbouring 2q gates collapse into single 2x2 / 4x4 matrices -- and (2) cut into
+// sweeps: maximal in-order groups of ops whose non-diagonal targets fit in one resident set of T qubits.
+#pragma once
+#include <algorithm>
+#include <complex>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "sv_internal.h"
+
+namespace rq {
+
+typedef std::complex<double> cd;
+
+struct HostOp {
+    enum Kind { DENSE = 1, DIAG = 2, PERM_X = 3, PERM_SWAP = 4 };
+    int kind = DENSE;
+    std::vector<unsigned> targets;   // DENSE: matrix bit b <-> targets[b].  DIAG: table bit b.  PERM_X: {t}.  PERM_SWAP: {a,b}
+    uint64_t cmask = 0;              // control qubits: op acts where all are 1
+    std::vector<cd> data;            // DENSE: 2^k x 2^k column-major.  DIAG: 2^k entries
+    const void* ext = nullptr;       // DENSE only: matrix stays in device memory (eager rocsvApplyMatrix)
+    bool dead = false;
+
+    uint64_t tmask() const { uint64_t m = 0; for (unsigned t : targets) m |= 1ull << t; return m; }
+    uint64_t qubits() const { return tmask() | cmask; }
+    // qubits that must be resident in the tile: everything the op does not act on diagonally
+    uint64_t nondiag() const { return kind == DIAG ? 0ull : tmask(); }
+    bool host_dense_uncontrolled() const { return kind == DENSE && cmask == 0 && ext == nullptr; }
+    double cost() const {            // rough FMA-equivalents per amplitude, for the sweep budget
+        const double frac = 1.0 / (double)(1ull << std::min(8, __builtin_popcountll(cmask)));
+        if (kind == DENSE) return 4.0 * (double)(1u << targets.size()) * frac + 2.0;
+        if (kind == DIAG) return 6.0 * frac + 1.0;
+        return 2.0 * frac + 1.0;
+    }
+};
+
+// ---- constructors for the reference's named gates (matrices as hipStateVec.cpp:276-427, 544-595) ----
+inline HostOp make_dense1(unsigned t, cd m00, cd m01, cd m10, cd m11, uint64_t cmask = 0) {
+    HostOp o; o.kind = HostOp::DENSE; o.targets = {t}; o.cmask = cmask; o.data = {m00, m10, m01, m11}; return o;   // column-major
+}
+inline HostOp make_phase(uint64_t qmask, cd ph) {                      // multiply by ph where all qubits of qmask are 1
+    HostOp o; o.kind = HostOp::DIAG; o.cmask = qmask; o.data = {ph}; return o;
+}
+inline HostOp make_diag1(unsigned t, cd d0, cd d1, uint64_t cmask = 0) {
+    HostOp o; o.kind = HostOp::DIAG; o.targets = {t}; o.cmask = cmask; o.data = {d0, d1}; return o;
+}
+inline HostOp make_x(unsigned t, uint64_t cmask = 0) { HostOp o; o.kind = HostOp::PERM_X; o.targets = {t}; o.cmask = cmask; return o; }
+inline HostOp make_swap(unsigned a, unsigned b, uint64_t cmask = 0) { HostOp o; o.kind = HostOp::PERM_SWAP; o.targets = {a, b}; o.cmask = cmask; return o; }
+
+// A diagonal table bit whose "0" half is all ones is a control: move it to cmask (halves the table and
+// lets the kernel enumerate only the amplitudes that change).
+inline void canonicalize_diag(HostOp& o) {
+    if (o.kind != HostOp::DIAG) return;
+    bool changed = true;
+    while (changed && !o.targets.empty()) {
+        changed = false;
+        const unsigned k = (unsigned)o.targets.size();
+        for (unsigned b = 0; b < k; ++b) {
+            bool ctl = true;
+            for (unsigned s = 0; s < (1u << k); ++s)
+                if (!((s >> b) & 1u) && o.data[s] != cd(1.0, 0.0)) { ctl = false; break; }
+            if (!ctl) continue;
+            std::vector<cd> nd;
+            for (unsigned s = 0; s < (1u << k); ++s)
+                if ((s >> b) & 1u) nd.push_back(o.data[s]);
+            o.cmask |= 1ull << o.targets[b];
+            o.targets.erase(o.targets.begin() + b);
+            o.data.swap(nd);
+            changed = true;
+            break;
+        }
+    }
+}
+
+// Turn a host matrix into the cheapest op kind: diagonal -> DIAG (+controls), else DENSE.
+inline HostOp make_matrix(const std::vector<unsigned>& targets, uint64_t cmask, const std::vector<cd>& colmajor) {
+    const unsigned k = (unsigned)targets.size(), D = 1u << k;
+    bool diag = k <= 4;
+    for (unsigned i = 0; i < D && diag; ++i)
+        for (unsigned j = 0; j < D; ++j)
+            if (i != j && colmajor[i + (size_t)j * D] != cd(0.0, 0.0)) { diag = false; break; }
+    HostOp o; o.targets = targets; o.cmask = cmask;
+    if (diag) {
+        o.kind = HostOp::DIAG;
+        o.data.resize(D);
+        for (unsigned i = 0; i < D; ++i) o.data[i] = colmajor[i + (size_t)i * D];
+        canonicalize_diag(o);
+    } else {
+        o.kind = HostOp::DENSE;
+        o.data = colmajor;
+    }
+    return o;
+}
+
+// ---- tiny host simulator over an explicit qubit list, used only to build fused matrices ------------
+// v has 2^m entries; bit i of its index <-> qs[i].  Applies op (whose qubits must all be in qs).
+inline void apply_small(const HostOp& o, const std::vector<unsigned>& qs, std::vector<cd>& v) {
+    const unsigned m = (unsigned)qs.size();
+    auto pos = [&](unsigned q) { for (unsigned i = 0; i < m; ++i) if (qs[i] == q) return i; return 0u; };
+    uint32_t cm = 0;
+    for (unsigned q = 0; q < 64; ++q) if ((o.cmask >> q) & 1ull) cm |= 1u << pos(q);
+    const unsigned k = (unsigned)o.targets.size();
+    std::vector<unsigned> tp(k);
+    uint32_t tm = 0;
+    for (unsigned b = 0; b < k; ++b) { tp[b] = pos(o.targets[b]); tm |= 1u << tp[b]; }
+    const uint32_t N = 1u << m;
+    if (o.kind == HostOp::DIAG) {
+        for (uint32_t i = 0; i < N; ++i) {
+            if ((i & cm) != cm) continue;
+            unsigned s = 0;
+            for (unsigned b = 0; b < k; ++b) s |= ((i >> tp[b]) & 1u) << b;
+            v[i] *= o.data[s];
+        }
+    } else if (o.kind == HostOp::PERM_X) {
+        for (uint32_t i = 0; i < N; ++i)
+            if ((i & cm) == cm && !(i & tm)) std::swap(v[i], v[i | tm]);
+    } else if (o.kind == HostOp::PERM_SWAP) {
+        const uint32_t a = 1u << tp[0], b = 1u << tp[1];
+        for (uint32_t i = 0; i < N; ++i)
+            if ((i & cm) == cm && (i & a) && !(i & b)) std::swap(v[i], v[(i ^ a) | b]);
+    } else {
+        const unsigned D = 1u << k;
+        std::vector<cd> in(D);
+        for (uint32_t i = 0; i < N; ++i) {
+            if ((i & cm) != cm || (i & tm)) continue;
+            std::vector<uint32_t> off(D);
+            for (unsigned j = 0; j < D; ++j) { uint32_t f = 0; for (unsigned b = 0; b < k; ++b) if ((j >> b) & 1u) f |= 1u << tp[b]; off[j] = f; }
+            for (unsigned j = 0; j < D; ++j) in[j] = v[i | off[j]];
+            for (unsigned r = 0; r < D; ++r) {
+                cd acc(0.0, 0.0);
+                for (unsigned j = 0; j < D; ++j) acc += o.data[r + (size_t)j * D] * in[j];
+                v[i | off[r]] = acc;
+            }
+        }
+    }
+}
+// column-major matrix of op over the ordered qubit list qs
+inline std::vector<cd> to_matrix(const HostOp& o, const std::vector<unsigned>& qs) {
+    const unsigned D = 1u << qs.size();
+    std::vector<cd> M((size_t)D * D);
+    for (unsigned j = 0; j < D; ++j) {
+        std::vector<cd> v(D, cd(0.0, 0.0));
+        v[j] = cd(1.0, 0.0);
+        apply_small(o, qs, v);
+        for (unsigned i = 0; i < D; ++i) M[i + (size_t)j * D] = v[i];
+    }
+    return M;
+}
+inline std::vector<cd> matmul(const std::vector<cd>& A, const std::vector<cd>& B, unsigned D) {   // A*B, column-major
+    std::vector<cd> C((size_t)D * D, cd(0.0, 0.0));
+    for (unsigned j = 0; j < D; ++j)
+        for (unsigned l = 0; l < D; ++l) {
+            const cd b = B[l + (size_t)j * D];
+            if (b == cd(0.0, 0.0)) continue;
+            for (unsigned i = 0; i < D; ++i) C[i + (size_t)j * D] += A[i + (size_t)l * D] * b;
+        }
+    return C;
+}
+
+// ---- algebraic fusion -------------------------------------------------------------------------------
+// Rule 1: an uncontrolled op on <= 2 qubits folds (left-multiplies) into the last op touching all of
+//         its qubits when that op is an uncontrolled host DENSE whose targets contain them.
+// Rule 2: an uncontrolled 2-qubit op absorbs (right-multiplies) the pending uncontrolled 1-qubit DENSE
+//         ops sitting directly before it on its qubits; permutation / diagonal 2q gates (CNOT, CZ, SWAP)
+//         are promoted to a dense 4x4 only when that lets them absorb such a neighbour
+//         (the reference's GateFusion.cpp:95-147 pattern: post * CNOT * pre as one 4x4).
+inline std::vector<HostOp> fuse_algebraic(const std::vector<HostOp>& in, unsigned n) {
+    std::vector<HostOp> out;
+    out.reserve(in.size());
+    std::vector<int> last(n > 64 ? n : 64, -1);
+    for (const HostOp& op : in) {
+        const uint64_t Q = op.qubits();
+        const int nq = __builtin_popcountll(Q);
+        std::vector<unsigned> qs;
+        for (unsigned q = 0; q < 64; ++q) if ((Q >> q) & 1ull) qs.push_back(q);
+        const bool small_host = op.ext == nullptr && nq >= 1 && nq <= 2 && op.targets.size() <= 2 &&
+                                (op.kind != HostOp::DENSE || op.cmask == 0 || nq <= 2);
+        bool absorbed = false;
+        if (small_host) {
+            // Rule 1
+            const int j = last[qs[0]];
+            bool same = j >= 0;
+            for (unsigned q : qs) same = same && last[q] == j;
+            if (same && out[j].host_dense_uncontrolled() && (out[j].tmask() & Q) == Q) {
+                HostOp& G = out[j];
+                const unsigned D = 1u << G.targets.size();
+                // op expressed over G's target order (identity on G's other targets)
+                std::vector<cd> U = to_matrix(op, G.targets);
+                G.data = matmul(U, G.data, D);
+                absorbed = true;
+            }
+        }
+        if (!absorbed && small_host && nq == 1 && op.kind == HostOp::DENSE && op.cmask == 0) {
+            // Rule 1b: the previous op on this qubit is a lone uncontrolled 1q diagonal / X: merge into one 2x2
+            const int j = last[qs[0]];
+            if (j >= 0 && !out[j].dead && out[j].ext == nullptr && out[j].qubits() == Q && out[j].kind != HostOp::DENSE) {
+                HostOp G;
+                G.kind = HostOp::DENSE;
+                G.targets = qs;
+                G.data = matmul(to_matrix(op, qs), to_matrix(out[j], qs), 2);
+                out[j] = G;
+                absorbed = true;
+            }
+        }
+        if (!absorbed && small_host && nq == 2) {
+            // Rule 2
+            std::vector<int> pend;
+            for (unsigned q : qs) {
+                const int j = last[q];
+                if (j >= 0 && !out[j].dead && out[j].host_dense_uncontrolled() && out[j].targets.size() == 1 &&
+                    out[j].targets[0] == q)
+                    pend.push_back(j);
+            }
+            const bool genuinely_dense = op.kind == HostOp::DENSE && op.cmask == 0;
+            if (genuinely_dense || !pend.empty()) {
+                HostOp G;
+                G.kind = HostOp::DENSE;
+                G.targets = (op.kind == HostOp::DENSE && op.cmask == 0) ? op.targets : qs;
+                G.data = to_matrix(op, G.targets);
+                for (int j : pend) {
+                    G.data = matmul(G.data, to_matrix(out[j], G.targets), 4);
+                    out[j].dead = true;
+                }
+                out.push_back(G);
+                for (unsigned q : qs) last[q] = (int)out.size() - 1;
+                absorbed = true;
+            }
+        }
+        if (!absorbed) {
+            out.push_back(op);
+            for (unsigned q : qs) last[q] = (int)out.size() - 1;
+        }
+    }
+    std::vector<HostOp> live;
+    live.reserve(out.size());
+    for (HostOp& o : out)
+        if (!o.dead) live.push_back(std::move(o));
+    return live;
+}
+
+// ---- sweep planner ----------------------------------------------------------------------------------
+struct SweepPlan {
+    std::vector<unsigned> res;       // ascending resident positions, size T
+    std::vector<int> ops;            // indices into the op list, program order
+    unsigned rowbits = 0;
+};
+
+struct PlanLimits {
+    unsigned tile_bits = RQ_MAX_TILE_BITS;
+    unsigned min_row_bits = RQ_MIN_ROW_BITS;
+    unsigned max_ops = 160;
+    unsigned pool_cplx = 1408;
+    double budget = 1e30;            // max summed HostOp::cost() per sweep (first op always accepted)
+    uint64_t never_resident = 0;     // positions that may not be resident (global qubits of a distributed state)
+};
+
+inline unsigned pool_need(const HostOp& o) {
+    if (o.ext) return 0;
+    if (o.kind == HostOp::DENSE) return 1u << (2 * o.targets.size());
+    if (o.kind == HostOp::DIAG) return 1u << o.targets.size();
+    return 0;
+}
+
+// Greedy in-order partition.  An op may join the current sweep when (a) no earlier deferred op conflicts
+// with it on a qubit (diagonal/control action on a shared qubit commutes, so only non-diagonal overlap
+// blocks) and (b) its non-diagonal targets fit in the resident set.  Diagonal factors and controls never
+// need residency: the kernel resolves them from the tile base.
+inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L) {
+    std::vector<SweepPlan> plans;
+    const unsigned T = std::min(n, L.tile_bits);
+    std::vector<char> done(ops.size(), 0);
+    size_t first = 0, remaining = ops.size();
+    while (remaining > 0) {
+        while (first < ops.size() && done[first]) ++first;
+        uint64_t R = 0;
+        const unsigned lowbits = std::min(std::min(L.min_row_bits, T), n);
+        for (unsigned p = 0; p < lowbits; ++p) R |= 1ull << p;
+        uint64_t blockedAny = 0, blockedND = 0;
+        unsigned nops = 0, pool = 0;
+        double cost = 0.0;
+        SweepPlan sp;
+        size_t scanned = 0;
+        for (size_t i = first; i < ops.size() && scanned < 8192; ++i) {
+            if (done[i]) continue;
+            ++scanned;
+            const HostOp& o = ops[i];
+            const uint64_t nd = o.nondiag(), dg = o.qubits() & ~nd;
+            bool ok = !((nd & (blockedAny | blockedND)) || (dg & blockedAny));
+            if (ok) {
+                const uint64_t newR = R | nd;
+                ok = __builtin_popcountll(newR) <= (int)T && !(nd & L.never_resident) && nops < L.max_ops &&
+                     pool + pool_need(o) <= L.pool_cplx && (nops == 0 || cost + o.cost() <= L.budget) &&
+                     (o.kind != HostOp::DENSE || o.targets.size() <= 4) && (o.kind != HostOp::DIAG || o.targets.size() <= 4) &&
+                     !(o.ext && nops > 0);
+                if (ok) {
+                    R = newR;
+                    sp.ops.push_back((int)i);
+                    done[i] = 1;
+                    --remaining;
+                    ++nops;
+                    pool += pool_need(o);
+                    cost += o.cost();
+                    if (o.ext) break;            // a device-matrix op travels alone (one ext pointer per program)
+                    continue;
+                }
+            }
+            blockedAny |= nd;
+            blockedND |= dg;
+        }
+        if (sp.ops.empty()) {                    // cannot happen for valid ops; avoid an endless loop
+            sp.ops.push_back((int)first);
+            done[first] = 1;
+            --remaining;
+            R |= ops[first].nondiag();
+        }
+        for (unsigned p = 0; p < n && __builtin_popcountll(R) < (int)T; ++p)
+            if (!((L.never_resident >> p) & 1ull)) R |= 1ull << p;
+        for (unsigned p = 0; p < 64; ++p) if ((R >> p) & 1ull) sp.res.push_back(p);
+        sp.rowbits = 0;
+        while (sp.rowbits < sp.res.size() && sp.res[sp.rowbits] == sp.rowbits) ++sp.rowbits;
+        plans.push_back(std::move(sp));
+    }
+    return plans;
+}
+
+// ---- program emission ---------------------------------------------------------------------------------
+template <typename Prog>
+inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp>& ops, unsigned n, size_t batch,
+                          uint64_t high_base) {
+    const unsigned T = (unsigned)sp.res.size();
+    P.hdr.n = n; P.hdr.T = T; P.hdr.nops = 0; P.hdr.rowbits = sp.rowbits;
+    P.hdr.ntiles = (uint64_t)batch << (n - T);
+    P.hdr.high_base = high_base;
+    P.hdr.ext_matrix = nullptr;
+    int local[64];
+    uint64_t R = 0;
+    for (int q = 0; q < 64; ++q) local[q] = -1;
+    for (unsigned j = 0; j < T; ++j) { P.hdr.res[j] = (uint8_t)sp.res[j]; local[sp.res[j]] = (int)j; R |= 1ull << sp.res[j]; }
+    unsigned pool = 0;
+    const unsigned maxops = (unsigned)(sizeof(P.ops) / sizeof(P.ops[0])), maxpool = (unsigned)(sizeof(P.pool) / sizeof(P.pool[0]));
+    for (int idx : sp.ops) {
+        const HostOp& o = ops[idx];
+        if (P.hdr.nops >= maxops) return false;
+        rq_tile_op& t = P.ops[P.hdr.nops++];
+        t = rq_tile_op{};
+        uint32_t fixmask = 0;
+        for (unsigned q = 0; q < 64; ++q) {
+            if (!((o.cmask >> q) & 1ull)) continue;
+            if (local[q] >= 0) { t.setmask |= 1u << local[q]; fixmask |= 1u << local[q]; }
+            else t.gcmask |= 1ull << q;
+        }
+        const unsigned k = (unsigned)o.targets.size();
+        if (o.kind == HostOp::DENSE) {
+            t.kind = RQ_OP_DENSE; t.k = (uint8_t)k;
+            for (unsigned b = 0; b < k; ++b) { if (local[o.targets[b]] < 0) return false; t.t[b] = (uint8_t)local[o.targets[b]]; fixmask |= 1u << t.t[b]; }
+            if (o.ext) { t.ext = 1; P.hdr.ext_matrix = o.ext; }
+            else {
+                const unsigned need = 1u << (2 * k);
+                if (pool + need > maxpool) return false;
+                t.moff = pool;
+                for (unsigned e = 0; e < need; ++e) { P.pool[pool + e].x = (rq_real)o.data[e].real(); P.pool[pool + e].y = (rq_real)o.data[e].imag(); }
+                pool += need;
+            }
+        } else if (o.kind == HostOp::DIAG) {
+            t.kind = RQ_OP_DIAG; t.k = (uint8_t)k;
+            for (unsigned b = 0; b < k; ++b) {
+                if (local[o.targets[b]] >= 0) t.t[b] = (uint8_t)local[o.targets[b]];
+                else { t.t[b] = 0xFF; t.gq[b] = (uint8_t)o.targets[b]; }
+            }
+            const unsigned need = 1u << k;
+            if (pool + need > maxpool) return false;
+            t.moff = pool;
+            for (unsigned e = 0; e < need; ++e) { P.pool[pool + e].x = (rq_real)o.data[e].real(); P.pool[pool + e].y = (rq_real)o.data[e].imag(); }
+            pool += need;
+        } else if (o.kind == HostOp::PERM_X) {
+            t.kind = RQ_OP_PERM;
+            if (local[o.targets[0]] < 0) return false;
+            t.xm = 1u << local[o.targets[0]];
+            fixmask |= t.xm;
+        } else {
+            t.kind = RQ_OP_PERM;
+            if (local[o.targets[0]] < 0 || local[o.targets[1]] < 0) return false;
+            const uint32_t a = 1u << local[o.targets[0]], b = 1u << local[o.targets[1]];
+            t.xm = a | b;
+            t.setmask |= a;                 // enumerate a=1,b=0; partner has a=0,b=1
+            fixmask |= a | b;
+        }
+        for (unsigned j = 0; j < T; ++j) if ((fixmask >> j) & 1u) t.fix[t.nfix++] = (uint8_t)j;
+    }
+    return true;
+}
+
+// ---- text dump of a plan (rocsvxPlanCircuit): enough to re-simulate it independently --------------------
+inline std::string dump_plan(const std::vector<SweepPlan>& plans, const std::vector<HostOp>& ops) {
+    std::string s;
+    char buf[128];
+    for (const SweepPlan& sp : plans) {
+        snprintf(buf, sizeof buf, "S %u %u res:", (unsigned)sp.res.size(), sp.rowbits);
+        s += buf;
+        for (unsigned r : sp.res) { snprintf(buf, sizeof buf, " %u", r); s += buf; }
+        s += "\n";
+        for (int i : sp.ops) {
+            const HostOp& o = ops[i];
+            snprintf(buf, sizeof buf, "O %d cmask %llx targets", o.kind, (unsigned long long)o.cmask);
+            s += buf;
+            for (unsigned t : o.targets) { snprintf(buf, sizeof buf, " %u", t); s += buf; }
+            s += " data";
+            for (const cd& c : o.data) { snprintf(buf, sizeof buf, " %.17g %.17g", c.real(), c.imag()); s += buf; }
+            s += "\n";
+        }
+    }
+    return s;
+}
+
+}  // namespace rq

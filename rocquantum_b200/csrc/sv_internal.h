@@ -1,0 +1,100 @@
+// rocquantum_b200/csrc/sv_internal.h
+// Shared host/device definitions of the sweep program that the tile-sweep kernel executes, and the
+// thin internal C ABI (rq_*) between the C++ host engine and the .cu launchers.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef ROCQ_PRECISION_DOUBLE
+typedef double rq_real;
+#else
+typedef float rq_real;
+#endif
+struct rq_cplx { rq_real x, y; };
+
+// ---- sweep program ---------------------------------------------------------------------------------
+// One launch of the tile-sweep kernel = one pass over HBM.  The state is cut into tiles of 2^T
+// amplitudes: T "resident" qubit positions res[0..T) (ascending; local bit j of a tile <-> global
+// position res[j]) and one tile per assignment of the other n-T bits.  A tile is staged in shared
+// memory with 1-D bulk async copies (one per contiguous row of 2^rowbits amplitudes), every op of the
+// program is applied to it in order, and it is written back with bulk async stores.
+enum : uint8_t { RQ_OP_DENSE = 1, RQ_OP_DIAG = 2, RQ_OP_PERM = 3 };
+
+struct rq_tile_op {                 // 56 bytes
+    uint8_t kind;                   // RQ_OP_*
+    uint8_t k;                      // DENSE: number of targets (1..4).  DIAG: number of table bits (0..3)
+    uint8_t nfix;                   // entries of fix[]: local positions held fixed while enumerating
+    uint8_t ext;                    // DENSE: 1 => matrix is read from hdr.ext_matrix (device pointer)
+    uint8_t t[4];                   // DENSE: local position of matrix bit b.  DIAG: local position of table bit b, 0xFF = non-resident
+    uint8_t gq[4];                  // DIAG: global position of table bit b when non-resident
+    uint8_t fix[16];                // ascending local positions (targets of DENSE/PERM and local controls)
+    uint32_t setmask;               // OR-ed into the enumerated local index (controls = 1; PERM select value)
+    uint32_t xm;                    // PERM: partner = idx ^ xm
+    uint32_t moff;                  // offset into pool[], in complex elements
+    uint32_t pad;
+    uint64_t gcmask;                // controls on non-resident positions: op is skipped for tiles whose base lacks a bit
+};
+
+struct rq_sweep_hdr {
+    uint32_t n;                     // qubits per state vector (local qubits in distributed mode)
+    uint32_t T;                     // tile bits
+    uint32_t nops;
+    uint32_t rowbits;               // log2(amplitudes per contiguous row)
+    uint64_t ntiles;                // batch * 2^(n-T)
+    uint64_t high_base;             // OR-ed into every tile's base index for predicates (rank << n_local)
+    const void* ext_matrix;         // device matrix of an op with ext = 1 (column-major, rq_cplx)
+    uint8_t res[16];                // ascending resident global positions
+};
+
+template <int MAXOPS, int POOL_CPLX>
+struct rq_program {
+    rq_sweep_hdr hdr;
+    rq_tile_op ops[MAXOPS];
+    rq_cplx pool[POOL_CPLX];
+};
+// Kernel parameters may be up to 32764 bytes (CUDA >= 12.1); the program travels as a
+// __grid_constant__ parameter so that op headers and gate matrices are read through the constant
+// cache with warp-uniform addresses.
+#ifdef ROCQ_PRECISION_DOUBLE
+typedef rq_program<8, 288> rq_program_small;        //  ~5.2 KB
+typedef rq_program<160, 1408> rq_program_large;     // ~31.6 KB
+#else
+typedef rq_program<8, 288> rq_program_small;        //  ~2.9 KB
+typedef rq_program<160, 2816> rq_program_large;     // ~31.6 KB
+#endif
+
+#define RQ_TILE_THREADS 256
+#ifdef ROCQ_PRECISION_DOUBLE
+#define RQ_MAX_TILE_BITS 12                          // 2^12 * 16 B = 64 KB
+#define RQ_MIN_ROW_BITS 4                            // rows >= 256 B
+#else
+#define RQ_MAX_TILE_BITS 13                          // 2^13 * 8 B = 64 KB
+#define RQ_MIN_ROW_BITS 5                            // rows >= 256 B
+#endif
+
+// ---- thin C ABI to the launchers (all return a cudaError_t as int; stream is a cudaStream_t) --------
+extern "C" {
+int rq_launch_sweep_small(rq_cplx* state, const rq_program_small* prog, void* stream);
+int rq_launch_sweep_large(rq_cplx* state, const rq_program_large* prog, void* stream);
+int rq_sweep_configure(void);    // opt in to > 48 KB dynamic shared memory; call once per device
+
+// generic k-qubit dense matrix with controls, matrix in device memory (column-major); any k <= 10
+int rq_launch_gather(rq_cplx* state, unsigned n, size_t batch, const unsigned* h_targets, unsigned k,
+                     uint64_t cmask, const rq_cplx* d_matrix, void* stream);
+
+int rq_launch_init_state(rq_cplx* state, size_t total_amps, int write_one, void* stream);
+
+// reductions: results land in d_out (device doubles / uint64), caller copies them back
+int rq_launch_pauli_expect(const rq_cplx* state, unsigned n, uint64_t xmask, uint64_t zmask, unsigned ny,
+                           double* d_partials, unsigned nblocks, double* d_out, void* stream);
+int rq_launch_fixed_masses(const rq_cplx* state, unsigned n, unsigned q, uint64_t* d_partials, unsigned nblocks,
+                           uint64_t* d_out4, void* stream);
+int rq_launch_collapse(rq_cplx* state, unsigned n, unsigned q, int outcome, double scale, void* stream);
+int rq_launch_chunk_masses(const rq_cplx* state, unsigned n, unsigned chunk_bits, uint64_t* d_chunk_hi,
+                           uint64_t* d_chunk_lo, void* stream);
+int rq_launch_sample(const rq_cplx* state, unsigned n, unsigned chunk_bits, const uint64_t* d_incl_hi,
+                     const uint64_t* d_incl_lo, uint64_t nchunks, uint64_t total_hi, uint64_t total_lo,
+                     uint64_t seed, uint64_t call, unsigned shots, uint64_t shot_offset, uint64_t* d_indices,
+                     void* stream);
+unsigned rq_reduce_blocks(void);
+}

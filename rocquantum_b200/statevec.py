@@ -1,0 +1,192 @@
+"""A small object wrapper over the C ABI: one handle + one owned state, gates by the reference's names.
+
+Used by the parity tests, bench.py and smoke().  Every method is one rocsv*/rocsvx* call; nothing is
+computed in Python."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+DT = {"c64": np.complex64, "c128": np.complex128}
+
+
+class RocsvError(RuntimeError):
+    def __init__(self, fn, status):
+        super().__init__(f"{fn} failed: {capi.STATUS_NAMES[status] if 0 <= status < 7 else status}")
+        self.status = status
+
+
+class StateVector:
+    def __init__(self, n: int, prec: str = "c64", batch: int = 1, fusion: bool = False, seed: int = 0):
+        self.lib = capi.load(prec)
+        self.prec, self.dtype, self.n, self.batch = prec, DT[prec], n, batch
+        self.h = C.c_void_p()
+        self._ck("rocsvCreate", self.lib.rocsvCreate(C.byref(self.h)))
+        self.d = C.c_void_p()
+        self._ck("rocsvAllocateState", self.lib.rocsvAllocateState(self.h, n, C.byref(self.d), batch))
+        self._ck("rocsvInitializeState", self.lib.rocsvInitializeState(self.h, self.d, n))
+        if fusion:
+            self.set_fusion(True)
+        if seed:
+            self.set_seed(seed)
+
+    @staticmethod
+    def _ck(fn, st):
+        if st != capi.SUCCESS:
+            raise RocsvError(fn, st)
+
+    def close(self):
+        if self.h:
+            self.lib.rocsvDestroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- control -------------------------------------------------------------------------------
+    def init(self):
+        self._ck("rocsvInitializeState", self.lib.rocsvInitializeState(self.h, self.d, self.n))
+
+    def set_fusion(self, on: bool):
+        self._ck("rocsvxSetFusion", self.lib.rocsvxSetFusion(self.h, int(on)))
+
+    def set_seed(self, seed: int):
+        self._ck("rocsvxSetSeed", self.lib.rocsvxSetSeed(self.h, seed))
+
+    def sync(self):
+        self._ck("rocsvxSynchronize", self.lib.rocsvxSynchronize(self.h))
+
+    def flush(self):
+        self._ck("rocsvxFlush", self.lib.rocsvxFlush(self.h))
+
+    def stats(self, reset=False) -> capi.Stats:
+        s = capi.Stats()
+        self._ck("rocsvxGetStats", self.lib.rocsvxGetStats(self.h, C.byref(s), int(reset)))
+        return s
+
+    def timer_start(self):
+        self._ck("rocsvxTimerStart", self.lib.rocsvxTimerStart(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._ck("rocsvxTimerStop", self.lib.rocsvxTimerStop(self.h, C.byref(ms)))
+        return ms.value
+
+    def set_state(self, v):
+        v = np.ascontiguousarray(v, dtype=self.dtype)
+        assert v.size == self.batch << self.n
+        self._ck("rocsvxSetStateVector", self.lib.rocsvxSetStateVector(self.h, self.d, v.ctypes.data_as(C.c_void_p)))
+
+    def state(self) -> np.ndarray:
+        out = np.empty(self.batch << self.n, dtype=self.dtype)
+        self._ck("rocsvGetStateVectorFull", self.lib.rocsvGetStateVectorFull(self.h, self.d, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def state_slice(self, b: int) -> np.ndarray:
+        out = np.empty(1 << self.n, dtype=self.dtype)
+        self._ck("rocsvGetStateVectorSlice", self.lib.rocsvGetStateVectorSlice(self.h, self.d, out.ctypes.data_as(C.c_void_p), b))
+        return out
+
+    # ---- gates, by the reference's names ---------------------------------------------------------
+    def gate_status(self, name, *a) -> int:
+        L, h, d, n = self.lib, self.h, self.d, self.n
+        name = name.lower()
+        t1 = {"h": "H", "x": "X", "y": "Y", "z": "Z", "s": "S", "sdg": "Sdg", "t": "T"}
+        if name in t1:
+            return getattr(L, "rocsvApply" + t1[name])(h, d, n, a[0])
+        if name in ("rx", "ry", "rz"):
+            return getattr(L, "rocsvApplyR" + name[1])(h, d, n, a[0], a[1])
+        if name in ("cnot", "cz", "swap"):
+            return getattr(L, "rocsvApply" + name.upper())(h, d, n, a[0], a[1])
+        if name in ("crx", "cry", "crz"):
+            return getattr(L, "rocsvApply" + name.upper())(h, d, n, a[0], a[1], a[2])
+        if name == "mcx":
+            return L.rocsvApplyMultiControlledX(h, d, n, capi.uarr(a[0]), len(a[0]), a[1])
+        if name == "cswap":
+            return L.rocsvApplyCSWAP(h, d, n, a[0], a[1], a[2])
+        raise ValueError(name)
+
+    def gate(self, name, *a):
+        self._ck(name, self.gate_status(name, *a))
+
+    def _device_matrix(self, M, k):
+        """Upload a (2^k,2^k) matrix column-major through the handle's pinned buffer -> returns device ptr owner."""
+        import torch  # device memory plumbing only
+        D = 1 << k
+        Mc = np.ascontiguousarray(np.asarray(M, dtype=self.dtype).reshape(D, D).T).reshape(-1)
+        t = torch.from_numpy(Mc.view(np.float32 if self.prec == "c64" else np.float64).copy()).cuda()
+        return t
+
+    def apply_matrix(self, targets, M, controls=()):
+        k = len(targets)
+        t = self._device_matrix(M, k)
+        if controls:
+            st = self.lib.rocsvApplyControlledMatrix(self.h, self.d, self.n, capi.uarr(controls), len(controls), capi.uarr(targets), k,
+                                                     C.c_void_p(t.data_ptr()))
+        else:
+            st = self.lib.rocsvApplyMatrix(self.h, self.d, self.n, capi.uarr(targets), k, C.c_void_p(t.data_ptr()), 1 << k)
+        self.sync()          # the device matrix must outlive the launch
+        self._ck("rocsvApplyMatrix", st)
+
+    def apply_fused_1q(self, target, M):
+        t = self._device_matrix(M, 1)
+        st = self.lib.rocsvApplyFusedSingleQubitMatrix(self.h, target, C.c_void_p(t.data_ptr()))
+        self.sync()
+        self._ck("rocsvApplyFusedSingleQubitMatrix", st)
+
+    def swap_index_bits(self, a, b):
+        self._ck("rocsvSwapIndexBits", self.lib.rocsvSwapIndexBits(self.h, a, b))
+
+    def apply_circuit(self, gates):
+        arr, keep = capi.make_ops(gates)
+        self._ck("rocsvxApplyCircuit", self.lib.rocsvxApplyCircuit(self.h, self.d, self.n, arr, len(list(gates)) if not isinstance(gates, list) else len(gates)))
+        del keep
+
+    # ---- reductions ----------------------------------------------------------------------------------
+    def norm2(self) -> float:
+        r = C.c_double()
+        self._ck("rocsvxGetNorm", self.lib.rocsvxGetNorm(self.h, self.d, self.n, C.byref(r)))
+        return r.value
+
+    def expect_pauli(self, paulis: str, qubits) -> float:
+        r = C.c_double()
+        self._ck("rocsvGetExpectationPauliString",
+                 self.lib.rocsvGetExpectationPauliString(self.h, self.d, self.n, paulis.encode(), capi.uarr(qubits), len(qubits), C.byref(r)))
+        return r.value
+
+    def expect_z(self, q):
+        r = C.c_double()
+        self._ck("Z", self.lib.rocsvGetExpectationValueSinglePauliZ(self.h, self.d, self.n, q, C.byref(r)))
+        return r.value
+
+    def expect_x(self, q):
+        r = C.c_double()
+        self._ck("X", self.lib.rocsvGetExpectationValueSinglePauliX(self.h, self.d, self.n, q, C.byref(r)))
+        return r.value
+
+    def expect_y(self, q):
+        r = C.c_double()
+        self._ck("Y", self.lib.rocsvGetExpectationValueSinglePauliY(self.h, self.d, self.n, q, C.byref(r)))
+        return r.value
+
+    def expect_zprod(self, qubits):
+        r = C.c_double()
+        self._ck("ZZ", self.lib.rocsvGetExpectationValuePauliProductZ(self.h, self.d, self.n, capi.uarr(qubits), len(qubits), C.byref(r)))
+        return r.value
+
+    def measure(self, q):
+        o, p = C.c_int(), C.c_double()
+        self._ck("rocsvMeasure", self.lib.rocsvMeasure(self.h, self.d, self.n, q, C.byref(o), C.byref(p)))
+        return o.value, p.value
+
+    def sample(self, qubits, shots) -> np.ndarray:
+        out = np.zeros(max(1, shots), dtype=np.uint64)
+        self._ck("rocsvSample", self.lib.rocsvSample(self.h, self.d, self.n, capi.uarr(qubits), len(qubits), shots,
+                                                     out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out[:shots]

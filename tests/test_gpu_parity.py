@@ -1,0 +1,271 @@
+"""Parity tests proper (-m gpu): the CUDA engine, called through the C ABI, against the oracle on the same
+seeded inputs, against the committed golden fixtures (outputs of the compiled reference), and -- at full size --
+through size-independent properties.  Tolerances are north_star's: 1e-5 relative (complex64), 1e-12 (complex128);
+sampled bitstrings and measurement outcomes must be bit-exact for the shared Philox stream."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import sv_oracle as so
+from rocquantum_b200 import capi, workloads
+from rocquantum_b200.statevec import StateVector
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = util.TOL
+PRECS = ["c64", "c128"]
+
+
+def _pair(n, prec, batch=1, seed=1, fusion=False):
+    v = util.random_state(n, batch, seed)
+    o = so.Oracle(n, prec, batch=batch); o.set_state(v)
+    g = StateVector(n, prec, batch=batch, fusion=fusion); g.set_state(v)
+    return o, g
+
+
+def test_native_library_is_loaded():
+    lib = capi.load("c64")
+    maps = open("/proc/self/maps").read()
+    assert "libhipStateVec.so" in maps
+    h = C.c_void_p()
+    assert lib.rocsvCreate(C.byref(h)) == capi.SUCCESS and h.value
+    assert lib.rocsvDestroy(h) == capi.SUCCESS
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_golden_vectors_through_the_c_abi(prec):
+    S, tol = 1 / math.sqrt(2), 1e-6
+    g = StateVector(2, prec); g.gate("h", 0); g.gate("cnot", 0, 1)
+    assert np.allclose(g.state(), [S, 0, 0, S], atol=tol)                      # Bell
+    g = StateVector(1, prec); g.gate("rx", 0, math.pi / 2)
+    assert np.allclose(g.state(), [math.cos(math.pi / 4), -1j * math.sin(math.pi / 4)], atol=tol)
+    g = StateVector(1, prec); g.gate("ry", 0, math.pi / 2)
+    assert np.allclose(g.state(), [math.cos(math.pi / 4), math.sin(math.pi / 4)], atol=tol)
+    g = StateVector(1, prec); g.gate("h", 0); g.gate("rz", 0, math.pi / 2)
+    assert np.allclose(g.state(), np.array([np.exp(-1j * math.pi / 4), np.exp(1j * math.pi / 4)]) * S, atol=tol)
+    g = StateVector(3, prec); g.gate("x", 0)
+    assert abs(g.state()[1] - 1) < tol
+    g.gate("cnot", 0, 1)
+    assert abs(g.state()[3] - 1) < tol
+    g = StateVector(3, prec); g.apply_fused_1q(0, so.gate_matrix("h"))         # test_hipStateVec_multi_gpu.cpp:300-339
+    st = g.state()
+    assert np.allclose(st[:2], [S, S], atol=tol) and np.abs(st[2:]).max() < tol
+    g = StateVector(3, prec); g.gate("x", 0); g.gate("x", 1); g.gate("mcx", [0, 1], 2)
+    assert abs(g.state()[7] - 1) < tol
+    g = StateVector(3, prec); g.gate("x", 0); g.gate("x", 1); g.gate("cswap", 0, 1, 2)
+    assert abs(g.state()[5] - 1) < tol
+    g = StateVector(3, prec); g.gate("h", 0); g.gate("cnot", 0, 1); g.gate("cnot", 1, 2)
+    assert abs(g.expect_zprod([0, 1]) - 1) < 1e-6 and abs(g.expect_pauli("XY", [1, 2])) < 1e-6
+    assert abs(g.expect_pauli("XYZ", [0, 1, 2])) < 1e-6
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name", ["c1_n10", "mixed_n10"])
+def test_compiled_reference_fixtures(prec, name):
+    want = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}_{prec}.npy"))
+    gates = workloads.c1_ghz_random_layers(10, 6, seed=20) if name == "c1_n10" else util.random_gates(10, 200, seed=4242, allow_matrix=False)
+    for fusion in (False, True):
+        g = StateVector(10, prec, fusion=fusion)
+        util.run_per_gate(g, gates)
+        assert util.rel_err(g.state(), want) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 13, 15])
+def test_every_named_gate_on_every_target(prec, n):
+    o, g = _pair(n, prec, seed=n)
+    th = 0.3 + n
+    for t in range(n):
+        for name in ("h", "x", "y", "z", "s", "sdg", "t"):
+            o.gate(name, t); g.gate(name, t)
+        for name in ("rx", "ry", "rz"):
+            o.gate(name, t, th); g.gate(name, t, th)
+    if n >= 2:
+        for a in range(n):
+            b = (a * 5 + 1) % n
+            if a == b:
+                continue
+            for name in ("cnot", "cz", "swap"):
+                o.gate(name, a, b); g.gate(name, a, b)
+            for name in ("crx", "cry", "crz"):
+                o.gate(name, a, b, th); g.gate(name, a, b, th)
+    if n >= 3:
+        for a in range(n):
+            b, c = (a + 1) % n, (a + n // 2 + 1) % n
+            if len({a, b, c}) < 3:
+                continue
+            o.gate("mcx", [a, b], c); g.gate("mcx", [a, b], c)
+            o.gate("cswap", a, b, c); g.gate("cswap", a, b, c)
+    assert util.rel_err(g.state(), o.state) < TOL[prec] * 10      # ~1e3 gates accumulate rounding
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("n,batch", [(4, 3), (9, 2), (14, 2), (16, 1), (18, 1)])
+def test_mixed_bag_eager_and_fused(prec, n, batch):
+    gates = util.random_gates(n, 120, seed=7 * n, maxk=min(4, n))
+    v = util.random_state(n, batch, seed=n)
+    o = so.Oracle(n, prec, batch=batch); o.set_state(v); util.run_on_oracle(o, gates)
+    e = StateVector(n, prec, batch=batch); e.set_state(v); util.run_per_gate(e, gates)
+    assert util.rel_err(e.state(), o.state) < TOL[prec] * 4
+    f = StateVector(n, prec, batch=batch); f.set_state(v); f.apply_circuit(gates)
+    assert util.rel_err(f.state(), o.state) < TOL[prec] * 4
+    d = StateVector(n, prec, batch=batch, fusion=True); d.set_state(v); util.run_per_gate(d, gates)
+    assert util.rel_err(d.state(), o.state) < TOL[prec] * 4
+    assert d.stats().sweeps < e.stats().sweeps
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7])
+def test_apply_matrix_k_qubits_with_controls(prec, k):
+    n = 11
+    rng = np.random.default_rng(k)
+    o, g = _pair(n, prec, seed=k)
+    for trial in range(3):
+        q = [int(x) for x in rng.permutation(n)]
+        nc = trial
+        U = workloads.haar_unitary(rng, 1 << k)
+        o.apply_matrix(q[:k], U, q[k:k + nc]); g.apply_matrix(q[:k], U, q[k:k + nc])
+    assert util.rel_err(g.state(), o.state) < TOL[prec] * 4
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_c1_config_full_state(prec):
+    """configs[0]: 20-qubit GHZ + 20 random layers, compared amplitude by amplitude."""
+    n = 20
+    gates = workloads.c1_ghz_random_layers(n, 20, seed=20)
+    o = so.Oracle(n, prec); util.run_on_oracle(o, gates)
+    g = StateVector(n, prec); g.apply_circuit(gates)
+    st = g.state()
+    assert util.rel_err(st, o.state) < TOL[prec] * 10
+    assert abs(g.norm2() - 1) < (1e-4 if prec == "c64" else 1e-11)
+    assert g.stats().sweeps < len(gates) // 5
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_c2_and_qft_configs_reduced(prec):
+    n = 22
+    for gates in (workloads.c2_random_unitary(n, 6, seed=30), workloads.c3_qft(n, seed=33)):
+        o = so.Oracle(n, prec); util.run_on_oracle(o, gates)
+        g = StateVector(n, prec); g.apply_circuit(gates)
+        assert util.rel_err(g.state(), o.state) < TOL[prec] * 10
+
+
+def test_qft_analytic():
+    """QFT of a basis state |x> has amplitudes exp(2 pi i x k / 2^n)/sqrt(2^n) (bit-reversed by the final swaps)."""
+    n = 16
+    rng = np.random.default_rng(33)
+    xbits = [int(rng.integers(2)) for _ in range(n)]
+    gates = workloads.c3_qft(n, seed=33)
+    g = StateVector(n, "c128"); g.apply_circuit(gates)
+    x = sum(b << q for q, b in enumerate(xbits))
+    # run_benchmark.py's QFT treats qubit 0 as the most significant input bit
+    xr = int(format(x, f"0{n}b")[::-1], 2)
+    k = np.arange(1 << n)
+    kr = np.zeros_like(k)
+    for b in range(n):                       # output index is bit-reversed as well
+        kr |= ((k >> b) & 1) << (n - 1 - b)
+    want = np.exp(2j * math.pi * xr * kr / (1 << n)) / math.sqrt(1 << n)
+    assert np.abs(g.state() - want).max() < 1e-10
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_expectations(prec):
+    n = 12
+    o, g = _pair(n, prec, seed=12)
+    gates = workloads.c5_vqe_ansatz(n, seed=5)
+    util.run_on_oracle(o, gates); util.run_per_gate(g, gates)
+    tol = 1e-5 if prec == "c64" else 1e-12
+    for q in (0, 5, 11):
+        assert abs(g.expect_z(q) - o.expect_pauli("Z", [q])) < tol
+        assert abs(g.expect_x(q) - o.expect_pauli("X", [q])) < tol
+        assert abs(g.expect_y(q) - o.expect_pauli("Y", [q])) < tol
+    assert abs(g.expect_zprod([1, 4, 9]) - o.expect_pauli("ZZZ", [1, 4, 9])) < tol
+    for ps, qs in workloads.random_pauli_strings(n, 40, 6, seed=5) + [("IXYZ", [0, 1, 2, 3]), ("YY", [10, 11]), ("YYY", [0, 6, 11])]:
+        assert abs(g.expect_pauli(ps, qs) - o.expect_pauli(ps, qs)) < tol, (ps, qs)
+    assert util.rel_err(g.state(), o.state) < TOL[prec]          # non-destructive
+    # the literal vqe_lih.py ansatz (4 qubits) + batched call
+    o4 = so.Oracle(4, prec); g4 = StateVector(4, prec)
+    util.run_on_oracle(o4, workloads.c5_vqe_ansatz(4, 5)); g4.apply_circuit(workloads.c5_vqe_ansatz(4, 5))
+    terms = [("ZZ", [0, 1]), ("XX", [2, 3]), ("Z", [0]), ("YY", [1, 2]), ("ZIZ", [0, 1, 3])]
+    paulis = "".join(t[0] for t in terms).encode()
+    qubits = capi.uarr([q for t in terms for q in t[1]])
+    offs, acc = [0], 0
+    for t in terms:
+        acc += len(t[0]); offs.append(acc)
+    res = (C.c_double * len(terms))()
+    assert g4.lib.rocsvxGetExpectationPauliBatch(g4.h, g4.d, 4, paulis, qubits, capi.uarr(offs), len(terms), res) == 0
+    for r, t in zip(res, terms):
+        assert abs(r - o4.expect_pauli(*t)) < tol
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_sampling_and_measure_bit_exact(prec):
+    n = 14
+    gates = workloads.c2_random_unitary(n, 4, seed=3)
+    o = so.Oracle(n, prec, seed=99); util.run_on_oracle(o, gates)
+    g = StateVector(n, prec, seed=99); g.set_state(o.state)      # identical amplitudes -> identical integer masses
+    qs = [3, 0, 13, 7]
+    assert np.array_equal(g.sample(qs, 5000), o.sample(qs, 5000))
+    assert np.array_equal(g.sample(list(range(n)), 3000), o.sample(list(range(n)), 3000))   # second call: next counter
+    for q in (2, 9, 13):
+        og, pg = g.measure(q)
+        oo, po = o.measure(q)
+        assert og == oo and pg == po
+        assert util.rel_err(g.state(), o.state) < TOL[prec]
+    # statistics of the reference's own checks: tests/test_bindings.py:66-68 (+-10 %)
+    b = StateVector(2, prec, seed=5); b.gate("h", 0); b.gate("cnot", 0, 1)
+    s = b.sample([0, 1], 2000)
+    assert set(np.unique(s)) <= {0, 3} and abs((s == 0).sum() - 1000) < 200
+
+
+def test_swap_index_bits_and_batch_slice():
+    n = 10
+    o, g = _pair(n, "c64", batch=2, seed=4)
+    for a, b in ((0, 9), (3, 4), (8, 2)):
+        o.swap_index_bits(a, b); g.swap_index_bits(a, b)
+    assert np.array_equal(g.state(), o.state)                       # pure data movement: bit-exact
+    assert np.array_equal(g.state_slice(1), o.state[1 << n:])
+
+
+def test_status_codes():
+    lib = capi.load("c64")
+    g = StateVector(3, "c64")
+    assert g.gate_status("h", 3) == capi.INVALID_VALUE               # hipStateVec.cpp:108-110
+    assert g.gate_status("cnot", 1, 1) == capi.INVALID_VALUE         # :439-443
+    assert g.gate_status("cswap", 0, 1, 1) == capi.INVALID_VALUE     # :657-664
+    assert lib.rocsvApplyMultiControlledX(g.h, g.d, 3, capi.uarr([0]), 0, 1) == capi.INVALID_VALUE   # :605-607
+    assert lib.rocsvApplyMultiControlledX(g.h, g.d, 3, capi.uarr([1]), 1, 1) == capi.INVALID_VALUE   # :619-622
+    assert lib.rocsvApplyMultiControlledX(g.h, g.d, 3, capi.uarr(list(range(64))), 64, 1) == capi.NOT_IMPLEMENTED  # :613-615
+    out = np.empty(8, dtype=np.complex64)
+    assert lib.rocsvGetStateVectorSlice(g.h, g.d, out.ctypes.data_as(C.c_void_p), 1) == capi.INVALID_VALUE   # :717-719
+    assert lib.rocsvApplyH(g.h, None, 3, 0) == capi.SUCCESS          # NULL d_state = the handle's state (:80-85)
+    assert abs(g.state()[1] - 1 / math.sqrt(2)) < 1e-6
+    assert lib.rocsvEnsurePinnedBuffer(g.h, 1 << 20) == capi.SUCCESS and lib.rocsvGetPinnedBufferPointer(g.h)
+    assert lib.rocsvFreePinnedBuffer(g.h) == capi.SUCCESS and not lib.rocsvGetPinnedBufferPointer(g.h)
+    assert lib.rocsvFreeState(g.h) == capi.SUCCESS
+    assert lib.rocsvApplyH(g.h, None, 3, 0) == capi.INVALID_VALUE    # no state any more (:282)
+
+
+def test_full_size_properties_30_qubits():
+    """BASELINE configs[1] size: properties that need no full-state oracle."""
+    n = 30
+    g = StateVector(n, "c64")
+    gates = workloads.c2_random_unitary(n, 3, seed=30)
+    g.apply_circuit(gates)
+    assert abs(g.norm2() - 1) < 1e-4                                  # unitarity
+    # running the inverse circuit returns to |0...0>
+    inv = []
+    for name, t, c, th, M in reversed(gates):
+        inv.append((name, t, c, th, np.asarray(M).conj().T))
+    g.apply_circuit(inv)
+    assert abs(g.expect_zprod([0]) - 1) < 1e-4 and abs(g.expect_zprod([29]) - 1) < 1e-4
+    s = g.sample(list(range(n)), 64)
+    assert not s.any()
+    # GHZ over all 30 qubits: only |0..0> and |1..1>, <Z0 Z29> = 1
+    g.init(); g.apply_circuit(workloads.ghz(n))
+    s = g.sample(list(range(n)), 256)
+    assert set(np.unique(s)) <= {0, (1 << n) - 1} and 0 < (s == 0).sum() < 256
+    assert abs(g.expect_zprod([0, 29]) - 1) < 1e-5 and abs(g.expect_pauli("X" * n, list(range(n))) - 1) < 1e-4

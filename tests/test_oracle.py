@@ -1,0 +1,138 @@
+"""The oracle against (a) the reference's own golden vectors, (b) the reference's own sources compiled
+under the host HIP shim (oracle/_ref), (c) the Random123 Philox known-answer vectors.  CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import sv_oracle as so
+from tests import util
+
+S = 1 / math.sqrt(2)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    assert so.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert so.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert so.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_fix88_is_exact_floor():
+    from fractions import Fraction
+    rng = np.random.default_rng(0)
+    for p in list(rng.uniform(0, 1, 50)) + [0.0, 1.0, 2.0 ** -60, 2.0 ** -88, 2.0 ** -89, 3e-27, 0.5]:
+        assert so.fix88(float(p)) == int(Fraction(float(p)) * (1 << 88))
+
+
+@pytest.mark.parametrize("prec", ["c64", "c128"])
+def test_reference_golden_vectors(prec):
+    tol = 1e-6   # the reference's own tolerance, test_hipStateVec_multi_gpu.cpp:28
+    # Bell: test_bindings.py:56-70, tests/test_bindings.py:42-49
+    o = so.Oracle(2, prec); o.gate("h", 0); o.gate("cnot", 0, 1)
+    assert np.allclose(o.state, [S, 0, 0, S], atol=tol)
+    # RX(pi/2)|0> = [cos pi/4, -i sin pi/4]: integrations/pennylane-rocq/tests/test_device.py:38-46
+    o = so.Oracle(1, prec); o.gate("rx", 0, math.pi / 2)
+    assert np.allclose(o.state, [math.cos(math.pi / 4), -1j * math.sin(math.pi / 4)], atol=tol)
+    # RY(pi/2)|0> = [cos pi/4, sin pi/4]: integrations/cirq-rocm/cirq_rocm/tests/test_simulator.py:34-41
+    o = so.Oracle(1, prec); o.gate("ry", 0, math.pi / 2)
+    assert np.allclose(o.state, [math.cos(math.pi / 4), math.sin(math.pi / 4)], atol=tol)
+    # H then RZ(pi/2) = [e^{-i pi/4}, e^{+i pi/4}]/sqrt2: integrations/qiskit-rocquantum-provider/tests/test_backend.py:36-44
+    o = so.Oracle(1, prec); o.gate("h", 0); o.gate("rz", 0, math.pi / 2)
+    assert np.allclose(o.state, np.array([np.exp(-1j * math.pi / 4), np.exp(1j * math.pi / 4)]) * S, atol=tol)
+    # 3 qubits: X(q0) -> index 1; X(q0),CNOT(0,1) -> index 3; H(q0) -> idx 0,1 = 1/sqrt2
+    # rocquantum/src/hipStateVec/test_hipStateVec_multi_gpu.cpp:185-207, 251-259, 300-339
+    o = so.Oracle(3, prec); o.gate("x", 0)
+    assert abs(o.state[1] - 1) < tol and np.abs(np.delete(o.state, 1)).max() < tol
+    o.gate("cnot", 0, 1)
+    assert abs(o.state[3] - 1) < tol and np.abs(np.delete(o.state, 3)).max() < tol
+    o = so.Oracle(3, prec); o.apply_matrix([0], so.gate_matrix("h"))
+    assert np.allclose(o.state[:2], [S, S], atol=tol) and np.abs(o.state[2:]).max() < tol
+    # CCX |011> -> |111> (3 -> 7), CSWAP(0;1,2) 3 -> 5: tests/test_advanced_gates.py:58-63, 77-82
+    o = so.Oracle(3, prec); o.gate("x", 0); o.gate("x", 1); o.gate("mcx", [0, 1], 2)
+    assert abs(o.state[7] - 1) < tol
+    o = so.Oracle(3, prec); o.gate("x", 0); o.gate("x", 1); o.gate("cswap", 0, 1, 2)
+    assert abs(o.state[5] - 1) < tol
+    # CRX(theta) on |10> (control=q0 set): tests/test_advanced_gates.py:31-42
+    th = 0.7
+    o = so.Oracle(2, prec); o.gate("x", 0); o.gate("crx", 0, 1, th)
+    assert np.allclose(o.state, [0, math.cos(th / 2), 0, -1j * math.sin(th / 2)], atol=tol)
+    # GHZ expectations: examples/expectation_example.py:55-57
+    o = so.Oracle(3, prec); o.gate("h", 0); o.gate("cnot", 0, 1); o.gate("cnot", 1, 2)
+    assert abs(o.expect_pauli("ZZ", [0, 1]) - 1) < 1e-6
+    assert abs(o.expect_pauli("XY", [1, 2])) < 1e-6
+    assert abs(o.expect_pauli("XYZ", [0, 1, 2])) < 1e-6
+    # d/dtheta <Z> of RX(theta)|0> = -sin(theta): examples/gradient_example.py:56-61 (parameter shift)
+    th = 0.37
+    z = []
+    for sgn in (+1, -1):
+        o = so.Oracle(1, prec); o.gate("rx", 0, th + sgn * math.pi / 2); z.append(o.expect_pauli("Z", [0]))
+    assert abs((z[0] - z[1]) / 2 + math.sin(th)) < 1e-6
+
+
+@pytest.mark.parametrize("prec", ["c64", "c128"])
+@pytest.mark.parametrize("n,batch", [(1, 1), (2, 3), (5, 1), (11, 2)])
+def test_oracle_matches_compiled_reference(prec, n, batch):
+    """Bit-exact agreement with the reference's own hipStateVec.cpp + kernels (25 defined entry points)."""
+    if not so.ref_available(prec):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    gates = util.random_gates(n, 250, seed=100 + n, allow_matrix=False)
+    v = util.random_state(n, batch, seed=n)
+    o = so.Oracle(n, prec, batch=batch); o.set_state(v)
+    r = so.RefLib(prec); r.allocate(n, batch); r.set_state(v)
+    util.run_on_oracle(o, gates)
+    util.run_on_ref(r, gates)
+    assert np.array_equal(o.state, r.state())
+    r.close()
+
+
+@pytest.mark.parametrize("prec", ["c64", "c128"])
+def test_golden_fixture_c1(prec):
+    """tests/golden/c1_n10_*.npy was produced by the compiled reference (tests/golden/make_golden.py)."""
+    import os
+    from rocquantum_b200 import workloads
+    path = os.path.join(os.path.dirname(__file__), "golden", f"c1_n10_{prec}.npy")
+    want = np.load(path)
+    o = so.Oracle(10, prec)
+    util.run_on_oracle(o, workloads.c1_ghz_random_layers(10, 6, seed=20))
+    assert np.array_equal(o.state, want)
+
+
+def test_init_state_only_first_batch_member():
+    # hipStateVec.cpp:260-268: (1,0) is written at absolute index 0 only
+    o = so.Oracle(3, "c64", batch=2)
+    assert o.state[0] == 1 and np.count_nonzero(o.state) == 1
+
+
+def test_apply_matrix_bit_order_and_controls():
+    # matrix index bit b <-> targets[b] (multi_qubit_kernels.hip:91-99); column-major is handled by the wrapper
+    rng = np.random.default_rng(3)
+    from rocquantum_b200.workloads import haar_unitary
+    n = 5
+    U = haar_unitary(rng, 4)
+    v = util.random_state(n, seed=9)
+    o = so.Oracle(n, "c128"); o.set_state(v); o.apply_matrix([3, 1], U, controls=[4])
+    psi = v.reshape([2] * n)                      # axis 0 = qubit n-1 ... axis n-1 = qubit 0
+    out = psi.copy()
+    sub = psi[1]                                  # control qubit 4 = 1; remaining axes: q3,q2,q1,q0
+    # U acts on (bit0 = q3, bit1 = q1): index = b_q3 + 2*b_q1
+    U4 = U.reshape(2, 2, 2, 2)                    # [o1, o0, i1, i0] with bit1 first
+    res = np.einsum("abcd,cxdy->axby", U4, sub.transpose(2, 1, 0, 3))   # in: [q1,q2,q3,q0] -> out [o_q1,q2,o_q3,q0]
+    out[1] = res.transpose(2, 1, 0, 3)
+    assert np.allclose(o.state, out.reshape(-1), atol=1e-12)
+
+
+def test_sampling_spec_and_statistics():
+    o = so.Oracle(3, "c128", seed=7); o.gate("h", 0); o.gate("cnot", 0, 1); o.gate("cnot", 1, 2)
+    s = o.sample([0, 1, 2], 4000)
+    assert set(np.unique(s)) <= {0, 7}
+    assert abs((s == 0).mean() - 0.5) < 0.05          # examples/sampling_example.py:58-59
+    # bit j of the result <-> measured[j]
+    o = so.Oracle(3, "c128"); o.gate("x", 2)
+    assert set(o.sample([2, 0], 10)) == {1} and set(o.sample([0, 2], 10)) == {2}
+    # measure collapses and renormalises
+    o = so.Oracle(2, "c128", seed=3); o.gate("h", 0); o.gate("cnot", 0, 1)
+    out, p = o.measure(0)
+    assert abs(p - 0.5) < 1e-12 and abs(o.norm2() - 1) < 1e-12
+    assert abs(o.state[3 if out else 0]) == pytest.approx(1.0)

@@ -1,0 +1,210 @@
+"""Test helpers: run gate-tuple circuits (rocquantum_b200.workloads format) on the oracle / the compiled
+reference, and re-simulate a sweep plan dumped by rocsvxPlanCircuit.  Test infrastructure only."""
+import ctypes as C
+
+import numpy as np
+
+from oracle import sv_oracle as so
+from rocquantum_b200 import capi
+
+TOL = {"c64": 1e-5, "c128": 1e-12}     # north_star: relative amplitude tolerance
+
+
+def run_on_oracle(o: so.Oracle, gates):
+    for g in gates:
+        name, targets, controls, theta = g[0], list(g[1]), list(g[2]), g[3]
+        if name == "matrix":
+            o.apply_matrix(targets, g[4], controls)
+        elif name in ("h", "x", "y", "z", "s", "sdg", "t"):
+            o.gate(name, targets[0])
+        elif name in ("rx", "ry", "rz"):
+            o.gate(name, targets[0], theta)
+        elif name == "cnot":
+            o.gate("cnot", controls[0], targets[0])
+        elif name in ("cz", "swap"):
+            o.gate(name, targets[0], targets[1])
+        elif name in ("crx", "cry", "crz"):
+            o.gate(name, controls[0], targets[0], theta)
+        elif name == "mcx":
+            o.gate("mcx", controls, targets[0])
+        elif name == "cswap":
+            o.gate("cswap", controls[0], targets[0], targets[1])
+        else:
+            raise ValueError(name)
+
+
+def run_on_ref(r: so.RefLib, gates):
+    """Only gates the reference defines (no 'matrix')."""
+    for g in gates:
+        name, targets, controls, theta = g[0], list(g[1]), list(g[2]), g[3]
+        if name in ("h", "x", "y", "z", "s", "sdg", "t"):
+            st = r.gate(name, targets[0])
+        elif name in ("rx", "ry", "rz"):
+            st = r.gate(name, targets[0], theta)
+        elif name == "cnot":
+            st = r.gate("cnot", controls[0], targets[0])
+        elif name in ("cz", "swap"):
+            st = r.gate(name, targets[0], targets[1])
+        elif name in ("crx", "cry", "crz"):
+            st = r.gate(name, controls[0], targets[0], theta)
+        elif name == "mcx":
+            st = r.gate("mcx", controls, targets[0])
+        elif name == "cswap":
+            st = r.gate("cswap", controls[0], targets[0], targets[1])
+        else:
+            raise ValueError(name)
+        assert st == 0
+
+
+def run_per_gate(sv, gates):
+    """Drive the C ABI one rocsvApply* call per gate, like Circuit.flush() in the reference."""
+    for g in gates:
+        name, targets, controls, theta = g[0], list(g[1]), list(g[2]), g[3]
+        if name == "matrix":
+            sv.apply_matrix(targets, g[4], controls)
+        elif name in ("h", "x", "y", "z", "s", "sdg", "t"):
+            sv.gate(name, targets[0])
+        elif name in ("rx", "ry", "rz"):
+            sv.gate(name, targets[0], theta)
+        elif name == "cnot":
+            sv.gate("cnot", controls[0], targets[0])
+        elif name in ("cz", "swap"):
+            sv.gate(name, targets[0], targets[1])
+        elif name in ("crx", "cry", "crz"):
+            sv.gate(name, controls[0], targets[0], theta)
+        elif name == "mcx":
+            sv.gate("mcx", controls, targets[0])
+        elif name == "cswap":
+            sv.gate("cswap", controls[0], targets[0], targets[1])
+        else:
+            raise ValueError(name)
+
+
+def plan(n, gates, tile_bits=0, prec="c64"):
+    """-> (num_sweeps, [ {T,rowbits,res,ops:[{kind,cmask,targets,data}]} ])  via rocsvxPlanCircuit (host only)."""
+    lib = capi.load(prec)
+    arr, keep = capi.make_ops(gates)
+    nsw = C.c_uint()
+    size = 1 << 16
+    while True:
+        buf = C.create_string_buffer(size)
+        st = lib.rocsvxPlanCircuit(n, tile_bits, arr, len(gates), C.byref(nsw), buf, size)
+        assert st == 0, st
+        txt = buf.value.decode()
+        if len(txt) < size - 2:
+            break
+        size *= 4
+    sweeps = []
+    for line in txt.splitlines():
+        tok = line.split()
+        if tok[0] == "S":
+            sweeps.append(dict(T=int(tok[1]), rowbits=int(tok[2]), res=[int(x) for x in tok[4:]], ops=[]))
+        else:
+            kind = int(tok[1])
+            cmask = int(tok[3], 16)
+            ti, di = tok.index("targets"), tok.index("data")
+            targets = [int(x) for x in tok[ti + 1:di]]
+            vals = [float(x) for x in tok[di + 1:]]
+            data = np.array(vals[0::2]) + 1j * np.array(vals[1::2])
+            sweeps[-1]["ops"].append(dict(kind=kind, cmask=cmask, targets=targets, data=data))
+    assert len(sweeps) == nsw.value
+    return nsw.value, sweeps
+
+
+def simulate_plan(o: so.Oracle, sweeps):
+    """Apply a dumped plan to an oracle state, checking each op only uses what its sweep makes resident."""
+    n = o.n
+    for sw in sweeps:
+        res = set(sw["res"])
+        assert len(res) == sw["T"] == min(n, sw["T"])
+        assert sw["res"][:sw["rowbits"]] == list(range(sw["rowbits"]))
+        for op in sw["ops"]:
+            controls = [q for q in range(64) if (op["cmask"] >> q) & 1]
+            t, k = op["targets"], len(op["targets"])
+            if op["kind"] == 1:      # DENSE
+                assert set(t) <= res, "dense target not resident"
+                M = op["data"].reshape(1 << k, 1 << k).T       # column-major -> M[i][j]
+                o.apply_matrix(t, M, controls)
+            elif op["kind"] == 2:    # DIAG (targets/controls may be non-resident)
+                if k == 0:
+                    idx = np.arange(1 << n)
+                    m = np.ones(1 << n, dtype=bool)
+                    for c in controls:
+                        m &= ((idx >> c) & 1).astype(bool)
+                    st = o.state.reshape(o.batch, 1 << n)
+                    st[:, m] = (st[:, m] * op["data"][0]).astype(o.dtype)
+                else:
+                    o.apply_matrix(t, np.diag(op["data"]), controls)
+            elif op["kind"] == 3:    # PERM_X
+                assert set(t) <= res
+                if controls:
+                    o.mcx(controls, t[0])
+                else:
+                    o.gate("x", t[0])
+            else:                    # PERM_SWAP
+                assert set(t) <= res
+                assert len(controls) <= 1
+                if controls:
+                    o.gate("cswap", controls[0], t[0], t[1])
+                else:
+                    o.gate("swap", t[0], t[1])
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.complex128)
+    b = np.asarray(b, dtype=np.complex128)
+    return float(np.abs(a - b).max() / max(1e-300, np.abs(b).max()))
+
+
+def random_state(n, batch=1, seed=0):
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal(batch << n) + 1j * rng.standard_normal(batch << n)
+    v = v.reshape(batch, 1 << n)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    return v.reshape(-1)
+
+
+def random_gates(n, count, seed, allow_matrix=True, maxk=3):
+    """A mixed bag over every gate family of the ABI."""
+    import math
+    from rocquantum_b200.workloads import haar_unitary
+    rng = np.random.default_rng(seed)
+    names = ["h", "x", "y", "z", "s", "sdg", "t", "rx", "ry", "rz"]
+    if n >= 2:
+        names += ["cnot", "cz", "swap", "crx", "cry", "crz"]
+    if n >= 3:
+        names += ["mcx", "cswap"]
+    if allow_matrix:
+        names += ["matrix", "matrix"]
+    out = []
+    for _ in range(count):
+        g = names[int(rng.integers(len(names)))]
+        q = [int(x) for x in rng.permutation(n)]
+        th = float(rng.uniform(0, 2 * math.pi))
+        if g in ("h", "x", "y", "z", "s", "sdg", "t"):
+            out.append((g, [q[0]], [], 0.0))
+        elif g in ("rx", "ry", "rz"):
+            out.append((g, [q[0]], [], th))
+        elif g == "cnot":
+            out.append((g, [q[1]], [q[0]], 0.0))
+        elif g in ("cz", "swap"):
+            out.append((g, [q[0], q[1]], [], 0.0))
+        elif g in ("crx", "cry", "crz"):
+            out.append((g, [q[1]], [q[0]], th))
+        elif g == "mcx":
+            nc = int(rng.integers(1, min(n - 1, 4) + 1))
+            out.append((g, [q[nc]], q[:nc], 0.0))
+        elif g == "cswap":
+            out.append((g, [q[1], q[2]], [q[0]], 0.0))
+        else:
+            k = int(rng.integers(1, min(maxk, n) + 1))
+            nc = int(rng.integers(0, min(2, n - k) + 1))
+            kind = int(rng.integers(3))
+            if kind == 0:
+                M = haar_unitary(rng, 1 << k)
+            elif kind == 1:
+                M = np.diag(np.exp(1j * rng.uniform(0, 2 * math.pi, size=1 << k)))
+            else:
+                M = np.diag(np.concatenate([np.ones((1 << k) - 1), [np.exp(1j * th)]]))
+            out.append(("matrix", q[:k], q[k:k + nc], 0.0, M))
+    return out

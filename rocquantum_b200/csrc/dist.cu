@@ -1,16 +1,72 @@
-// rocquantum_b200/csrc/dist.cu -- distributed state over NCCL (one process per GPU).
-// See dist.h.  The reference documents this path (MULTI_GPU_GUIDE.md, hipStateVec.h:84-137) but defines
-// none of it; its packing kernels (swap_kernels.hip:46-89) use atomic cursors whose arrival order is
-// nondeterministic.  Here a k-bit global<->local exchange moves, per peer, block-contiguous runs that land
-// directly in their final position -- no counts, no packing pass.
+// rocquantum_b200/csrc/dist.cu -- distributed state over NCCL, one process per GPU (see dist.h).
+//
+// The reference documents this path (MULTI_GPU_GUIDE.md, hipStateVec.h:84-137) but defines none of it; its
+// packing kernels (swap_kernels.hip:46-89) use atomic cursors whose arrival order is nondeterministic, so a
+// receiver could not place the data.  Here a k-bit global<->local exchange moves, per peer, block-contiguous
+// runs that land directly in their final position (no counts, no packing pass):
+//   * the engine keeps a logical->physical qubit map; physical positions >= n_local are the rank bits;
+//   * a gate with a non-diagonal target on a rank bit triggers an exchange that swaps k rank bits with the
+//     top k local bits (the evicted logical qubits are first moved to those top slots by PERM ops that ride in
+//     the preceding fused sweep), chosen by farthest-next-use when a whole circuit is known;
+//   * controls and diagonal gates on rank bits need no communication (the tile base carries the rank);
+//   * scalars (probability masses, expectation values) are exact all-gathers / fp64 all-reduces.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
-#include "dist.h"
+#include "engine.h"
 
 namespace rq {
+
+// ---- NCCL through dlopen: the library has no link-time dependency on it --------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { fprintf(stderr, "hipStateVec(B200): cannot load libnccl: %s\n", dlerror()); return false; }
+#define RQ_SYM(f) f = reinterpret_cast<decltype(f)>(dlsym(lib, "nccl" #f)); if (!f) { fprintf(stderr, "hipStateVec(B200): nccl" #f " missing\n"); return false; }
+        RQ_SYM(GetUniqueId) RQ_SYM(CommInitRank) RQ_SYM(CommDestroy) RQ_SYM(Send) RQ_SYM(Recv) RQ_SYM(GroupStart) RQ_SYM(GroupEnd)
+        RQ_SYM(AllReduce) RQ_SYM(AllGather) RQ_SYM(GetErrorString)
+#undef RQ_SYM
+        return true;
+    }
+};
+static NcclApi g_nccl;
+
+#define RQ_NCCL(call)                                                                             \
+    do {                                                                                          \
+        const ncclResult_t _r = (call);                                                           \
+        if (_r != ncclSuccess) {                                                                  \
+            fprintf(stderr, "hipStateVec(B200): %s failed: %s\n", #call, g_nccl.GetErrorString(_r)); \
+            return ROCQ_STATUS_RCCL_ERROR;                                                        \
+        }                                                                                         \
+    } while (0)
+#define RQ_CU(call)                                                                               \
+    do {                                                                                          \
+        const cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess) {                                                                  \
+            fprintf(stderr, "hipStateVec(B200): %s failed: %s\n", #call, cudaGetErrorString(_e)); \
+            return ROCQ_STATUS_HIP_ERROR;                                                         \
+        }                                                                                         \
+    } while (0)
+#define RQ_OK(call) do { const rocqStatus_t _s = (call); if (_s != ROCQ_STATUS_SUCCESS) return _s; } while (0)
 
 // Swapping global bits G[i] (absolute positions >= n_local) with local bits L[i]: this rank keeps the
 // amplitudes whose local pattern on L equals its own rank pattern on G; for every other pattern b it sends
@@ -25,8 +81,7 @@ size_t plan_exchange(unsigned n_local, int nranks, int rank, const unsigned* loc
     unsigned own = 0;                                   // own pattern: bit i = rank's value on global_bits[i]
     for (unsigned i = 0; i < npairs; ++i) own |= (unsigned)(((uint64_t)rank >> (global_bits[i] - n_local)) & 1ull) << i;
     const uint64_t run = 1ull << minl;
-    // free local bits above minl that are not exchanged enumerate the runs of one pattern
-    std::vector<unsigned> freebits;
+    std::vector<unsigned> freebits;                     // non-exchanged local bits above minl enumerate the runs
     for (unsigned p = minl; p < n_local; ++p) if (!((lmask >> p) & 1ull)) freebits.push_back(p);
     const uint64_t nruns = 1ull << freebits.size();
     size_t count = 0;
@@ -49,45 +104,446 @@ size_t plan_exchange(unsigned n_local, int nranks, int rank, const unsigned* loc
     return count;
 }
 
-rocqStatus_t Dist::init(rocsvInternalHandle*, int, int, const void*) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
-rocqStatus_t Dist::allocate(rocsvInternalHandle*, unsigned) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
-rocqStatus_t Dist::initialize(rocsvInternalHandle*) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
-void Dist::shutdown() {}
-rocqStatus_t Dist::localize(rocsvInternalHandle*, HostOp&) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
-rocqStatus_t Dist::run_circuit(rocsvInternalHandle*, std::vector<HostOp>&) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
-rocqStatus_t Dist::swap_index_bits(rocsvInternalHandle*, unsigned, unsigned) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
-rocqStatus_t Dist::canonicalize(rocsvInternalHandle*) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
-rocqStatus_t Dist::allreduce_sum(rocsvInternalHandle*, double*, unsigned) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
-rocqStatus_t Dist::pauli_expect(rocsvInternalHandle*, uint64_t, uint64_t, unsigned, double*) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
-rocqStatus_t Dist::measure(rocsvInternalHandle*, unsigned, int*, double*) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
-rocqStatus_t Dist::sample(rocsvInternalHandle*, const unsigned*, unsigned, unsigned, uint64_t*) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
+// ---- lifecycle -------------------------------------------------------------------------------------------
+rocqStatus_t Dist::init(rocsvInternalHandle* h, int rank_, int nranks_, const void* id128) {
+    (void)h;
+    if (nranks_ < 1 || (nranks_ & (nranks_ - 1)) || rank_ < 0 || rank_ >= nranks_) return ROCQ_STATUS_INVALID_VALUE;   // hipStateVec.h:86
+    if (inited) return ROCQ_STATUS_INVALID_VALUE;
+    rank = rank_;
+    nranks = nranks_;
+    if (nranks > 1) {
+        if (!id128) return ROCQ_STATUS_INVALID_VALUE;
+        if (!g_nccl.load()) return ROCQ_STATUS_RCCL_ERROR;
+        ncclUniqueId id;
+        static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id size");
+        memcpy(&id, id128, 128);
+        ncclComm_t c = nullptr;
+        RQ_NCCL(g_nccl.CommInitRank(&c, nranks, id, rank));
+        comm = c;
+        RQ_CU(cudaMalloc(&d_gather, (size_t)(64 + 8 * nranks) * sizeof(uint64_t)));
+    }
+    inited = true;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+void Dist::shutdown() {
+    if (staging) { cudaFree(staging); staging = nullptr; }
+    if (d_gather) { cudaFree(d_gather); d_gather = nullptr; }
+    if (comm) { g_nccl.CommDestroy((ncclComm_t)comm); comm = nullptr; }
+    inited = false;
+    n_total = 0;
+}
+
+rocqStatus_t Dist::allocate(rocsvInternalHandle* h, unsigned total_qubits) {
+    if (!inited) { rank = 0; nranks = 1; inited = true; }            // single process, single GPU: a plain state
+    unsigned M = 0;
+    while ((1 << M) < nranks) ++M;
+    if (total_qubits < M || total_qubits > 60) return ROCQ_STATUS_INVALID_VALUE;
+    n_total = 0;                                                      // inactive while (re)allocating
+    const rocqStatus_t s = rocsvAllocateState(h, total_qubits - M, nullptr, 1);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    n_global = M;
+    n_local = total_qubits - M;
+    n_total = total_qubits;
+    map.resize(n_total);
+    for (unsigned q = 0; q < n_total; ++q) map[q] = q;
+    if (staging) { cudaFree(staging); staging = nullptr; }
+    if (nranks > 1) {
+        const uint64_t slice = 1ull << n_local;
+        staging_amps = std::min<uint64_t>(slice, 1ull << 22) * (uint64_t)(nranks - 1);     // <= 32 MiB (c64) per peer
+        if (cudaMalloc(&staging, staging_amps * sizeof(rq_cplx)) != cudaSuccess) { cudaGetLastError(); return ROCQ_STATUS_ALLOCATION_FAILED; }
+    }
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t Dist::initialize(rocsvInternalHandle* h) {
+    if (!active() || !h->d_state) return ROCQ_STATUS_INVALID_VALUE;
+    h->queue.clear();
+    for (unsigned q = 0; q < n_total; ++q) map[q] = q;
+    const int e = rq_launch_init_state(h->d_state, (size_t)1 << n_local, rank == 0, h->stream);     // hipStateVec.h:97-99
+    h->stats.kernelLaunches++;
+    h->numQubits = n_local;
+    return e == 0 ? ROCQ_STATUS_SUCCESS : ROCQ_STATUS_HIP_ERROR;
+}
+
+// ---- the exchange -------------------------------------------------------------------------------------------
+// swap the k rank bits gpos[] with the top-k local bits (n_local-k .. n_local-1, paired in order)
+static rocqStatus_t exchange_top(rocsvInternalHandle* h, Dist& d, const std::vector<unsigned>& gpos) {
+    const unsigned k = (unsigned)gpos.size();
+    if (k == 0) return ROCQ_STATUS_SUCCESS;
+    std::vector<unsigned> lpos(k);
+    for (unsigned i = 0; i < k; ++i) lpos[i] = d.n_local - k + i;
+    std::vector<rocsvxExchangeSeg> segs((size_t)(1u << k));
+    const size_t ns = plan_exchange(d.n_local, d.nranks, d.rank, lpos.data(), gpos.data(), k, segs.data(), segs.size());
+    const uint64_t run = 1ull << (d.n_local - k);
+    const uint64_t chunk = std::min<uint64_t>(run, d.staging_amps / (uint64_t)std::max<size_t>(ns, 1));
+    ncclComm_t comm = (ncclComm_t)d.comm;
+    for (uint64_t c = 0; c < run; c += chunk) {
+        const uint64_t len = std::min<uint64_t>(chunk, run - c);
+        RQ_NCCL(g_nccl.GroupStart());
+        for (size_t i = 0; i < ns; ++i) {
+            RQ_NCCL(g_nccl.Send(h->d_state + segs[i].sendOffset + c, len * sizeof(rq_cplx), ncclChar, segs[i].peer, comm, h->stream));
+            RQ_NCCL(g_nccl.Recv(d.staging + i * chunk, len * sizeof(rq_cplx), ncclChar, segs[i].peer, comm, h->stream));
+        }
+        RQ_NCCL(g_nccl.GroupEnd());
+        for (size_t i = 0; i < ns; ++i)
+            RQ_CU(cudaMemcpyAsync(h->d_state + segs[i].recvOffset + c, d.staging + i * chunk, len * sizeof(rq_cplx),
+                                  cudaMemcpyDeviceToDevice, h->stream));
+    }
+    d.exchanges++;
+    d.exchanged_amps += run * ns;
+    // relabel: the logical qubits at lpos[i] and gpos[i] trade places
+    for (unsigned i = 0; i < k; ++i)
+        for (unsigned q = 0; q < d.n_total; ++q) {
+            if (d.map[q] == lpos[i]) d.map[q] = gpos[i];
+            else if (d.map[q] == gpos[i]) d.map[q] = lpos[i];
+        }
+    return ROCQ_STATUS_SUCCESS;
+}
+
+static unsigned logical_at(const Dist& d, unsigned phys) {
+    for (unsigned q = 0; q < d.n_total; ++q) if (d.map[q] == phys) return q;
+    return ~0u;
+}
+
+// Make the logical qubits `bring` (currently on rank bits) local by trading them with the logical qubits
+// `evict` (currently local).  The evictees are first moved to the top local slots with PERM_SWAP ops appended to
+// `pending` (physical positions), which is then executed fused, and the slices are exchanged.
+static rocqStatus_t trade(rocsvInternalHandle* h, Dist& d, const std::vector<unsigned>& bring, const std::vector<unsigned>& evict,
+                          std::vector<HostOp>& pending) {
+    const unsigned k = (unsigned)bring.size();
+    std::vector<unsigned> slots(k);
+    for (unsigned i = 0; i < k; ++i) slots[i] = d.n_local - k + i;
+    auto is_evictee = [&](unsigned logical) { return std::find(evict.begin(), evict.end(), logical) != evict.end(); };
+    for (unsigned i = 0; i < k; ++i) {
+        const unsigned p = d.map[evict[i]];
+        if (p >= d.n_local - k) continue;                               // already in a top slot
+        for (unsigned s : slots) {
+            const unsigned occupant = logical_at(d, s);
+            if (is_evictee(occupant)) continue;
+            pending.push_back(make_swap(p, s));
+            d.map[occupant] = p;
+            d.map[evict[i]] = s;
+            break;
+        }
+    }
+    if (!pending.empty()) {
+        RQ_OK(rq_engine_run(h, h->d_state, d.n_local, pending, true));
+        pending.clear();
+    }
+    // pair each top slot with the rank bit it trades with: slot order is fixed, so order gpos by slot
+    std::vector<unsigned> gpos(k);
+    std::vector<unsigned> bring_left = bring;
+    for (unsigned i = 0; i < k; ++i) { gpos[i] = d.map[bring_left[i]]; }
+    return exchange_top(h, d, gpos);
+}
+
+static void to_physical(const Dist& d, const HostOp& in, HostOp& out) {
+    out = in;
+    for (unsigned& t : out.targets) t = d.map[t];
+    uint64_t cm = 0;
+    for (unsigned q = 0; q < d.n_total; ++q) if ((in.cmask >> q) & 1ull) cm |= 1ull << d.map[q];
+    out.cmask = cm;
+}
+
+rocqStatus_t Dist::localize(rocsvInternalHandle* h, HostOp& op) {
+    HostOp phys;
+    to_physical(*this, op, phys);
+    const uint64_t gm = global_mask();
+    if (phys.nondiag() & gm) {
+        if (nranks == 1) return ROCQ_STATUS_FAILURE;
+        RQ_OK(rq_engine_flush(h));                                        // queued ops use the current layout
+        std::vector<unsigned> bring, evict;
+        for (unsigned t : op.targets) if ((1ull << map[t]) & gm & phys.nondiag()) bring.push_back(t);
+        const uint64_t used = op.qubits();                                // logical
+        for (unsigned p = n_local; p-- > 0 && evict.size() < bring.size();) {
+            const unsigned l = logical_at(*this, p);
+            if (!((used >> l) & 1ull)) evict.push_back(l);
+        }
+        if (evict.size() < bring.size()) return ROCQ_STATUS_NOT_IMPLEMENTED;   // more targets than free local qubits
+        std::vector<HostOp> pending;
+        RQ_OK(trade(h, *this, bring, evict, pending));
+        to_physical(*this, op, phys);
+    }
+    op = phys;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+// Whole-circuit path: translate in order, and on a global non-diagonal target trade ALL rank bits at once for the
+// local qubits whose next non-diagonal use is farthest (Belady), so one exchange is amortised over many layers.
+rocqStatus_t Dist::run_circuit(rocsvInternalHandle* h, std::vector<HostOp>& ops) {
+    const uint64_t gm = global_mask();
+    std::vector<HostOp> pending;
+    cudaEventRecord(h->ev0, h->stream);
+    for (size_t i = 0; i < ops.size(); ++i) {
+        HostOp phys;
+        to_physical(*this, ops[i], phys);
+        if ((phys.nondiag() & gm) && nranks > 1) {
+            // next non-diagonal use of every logical qubit from op i on
+            std::vector<size_t> next(n_total, ops.size() + n_total);
+            unsigned found = 0;
+            for (size_t j = i; j < ops.size() && found < n_total; ++j) {
+                const uint64_t nd = ops[j].nondiag();
+                for (unsigned q = 0; q < n_total; ++q)
+                    if (((nd >> q) & 1ull) && next[q] >= ops.size()) { next[q] = j; ++found; }
+            }
+            for (unsigned q = 0; q < n_total; ++q) if (next[q] >= ops.size()) next[q] = ops.size() + q;   // never used again: stable order
+            std::vector<unsigned> order(n_total);
+            for (unsigned q = 0; q < n_total; ++q) order[q] = q;
+            std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return next[a] > next[b]; });
+            std::vector<char> want_global(n_total, 0);
+            for (unsigned r = 0; r < n_global; ++r) want_global[order[r]] = 1;
+            std::vector<unsigned> bring, evict;
+            for (unsigned q = 0; q < n_total; ++q) {
+                const bool is_global = map[q] >= n_local;
+                if (is_global && !want_global[q]) bring.push_back(q);
+                if (!is_global && want_global[q]) evict.push_back(q);
+            }
+            if (bring.size() != evict.size() || bring.empty()) return ROCQ_STATUS_FAILURE;
+            RQ_OK(trade(h, *this, bring, evict, pending));
+            to_physical(*this, ops[i], phys);
+            if (phys.nondiag() & gm) return ROCQ_STATUS_FAILURE;
+        }
+        pending.push_back(std::move(phys));
+    }
+    if (!pending.empty()) RQ_OK(rq_engine_run(h, h->d_state, n_local, pending, true));
+    cudaEventRecord(h->ev1, h->stream);
+    h->stats.lastSweepMs = -1.0;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t Dist::swap_index_bits(rocsvInternalHandle* h, unsigned q1, unsigned q2) {
+    // Physically relabelling two index bits equals a SWAP gate on the two logical qubits (hipStateVec.h:123-137).
+    // local<->local: a PERM sweep; local<->global: one exchange; global<->global: relabel through a local slot
+    // (the reference leaves this case NOT_IMPLEMENTED, MULTI_GPU_GUIDE.md:50).
+    HostOp op = make_swap(q1, q2);
+    RQ_OK(localize(h, op));
+    std::vector<HostOp> one{op};
+    return rq_engine_run(h, h->d_state, n_local, one, false);
+}
+
+// restore the identity layout (needed before the slice is handed to the caller)
+rocqStatus_t Dist::canonicalize(rocsvInternalHandle* h) {
+    bool ident = true;
+    for (unsigned q = 0; q < n_total; ++q) ident = ident && map[q] == q;
+    if (ident) return ROCQ_STATUS_SUCCESS;
+    RQ_OK(rq_engine_flush(h));
+    std::vector<HostOp> pending;
+    if (nranks > 1) {
+        // 1) every logical qubit that belongs on a rank bit but sits elsewhere, and vice versa
+        std::vector<unsigned> bring, evict;
+        for (unsigned q = 0; q < n_total; ++q) {
+            const bool is_global = map[q] >= n_local, should = q >= n_local;
+            if (is_global && !should) bring.push_back(q);
+            if (!is_global && should) evict.push_back(q);
+        }
+        if (!bring.empty()) RQ_OK(trade(h, *this, bring, evict, pending));
+        // 2) rank bits holding the wrong global qubit: rotate each through a local slot
+        for (unsigned g = n_local; g < n_total; ++g) {
+            if (map[g] == g) continue;
+            const unsigned occupant = logical_at(*this, g);               // logical at position g (another global qubit)
+            const unsigned spare = logical_at(*this, n_local - 1);
+            RQ_OK(trade(h, *this, {occupant}, {spare}, pending));         // occupant -> local, spare -> position g
+            RQ_OK(trade(h, *this, {g}, {occupant}, pending));             // logical g -> local, occupant -> g's old position
+            RQ_OK(trade(h, *this, {spare}, {g}, pending));                // logical g -> position g, spare -> local
+        }
+    }
+    // 3) local positions: cycle decomposition with swaps
+    for (unsigned q = 0; q < n_local; ++q) {
+        if (map[q] == q) continue;
+        const unsigned p = map[q], other = logical_at(*this, q);
+        pending.push_back(make_swap(p, q));
+        map[other] = p;
+        map[q] = q;
+    }
+    if (!pending.empty()) RQ_OK(rq_engine_run(h, h->d_state, n_local, pending, true));
+    return ROCQ_STATUS_SUCCESS;
+}
+
+// ---- scalars ---------------------------------------------------------------------------------------------------
+rocqStatus_t Dist::allreduce_sum(rocsvInternalHandle* h, double* v, unsigned count) {
+    if (nranks == 1) return ROCQ_STATUS_SUCCESS;
+    if (count > 32) return ROCQ_STATUS_INVALID_VALUE;
+    double* dbuf = reinterpret_cast<double*>(d_gather);
+    RQ_CU(cudaMemcpyAsync(dbuf, v, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    RQ_NCCL(g_nccl.AllReduce(dbuf, dbuf, count, ncclDouble, ncclSum, (ncclComm_t)comm, h->stream));
+    return rq_engine_fetch(h, dbuf, v, count * sizeof(double));
+}
+
+// gather `count` u64 from every rank: out[r*count + i]
+static rocqStatus_t allgather_u64(rocsvInternalHandle* h, Dist& d, const uint64_t* mine, unsigned count, std::vector<uint64_t>& out) {
+    out.assign((size_t)count * d.nranks, 0);
+    if (d.nranks == 1) { for (unsigned i = 0; i < count; ++i) out[i] = mine[i]; return ROCQ_STATUS_SUCCESS; }
+    if (count > 8) return ROCQ_STATUS_INVALID_VALUE;
+    uint64_t* send = d.d_gather;
+    uint64_t* recv = d.d_gather + 64;
+    RQ_CU(cudaMemcpyAsync(send, mine, count * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    RQ_NCCL(g_nccl.AllGather(send, recv, count, ncclUint64, (ncclComm_t)d.comm, h->stream));
+    return rq_engine_fetch(h, recv, out.data(), out.size() * sizeof(uint64_t));
+}
+
+rocqStatus_t Dist::pauli_expect(rocsvInternalHandle* h, uint64_t xm, uint64_t zm, unsigned ny, double* result) {
+    // X/Y factors pair amplitudes across the flipped bits: those qubits must be local
+    const uint64_t gm = global_mask();
+    std::vector<unsigned> bring;
+    for (unsigned q = 0; q < n_total; ++q) if (((xm >> q) & 1ull) && ((1ull << map[q]) & gm)) bring.push_back(q);
+    if (!bring.empty()) {
+        std::vector<unsigned> evict;
+        for (unsigned p = n_local; p-- > 0 && evict.size() < bring.size();) {
+            const unsigned l = logical_at(*this, p);
+            if (!((xm >> l) & 1ull)) evict.push_back(l);
+        }
+        if (evict.size() < bring.size()) return ROCQ_STATUS_NOT_IMPLEMENTED;
+        std::vector<HostOp> pending;
+        RQ_OK(trade(h, *this, bring, evict, pending));
+    }
+    uint64_t pxm = 0, pzm = 0;
+    for (unsigned q = 0; q < n_total; ++q) {
+        if ((xm >> q) & 1ull) pxm |= 1ull << map[q];
+        if ((zm >> q) & 1ull) pzm |= 1ull << map[q];
+    }
+    const uint64_t lmask = (1ull << n_local) - 1ull;
+    const unsigned nb = rq_reduce_blocks();
+    if (rq_launch_pauli_expect(h->d_state, n_local, pxm & lmask, pzm & lmask, ny, h->d_partials, nb, h->d_partials + nb, h->stream) != 0)
+        return ROCQ_STATUS_HIP_ERROR;
+    h->stats.kernelLaunches += 2;
+    double v = 0.0;
+    RQ_OK(rq_engine_fetch(h, h->d_partials + nb, &v, sizeof v));
+    if (__builtin_popcountll(((uint64_t)rank << n_local) & pzm) & 1) v = -v;       // Z factors on rank bits: a sign per rank
+    RQ_OK(allreduce_sum(h, &v, 1));
+    *result = v;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+typedef unsigned __int128 u128;
+static inline u128 mul_u53(u128 S, uint64_t U) {
+    const u128 A = (u128)(uint64_t)S * U, B = (u128)(uint64_t)(S >> 64) * U;
+    return (B << 11) + (A >> 53);
+}
+static inline double u128_to_double(u128 v) { return (double)(uint64_t)(v >> 64) * 0x1p64 + (double)(uint64_t)v; }
+
+rocqStatus_t Dist::measure(rocsvInternalHandle* h, unsigned q, int* outcome, double* probability) {
+    const unsigned p = map[q];
+    const bool local = p < n_local;
+    const unsigned nb = rq_reduce_blocks();
+    if (rq_launch_fixed_masses(h->d_state, n_local, local ? p : 63u, h->d_upartials, nb, h->d_upartials + 4 * nb, h->stream) != 0)
+        return ROCQ_STATUS_HIP_ERROR;
+    h->stats.kernelLaunches += 2;
+    uint64_t m[4];
+    RQ_OK(rq_engine_fetch(h, h->d_upartials + 4 * nb, m, sizeof m));
+    std::vector<uint64_t> all;
+    RQ_OK(allgather_u64(h, *this, m, 4, all));
+    u128 S0 = 0, S1 = 0;
+    for (int r = 0; r < nranks; ++r) {
+        const u128 a0 = ((u128)all[4 * r] << 64) | all[4 * r + 1], a1 = ((u128)all[4 * r + 2] << 64) | all[4 * r + 3];
+        if (local) { S0 += a0; S1 += a1; }
+        else if ((r >> (p - n_local)) & 1) S1 += a0 + a1;
+        else S0 += a0 + a1;
+    }
+    const uint64_t U = rq_uniform53(h->seed, h->draws++, 0);                  // same stream on every rank
+    const int out = mul_u53(S0 + S1, U) < S0 ? 0 : 1;
+    const double tot = u128_to_double(S0 + S1), mass = u128_to_double(out ? S1 : S0);
+    if (!(mass > 0.0)) return ROCQ_STATUS_FAILURE;
+    *outcome = out;
+    if (probability) *probability = mass / tot;
+    const double scale = 1.0 / std::sqrt(mass * 0x1p-88);
+    int e;
+    if (local) e = rq_launch_collapse(h->d_state, n_local, p, out, scale, h->stream);
+    else if ((int)((rank >> (p - n_local)) & 1) == out) e = rq_launch_collapse(h->d_state, n_local, 63u, 0, scale, h->stream);   // keep: scale all
+    else e = rq_launch_init_state(h->d_state, (size_t)1 << n_local, 0, h->stream);                                              // discard: zero all
+    h->stats.kernelLaunches++;
+    return e == 0 ? ROCQ_STATUS_SUCCESS : ROCQ_STATUS_HIP_ERROR;
+}
+
+rocqStatus_t Dist::sample(rocsvInternalHandle* h, const unsigned* measured, unsigned nm, unsigned shots, uint64_t* out) {
+    const unsigned n = n_local;
+    const unsigned cb = n < 10 ? n : (n > 30 ? n - 20 : 10);
+    const uint64_t nchunks = 1ull << (n - cb);
+    uint64_t* d_hi = nullptr;
+    RQ_CU(cudaMallocAsync(&d_hi, (2 * nchunks + shots) * sizeof(uint64_t), h->stream));
+    uint64_t* d_lo = d_hi + nchunks;
+    uint64_t* d_idx = d_hi + 2 * nchunks;
+    if (rq_launch_chunk_masses(h->d_state, n, cb, d_hi, d_lo, h->stream) != 0) return ROCQ_STATUS_HIP_ERROR;
+    std::vector<uint64_t> hv(2 * nchunks);
+    RQ_CU(cudaMemcpyAsync(hv.data(), d_hi, 2 * nchunks * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    RQ_CU(cudaStreamSynchronize(h->stream));
+    u128 acc = 0;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        acc += ((u128)hv[c] << 64) | hv[nchunks + c];
+        hv[c] = (uint64_t)(acc >> 64);
+        hv[nchunks + c] = (uint64_t)acc;
+    }
+    RQ_CU(cudaMemcpyAsync(d_hi, hv.data(), 2 * nchunks * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    const uint64_t mine[2] = {(uint64_t)(acc >> 64), (uint64_t)acc};
+    std::vector<uint64_t> all;
+    RQ_OK(allgather_u64(h, *this, mine, 2, all));
+    u128 total = 0, win = 0;
+    for (int r = 0; r < nranks; ++r) {
+        const u128 m = ((u128)all[2 * r] << 64) | all[2 * r + 1];
+        if (r < rank) win += m;
+        total += m;
+    }
+    if (total == 0) { cudaFreeAsync(d_hi, h->stream); return ROCQ_STATUS_FAILURE; }
+    if (acc == 0) {
+        RQ_CU(cudaMemsetAsync(d_idx, 0xFF, (size_t)shots * sizeof(uint64_t), h->stream));
+    } else if (rq_launch_sample(h->d_state, n, cb, d_hi, d_lo, nchunks, (uint64_t)(total >> 64), (uint64_t)total, (uint64_t)(win >> 64),
+                                (uint64_t)win, h->seed, h->draws, shots, 0, d_idx, h->stream) != 0) {
+        return ROCQ_STATUS_HIP_ERROR;
+    }
+    h->draws++;
+    h->stats.kernelLaunches += 2;
+    std::vector<uint64_t> idx(shots);
+    RQ_CU(cudaMemcpyAsync(idx.data(), d_idx, (size_t)shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    RQ_CU(cudaStreamSynchronize(h->stream));
+    for (unsigned s = 0; s < shots; ++s) {
+        uint64_t bits = 0;
+        if (idx[s] != ~0ull) {
+            const uint64_t phys = ((uint64_t)rank << n_local) | idx[s];
+            for (unsigned j = 0; j < nm; ++j) bits |= ((phys >> map[measured[j]]) & 1ull) << j;
+        }
+        idx[s] = bits;
+    }
+    if (nranks > 1) {                                                       // exactly one rank owns each shot: sum = gather
+        RQ_CU(cudaMemcpyAsync(d_idx, idx.data(), (size_t)shots * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        RQ_NCCL(g_nccl.AllReduce(d_idx, d_idx, shots, ncclUint64, ncclSum, (ncclComm_t)comm, h->stream));
+        RQ_CU(cudaMemcpyAsync(idx.data(), d_idx, (size_t)shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+        RQ_CU(cudaStreamSynchronize(h->stream));
+    }
+    cudaFreeAsync(d_hi, h->stream);
+    memcpy(out, idx.data(), (size_t)shots * sizeof(uint64_t));
+    return ROCQ_STATUS_SUCCESS;
+}
 
 }  // namespace rq
-
-rq::Dist& rq_engine_dist(rocsvInternalHandle* h);
 
 extern "C" {
 
 rocqStatus_t rocsvAllocateDistributedState(rocsvHandle_t h, unsigned totalNumQubits) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
-    return rq_engine_dist(h).allocate(h, totalNumQubits);
+    return h->dist.allocate(h, totalNumQubits);
 }
 rocqStatus_t rocsvInitializeDistributedState(rocsvHandle_t h) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
-    return rq_engine_dist(h).initialize(h);
+    return h->dist.initialize(h);
 }
-rocqStatus_t rocsvxDistGetUniqueId(void*) { return ROCQ_STATUS_NOT_IMPLEMENTED; }
+rocqStatus_t rocsvxDistGetUniqueId(void* id128) {
+    if (!id128) return ROCQ_STATUS_INVALID_VALUE;
+    if (!rq::g_nccl.load()) return ROCQ_STATUS_RCCL_ERROR;
+    ncclUniqueId id;
+    if (rq::g_nccl.GetUniqueId(&id) != ncclSuccess) return ROCQ_STATUS_RCCL_ERROR;
+    memcpy(id128, &id, 128);
+    return ROCQ_STATUS_SUCCESS;
+}
 rocqStatus_t rocsvxDistInit(rocsvHandle_t h, int rank, int numRanks, const void* id128) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
-    return rq_engine_dist(h).init(h, rank, numRanks, id128);
+    return h->dist.init(h, rank, numRanks, id128);
 }
 rocqStatus_t rocsvxDistGetInfo(rocsvHandle_t h, int* rank, int* numRanks, unsigned* numLocalQubits, rocComplex** d_localSlice) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
-    rq::Dist& d = rq_engine_dist(h);
-    if (rank) *rank = d.rank;
-    if (numRanks) *numRanks = d.nranks;
-    if (numLocalQubits) *numLocalQubits = d.n_local;
-    (void)d_localSlice;
+    if (rank) *rank = h->dist.rank;
+    if (numRanks) *numRanks = h->dist.nranks;
+    if (numLocalQubits) *numLocalQubits = h->dist.n_local;
+    if (d_localSlice) *d_localSlice = reinterpret_cast<rocComplex*>(h->d_state);
     return ROCQ_STATUS_SUCCESS;
 }
 rocqStatus_t rocsvxDistPlanExchange(unsigned numLocalQubits, int numRanks, int rank, const unsigned* localBits,

@@ -16,9 +16,7 @@
 #include <vector>
 
 #include "../../include/hipStateVec.h"
-#include "dist.h"
-#include "host_ops.h"
-#include "sv_internal.h"
+#include "engine.h"
 
 using rq::cd;
 using rq::HostOp;
@@ -26,32 +24,6 @@ using rq::HostOp;
 static_assert(sizeof(rocComplex) == sizeof(rq_cplx), "rocComplex layout");
 static_assert(sizeof(rq_program_large) <= 32764, "kernel parameter limit");
 
-struct rocsvInternalHandle {
-    cudaStream_t stream = nullptr;
-    size_t batchSize = 1;
-    unsigned numQubits = 0;
-    rq_cplx* d_state = nullptr;
-    bool ownsState = false;
-    // deferred gate queue (fusion mode)
-    bool fusion = false;
-    std::vector<HostOp> queue;
-    rq_cplx* queue_state = nullptr;
-    unsigned queue_n = 0;
-    // RNG
-    uint64_t seed = 0, draws = 0;
-    // scratch
-    double* d_partials = nullptr;       // RBLOCKS doubles + 8 results
-    uint64_t* d_upartials = nullptr;    // 4*RBLOCKS + 4
-    void* h_scratch = nullptr;          // pinned, 4 KB
-    void* pinned = nullptr;             // user-visible pinned buffer (rocsvEnsurePinnedBuffer)
-    size_t pinnedSize = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
-    // tuning
-    unsigned tileBits = RQ_MAX_TILE_BITS;
-    double budget = 1e30;
-    rocsvxStats stats{};
-    rq::Dist dist;
-};
 
 namespace {
 
@@ -242,12 +214,13 @@ uint64_t uniform53(uint64_t seed, uint64_t call, uint64_t shot) {
 
 }  // namespace
 
-// needed by dist.cpp
+// hooks for dist.cu
 rocqStatus_t rq_engine_flush(rocsvInternalHandle* h) { return flush(h); }
-cudaStream_t rq_engine_stream(rocsvInternalHandle* h) { return h->stream; }
-rq::Dist& rq_engine_dist(rocsvInternalHandle* h) { return h->dist; }
-rocqStatus_t rq_engine_run(rocsvInternalHandle* h, rq_cplx* state, unsigned n, const std::vector<HostOp>& ops) { return run_ops(h, state, n, ops, false); }
-void rq_engine_count_launch(rocsvInternalHandle* h, unsigned k) { h->stats.kernelLaunches += k; }
+rocqStatus_t rq_engine_run(rocsvInternalHandle* h, rq_cplx* state, unsigned n, const std::vector<HostOp>& ops, bool fused) {
+    return run_ops(h, state, n, ops, fused);
+}
+rocqStatus_t rq_engine_fetch(rocsvInternalHandle* h, const void* dsrc, void* hdst, size_t bytes) { return fetch(h, dsrc, hdst, bytes); }
+uint64_t rq_uniform53(uint64_t seed, uint64_t call, uint64_t shot) { return uniform53(seed, call, shot); }
 
 extern "C" {
 
@@ -629,7 +602,7 @@ rocqStatus_t rocsvSample(rocsvHandle_t h, rocComplex* d, unsigned n, const unsig
     if (acc == 0) { cudaFreeAsync(d_hi, h->stream); return ROCQ_STATUS_FAILURE; }
     RQ_CUDA(cudaMemcpyAsync(d_hi, hv.data(), 2 * nchunks * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream), "scan H2D");
     RQ_CUDA(cudaMallocAsync(&d_idx, (size_t)numShots * sizeof(uint64_t), h->stream), "shot scratch");
-    RQ_CUDA(rq_launch_sample(state, n, cb, d_hi, d_lo, nchunks, (uint64_t)(acc >> 64), (uint64_t)acc, h->seed, h->draws++, numShots, 0,
+    RQ_CUDA(rq_launch_sample(state, n, cb, d_hi, d_lo, nchunks, (uint64_t)(acc >> 64), (uint64_t)acc, 0, 0, h->seed, h->draws++, numShots, 0,
                              d_idx, h->stream), "sample");
     h->stats.kernelLaunches += 2;
     std::vector<uint64_t> idx(numShots);

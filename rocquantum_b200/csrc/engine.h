@@ -1,0 +1,43 @@
+// rocquantum_b200/csrc/engine.h -- the handle behind rocsvHandle_t and the hooks dist.cu uses.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "../../include/hipStateVec.h"
+#include "dist.h"
+#include "host_ops.h"
+#include "sv_internal.h"
+
+// Reference handle: hipStateVec.cpp:62-68 {stream, batchSize, numQubits, d_state, ownsState}.
+struct rocsvInternalHandle {
+    cudaStream_t stream = nullptr;
+    size_t batchSize = 1;
+    unsigned numQubits = 0;
+    rq_cplx* d_state = nullptr;
+    bool ownsState = false;
+    // deferred gate queue (fusion mode)
+    bool fusion = false;
+    std::vector<rq::HostOp> queue;
+    rq_cplx* queue_state = nullptr;
+    unsigned queue_n = 0;
+    // RNG
+    uint64_t seed = 0, draws = 0;
+    // scratch
+    double* d_partials = nullptr;       // RBLOCKS doubles + 8 results
+    uint64_t* d_upartials = nullptr;    // 4*RBLOCKS + 4
+    void* h_scratch = nullptr;          // pinned, 4 KB
+    void* pinned = nullptr;             // user-visible pinned buffer (rocsvEnsurePinnedBuffer)
+    size_t pinnedSize = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
+    // tuning
+    unsigned tileBits = RQ_MAX_TILE_BITS;
+    double budget = 1e30;
+    rocsvxStats stats{};
+    rq::Dist dist;
+};
+
+rocqStatus_t rq_engine_flush(rocsvInternalHandle* h);
+rocqStatus_t rq_engine_run(rocsvInternalHandle* h, rq_cplx* state, unsigned n, const std::vector<rq::HostOp>& ops, bool fused);
+rocqStatus_t rq_engine_fetch(rocsvInternalHandle* h, const void* dsrc, void* hdst, size_t bytes);
+uint64_t rq_uniform53(uint64_t seed, uint64_t call, uint64_t shot);

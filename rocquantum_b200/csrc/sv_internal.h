@@ -94,7 +94,7 @@ int rq_launch_chunk_masses(const rq_cplx* state, unsigned n, unsigned chunk_bits
                            uint64_t* d_chunk_lo, void* stream);
 int rq_launch_sample(const rq_cplx* state, unsigned n, unsigned chunk_bits, const uint64_t* d_incl_hi,
                      const uint64_t* d_incl_lo, uint64_t nchunks, uint64_t total_hi, uint64_t total_lo,
-                     uint64_t seed, uint64_t call, unsigned shots, uint64_t shot_offset, uint64_t* d_indices,
-                     void* stream);
+                     uint64_t win_hi, uint64_t win_lo, uint64_t seed, uint64_t call, unsigned shots,
+                     uint64_t shot_offset, uint64_t* d_indices, void* stream);
 unsigned rq_reduce_blocks(void);
 }

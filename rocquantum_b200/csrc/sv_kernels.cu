@@ -293,9 +293,11 @@ __device__ __forceinline__ u128 mul_u53(const u128 S, const uint64_t U) {
 // one warp per shot: index = min{ i : r < sum_{j<=i} q_j }, r = floor(U * S / 2^53)
 __global__ void __launch_bounds__(RT) sample_kernel(const rq_cplx* __restrict__ state, unsigned n, unsigned chunk_bits,
                                                     const uint64_t* __restrict__ incl_hi, const uint64_t* __restrict__ incl_lo,
-                                                    uint64_t nchunks, uint64_t total_hi, uint64_t total_lo, uint64_t seed,
-                                                    uint64_t call, unsigned shots, uint64_t shot_offset,
-                                                    uint64_t* __restrict__ indices) {
+                                                    uint64_t nchunks, uint64_t total_hi, uint64_t total_lo, uint64_t win_hi,
+                                                    uint64_t win_lo, uint64_t seed, uint64_t call, unsigned shots,
+                                                    uint64_t shot_offset, uint64_t* __restrict__ indices) {
+    // total = mass of the whole (possibly distributed) state; win = mass held by lower ranks.  A shot whose
+    // threshold r falls outside [win, win + local mass) belongs to another rank: sentinel ~0.
     const unsigned lane = threadIdx.x & 31;
     const unsigned warps = gridDim.x * (RT / 32);
     for (unsigned s = blockIdx.x * (RT / 32) + (threadIdx.x >> 5); s < shots; s += warps) {
@@ -304,7 +306,12 @@ __global__ void __launch_bounds__(RT) sample_kernel(const rq_cplx* __restrict__ 
         philox4x32_10((uint32_t)shot, (uint32_t)(shot >> 32), (uint32_t)call, (uint32_t)(call >> 32), (uint32_t)seed,
                       (uint32_t)(seed >> 32), x0, x1);
         const uint64_t U = (((uint64_t)x0 << 32) | x1) >> 11;
-        const u128 r = mul_u53(u128{total_hi, total_lo}, U);
+        u128 r = mul_u53(u128{total_hi, total_lo}, U);
+        const u128 win = {win_hi, win_lo};
+        const u128 local_total = {incl_hi[nchunks - 1], incl_lo[nchunks - 1]};
+        bool mine = !lt128(r, win);
+        if (mine) { r = sub128(r, win); mine = lt128(r, local_total); }
+        if (!mine) { if (lane == 0) indices[s] = ~0ull; continue; }
         uint64_t lo = 0, hi = nchunks - 1;                          // first chunk with r < incl[c]
         while (lo < hi) {
             const uint64_t mid = lo + ((hi - lo) >> 1);
@@ -395,12 +402,13 @@ extern "C" int rq_launch_chunk_masses(const rq_cplx* state, unsigned n, unsigned
 }
 
 extern "C" int rq_launch_sample(const rq_cplx* state, unsigned n, unsigned chunk_bits, const uint64_t* d_incl_hi,
-                                const uint64_t* d_incl_lo, uint64_t nchunks, uint64_t total_hi, uint64_t total_lo, uint64_t seed,
-                                uint64_t call, unsigned shots, uint64_t shot_offset, uint64_t* d_indices, void* stream) {
+                                const uint64_t* d_incl_lo, uint64_t nchunks, uint64_t total_hi, uint64_t total_lo, uint64_t win_hi,
+                                uint64_t win_lo, uint64_t seed, uint64_t call, unsigned shots, uint64_t shot_offset,
+                                uint64_t* d_indices, void* stream) {
     unsigned blocks = (shots + (RT / 32) - 1) / (RT / 32);
     if (blocks > RBLOCKS) blocks = RBLOCKS;
     if (blocks == 0) blocks = 1;
     sample_kernel<<<blocks, RT, 0, (cudaStream_t)stream>>>(state, n, chunk_bits, d_incl_hi, d_incl_lo, nchunks, total_hi, total_lo,
-                                                           seed, call, shots, shot_offset, d_indices);
+                                                           win_hi, win_lo, seed, call, shots, shot_offset, d_indices);
     return (int)cudaGetLastError();
 }

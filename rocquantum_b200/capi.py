@@ -93,6 +93,7 @@ PROTOTYPES = {
     "rocsvxDistGetUniqueId": [_p],
     "rocsvxDistInit": [_h, C.c_int, C.c_int, _p],
     "rocsvxDistGetInfo": [_h, C.POINTER(C.c_int), C.POINTER(C.c_int), _up, C.POINTER(_p)],
+    "rocsvxDistPlanCircuit": [_u, C.c_int, C.POINTER(GateOp), _sz, C.c_int, C.c_int, _up, C.c_char_p, _sz],
     "rocsvxDistPlanExchange": [_u, C.c_int, C.c_int, _up, _up, _u, C.POINTER(ExchangeSeg), _sz, C.POINTER(_sz)],
 }
 SYMBOLS = sorted(PROTOTYPES)

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "dist_plan.h"
 #include "engine.h"
 
 namespace rq {
@@ -145,12 +146,11 @@ rocqStatus_t Dist::allocate(rocsvInternalHandle* h, unsigned total_qubits) {
     n_global = M;
     n_local = total_qubits - M;
     n_total = total_qubits;
-    map.resize(n_total);
-    for (unsigned q = 0; q < n_total; ++q) map[q] = q;
+    plan.reset(n_total, n_local);
     if (staging) { cudaFree(staging); staging = nullptr; }
     if (nranks > 1) {
         const uint64_t slice = 1ull << n_local;
-        staging_amps = std::min<uint64_t>(slice, 1ull << 22) * (uint64_t)(nranks - 1);     // <= 32 MiB (c64) per peer
+        staging_amps = std::min<uint64_t>(slice, 1ull << 25) * (uint64_t)(nranks - 1);     // <= 256 MiB (c64) per peer
         if (cudaMalloc(&staging, staging_amps * sizeof(rq_cplx)) != cudaSuccess) { cudaGetLastError(); return ROCQ_STATUS_ALLOCATION_FAILED; }
     }
     return ROCQ_STATUS_SUCCESS;
@@ -159,7 +159,7 @@ rocqStatus_t Dist::allocate(rocsvInternalHandle* h, unsigned total_qubits) {
 rocqStatus_t Dist::initialize(rocsvInternalHandle* h) {
     if (!active() || !h->d_state) return ROCQ_STATUS_INVALID_VALUE;
     h->queue.clear();
-    for (unsigned q = 0; q < n_total; ++q) map[q] = q;
+    plan.reset(n_total, n_local);
     const int e = rq_launch_init_state(h->d_state, (size_t)1 << n_local, rank == 0, h->stream);     // hipStateVec.h:97-99
     h->stats.kernelLaunches++;
     h->numQubits = n_local;
@@ -167,8 +167,8 @@ rocqStatus_t Dist::initialize(rocsvInternalHandle* h) {
 }
 
 // ---- the exchange -------------------------------------------------------------------------------------------
-// swap the k rank bits gpos[] with the top-k local bits (n_local-k .. n_local-1, paired in order)
-static rocqStatus_t exchange_top(rocsvInternalHandle* h, Dist& d, const std::vector<unsigned>& gpos) {
+// move the data of one EXCHANGE step: the k rank bits gpos[] trade places with the top-k local bits
+static rocqStatus_t exchange_data(rocsvInternalHandle* h, Dist& d, const std::vector<unsigned>& gpos) {
     const unsigned k = (unsigned)gpos.size();
     if (k == 0) return ROCQ_STATUS_SUCCESS;
     std::vector<unsigned> lpos(k);
@@ -192,121 +192,41 @@ static rocqStatus_t exchange_top(rocsvInternalHandle* h, Dist& d, const std::vec
     }
     d.exchanges++;
     d.exchanged_amps += run * ns;
-    // relabel: the logical qubits at lpos[i] and gpos[i] trade places
-    for (unsigned i = 0; i < k; ++i)
-        for (unsigned q = 0; q < d.n_total; ++q) {
-            if (d.map[q] == lpos[i]) d.map[q] = gpos[i];
-            else if (d.map[q] == gpos[i]) d.map[q] = lpos[i];
-        }
     return ROCQ_STATUS_SUCCESS;
 }
 
-static unsigned logical_at(const Dist& d, unsigned phys) {
-    for (unsigned q = 0; q < d.n_total; ++q) if (d.map[q] == phys) return q;
-    return ~0u;
-}
-
-// Make the logical qubits `bring` (currently on rank bits) local by trading them with the logical qubits
-// `evict` (currently local).  The evictees are first moved to the top local slots with PERM_SWAP ops appended to
-// `pending` (physical positions), which is then executed fused, and the slices are exchanged.
-static rocqStatus_t trade(rocsvInternalHandle* h, Dist& d, const std::vector<unsigned>& bring, const std::vector<unsigned>& evict,
-                          std::vector<HostOp>& pending) {
-    const unsigned k = (unsigned)bring.size();
-    std::vector<unsigned> slots(k);
-    for (unsigned i = 0; i < k; ++i) slots[i] = d.n_local - k + i;
-    auto is_evictee = [&](unsigned logical) { return std::find(evict.begin(), evict.end(), logical) != evict.end(); };
-    for (unsigned i = 0; i < k; ++i) {
-        const unsigned p = d.map[evict[i]];
-        if (p >= d.n_local - k) continue;                               // already in a top slot
-        for (unsigned s : slots) {
-            const unsigned occupant = logical_at(d, s);
-            if (is_evictee(occupant)) continue;
-            pending.push_back(make_swap(p, s));
-            d.map[occupant] = p;
-            d.map[evict[i]] = s;
-            break;
-        }
+// execute and clear the planner's steps
+static rocqStatus_t execute_steps(rocsvInternalHandle* h, Dist& d) {
+    for (DistStep& st : d.plan.steps) {
+        if (st.kind == DistStep::RUN) RQ_OK(rq_engine_run(h, h->d_state, d.n_local, st.ops, true));
+        else RQ_OK(exchange_data(h, d, st.gpos));
     }
-    if (!pending.empty()) {
-        RQ_OK(rq_engine_run(h, h->d_state, d.n_local, pending, true));
-        pending.clear();
-    }
-    // pair each top slot with the rank bit it trades with: slot order is fixed, so order gpos by slot
-    std::vector<unsigned> gpos(k);
-    std::vector<unsigned> bring_left = bring;
-    for (unsigned i = 0; i < k; ++i) { gpos[i] = d.map[bring_left[i]]; }
-    return exchange_top(h, d, gpos);
-}
-
-static void to_physical(const Dist& d, const HostOp& in, HostOp& out) {
-    out = in;
-    for (unsigned& t : out.targets) t = d.map[t];
-    uint64_t cm = 0;
-    for (unsigned q = 0; q < d.n_total; ++q) if ((in.cmask >> q) & 1ull) cm |= 1ull << d.map[q];
-    out.cmask = cm;
+    d.plan.steps.clear();
+    return ROCQ_STATUS_SUCCESS;
 }
 
 rocqStatus_t Dist::localize(rocsvInternalHandle* h, HostOp& op) {
-    HostOp phys;
-    to_physical(*this, op, phys);
-    const uint64_t gm = global_mask();
-    if (phys.nondiag() & gm) {
+    plan.steps.clear();
+    plan.pending.clear();
+    if (!plan.add_op(op)) return ROCQ_STATUS_NOT_IMPLEMENTED;          // more global targets than free local qubits
+    HostOp phys = std::move(plan.pending.back());
+    plan.pending.clear();
+    if (!plan.steps.empty()) {
         if (nranks == 1) return ROCQ_STATUS_FAILURE;
-        RQ_OK(rq_engine_flush(h));                                        // queued ops use the current layout
-        std::vector<unsigned> bring, evict;
-        for (unsigned t : op.targets) if ((1ull << map[t]) & gm & phys.nondiag()) bring.push_back(t);
-        const uint64_t used = op.qubits();                                // logical
-        for (unsigned p = n_local; p-- > 0 && evict.size() < bring.size();) {
-            const unsigned l = logical_at(*this, p);
-            if (!((used >> l) & 1ull)) evict.push_back(l);
-        }
-        if (evict.size() < bring.size()) return ROCQ_STATUS_NOT_IMPLEMENTED;   // more targets than free local qubits
-        std::vector<HostOp> pending;
-        RQ_OK(trade(h, *this, bring, evict, pending));
-        to_physical(*this, op, phys);
+        RQ_OK(rq_engine_flush(h));                                        // queued ops use the previous layout
+        RQ_OK(execute_steps(h, *this));
     }
-    op = phys;
+    op = std::move(phys);
     return ROCQ_STATUS_SUCCESS;
 }
 
-// Whole-circuit path: translate in order, and on a global non-diagonal target trade ALL rank bits at once for the
-// local qubits whose next non-diagonal use is farthest (Belady), so one exchange is amortised over many layers.
 rocqStatus_t Dist::run_circuit(rocsvInternalHandle* h, std::vector<HostOp>& ops) {
-    const uint64_t gm = global_mask();
-    std::vector<HostOp> pending;
+    plan.steps.clear();
+    plan.pending.clear();
+    if (!plan.add_circuit(ops)) return ROCQ_STATUS_FAILURE;
+    plan.flush_pending();
     cudaEventRecord(h->ev0, h->stream);
-    for (size_t i = 0; i < ops.size(); ++i) {
-        HostOp phys;
-        to_physical(*this, ops[i], phys);
-        if ((phys.nondiag() & gm) && nranks > 1) {
-            // next non-diagonal use of every logical qubit from op i on
-            std::vector<size_t> next(n_total, ops.size() + n_total);
-            unsigned found = 0;
-            for (size_t j = i; j < ops.size() && found < n_total; ++j) {
-                const uint64_t nd = ops[j].nondiag();
-                for (unsigned q = 0; q < n_total; ++q)
-                    if (((nd >> q) & 1ull) && next[q] >= ops.size()) { next[q] = j; ++found; }
-            }
-            for (unsigned q = 0; q < n_total; ++q) if (next[q] >= ops.size()) next[q] = ops.size() + q;   // never used again: stable order
-            std::vector<unsigned> order(n_total);
-            for (unsigned q = 0; q < n_total; ++q) order[q] = q;
-            std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return next[a] > next[b]; });
-            std::vector<char> want_global(n_total, 0);
-            for (unsigned r = 0; r < n_global; ++r) want_global[order[r]] = 1;
-            std::vector<unsigned> bring, evict;
-            for (unsigned q = 0; q < n_total; ++q) {
-                const bool is_global = map[q] >= n_local;
-                if (is_global && !want_global[q]) bring.push_back(q);
-                if (!is_global && want_global[q]) evict.push_back(q);
-            }
-            if (bring.size() != evict.size() || bring.empty()) return ROCQ_STATUS_FAILURE;
-            RQ_OK(trade(h, *this, bring, evict, pending));
-            to_physical(*this, ops[i], phys);
-            if (phys.nondiag() & gm) return ROCQ_STATUS_FAILURE;
-        }
-        pending.push_back(std::move(phys));
-    }
-    if (!pending.empty()) RQ_OK(rq_engine_run(h, h->d_state, n_local, pending, true));
+    RQ_OK(execute_steps(h, *this));
     cudaEventRecord(h->ev1, h->stream);
     h->stats.lastSweepMs = -1.0;
     return ROCQ_STATUS_SUCCESS;
@@ -314,7 +234,7 @@ rocqStatus_t Dist::run_circuit(rocsvInternalHandle* h, std::vector<HostOp>& ops)
 
 rocqStatus_t Dist::swap_index_bits(rocsvInternalHandle* h, unsigned q1, unsigned q2) {
     // Physically relabelling two index bits equals a SWAP gate on the two logical qubits (hipStateVec.h:123-137).
-    // local<->local: a PERM sweep; local<->global: one exchange; global<->global: relabel through a local slot
+    // local<->local: a PERM sweep; local<->global: one exchange; global<->global: through local slots
     // (the reference leaves this case NOT_IMPLEMENTED, MULTI_GPU_GUIDE.md:50).
     HostOp op = make_swap(q1, q2);
     RQ_OK(localize(h, op));
@@ -324,40 +244,11 @@ rocqStatus_t Dist::swap_index_bits(rocsvInternalHandle* h, unsigned q1, unsigned
 
 // restore the identity layout (needed before the slice is handed to the caller)
 rocqStatus_t Dist::canonicalize(rocsvInternalHandle* h) {
-    bool ident = true;
-    for (unsigned q = 0; q < n_total; ++q) ident = ident && map[q] == q;
-    if (ident) return ROCQ_STATUS_SUCCESS;
     RQ_OK(rq_engine_flush(h));
-    std::vector<HostOp> pending;
-    if (nranks > 1) {
-        // 1) every logical qubit that belongs on a rank bit but sits elsewhere, and vice versa
-        std::vector<unsigned> bring, evict;
-        for (unsigned q = 0; q < n_total; ++q) {
-            const bool is_global = map[q] >= n_local, should = q >= n_local;
-            if (is_global && !should) bring.push_back(q);
-            if (!is_global && should) evict.push_back(q);
-        }
-        if (!bring.empty()) RQ_OK(trade(h, *this, bring, evict, pending));
-        // 2) rank bits holding the wrong global qubit: rotate each through a local slot
-        for (unsigned g = n_local; g < n_total; ++g) {
-            if (map[g] == g) continue;
-            const unsigned occupant = logical_at(*this, g);               // logical at position g (another global qubit)
-            const unsigned spare = logical_at(*this, n_local - 1);
-            RQ_OK(trade(h, *this, {occupant}, {spare}, pending));         // occupant -> local, spare -> position g
-            RQ_OK(trade(h, *this, {g}, {occupant}, pending));             // logical g -> local, occupant -> g's old position
-            RQ_OK(trade(h, *this, {spare}, {g}, pending));                // logical g -> position g, spare -> local
-        }
-    }
-    // 3) local positions: cycle decomposition with swaps
-    for (unsigned q = 0; q < n_local; ++q) {
-        if (map[q] == q) continue;
-        const unsigned p = map[q], other = logical_at(*this, q);
-        pending.push_back(make_swap(p, q));
-        map[other] = p;
-        map[q] = q;
-    }
-    if (!pending.empty()) RQ_OK(rq_engine_run(h, h->d_state, n_local, pending, true));
-    return ROCQ_STATUS_SUCCESS;
+    plan.steps.clear();
+    plan.pending.clear();
+    plan.canonicalize();
+    return execute_steps(h, *this);
 }
 
 // ---- scalars ---------------------------------------------------------------------------------------------------
@@ -384,19 +275,11 @@ static rocqStatus_t allgather_u64(rocsvInternalHandle* h, Dist& d, const uint64_
 
 rocqStatus_t Dist::pauli_expect(rocsvInternalHandle* h, uint64_t xm, uint64_t zm, unsigned ny, double* result) {
     // X/Y factors pair amplitudes across the flipped bits: those qubits must be local
-    const uint64_t gm = global_mask();
-    std::vector<unsigned> bring;
-    for (unsigned q = 0; q < n_total; ++q) if (((xm >> q) & 1ull) && ((1ull << map[q]) & gm)) bring.push_back(q);
-    if (!bring.empty()) {
-        std::vector<unsigned> evict;
-        for (unsigned p = n_local; p-- > 0 && evict.size() < bring.size();) {
-            const unsigned l = logical_at(*this, p);
-            if (!((xm >> l) & 1ull)) evict.push_back(l);
-        }
-        if (evict.size() < bring.size()) return ROCQ_STATUS_NOT_IMPLEMENTED;
-        std::vector<HostOp> pending;
-        RQ_OK(trade(h, *this, bring, evict, pending));
-    }
+    plan.steps.clear();
+    plan.pending.clear();
+    if (!plan.make_local(xm)) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    RQ_OK(execute_steps(h, *this));
+    const std::vector<unsigned>& map = plan.map;
     uint64_t pxm = 0, pzm = 0;
     for (unsigned q = 0; q < n_total; ++q) {
         if ((xm >> q) & 1ull) pxm |= 1ull << map[q];
@@ -423,7 +306,7 @@ static inline u128 mul_u53(u128 S, uint64_t U) {
 static inline double u128_to_double(u128 v) { return (double)(uint64_t)(v >> 64) * 0x1p64 + (double)(uint64_t)v; }
 
 rocqStatus_t Dist::measure(rocsvInternalHandle* h, unsigned q, int* outcome, double* probability) {
-    const unsigned p = map[q];
+    const unsigned p = plan.map[q];
     const bool local = p < n_local;
     const unsigned nb = rq_reduce_blocks();
     if (rq_launch_fixed_masses(h->d_state, n_local, local ? p : 63u, h->d_upartials, nb, h->d_upartials + 4 * nb, h->stream) != 0)
@@ -499,7 +382,7 @@ rocqStatus_t Dist::sample(rocsvInternalHandle* h, const unsigned* measured, unsi
         uint64_t bits = 0;
         if (idx[s] != ~0ull) {
             const uint64_t phys = ((uint64_t)rank << n_local) | idx[s];
-            for (unsigned j = 0; j < nm; ++j) bits |= ((phys >> map[measured[j]]) & 1ull) << j;
+            for (unsigned j = 0; j < nm; ++j) bits |= ((phys >> plan.map[measured[j]]) & 1ull) << j;
         }
         idx[s] = bits;
     }

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/hipStateVec.h"
+#include "dist_plan.h"
 #include "host_ops.h"
 
 struct rocsvInternalHandle;
@@ -17,7 +18,7 @@ struct Dist {
     bool inited = false;             // rocsvxDistInit done
     int rank = 0, nranks = 1;
     unsigned n_total = 0, n_local = 0, n_global = 0;
-    std::vector<unsigned> map;       // logical qubit -> physical position
+    DistPlanner plan;                // logical->physical map + step planner (dist_plan.h)
     void* comm = nullptr;            // ncclComm_t
     void* nccl = nullptr;            // dlopen handle
     rq_cplx* staging = nullptr;      // exchange staging (device)

@@ -65,7 +65,7 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
         while (j < ops.size() && ops[j].targets.size() <= 4) ++j;
         if (j > i) {
             std::vector<HostOp> seg(ops.begin() + i, ops.begin() + j);
-            if (fused && seg.size() > 1) seg = rq::fuse_algebraic(seg, n);
+            if (fused && seg.size() > 1) seg = rq::fuse_algebraic(seg, n, h->dist.active() ? h->dist.global_mask() : 0ull);
             const bool large = seg.size() > 1;
             const rq::PlanLimits L = limits_for(h, large);
             const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(seg, n, L);
@@ -106,8 +106,12 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
                 h->stats.h2dBytes += D * D * sizeof(rq_cplx);
                 dm = tmp;
             }
-            RQ_CUDA(rq_launch_gather(state, n, h->batchSize, o.targets.data(), k, o.cmask, dm, h->stream), "gather launch");
-            h->stats.kernelLaunches++;
+            // controls on rank bits of a distributed state select whole slices: resolve them here
+            const uint64_t lmask = n >= 64 ? ~0ull : ((1ull << n) - 1ull), gctl = o.cmask & ~lmask;
+            if ((h->dist.high_base() & gctl) == gctl) {
+                RQ_CUDA(rq_launch_gather(state, n, h->batchSize, o.targets.data(), k, o.cmask & lmask, dm, h->stream), "gather launch");
+                h->stats.kernelLaunches++;
+            }
             h->stats.opsExecuted++;
             if (tmp) RQ_CUDA(cudaFreeAsync(tmp, h->stream), "cudaFreeAsync");
             ++i;
@@ -784,6 +788,62 @@ rocqStatus_t rocsvxPlanCircuit(unsigned n, unsigned tileBits, const rocsvxGateOp
     if (numSweeps) *numSweeps = (unsigned)plans.size();
     if (buf && bufSize) {
         const std::string txt = rq::dump_plan(plans, fused);
+        const size_t m = txt.size() < bufSize - 1 ? txt.size() : bufSize - 1;
+        memcpy(buf, txt.data(), m);
+        buf[m] = 0;
+    }
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t rocsvxDistPlanCircuit(unsigned n, int numRanks, const rocsvxGateOp* ops, size_t numOps, int mode, int canonicalize,
+                                   unsigned* numExchanges, char* buf, size_t bufSize) {
+    if ((!ops && numOps) || numRanks < 1 || (numRanks & (numRanks - 1))) return ROCQ_STATUS_INVALID_VALUE;
+    unsigned M = 0;
+    while ((1 << M) < numRanks) ++M;
+    if (n < M) return ROCQ_STATUS_INVALID_VALUE;
+    std::vector<HostOp> hops;
+    const rocqStatus_t s = convert_ops(n, ops, numOps, hops);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    rq::DistPlanner P;
+    P.reset(n, n - M);
+    if ((mode & 1) == 0) { if (!P.add_circuit(hops)) return ROCQ_STATUS_FAILURE; }
+    else for (const HostOp& o : hops) if (!P.add_op(o)) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    P.flush_pending();
+    if (canonicalize) P.canonicalize();
+    unsigned nx = 0;
+    for (const rq::DistStep& st : P.steps) nx += st.kind == rq::DistStep::EXCHANGE;
+    if (numExchanges) *numExchanges = nx;
+    if (buf && bufSize) {
+        std::string txt;
+        if (mode & 2) {
+            // the full pipeline: every RUN step fused and cut into sweeps exactly as the engine does on a slice
+            rq::PlanLimits L;
+            L.max_ops = sizeof(rq_program_large::ops) / sizeof(rq_tile_op);
+            L.pool_cplx = sizeof(rq_program_large::pool) / sizeof(rq_cplx);
+            L.never_resident = P.global_mask();
+            if (const char* e = getenv("ROCQ_TILE_BITS")) { const int t = atoi(e); if (t >= 1 && t <= RQ_MAX_TILE_BITS) L.tile_bits = (unsigned)t; }
+            static thread_local rq_program_large prog;
+            for (const rq::DistStep& st : P.steps) {
+                if (st.kind == rq::DistStep::EXCHANGE) {
+                    txt += "X";
+                    for (unsigned g : st.gpos) txt += " " + std::to_string(g);
+                    txt += "\n";
+                    continue;
+                }
+                txt += "R\n";
+                for (const HostOp& o : st.ops) if (o.targets.size() > 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
+                std::vector<HostOp> fused = st.ops.size() > 1 ? rq::fuse_algebraic(st.ops, n - M, P.global_mask()) : st.ops;
+                const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(fused, n - M, L);
+                for (const rq::SweepPlan& sp : plans)
+                    if (!rq::build_program(prog, sp, fused, n - M, 1, 0)) return ROCQ_STATUS_FAILURE;
+                txt += rq::dump_plan(plans, fused);
+            }
+            txt += "M";
+            for (unsigned q = 0; q < n; ++q) txt += " " + std::to_string(P.map[q]);
+            txt += "\n";
+        } else {
+            txt = P.dump();
+        }
         const size_t m = txt.size() < bufSize - 1 ? txt.size() : bufSize - 1;
         memcpy(buf, txt.data(), m);
         buf[m] = 0;

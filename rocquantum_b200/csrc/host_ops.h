@@ -172,7 +172,9 @@ inline std::vector<cd> matmul(const std::vector<cd>& A, const std::vector<cd>& B
 //         ops sitting directly before it on its qubits; permutation / diagonal 2q gates (CNOT, CZ, SWAP)
 //         are promoted to a dense 4x4 only when that lets them absorb such a neighbour
 //         (the reference's GateFusion.cpp:95-147 pattern: post * CNOT * pre as one 4x4).
-inline std::vector<HostOp> fuse_algebraic(const std::vector<HostOp>& in, unsigned n) {
+// `forbid`: positions that may never become targets of a DENSE op (rank bits of a distributed state); promotion of a
+//         diagonal / controlled 2q gate to a dense 4x4 is skipped when it touches one of them.
+inline std::vector<HostOp> fuse_algebraic(const std::vector<HostOp>& in, unsigned n, uint64_t forbid = 0) {
     std::vector<HostOp> out;
     out.reserve(in.size());
     std::vector<int> last(n > 64 ? n : 64, -1);
@@ -220,7 +222,7 @@ inline std::vector<HostOp> fuse_algebraic(const std::vector<HostOp>& in, unsigne
                     pend.push_back(j);
             }
             const bool genuinely_dense = op.kind == HostOp::DENSE && op.cmask == 0;
-            if (genuinely_dense || !pend.empty()) {
+            if ((genuinely_dense || !pend.empty()) && !(Q & forbid)) {
                 HostOp G;
                 G.kind = HostOp::DENSE;
                 G.targets = (op.kind == HostOp::DENSE && op.cmask == 0) ? op.targets : qs;
@@ -336,6 +338,8 @@ template <typename Prog>
 inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp>& ops, unsigned n, size_t batch,
                           uint64_t high_base) {
     const unsigned T = (unsigned)sp.res.size();
+    if (T > n) return false;
+    for (unsigned r : sp.res) if (r >= n) return false;          // e.g. a rank bit of a distributed state: never resident
     P.hdr.n = n; P.hdr.T = T; P.hdr.nops = 0; P.hdr.rowbits = sp.rowbits;
     P.hdr.ntiles = (uint64_t)batch << (n - T);
     P.hdr.high_base = high_base;

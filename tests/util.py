@@ -208,3 +208,53 @@ def random_gates(n, count, seed, allow_matrix=True, maxk=3):
                 M = np.diag(np.concatenate([np.ones((1 << k) - 1), [np.exp(1j * th)]]))
             out.append(("matrix", q[:k], q[k:k + nc], 0.0, M))
     return out
+
+
+def dist_plan(n, nranks, gates, mode=0, canonicalize=True, prec="c64"):
+    """-> (num_exchanges, steps, final_map): steps = [("R", [op dicts]) | ("X", [gpos])]  (rocsvxDistPlanCircuit, host only)"""
+    lib = capi.load(prec)
+    arr, keep = capi.make_ops(gates)
+    nx = C.c_uint()
+    size = 1 << 18
+    while True:
+        buf = C.create_string_buffer(size)
+        st = lib.rocsvxDistPlanCircuit(n, nranks, arr, len(gates), mode, int(canonicalize), C.byref(nx), buf, size)
+        assert st == 0, st
+        txt = buf.value.decode()
+        if len(txt) < size - 2:
+            break
+        size *= 4
+    steps, fmap = [], None
+    for line in txt.splitlines():
+        tok = line.split()
+        if tok[0] == "R":
+            steps.append(("R", []))
+        elif tok[0] == "S":
+            assert all(int(x) < n - (nranks.bit_length() - 1) for x in tok[4:]), "rank bit made resident"
+        elif tok[0] == "X":
+            steps.append(("X", [int(x) for x in tok[1:]]))
+        elif tok[0] == "M":
+            fmap = [int(x) for x in tok[1:]]
+        else:
+            kind, cmask = int(tok[1]), int(tok[3], 16)
+            ti, di = tok.index("targets"), tok.index("data")
+            vals = [float(x) for x in tok[di + 1:]]
+            steps[-1][1].append(dict(kind=kind, cmask=cmask, targets=[int(x) for x in tok[ti + 1:di]],
+                                     data=np.array(vals[0::2]) + 1j * np.array(vals[1::2])))
+    return nx.value, steps, fmap
+
+
+def simulate_dist_plan(o: so.Oracle, n_local, steps):
+    """Re-simulate a distributed plan on ONE full state indexed by physical position (qubit = physical position)."""
+    n = o.n
+    for kind, payload in steps:
+        if kind == "X":
+            k = len(payload)
+            for i, g in enumerate(payload):
+                assert g >= n_local
+                o.swap_index_bits(n_local - k + i, g)
+        else:
+            for op in payload:
+                if op["kind"] != 2:
+                    assert all(t < n_local for t in op["targets"]), "non-diagonal target on a rank bit"
+            simulate_plan(o, [dict(T=n, rowbits=n, res=list(range(n)), ops=payload)])

@@ -60,12 +60,44 @@ def build(force: bool = False, verbose: bool = False) -> list[str]:
     out = []
     for path, objs in libs:
         if force or _newer(path, objs):
-            _run([NVCC, *ARCH, "-shared", "-ccbin", HOSTCXX, "-o", path, *objs, "-lcudart", "-ldl"])
+            _run([NVCC, *ARCH, "-shared", "-ccbin", HOSTCXX, "-Xlinker", "-Bsymbolic", "-o", path, *objs, "-lcudart", "-ldl"])
         out.append(path)
         if verbose:
             print("built", path)
     return out
 
 
+def build_bindings(force: bool = False, verbose: bool = False) -> list[str]:
+    """The reference's two pybind11 modules + C++ facades, compiled with g++ against the engine libraries:
+         rocquantum_b200/lib/rocquantum_bind*.so      (QuantumSimulator/QSim, MLIRCompiler)   -> libhipStateVec_f64.so
+         rocquantum_b200/lib/_rocq_hip_backend*.so    (rocsv* free functions, GateFusion)     -> libhipStateVec.so"""
+    import sysconfig
+    import pybind11
+    build(force=force)
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    inc = ["-I", os.path.join(HERE, "..", "include"), "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
+           "-I", "/usr/local/cuda/include"]
+    fac = os.path.join(CSRC, "facade")
+    common = [HOSTCXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-Wno-unused-function", *inc]
+    rpath = ["-L", LIB, "-Wl,-rpath,$ORIGIN", "-L", "/usr/local/cuda/lib64", "-lcudart"]
+    mods = [
+        ("rocquantum_bind" + ext, ["bind_rocquantum.cpp", "QuantumSimulator.cpp", "HipStateVecBackend.cpp"], ["-DROCQ_PRECISION_DOUBLE"], "-l:libhipStateVec_f64.so"),
+        ("_rocq_hip_backend" + ext, ["bind_rocq_hip_backend.cpp", "GateFusion.cpp"], [], "-l:libhipStateVec.so"),
+    ]
+    out = []
+    hdrs = [os.path.join(HERE, "..", "include", h) for h in ("hipStateVec.h", "rocquantum/QuantumSimulator.h", "rocquantum/GateFusion.h",
+                                                            "rocqCompiler/QuantumBackend.h", "rocqCompiler/HipStateVecBackend.h")]
+    for name, srcs, defs, lib in mods:
+        target = os.path.join(LIB, name)
+        deps = [os.path.join(fac, s) for s in srcs] + hdrs + [os.path.abspath(__file__)]
+        if force or _newer(target, deps):
+            _run([*common, *defs, *[os.path.join(fac, s) for s in srcs], "-o", target, *rpath, lib])
+        out.append(target)
+        if verbose:
+            print("built", target)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
+    build_bindings(force="--force" in sys.argv, verbose=True)

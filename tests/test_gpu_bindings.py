@@ -1,0 +1,108 @@
+"""The reference's own Python-level tests, re-stated against the rebuilt modules (-m gpu):
+test_bindings.py:24-86 / tests/test_bindings.py:16-71 (QSim Bell state, measure statistics, 2x2 ApplyGate),
+the three plugin known-answer vectors, and a python/rocq/api.py-style flow over _rocq_hip_backend."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rocquantum_b200", "lib")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _bindings():
+    from rocquantum_b200 import build
+    build.build_bindings()
+    if LIB not in sys.path:
+        sys.path.insert(0, LIB)
+
+
+def test_qsim_bell_state_and_measure():
+    import rocquantum_bind as rb
+    sim = rb.QSim(2)
+    sim.ApplyGate("H", 0)
+    sim.ApplyGate("CNOT", 0, 1)
+    sim.Execute()
+    sv = sim.GetStateVector()
+    assert sv.shape == (4,) and sv.dtype == np.complex128
+    assert np.allclose(sv, np.array([1, 0, 0, 1]) / math.sqrt(2), atol=1e-12)
+    res = sim.measure([0, 1], 2000)
+    assert len(res) == 2000 and set(res) <= {0, 3}
+    assert abs(res.count(0) - 1000) < 200 and abs(res.count(3) - 1000) < 200       # +-10 %, tests/test_bindings.py:66-68
+    x = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+    sim.reset(); sim.ApplyGate(x, 1)
+    assert abs(sim.get_statevector()[2] - 1) < 1e-12
+    with pytest.raises(ValueError):
+        sim.apply_matrix(np.eye(3, dtype=np.complex128), [0])                        # std::invalid_argument, bindings.cpp:50-52
+    with pytest.raises(IndexError):
+        sim.apply_gate("H", [5])                                                     # std::out_of_range
+
+
+def test_plugin_known_answers():
+    import rocquantum_bind as rb
+    s = rb.QuantumSimulator(1); s.apply_gate("RX", [0], [math.pi / 2])
+    assert np.allclose(s.get_statevector(), [math.cos(math.pi / 4), -1j * math.sin(math.pi / 4)], atol=1e-12)
+    s = rb.QuantumSimulator(1); s.apply_gate("RY", [0], [math.pi / 2])
+    assert np.allclose(s.get_statevector(), [math.cos(math.pi / 4), math.sin(math.pi / 4)], atol=1e-12)
+    s = rb.QuantumSimulator(1); s.apply_gate("Hadamard", [0]); s.apply_gate("rz", [0], [math.pi / 2])
+    assert np.allclose(s.get_statevector(), np.array([np.exp(-1j * math.pi / 4), np.exp(1j * math.pi / 4)]) / math.sqrt(2), atol=1e-12)
+    # names the plugins send (rocq_device.py:17-21, roc_quantum_simulator.py:11-14); CNOT with control < target at n = 3
+    s = rb.QuantumSimulator(3)
+    for g, t in (("PauliX", [0]), ("CNOT", [0, 1]), ("CX", [1, 2]), ("S", [0]), ("T", [1]), ("CZ", [0, 2]), ("SWAP", [0, 1]), ("PauliZ", [2]), ("Identity", [1])):
+        s.apply_gate(g, t)
+    sv = s.get_statevector()
+    assert abs(abs(sv[7]) - 1) < 1e-12 and abs(np.vdot(sv, sv) - 1) < 1e-12
+    # 2-qubit matrix (next-row extension): CNOT as a row-major 4x4 over targets [control, target]
+    s = rb.QuantumSimulator(2); s.apply_gate("X", [0])
+    cn = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=np.complex128)
+    s.apply_matrix(cn, [0, 1])
+    assert abs(s.get_statevector()[3] - 1) < 1e-12
+    c = rb.MLIRCompiler(2, "hip_statevec")
+    with pytest.raises(RuntimeError):
+        c.emit_qir("module {}")
+    with pytest.raises(ValueError):
+        rb.MLIRCompiler(2, "nope")
+
+
+def test_rocq_api_style_flow():
+    """What python/rocq/api.py does: Simulator -> handle, Circuit -> allocate/initialize, flush -> apply_*, then readbacks."""
+    import _rocq_hip_backend as b
+    h = b.RocsvHandle()
+    n = 3
+    d = b.allocate_state_internal(h, n)
+    assert b.initialize_state(h, d, n) == b.rocqStatus.SUCCESS
+    assert b.apply_h(h, d, n, 0) == b.rocqStatus.SUCCESS
+    assert b.apply_cnot(h, d, n, 0, 1) == b.rocqStatus.SUCCESS
+    assert b.apply_cnot(h, d, n, 1, 2) == b.rocqStatus.SUCCESS
+    assert b.apply_h(h, d, n, 7) == b.rocqStatus.INVALID_VALUE                     # status returned, not thrown (api.py:85)
+    sv = b.get_state_vector_full(h, d, n, 1)
+    assert sv.dtype == np.complex64 and np.allclose(sv[[0, 7]], 1 / math.sqrt(2), atol=1e-6)
+    assert abs(b.get_expectation_value_pauli_product_z(h, d, n, [0, 1]) - 1) < 1e-6   # examples/expectation_example.py:55-57
+    assert abs(b.get_expectation_pauli_string(h, d, n, "XY", [1, 2])) < 1e-6
+    assert abs(b.get_expectation_value_z(h, d, n, 0)) < 1e-6
+    s = b.sample(h, d, n, [0, 1, 2], 1000)
+    assert s.dtype == np.uint64 and set(np.unique(s)) <= {0, 7}
+    out, p = b.measure(h, d, n, 1)
+    assert out in (0, 1) and abs(p - 0.5) < 1e-6
+    # device matrix path: api.py:27-34 sends a C-contiguous matrix; the ABI reads it column-major (hipStateVec.h:147)
+    b.initialize_state(h, d, n)
+    xm = b.create_device_matrix_from_numpy(np.array([[0, 1], [1, 0]], dtype=np.complex64))
+    assert b.apply_matrix(h, d, n, [2], xm, 2) == b.rocqStatus.SUCCESS
+    assert b.apply_controlled_matrix(h, d, n, [2], [0], xm) == b.rocqStatus.SUCCESS
+    assert abs(b.get_state_vector_slice(h, d, n, 1, 0)[5] - 1) < 1e-6
+    with pytest.raises(RuntimeError):
+        b.get_expectation_pauli_string(h, d, n, "XYZ", [0, 1])
+    # GateFusion.processQueue: the whole queue in one fused submission
+    b.initialize_state(h, d, n)
+    q = []
+    for name, t, c, prm in (("H", [0], [], []), ("CNOT", [1], [0], []), ("RY", [2], [], [0.3]), ("CNOT", [2], [1], []), ("RZ", [0], [], [0.5])):
+        op = b.GateOp(); op.name, op.targets, op.controls, op.params = name, t, c, prm
+        q.append(op)
+    assert b.GateFusion(h, d, n).process_queue(q) == b.rocqStatus.SUCCESS
+    got = b.get_state_vector_full(h, d, n, 1)
+    from oracle import sv_oracle as so
+    o = so.Oracle(n, "c64"); o.gate("h", 0); o.gate("cnot", 0, 1); o.gate("ry", 2, 0.3); o.gate("cnot", 1, 2); o.gate("rz", 0, 0.5)
+    assert np.abs(got - o.state).max() < 1e-6

@@ -279,7 +279,10 @@ def run_engine(args):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("tile_sweep_dram_bytes_per_launch")
+            tj = json.load(open(prof))
+            # ncu capture at a smaller state (see the file); DRAM bytes scale with the state, so report per launch of THIS run
+            roofline["traffic"] = tj["traffic_over_algorithmic"] * sweep_bytes
+            roofline["traffic_source"] = tj["source"]
         except Exception:
             pass
 

@@ -333,6 +333,79 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
     return plans;
 }
 
+// ---- phases: which ops share one shared-memory round trip of the tile (see rq_phase) -------------------------------
+template <typename Prog>
+inline void build_phases(Prog& P, unsigned T) {
+    const unsigned V = RQ_WINDOW_BITS, MINP = RQ_WINDOW_MIN_POS;
+    P.hdr.nphases = 0;
+    P.hdr.max_phase_ops = 0;
+    const unsigned nops = P.hdr.nops;
+    auto legacy = [&](unsigned i) {
+        rq_phase& ph = P.phases[P.hdr.nphases++];
+        ph = rq_phase{};
+        ph.kind = 0; ph.first = (uint8_t)i; ph.count = 1;
+        if (P.hdr.max_phase_ops < 1) P.hdr.max_phase_ops = 1;
+    };
+    // window-eligible: DIAG (needs nothing); DENSE k<=2 from the pool and PERM with every target at a position >= MINP
+    auto need_of = [&](const rq_tile_op& o, uint32_t& need) -> bool {
+        need = 0;
+        if (o.kind == RQ_OP_DIAG) return true;
+        if (o.kind == RQ_OP_DENSE) {
+            if (o.ext || o.k > 2) return false;
+            for (unsigned b = 0; b < o.k; ++b) { if (o.t[b] < MINP) return false; need |= 1u << o.t[b]; }
+            return true;
+        }
+        // PERM: xm holds the target positions
+        for (unsigned j = 0; j < T; ++j) if ((o.xm >> j) & 1u) { if (j < MINP) return false; need |= 1u << j; }
+        return true;
+    };
+    if (T < MINP + V) { for (unsigned i = 0; i < nops; ++i) legacy(i); return; }
+    unsigned i = 0;
+    while (i < nops) {
+        uint32_t need = 0;
+        if (!need_of(P.ops[i], need)) { legacy(i++); continue; }
+        uint32_t W = 0;
+        const unsigned first = i;
+        while (i < nops) {
+            uint32_t nd = 0;
+            if (!need_of(P.ops[i], nd)) break;
+            if ((unsigned)__builtin_popcount(W | nd) > V) break;
+            W |= nd;
+            ++i;
+        }
+        if (W == 0 || i - first < 2) {                     // diagonal-only run, or a single op: nothing to share
+            for (unsigned j = first; j < i; ++j) legacy(j);
+            continue;
+        }
+        for (unsigned p = T; p-- > MINP && (unsigned)__builtin_popcount(W) < V;) if (!((W >> p) & 1u)) W |= 1u << p;
+        rq_phase& ph = P.phases[P.hdr.nphases++];
+        ph = rq_phase{};
+        ph.kind = 1; ph.v = (uint8_t)V; ph.first = (uint8_t)first; ph.count = (uint8_t)(i - first);
+        int widx[32];
+        unsigned nb = 0;
+        for (unsigned p = 0; p < T; ++p) { widx[p] = -1; if ((W >> p) & 1u) { ph.w[nb] = (uint8_t)p; widx[p] = (int)nb++; } }
+        if (ph.count > P.hdr.max_phase_ops) P.hdr.max_phase_ops = ph.count;
+        for (unsigned j = first; j < i; ++j) {
+            rq_tile_op& o = P.ops[j];
+            if (o.kind == RQ_OP_DIAG) { o.cm_in = 0; o.cm_out = 0; continue; }      // controls are evaluated per amplitude
+            uint32_t lc = o.setmask;                       // local controls (+ for SWAP the select bit, removed below)
+            if (o.kind == RQ_OP_DENSE) {
+                for (unsigned b = 0; b < o.k; ++b) o.wt[b] = (uint8_t)widx[o.t[b]];
+            } else {
+                unsigned b = 0;
+                for (unsigned p = 0; p < T; ++p) if ((o.xm >> p) & 1u) o.wt[b++] = (uint8_t)widx[p];
+                o.k = (uint8_t)b;                          // 1 = X-type, 2 = SWAP-type
+                lc &= ~o.xm;
+            }
+            o.cm_in = 0; o.cm_out = 0;
+            for (unsigned p = 0; p < T; ++p) {
+                if (!((lc >> p) & 1u)) continue;
+                if (widx[p] >= 0) o.cm_in |= (uint8_t)(1u << widx[p]); else o.cm_out |= 1u << p;
+            }
+        }
+    }
+}
+
 // ---- program emission ---------------------------------------------------------------------------------
 template <typename Prog>
 inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp>& ops, unsigned n, size_t batch,
@@ -370,7 +443,18 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
                 const unsigned need = 1u << (2 * k);
                 if (pool + need > maxpool) return false;
                 t.moff = pool;
-                for (unsigned e = 0; e < need; ++e) { P.pool[pool + e].x = (rq_real)o.data[e].real(); P.pool[pool + e].y = (rq_real)o.data[e].imag(); }
+                const bool flip = k == 2 && t.t[0] > t.t[1];          // keep 2q targets ascending: matrix bit 0 <-> lower position
+                if (flip) std::swap(t.t[0], t.t[1]);
+                for (unsigned e = 0; e < need; ++e) {
+                    unsigned src = e;
+                    if (flip) {                                       // swap the two index bits of row and column
+                        const unsigned r = e & 3u, c = e >> 2;
+                        const unsigned rs = ((r & 1u) << 1) | (r >> 1), cs = ((c & 1u) << 1) | (c >> 1);
+                        src = rs + 4u * cs;
+                    }
+                    P.pool[pool + e].x = (rq_real)o.data[src].real();
+                    P.pool[pool + e].y = (rq_real)o.data[src].imag();
+                }
                 pool += need;
             }
         } else if (o.kind == HostOp::DIAG) {
@@ -399,6 +483,7 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
         }
         for (unsigned j = 0; j < T; ++j) if ((fixmask >> j) & 1u) t.fix[t.nfix++] = (uint8_t)j;
     }
+    build_phases(P, T);
     return true;
 }
 

@@ -20,7 +20,7 @@ struct rq_cplx { rq_real x, y; };
 // program is applied to it in order, and it is written back with bulk async stores.
 enum : uint8_t { RQ_OP_DENSE = 1, RQ_OP_DIAG = 2, RQ_OP_PERM = 3 };
 
-struct rq_tile_op {                 // 56 bytes
+struct rq_tile_op {                 // 64 bytes
     uint8_t kind;                   // RQ_OP_*
     uint8_t k;                      // DENSE: number of targets (1..4).  DIAG: number of table bits (0..3)
     uint8_t nfix;                   // entries of fix[]: local positions held fixed while enumerating
@@ -31,8 +31,21 @@ struct rq_tile_op {                 // 56 bytes
     uint32_t setmask;               // OR-ed into the enumerated local index (controls = 1; PERM select value)
     uint32_t xm;                    // PERM: partner = idx ^ xm
     uint32_t moff;                  // offset into pool[], in complex elements
-    uint32_t pad;
+    uint32_t cm_out;                // register phases: local controls outside the phase window (checked on the group base)
     uint64_t gcmask;                // controls on non-resident positions: op is skipped for tiles whose base lacks a bit
+    uint8_t wt[4];                  // register phases: window-bit index (0..V-1) of target b
+    uint8_t cm_in;                  // register phases: controls inside the window, in window-bit coordinates
+    uint8_t pad[3];
+};
+
+// A phase is what happens between two shared-memory round trips of the tile.
+//   kind 0: one op, applied in place in shared memory (any op).
+//   kind 1: register window -- every thread loads the 2^v amplitudes that differ in the v window bits w[] (local
+//           positions >= 4, so the loads are bank-conflict free), applies ops first..first+count-1 whose non-diagonal
+//           targets all lie in the window entirely in registers, and stores them back once.
+struct rq_phase {
+    uint8_t kind, v, first, count;
+    uint8_t w[4];                   // ascending local positions
 };
 
 struct rq_sweep_hdr {
@@ -40,6 +53,8 @@ struct rq_sweep_hdr {
     uint32_t T;                     // tile bits
     uint32_t nops;
     uint32_t rowbits;               // log2(amplitudes per contiguous row)
+    uint32_t nphases;
+    uint32_t max_phase_ops;         // largest rq_phase::count (selects the kernel variant)
     uint64_t ntiles;                // batch * 2^(n-T)
     uint64_t high_base;             // OR-ed into every tile's base index for predicates (rank << n_local)
     const void* ext_matrix;         // device matrix of an op with ext = 1 (column-major, rq_cplx)
@@ -50,20 +65,27 @@ template <int MAXOPS, int POOL_CPLX>
 struct rq_program {
     rq_sweep_hdr hdr;
     rq_tile_op ops[MAXOPS];
+    rq_phase phases[MAXOPS];
     rq_cplx pool[POOL_CPLX];
 };
 // Kernel parameters may be up to 32764 bytes (CUDA >= 12.1); the program travels as a
 // __grid_constant__ parameter so that op headers and gate matrices are read through the constant
 // cache with warp-uniform addresses.
 #ifdef ROCQ_PRECISION_DOUBLE
-typedef rq_program<8, 288> rq_program_small;        //  ~5.2 KB
-typedef rq_program<160, 1408> rq_program_large;     // ~31.6 KB
+typedef rq_program<8, 288> rq_program_small;        //  ~5.3 KB
+typedef rq_program<160, 1248> rq_program_large;     // ~31.6 KB
 #else
-typedef rq_program<8, 288> rq_program_small;        //  ~2.9 KB
-typedef rq_program<160, 2816> rq_program_large;     // ~31.6 KB
+typedef rq_program<8, 288> rq_program_small;        //  ~3.0 KB
+typedef rq_program<160, 2496> rq_program_large;     // ~31.6 KB
 #endif
 
 #define RQ_TILE_THREADS 256
+#define RQ_WINDOW_MIN_POS 4                          // register-window bits sit at local positions >= 4: conflict-free LDS/STS
+#ifdef ROCQ_PRECISION_DOUBLE
+#define RQ_WINDOW_BITS 3                             // 8 amplitudes = 32 registers per thread
+#else
+#define RQ_WINDOW_BITS 4                             // 16 amplitudes = 32 registers per thread
+#endif
 #ifdef ROCQ_PRECISION_DOUBLE
 #define RQ_MAX_TILE_BITS 12                          // 2^12 * 16 B = 64 KB
 #define RQ_MIN_ROW_BITS 4                            // rows >= 256 B

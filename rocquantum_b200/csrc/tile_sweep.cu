@@ -67,15 +67,52 @@ __device__ __forceinline__ rq_cplx ldg_cplx(const rq_cplx* p) {
     r.y = v.y;
     return r;
 }
-__device__ __forceinline__ rq_cplx cmul(rq_cplx a, rq_cplx b) {
-    rq_cplx r;
-    r.x = a.x * b.x - a.y * b.y;
-    r.y = a.x * b.y + a.y * b.x;
+// ---- complex multiply-accumulate -----------------------------------------------------------------------
+// complex64: Blackwell's packed fp32 FMA (PTX fma.rn.f32x2, SASS FFMA2) does one complex MAC in TWO instructions:
+//   acc(re,im) += m.re * (v.re, v.im);   acc(re,im) += m.im * (-v.im, v.re)
+// (scalar-broadcast and half-swap are operand modifiers of FFMA2), instead of the 6 (FMUL+FFMA+FADD per component)
+// that `acc += m*v` compiles to without reassociation.  complex128: explicit 4-FMA chains (DFMA).
+#ifdef ROCQ_PRECISION_DOUBLE
+struct cin { double x, y; };
+struct cacc { double x, y; };
+__device__ __forceinline__ cin cprep(const rq_cplx a) { return cin{a.x, a.y}; }
+__device__ __forceinline__ cacc czero() { return cacc{0.0, 0.0}; }
+__device__ __forceinline__ void cmac(cacc& acc, const rq_cplx m, const cin v) {
+    acc.x = fma(m.x, v.x, acc.x);
+    acc.x = fma(-m.y, v.y, acc.x);
+    acc.y = fma(m.x, v.y, acc.y);
+    acc.y = fma(m.y, v.x, acc.y);
+}
+__device__ __forceinline__ rq_cplx cget(const cacc a) { return rq_cplx{a.x, a.y}; }
+#else
+struct cin { uint64_t p, q; };            // (re, im) and (-im, re)
+typedef uint64_t cacc;
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
-__device__ __forceinline__ void cfma(rq_cplx& acc, rq_cplx m, rq_cplx v) {
-    acc.x += m.x * v.x - m.y * v.y;
-    acc.y += m.x * v.y + m.y * v.x;
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ cin cprep(const rq_cplx a) { return cin{pack2(a.x, a.y), pack2(-a.y, a.x)}; }
+__device__ __forceinline__ cacc czero() { return 0ull; }
+__device__ __forceinline__ void cmac(cacc& acc, const rq_cplx m, const cin v) {
+    acc = fma2(pack2(m.x, m.x), v.p, acc);
+    acc = fma2(pack2(m.y, m.y), v.q, acc);
+}
+__device__ __forceinline__ rq_cplx cget(const cacc a) {
+    rq_cplx r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a));
+    return r;
+}
+#endif
+__device__ __forceinline__ rq_cplx cmul(rq_cplx a, rq_cplx b) {
+    cacc acc = czero();
+    cmac(acc, a, cprep(b));
+    return cget(acc);
 }
 
 // deposit the bits of g around the fixed positions fix[0..nfix) (ascending), leaving zeros there
@@ -104,18 +141,18 @@ __device__ __forceinline__ void op_dense(rq_cplx* sm, const rq_tile_op& o, const
     const rq_cplx* M = EXT ? ext : (pool + o.moff);
     for (uint32_t g = tid; g < ngroups; g += NT) {
         const uint32_t base = spread(g, o) | o.setmask;
-        rq_cplx a[D];
+        cin a[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) a[j] = sm[base | off[j]];
+        for (int j = 0; j < D; ++j) a[j] = cprep(sm[base | off[j]]);
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-            rq_cplx acc = {0, 0};
+            cacc acc = czero();
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 const rq_cplx m = EXT ? ldg_cplx(M + i + j * D) : M[i + j * D];   // column-major, as the API
-                cfma(acc, m, a[j]);
+                cmac(acc, m, a[j]);
             }
-            sm[base | off[i]] = acc;
+            sm[base | off[i]] = cget(acc);
         }
     }
 }
@@ -149,10 +186,173 @@ __device__ __forceinline__ void op_perm(rq_cplx* sm, const rq_tile_op& o, uint32
     }
 }
 
-// WIDE = false: dense ops of 1-2 qubits only, <= 64 registers so that 4+ tiles per SM are in flight.
-// WIDE = true : also 3- and 4-qubit dense ops (16 amplitudes per thread in registers), fewer tiles per SM.
-template <typename Prog, bool WIDE>
-__global__ void __launch_bounds__(NT, WIDE ? 1 : 4) tile_sweep_kernel(rq_cplx* __restrict__ state, const __grid_constant__ Prog prog) {
+// ---- register-window phases ---------------------------------------------------------------------------
+// Every thread owns the D = 2^V amplitudes that differ in the V window bits; all ops of the phase act on them in
+// registers, so the tile makes ONE shared-memory round trip per phase instead of one per op.  Window bits sit at
+// local positions >= 4: for a fixed register slot the lanes of a warp read consecutive amplitudes (no bank conflicts).
+template <int V, int W>
+__device__ __forceinline__ void win_dense1(rq_cplx (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
+    const rq_cplx m00 = M[0], m10 = M[1], m01 = M[2], m11 = M[3];          // column-major
+#pragma unroll
+    for (int j = 0; j < (1 << V); ++j) {
+        if (j & (1 << W)) continue;
+        if ((j & cm_in) != cm_in) continue;
+        const cin a0 = cprep(a[j]), a1 = cprep(a[j | (1 << W)]);
+        cacc r0 = czero(), r1 = czero();
+        cmac(r0, m00, a0); cmac(r0, m01, a1);
+        cmac(r1, m10, a0); cmac(r1, m11, a1);
+        a[j] = cget(r0);
+        a[j | (1 << W)] = cget(r1);
+    }
+}
+// matrix bit 0 <-> window bit W0, matrix bit 1 <-> window bit W1 (the host orders the targets ascending)
+template <int V, int W0, int W1>
+__device__ __forceinline__ void win_dense2(rq_cplx (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
+    rq_cplx m[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) m[e] = M[e];
+#pragma unroll
+    for (int j = 0; j < (1 << V); ++j) {
+        if (j & ((1 << W0) | (1 << W1))) continue;
+        if ((j & cm_in) != cm_in) continue;
+        const cin x0 = cprep(a[j]), x1 = cprep(a[j | (1 << W0)]), x2 = cprep(a[j | (1 << W1)]), x3 = cprep(a[j | (1 << W0) | (1 << W1)]);
+        rq_cplx r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            cacc acc = czero();
+            cmac(acc, m[i], x0); cmac(acc, m[i + 4], x1); cmac(acc, m[i + 8], x2); cmac(acc, m[i + 12], x3);
+            r[i] = cget(acc);
+        }
+        a[j] = r[0]; a[j | (1 << W0)] = r[1]; a[j | (1 << W1)] = r[2]; a[j | (1 << W0) | (1 << W1)] = r[3];
+    }
+}
+template <int V, int W>
+__device__ __forceinline__ void win_x(rq_cplx (&a)[1 << V], uint32_t cm_in) {
+#pragma unroll
+    for (int j = 0; j < (1 << V); ++j) {
+        if (j & (1 << W)) continue;
+        if ((j & cm_in) != cm_in) continue;
+        const rq_cplx t = a[j];
+        a[j] = a[j | (1 << W)];
+        a[j | (1 << W)] = t;
+    }
+}
+template <int V, int W0, int W1>
+__device__ __forceinline__ void win_swap(rq_cplx (&a)[1 << V], uint32_t cm_in) {
+#pragma unroll
+    for (int j = 0; j < (1 << V); ++j) {
+        if (j & ((1 << W0) | (1 << W1))) continue;
+        if ((j & cm_in) != cm_in) continue;
+        const rq_cplx t = a[j | (1 << W0)];
+        a[j | (1 << W0)] = a[j | (1 << W1)];
+        a[j | (1 << W1)] = t;
+    }
+}
+
+template <int V>
+__device__ __forceinline__ void win_dispatch1(rq_cplx (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense) {
+    const uint32_t w = o.wt[0], ci = o.cm_in;
+    if (dense) {
+        if (w == 0) win_dense1<V, 0>(a, M, ci);
+        else if (w == 1) win_dense1<V, 1>(a, M, ci);
+        else if (w == 2) win_dense1<V, 2>(a, M, ci);
+        else if (V > 3) win_dense1<V, (V > 3 ? 3 : 0)>(a, M, ci);
+    } else {
+        if (w == 0) win_x<V, 0>(a, ci);
+        else if (w == 1) win_x<V, 1>(a, ci);
+        else if (w == 2) win_x<V, 2>(a, ci);
+        else if (V > 3) win_x<V, (V > 3 ? 3 : 0)>(a, ci);
+    }
+}
+template <int V>
+__device__ __forceinline__ void win_dispatch2(rq_cplx (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense) {
+    const uint32_t pair = o.wt[0] * 4u + o.wt[1], ci = o.cm_in;      // wt[0] < wt[1]
+#define RQ_PAIR(A, B)                                            \
+    case (A) * 4 + (B):                                          \
+        if (dense) win_dense2<V, A, B>(a, M, ci);                \
+        else win_swap<V, A, B>(a, ci);                           \
+        break;
+    switch (pair) {
+        RQ_PAIR(0, 1) RQ_PAIR(0, 2) RQ_PAIR(1, 2)
+        default:
+            if (V > 3) {
+                switch (pair) {
+                    RQ_PAIR(0, (V > 3 ? 3 : 1)) RQ_PAIR(1, (V > 3 ? 3 : 2)) RQ_PAIR(2, (V > 3 ? 3 : 2) + (V > 3 ? 0 : 1))
+                    default: break;
+                }
+            }
+            break;
+    }
+#undef RQ_PAIR
+}
+
+template <int V, typename Prog>
+__device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint32_t tid,
+                                                 uint64_t gbase) {
+    constexpr int D = 1 << V;
+    uint32_t stride[V];
+#pragma unroll
+    for (int b = 0; b < V; ++b) stride[b] = 1u << ph.w[b];
+    const uint32_t ngroups = 1u << (T - V);
+    for (uint32_t g = tid; g < ngroups; g += NT) {
+        uint32_t base = g;
+#pragma unroll
+        for (int b = 0; b < V; ++b) {
+            const uint32_t p = ph.w[b];
+            base = ((base >> p) << (p + 1)) | (base & ((1u << p) - 1u));
+        }
+        rq_cplx a[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            uint32_t idx = base;
+#pragma unroll
+            for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
+            a[j] = sm[idx];
+        }
+        for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
+            const rq_tile_op& o = prog.ops[oi];
+            if ((gbase & o.gcmask) != o.gcmask) continue;
+            if ((base & o.cm_out) != o.cm_out) continue;
+            const rq_cplx* M = prog.pool + o.moff;
+            if (o.kind == RQ_OP_DIAG) {
+                uint32_t selbase = 0;
+                for (uint32_t b = 0; b < o.k; ++b)
+                    if (o.t[b] == 0xFF) selbase |= (uint32_t)((gbase >> o.gq[b]) & 1ull) << b;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    uint32_t idx = base;
+#pragma unroll
+                    for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
+                    if ((idx & o.setmask) != o.setmask) continue;
+                    uint32_t sel = selbase;
+                    for (uint32_t b = 0; b < o.k; ++b)
+                        if (o.t[b] != 0xFF) sel |= ((idx >> o.t[b]) & 1u) << b;
+                    a[j] = cmul(M[sel], a[j]);
+                }
+            } else if (o.kind == RQ_OP_DENSE) {
+                if (o.k == 1) win_dispatch1<V>(a, o, M, true);
+                else win_dispatch2<V>(a, o, M, true);
+            } else {
+                if (o.k == 1) win_dispatch1<V>(a, o, M, false);
+                else win_dispatch2<V>(a, o, M, false);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            uint32_t idx = base;
+#pragma unroll
+            for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
+            sm[idx] = a[j];
+        }
+    }
+}
+
+// MODE 0 (narrow): one op per shared-memory pass, dense ops of 1-2 qubits only, <= 64 registers so that 3+ tiles per SM
+//                  are in flight -- the variant for one-gate and lightly fused sweeps (HBM-bound).
+// MODE 1 (wide)  : also 3- and 4-qubit dense ops (16 amplitudes per thread in registers).
+// MODE 2 (phased): register-window phases for heavily fused sweeps (compute-bound): several ops per smem round trip.
+template <typename Prog, int MODE>
+__global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? 2 : 1)) tile_sweep_kernel(rq_cplx* __restrict__ state, const __grid_constant__ Prog prog) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     rq_cplx* sm = reinterpret_cast<rq_cplx*>(smem_raw);
     __shared__ __align__(8) uint64_t bar_storage;
@@ -188,7 +388,19 @@ __global__ void __launch_bounds__(NT, WIDE ? 1 : 4) tile_sweep_kernel(rq_cplx* _
     mbar_wait(bar, 0);
 
     const rq_cplx* ext = reinterpret_cast<const rq_cplx*>(prog.hdr.ext_matrix);
-    for (uint32_t i = 0; i < prog.hdr.nops; ++i) {
+    constexpr bool WIDE = MODE != 0;
+    const uint32_t nsteps = MODE == 2 ? prog.hdr.nphases : prog.hdr.nops;
+    for (uint32_t step = 0; step < nsteps; ++step) {
+        uint32_t i = step;
+        if (MODE == 2) {
+            const rq_phase& ph = prog.phases[step];
+            if (ph.kind == 1) {
+                run_window_phase<RQ_WINDOW_BITS>(sm, prog, ph, T, tid, gbase);
+                __syncthreads();
+                continue;
+            }
+            i = ph.first;
+        }
         const rq_tile_op& o = prog.ops[i];
         if ((gbase & o.gcmask) != o.gcmask) continue;          // uniform per tile: no divergent barrier
         switch (o.kind) {
@@ -228,12 +440,15 @@ __global__ void __launch_bounds__(NT, WIDE ? 1 : 4) tile_sweep_kernel(rq_cplx* _
 template <typename Prog>
 int launch(rq_cplx* state, const Prog* prog, void* stream) {
     const size_t smem = sizeof(rq_cplx) << prog->hdr.T;
+    const unsigned grid = (unsigned)prog->hdr.ntiles;
     bool wide = false;
     for (uint32_t i = 0; i < prog->hdr.nops; ++i) wide |= (prog->ops[i].kind == RQ_OP_DENSE && prog->ops[i].k > 2);
-    if (wide)
-        tile_sweep_kernel<Prog, true><<<(unsigned)prog->hdr.ntiles, NT, smem, (cudaStream_t)stream>>>(state, *prog);
+    if (prog->hdr.nphases > 0 && prog->hdr.max_phase_ops >= 2)
+        tile_sweep_kernel<Prog, 2><<<grid, NT, smem, (cudaStream_t)stream>>>(state, *prog);
+    else if (wide)
+        tile_sweep_kernel<Prog, 1><<<grid, NT, smem, (cudaStream_t)stream>>>(state, *prog);
     else
-        tile_sweep_kernel<Prog, false><<<(unsigned)prog->hdr.ntiles, NT, smem, (cudaStream_t)stream>>>(state, *prog);
+        tile_sweep_kernel<Prog, 0><<<grid, NT, smem, (cudaStream_t)stream>>>(state, *prog);
     return (int)cudaGetLastError();
 }
 
@@ -241,10 +456,12 @@ int launch(rq_cplx* state, const Prog* prog, void* stream) {
 
 extern "C" int rq_sweep_configure(void) {
     const int bytes = (int)(sizeof(rq_cplx) << RQ_MAX_TILE_BITS);
-    cudaError_t e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_small, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_small, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_large, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_large, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_small, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_small, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_small, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_large, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_large, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_large, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return (int)e;
 }
 extern "C" int rq_launch_sweep_small(rq_cplx* state, const rq_program_small* prog, void* stream) { return launch(state, prog, stream); }

@@ -116,6 +116,10 @@ def host_ram_gb():
     return 0.0
 
 
+def unit_for(n):
+    return "gates/s" if n == 30 else "gates/s (30-qubit equivalent: gates*2^(n-30)/s)"
+
+
 def workload_for(ngpus):
     from rocquantum_b200 import workloads
     if ngpus == 1:
@@ -164,11 +168,11 @@ def run_reference(args):
     value = len(gates) / circuit_s * 2.0 ** (n - 30)
     sample = (f"1 one-qubit + 1 two-qubit Haar gate of the workload per step at {n_run} qubits"
               + ("" if n_run == n else f", extrapolated x2^{n - n_run} to {n} qubits") + "; one full pass per gate (no fusion), OpenMP")
-    line = {"impl": "reference", "metric": "gates_per_sec", "value": value, "unit": "gates/s (30-qubit equivalent)", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": "gates_per_sec", "value": value, "unit": unit_for(n), "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": circuit_s * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "c64", "data": "synthetic", "config": {"workload": wl},
-            "cpu_baseline": {"value": value, "unit": "gates/s (30-qubit equivalent)", "cores": os.cpu_count(), "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "gates/s (30-qubit equivalent)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": value, "unit": unit_for(n), "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit_for(n), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -303,13 +307,13 @@ def run_engine(args):
         except Exception as ex:                      # the baseline must not take the bench down
             cpu = {"value": None, "unit": "gates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 
-    line = {"metric": "gates_per_sec", "value": value, "unit": "gates/s" if n == 30 else "gates/s (30-qubit equivalent: gates*2^(n-30)/s)",
+    line = {"metric": "gates_per_sec", "value": value, "unit": unit_for(n),
             "n_gpus": ngpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
             "config": {"workload": wl, "qubits": n, "gates": ngates, "l2": "state (8 * 2^n_local bytes) is far larger than the 126 MB L2",
                        "timing": "K steps between stream-sync + barrier, max over ranks; per-sweep time from CUDA events on the engine's stream"},
             "clocks": clk, "device_ms_per_step": dev_ms / args.steps,
-            "e2e": {"value": e2e_value, "unit": "gates/s" if n == 30 else "gates/s (30-qubit equivalent)",
+            "e2e": {"value": e2e_value, "unit": unit_for(n),
                     "h2d_bytes_per_step": st_e2e.h2dBytes // args.steps, "d2h_bytes_per_step": d2h,
                     "what": "rocsvInitializeState + rocsvxApplyCircuit(host gate list) + <Z0> and 256 sampled bitstrings read back, every step; "
                             "the gate list reaches the device as sweep programs in kernel parameters"},

@@ -106,22 +106,30 @@ void SFX(orc_cswap)(CPLX* s, unsigned n, size_t batch, unsigned long long cmask,
 void SFX(orc_apply_matrix)(CPLX* s, unsigned n, size_t batch, const unsigned* targets, unsigned k,
                            const unsigned* controls, unsigned nc, const CPLX* M) {
     size_t N = (size_t)1 << n, dim = (size_t)1 << k;
-    size_t tmask = 0, cmask = 0;
-    for (unsigned b = 0; b < k; ++b) tmask |= (size_t)1 << targets[b];
+    size_t cmask = 0, fixed = 0;
+    for (unsigned b = 0; b < k; ++b) fixed |= (size_t)1 << targets[b];
     for (unsigned b = 0; b < nc; ++b) cmask |= (size_t)1 << controls[b];
+    fixed |= cmask;
+    unsigned fixpos[64], nfix = 0;
+    for (unsigned p = 0; p < n; ++p) if ((fixed >> p) & 1) fixpos[nfix++] = p;
     size_t* off = (size_t*)malloc(dim * sizeof(size_t));
     for (size_t j = 0; j < dim; ++j) {
         size_t o = 0;
         for (unsigned b = 0; b < k; ++b) if ((j >> b) & 1) o |= (size_t)1 << targets[b];
         off[j] = o;
     }
+    const size_t groups = N >> nfix;                       /* one group per assignment of the free bits */
     #pragma omp parallel
     {
         CPLX* in = (CPLX*)malloc(dim * sizeof(CPLX));
         #pragma omp for schedule(static)
-        for (size_t i = 0; i < batch * N; ++i) {
-            size_t l = i % N;
-            if ((l & tmask) != 0 || (l & cmask) != cmask) continue;   /* one group per base index */
+        for (size_t g = 0; g < batch * groups; ++g) {
+            size_t base = g % groups;
+            for (unsigned f = 0; f < nfix; ++f) {          /* deposit the free bits around the fixed positions */
+                const unsigned p = fixpos[f];
+                base = ((base >> p) << (p + 1)) | (base & (((size_t)1 << p) - 1));
+            }
+            const size_t i = (g / groups) * N + (base | cmask);
             for (size_t j = 0; j < dim; ++j) in[j] = s[i + off[j]];
             for (size_t r = 0; r < dim; ++r) {
                 CPLX acc = {(REAL)0, (REAL)0};

@@ -333,10 +333,49 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
     return plans;
 }
 
+// ---- order of the ops inside one sweep ---------------------------------------------------------------------------
+// Ops that commute (disjoint qubits, or acting diagonally on the shared ones) may be reordered inside a sweep.  This
+// pulls together the ops that fit in one register window of V qubits (same greedy/blocked-set rule as plan_sweeps, one
+// level down), so that build_phases finds long phases: for a brick circuit {(a,b),(c,d),(b,c)} instead of {(a,b),(c,d)}.
+inline std::vector<int> phase_friendly_order(const SweepPlan& sp, const std::vector<HostOp>& ops, unsigned V) {
+    std::vector<int> rest = sp.ops, out;
+    out.reserve(rest.size());
+    while (!rest.empty()) {
+        uint64_t W = 0, blockedAny = 0, blockedND = 0;
+        std::vector<int> keep;
+        bool took = false;
+        for (int idx : rest) {
+            const HostOp& o = ops[idx];
+            const uint64_t nd = o.nondiag(), dg = o.qubits() & ~nd;
+            const bool eligible = o.kind == HostOp::DIAG || o.kind == HostOp::PERM_X || o.kind == HostOp::PERM_SWAP ||
+                                  (o.kind == HostOp::DENSE && o.targets.size() <= 2 && !o.ext);
+            const bool free_ = !((nd & (blockedAny | blockedND)) || (dg & blockedAny));
+            if (free_ && eligible && (unsigned)__builtin_popcountll(W | nd) <= V) {
+                W |= nd;
+                out.push_back(idx);
+                took = true;
+            } else if (free_ && !took && !eligible) {          // a wide / device-matrix op at the head: runs alone
+                out.push_back(idx);
+                took = true;
+                blockedAny |= nd;
+                blockedND |= dg;
+                W = ~0ull;                                       // nothing joins it
+            } else {
+                keep.push_back(idx);
+                blockedAny |= nd;
+                blockedND |= dg;
+            }
+        }
+        if (!took) { out.push_back(keep.front()); keep.erase(keep.begin()); }
+        rest.swap(keep);
+    }
+    return out;
+}
+
 // ---- phases: which ops share one shared-memory round trip of the tile (see rq_phase) -------------------------------
 template <typename Prog>
 inline void build_phases(Prog& P, unsigned T) {
-    const unsigned V = RQ_WINDOW_BITS, MINP = RQ_WINDOW_MIN_POS;
+    const unsigned V = RQ_WINDOW_BITS, MINP = P.hdr.swz ? 0u : (unsigned)RQ_WINDOW_MIN_POS;
     P.hdr.nphases = 0;
     P.hdr.max_phase_ops = 0;
     const unsigned nops = P.hdr.nops;
@@ -423,7 +462,8 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
     for (unsigned j = 0; j < T; ++j) { P.hdr.res[j] = (uint8_t)sp.res[j]; local[sp.res[j]] = (int)j; R |= 1ull << sp.res[j]; }
     unsigned pool = 0;
     const unsigned maxops = (unsigned)(sizeof(P.ops) / sizeof(P.ops[0])), maxpool = (unsigned)(sizeof(P.pool) / sizeof(P.pool[0]));
-    for (int idx : sp.ops) {
+    const std::vector<int> order = phase_friendly_order(sp, ops, RQ_WINDOW_BITS);
+    for (int idx : order) {
         const HostOp& o = ops[idx];
         if (P.hdr.nops >= maxops) return false;
         rq_tile_op& t = P.ops[P.hdr.nops++];
@@ -483,6 +523,18 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
         }
         for (unsigned j = 0; j < T; ++j) if ((fixmask >> j) & 1u) t.fix[t.nfix++] = (uint8_t)j;
     }
+    // ops with a non-diagonal target on one of the bank-selecting bits would serialise on shared-memory banks:
+    // such sweeps keep the tile XOR-swizzled (needs 2*RQ_SWZ_BITS local bits)
+    P.hdr.swz = 0;
+    if (T >= 2 * RQ_SWZ_BITS) {
+        for (unsigned i = 0; i < P.hdr.nops; ++i) {
+            const rq_tile_op& t = P.ops[i];
+            uint32_t tm = 0;
+            if (t.kind == RQ_OP_DENSE) for (unsigned b = 0; b < t.k; ++b) tm |= 1u << t.t[b];
+            else if (t.kind == RQ_OP_PERM) tm = t.xm;
+            if (tm & ((1u << RQ_SWZ_BITS) - 1u)) P.hdr.swz = 1;
+        }
+    }
     build_phases(P, T);
     return true;
 }
@@ -496,7 +548,7 @@ inline std::string dump_plan(const std::vector<SweepPlan>& plans, const std::vec
         s += buf;
         for (unsigned r : sp.res) { snprintf(buf, sizeof buf, " %u", r); s += buf; }
         s += "\n";
-        for (int i : sp.ops) {
+        for (int i : phase_friendly_order(sp, ops, RQ_WINDOW_BITS)) {      // the order the kernel executes
             const HostOp& o = ops[i];
             snprintf(buf, sizeof buf, "O %d cmask %llx targets", o.kind, (unsigned long long)o.cmask);
             s += buf;

@@ -55,6 +55,8 @@ struct rq_sweep_hdr {
     uint32_t rowbits;               // log2(amplitudes per contiguous row)
     uint32_t nphases;
     uint32_t max_phase_ops;         // largest rq_phase::count (selects the kernel variant)
+    uint32_t swz;                   // 1: the tile lives XOR-swizzled in shared memory (ops on the lowest local bits)
+    uint32_t pad;
     uint64_t ntiles;                // batch * 2^(n-T)
     uint64_t high_base;             // OR-ed into every tile's base index for predicates (rank << n_local)
     const void* ext_matrix;         // device matrix of an op with ext = 1 (column-major, rq_cplx)
@@ -80,7 +82,16 @@ typedef rq_program<160, 2496> rq_program_large;     // ~31.6 KB
 #endif
 
 #define RQ_TILE_THREADS 256
-#define RQ_WINDOW_MIN_POS 4                          // register-window bits sit at local positions >= 4: conflict-free LDS/STS
+// Shared-memory bank geometry: an LDS.64 (complex64) wavefront is 16 lanes x 8 B, an LDS.128 (complex128) wavefront
+// 8 lanes x 16 B, so the lowest RQ_SWZ_BITS index bits select the bank group.  Ops whose targets include one of those
+// bits would serialise (all lanes of a wavefront agree on them), so such sweeps keep the tile XOR-swizzled:
+//   phys(idx) = idx ^ ((idx >> RQ_SWZ_BITS) & (2^RQ_SWZ_BITS - 1))
+#ifdef ROCQ_PRECISION_DOUBLE
+#define RQ_SWZ_BITS 3
+#else
+#define RQ_SWZ_BITS 4
+#endif
+#define RQ_WINDOW_MIN_POS RQ_SWZ_BITS                // without the swizzle, register-window bits sit above the bank bits
 #ifdef ROCQ_PRECISION_DOUBLE
 #define RQ_WINDOW_BITS 3                             // 8 amplitudes = 32 registers per thread
 #else

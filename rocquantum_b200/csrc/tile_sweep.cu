@@ -25,6 +25,11 @@ constexpr int NT = RQ_TILE_THREADS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+template <bool SWZ>
+__device__ __forceinline__ uint32_t sidx(uint32_t idx) {
+    return SWZ ? (idx ^ ((idx >> RQ_SWZ_BITS) & ((1u << RQ_SWZ_BITS) - 1u))) : idx;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -124,7 +129,7 @@ __device__ __forceinline__ uint32_t spread(uint32_t g, const rq_tile_op& o) {
     return g;
 }
 
-template <int K, bool EXT>
+template <int K, bool EXT, bool SWZ>
 __device__ __forceinline__ void op_dense(rq_cplx* sm, const rq_tile_op& o, const rq_cplx* pool, const rq_cplx* ext,
                                          uint32_t T, uint32_t tid) {
     constexpr int D = 1 << K;
@@ -143,7 +148,7 @@ __device__ __forceinline__ void op_dense(rq_cplx* sm, const rq_tile_op& o, const
         const uint32_t base = spread(g, o) | o.setmask;
         cin a[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) a[j] = cprep(sm[base | off[j]]);
+        for (int j = 0; j < D; ++j) a[j] = cprep(sm[sidx<SWZ>(base | off[j])]);
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             cacc acc = czero();
@@ -152,13 +157,14 @@ __device__ __forceinline__ void op_dense(rq_cplx* sm, const rq_tile_op& o, const
                 const rq_cplx m = EXT ? ldg_cplx(M + i + j * D) : M[i + j * D];   // column-major, as the API
                 cmac(acc, m, a[j]);
             }
-            sm[base | off[i]] = cget(acc);
+            sm[sidx<SWZ>(base | off[i])] = cget(acc);
         }
     }
 }
 
 // diagonal: amp[idx] *= d[sel], sel bit b taken from the local index or, for a non-resident qubit,
 // from the tile base.  Qubits whose "0" entries are all 1 were turned into controls by the host.
+template <bool SWZ>
 __device__ __forceinline__ void op_diag(rq_cplx* sm, const rq_tile_op& o, const rq_cplx* pool, uint32_t T, uint32_t tid,
                                         uint64_t gbase) {
     uint32_t selbase = 0;
@@ -171,15 +177,17 @@ __device__ __forceinline__ void op_diag(rq_cplx* sm, const rq_tile_op& o, const 
         uint32_t sel = selbase;
         for (uint32_t b = 0; b < o.k; ++b)
             if (o.t[b] != 0xFF) sel |= ((idx >> o.t[b]) & 1u) << b;
-        sm[idx] = cmul(D[sel], sm[idx]);
+        const uint32_t pi = sidx<SWZ>(idx);
+        sm[pi] = cmul(D[sel], sm[pi]);
     }
 }
 
 // pair permutation: swap(idx, idx ^ xm) over the idx whose fixed bits equal setmask
+template <bool SWZ>
 __device__ __forceinline__ void op_perm(rq_cplx* sm, const rq_tile_op& o, uint32_t T, uint32_t tid) {
     const uint32_t ngroups = 1u << (T - o.nfix);
     for (uint32_t g = tid; g < ngroups; g += NT) {
-        const uint32_t i0 = spread(g, o) | o.setmask, i1 = i0 ^ o.xm;
+        const uint32_t l0 = spread(g, o) | o.setmask, i0 = sidx<SWZ>(l0), i1 = sidx<SWZ>(l0 ^ o.xm);
         const rq_cplx a = sm[i0], b = sm[i1];
         sm[i0] = b;
         sm[i1] = a;
@@ -286,7 +294,7 @@ __device__ __forceinline__ void win_dispatch2(rq_cplx (&a)[1 << V], const rq_til
 #undef RQ_PAIR
 }
 
-template <int V, typename Prog>
+template <int V, bool SWZ, typename Prog>
 __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint32_t tid,
                                                  uint64_t gbase) {
     constexpr int D = 1 << V;
@@ -307,7 +315,7 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
             uint32_t idx = base;
 #pragma unroll
             for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
-            a[j] = sm[idx];
+            a[j] = sm[sidx<SWZ>(idx)];
         }
         for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
             const rq_tile_op& o = prog.ops[oi];
@@ -342,7 +350,7 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
             uint32_t idx = base;
 #pragma unroll
             for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
-            sm[idx] = a[j];
+            sm[sidx<SWZ>(idx)] = a[j];
         }
     }
 }
@@ -351,7 +359,23 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
 //                  are in flight -- the variant for one-gate and lightly fused sweeps (HBM-bound).
 // MODE 1 (wide)  : also 3- and 4-qubit dense ops (16 amplitudes per thread in registers).
 // MODE 2 (phased): register-window phases for heavily fused sweeps (compute-bound): several ops per smem round trip.
-template <typename Prog, int MODE>
+// SWZ: the tile is kept XOR-swizzled in shared memory (sv_internal.h) between a swizzle pass after the TMA load and
+//      an unswizzle pass before the TMA store; chosen for sweeps with ops on the lowest local bits.
+template <bool SWZ>
+__device__ __forceinline__ void swizzle_pass(rq_cplx* sm, uint32_t T, uint32_t tid) {
+    if (!SWZ) return;
+    for (uint32_t idx = tid; idx < (1u << T); idx += NT) {       // an involution inside each aligned group: swap pairs
+        const uint32_t p = sidx<true>(idx);
+        if (idx < p) {
+            const rq_cplx a = sm[idx], b = sm[p];
+            sm[idx] = b;
+            sm[p] = a;
+        }
+    }
+    __syncthreads();
+}
+
+template <typename Prog, int MODE, bool SWZ>
 __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? 2 : 1)) tile_sweep_kernel(rq_cplx* __restrict__ state, const __grid_constant__ Prog prog) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     rq_cplx* sm = reinterpret_cast<rq_cplx*>(smem_raw);
@@ -386,6 +410,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? 2 : 1)) tile_
         bulk_g2s(smem_u32(sm) + r * rowbytes, gtile + goff, rowbytes, bar);
     }
     mbar_wait(bar, 0);
+    swizzle_pass<SWZ>(sm, T, tid);
 
     const rq_cplx* ext = reinterpret_cast<const rq_cplx*>(prog.hdr.ext_matrix);
     constexpr bool WIDE = MODE != 0;
@@ -395,7 +420,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? 2 : 1)) tile_
         if (MODE == 2) {
             const rq_phase& ph = prog.phases[step];
             if (ph.kind == 1) {
-                run_window_phase<RQ_WINDOW_BITS>(sm, prog, ph, T, tid, gbase);
+                run_window_phase<RQ_WINDOW_BITS, SWZ>(sm, prog, ph, T, tid, gbase);
                 __syncthreads();
                 continue;
             }
@@ -407,26 +432,27 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? 2 : 1)) tile_
             case RQ_OP_DENSE:
                 if (o.ext) {
                     switch (o.k) {
-                        case 1: op_dense<1, true>(sm, o, prog.pool, ext, T, tid); break;
-                        case 2: op_dense<2, true>(sm, o, prog.pool, ext, T, tid); break;
-                        case 3: if (WIDE) op_dense<3, true>(sm, o, prog.pool, ext, T, tid); break;
-                        default: if (WIDE) op_dense<4, true>(sm, o, prog.pool, ext, T, tid); break;
+                        case 1: op_dense<1, true, SWZ>(sm, o, prog.pool, ext, T, tid); break;
+                        case 2: op_dense<2, true, SWZ>(sm, o, prog.pool, ext, T, tid); break;
+                        case 3: if (WIDE) op_dense<3, true, SWZ>(sm, o, prog.pool, ext, T, tid); break;
+                        default: if (WIDE) op_dense<4, true, SWZ>(sm, o, prog.pool, ext, T, tid); break;
                     }
                 } else {
                     switch (o.k) {
-                        case 1: op_dense<1, false>(sm, o, prog.pool, ext, T, tid); break;
-                        case 2: op_dense<2, false>(sm, o, prog.pool, ext, T, tid); break;
-                        case 3: if (WIDE) op_dense<3, false>(sm, o, prog.pool, ext, T, tid); break;
-                        default: if (WIDE) op_dense<4, false>(sm, o, prog.pool, ext, T, tid); break;
+                        case 1: op_dense<1, false, SWZ>(sm, o, prog.pool, ext, T, tid); break;
+                        case 2: op_dense<2, false, SWZ>(sm, o, prog.pool, ext, T, tid); break;
+                        case 3: if (WIDE) op_dense<3, false, SWZ>(sm, o, prog.pool, ext, T, tid); break;
+                        default: if (WIDE) op_dense<4, false, SWZ>(sm, o, prog.pool, ext, T, tid); break;
                     }
                 }
                 break;
-            case RQ_OP_DIAG: op_diag(sm, o, prog.pool, T, tid, gbase); break;
-            default: op_perm(sm, o, T, tid); break;
+            case RQ_OP_DIAG: op_diag<SWZ>(sm, o, prog.pool, T, tid, gbase); break;
+            default: op_perm<SWZ>(sm, o, T, tid); break;
         }
         __syncthreads();
     }
 
+    swizzle_pass<SWZ>(sm, T, tid);      // back to the linear layout the bulk stores expect
     fence_async_smem();       // generic-proxy writes to smem -> visible to the async (TMA) proxy
     __syncthreads();
     for (uint32_t r = tid; r < nrows; r += NT) {
@@ -443,12 +469,15 @@ int launch(rq_cplx* state, const Prog* prog, void* stream) {
     const unsigned grid = (unsigned)prog->hdr.ntiles;
     bool wide = false;
     for (uint32_t i = 0; i < prog->hdr.nops; ++i) wide |= (prog->ops[i].kind == RQ_OP_DENSE && prog->ops[i].k > 2);
-    if (prog->hdr.nphases > 0 && prog->hdr.max_phase_ops >= 2)
-        tile_sweep_kernel<Prog, 2><<<grid, NT, smem, (cudaStream_t)stream>>>(state, *prog);
-    else if (wide)
-        tile_sweep_kernel<Prog, 1><<<grid, NT, smem, (cudaStream_t)stream>>>(state, *prog);
-    else
-        tile_sweep_kernel<Prog, 0><<<grid, NT, smem, (cudaStream_t)stream>>>(state, *prog);
+    const int mode = (prog->hdr.nphases > 0 && prog->hdr.max_phase_ops >= 2) ? 2 : (wide ? 1 : 0);
+    cudaStream_t st = (cudaStream_t)stream;
+#define RQ_LAUNCH(M, S) tile_sweep_kernel<Prog, M, S><<<grid, NT, smem, st>>>(state, *prog)
+    if (prog->hdr.swz) {
+        if (mode == 2) RQ_LAUNCH(2, true); else if (mode == 1) RQ_LAUNCH(1, true); else RQ_LAUNCH(0, true);
+    } else {
+        if (mode == 2) RQ_LAUNCH(2, false); else if (mode == 1) RQ_LAUNCH(1, false); else RQ_LAUNCH(0, false);
+    }
+#undef RQ_LAUNCH
     return (int)cudaGetLastError();
 }
 
@@ -456,12 +485,13 @@ int launch(rq_cplx* state, const Prog* prog, void* stream) {
 
 extern "C" int rq_sweep_configure(void) {
     const int bytes = (int)(sizeof(rq_cplx) << RQ_MAX_TILE_BITS);
-    cudaError_t e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_small, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_small, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_small, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_large, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_large, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<rq_program_large, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaSuccess;
+#define RQ_ATTR(P, M, S) if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<P, M, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+    RQ_ATTR(rq_program_small, 0, false); RQ_ATTR(rq_program_small, 1, false); RQ_ATTR(rq_program_small, 2, false);
+    RQ_ATTR(rq_program_small, 0, true);  RQ_ATTR(rq_program_small, 1, true);  RQ_ATTR(rq_program_small, 2, true);
+    RQ_ATTR(rq_program_large, 0, false); RQ_ATTR(rq_program_large, 1, false); RQ_ATTR(rq_program_large, 2, false);
+    RQ_ATTR(rq_program_large, 0, true);  RQ_ATTR(rq_program_large, 1, true);  RQ_ATTR(rq_program_large, 2, true);
+#undef RQ_ATTR
     return (int)e;
 }
 extern "C" int rq_launch_sweep_small(rq_cplx* state, const rq_program_small* prog, void* stream) { return launch(state, prog, stream); }

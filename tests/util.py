@@ -14,7 +14,10 @@ def run_on_oracle(o: so.Oracle, gates):
     for g in gates:
         name, targets, controls, theta = g[0], list(g[1]), list(g[2]), g[3]
         if name == "matrix":
-            o.apply_matrix(targets, g[4], controls)
+            if len(targets) == 1 and not controls:
+                o.matrix1(targets[0], g[4])          # the reference's own 1q kernel arithmetic (single_qubit_kernels.hip:28-72)
+            else:
+                o.apply_matrix(targets, g[4], controls)
         elif name in ("h", "x", "y", "z", "s", "sdg", "t"):
             o.gate(name, targets[0])
         elif name in ("rx", "ry", "rz"):

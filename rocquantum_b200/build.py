@@ -14,8 +14,9 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "lib")
-OBJ = os.path.join(HERE, "_obj")
+LIB = os.environ.get("ROCQ_LIB_DIR", os.path.join(HERE, "lib"))          # tuning variants build elsewhere
+OBJ = os.environ.get("ROCQ_OBJ_DIR", os.path.join(HERE, "_obj"))
+EXTRA = os.environ.get("ROCQ_EXTRA_DEFS", "").split()
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -53,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> list[str]:
             o = os.path.join(OBJ, f"{os.path.splitext(src)[0]}.{tag}.o")
             objs.append(o)
             if force or _newer(o, [s] + hdrs):
-                jobs.append([NVCC, *ARCH, *COMMON, *defs, "-c", s, "-o", o])
+                jobs.append([NVCC, *ARCH, *COMMON, *defs, *EXTRA, "-c", s, "-o", o])
         libs.append((os.path.join(LIB, libname), objs))
     with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(_run, jobs))

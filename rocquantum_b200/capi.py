@@ -102,7 +102,7 @@ REFERENCE_SYMBOLS = sorted(s for s in PROTOTYPES if not s.startswith("rocsvx")) 
 
 def lib_path(prec: str = "c64") -> str:
     name = {"c64": "libhipStateVec.so", "c128": "libhipStateVec_f64.so"}[prec]
-    return os.path.join(_HERE, "lib", name)
+    return os.path.join(os.environ.get("ROCQ_LIB_DIR", os.path.join(_HERE, "lib")), name)
 
 
 def load(prec: str = "c64") -> C.CDLL:

@@ -266,7 +266,7 @@ struct PlanLimits {
 
 inline unsigned pool_need(const HostOp& o) {
     if (o.ext) return 0;
-    if (o.kind == HostOp::DENSE) return 1u << (2 * o.targets.size());
+    if (o.kind == HostOp::DENSE) return RQ_MSLOTS * (1u << (2 * o.targets.size())) + 1u;     // +1: slot alignment
     if (o.kind == HostOp::DIAG) return 1u << o.targets.size();
     return 0;
 }
@@ -481,7 +481,8 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
             if (o.ext) { t.ext = 1; P.hdr.ext_matrix = o.ext; }
             else {
                 const unsigned need = 1u << (2 * k);
-                if (pool + need > maxpool) return false;
+                if (RQ_MSLOTS == 2 && (pool & 1u)) ++pool;         // 16-byte alignment of the two-slot elements
+                if (pool + RQ_MSLOTS * need > maxpool) return false;
                 t.moff = pool;
                 const bool flip = k == 2 && t.t[0] > t.t[1];          // keep 2q targets ascending: matrix bit 0 <-> lower position
                 if (flip) std::swap(t.t[0], t.t[1]);
@@ -492,10 +493,12 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
                         const unsigned rs = ((r & 1u) << 1) | (r >> 1), cs = ((c & 1u) << 1) | (c >> 1);
                         src = rs + 4u * cs;
                     }
-                    P.pool[pool + e].x = (rq_real)o.data[src].real();
-                    P.pool[pool + e].y = (rq_real)o.data[src].imag();
+                    const rq_real re = (rq_real)o.data[src].real(), im = (rq_real)o.data[src].imag();
+                    P.pool[pool + RQ_MSLOTS * e].x = re;
+                    P.pool[pool + RQ_MSLOTS * e].y = im;
+                    if (RQ_MSLOTS == 2) { P.pool[pool + 2 * e + 1].x = -im; P.pool[pool + 2 * e + 1].y = im; }
                 }
-                pool += need;
+                pool += RQ_MSLOTS * need;
             }
         } else if (o.kind == HostOp::DIAG) {
             t.kind = RQ_OP_DIAG; t.k = (uint8_t)k;

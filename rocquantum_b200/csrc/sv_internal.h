@@ -68,7 +68,7 @@ struct rq_program {
     rq_sweep_hdr hdr;
     rq_tile_op ops[MAXOPS];
     rq_phase phases[MAXOPS];
-    rq_cplx pool[POOL_CPLX];
+    alignas(16) rq_cplx pool[POOL_CPLX];
 };
 // Kernel parameters may be up to 32764 bytes (CUDA >= 12.1); the program travels as a
 // __grid_constant__ parameter so that op headers and gate matrices are read through the constant
@@ -81,6 +81,12 @@ typedef rq_program<8, 288> rq_program_small;        //  ~3.0 KB
 typedef rq_program<160, 2496> rq_program_large;     // ~31.6 KB
 #endif
 
+// pool slots per element of a dense matrix: complex64 stores (re,im) and the precomputed pair (-im,+im) for FFMA2
+#ifdef ROCQ_PRECISION_DOUBLE
+#define RQ_MSLOTS 1
+#else
+#define RQ_MSLOTS 2
+#endif
 #define RQ_TILE_THREADS 256
 // Shared-memory bank geometry: an LDS.64 (complex64) wavefront is 16 lanes x 8 B, an LDS.128 (complex128) wavefront
 // 8 lanes x 16 B, so the lowest RQ_SWZ_BITS index bits select the bank group.  Ops whose targets include one of those
@@ -92,10 +98,15 @@ typedef rq_program<160, 2496> rq_program_large;     // ~31.6 KB
 #define RQ_SWZ_BITS 4
 #endif
 #define RQ_WINDOW_MIN_POS RQ_SWZ_BITS                // without the swizzle, register-window bits sit above the bank bits
+#ifndef RQ_WINDOW_BITS
 #ifdef ROCQ_PRECISION_DOUBLE
 #define RQ_WINDOW_BITS 3                             // 8 amplitudes = 32 registers per thread
 #else
 #define RQ_WINDOW_BITS 4                             // 16 amplitudes = 32 registers per thread
+#endif
+#endif
+#ifndef RQ_PHASED_MIN_BLOCKS
+#define RQ_PHASED_MIN_BLOCKS 2                       // resident CTAs per SM the phased variant is compiled for
 #endif
 #ifdef ROCQ_PRECISION_DOUBLE
 #define RQ_MAX_TILE_BITS 12                          // 2^12 * 16 B = 64 KB

@@ -120,6 +120,50 @@ __device__ __forceinline__ rq_cplx cmul(rq_cplx a, rq_cplx b) {
     return cget(acc);
 }
 
+// ---- register amplitudes of the window phases -------------------------------------------------------------------
+// complex64: an amplitude stays a packed 64-bit (re,im) register pair from LDS.64 to STS.64, and a complex MAC is
+//   acc += (m.re,m.re) * (v.re,v.im);  acc += (-m.im,+m.im) * (v.im,v.re)
+// i.e. two FFMA2 with no per-amplitude fix-up: the scalar broadcast and the half swap are FFMA2 operand modifiers and
+// the pair (-im,+im) is precomputed by the host in the second pool slot of every dense matrix element.
+#ifdef ROCQ_PRECISION_DOUBLE
+typedef rq_cplx ramp;
+struct mel { double re, im; };
+__device__ __forceinline__ ramp ramp_load(const rq_cplx* sm, uint32_t i) { return sm[i]; }
+__device__ __forceinline__ void ramp_store(rq_cplx* sm, uint32_t i, const ramp v) { sm[i] = v; }
+__device__ __forceinline__ mel mload(const rq_cplx* M, int e) { const rq_cplx m = M[e]; return mel{m.x, m.y}; }
+__device__ __forceinline__ ramp rzero() { return rq_cplx{0.0, 0.0}; }
+__device__ __forceinline__ void rmac(ramp& acc, const mel m, const ramp v) {
+    acc.x = fma(m.re, v.x, acc.x);
+    acc.x = fma(-m.im, v.y, acc.x);
+    acc.y = fma(m.re, v.y, acc.y);
+    acc.y = fma(m.im, v.x, acc.y);
+}
+__device__ __forceinline__ ramp rmul(const rq_cplx d, const ramp v) { return cmul(d, v); }
+#else
+typedef uint64_t ramp;
+struct mel { float re; uint64_t im2; };
+__device__ __forceinline__ ramp ramp_load(const rq_cplx* sm, uint32_t i) { return *reinterpret_cast<const uint64_t*>(sm + i); }
+__device__ __forceinline__ void ramp_store(rq_cplx* sm, uint32_t i, const ramp v) { *reinterpret_cast<uint64_t*>(sm + i) = v; }
+__device__ __forceinline__ mel mload(const rq_cplx* M, int e) {
+    const float4 q = *reinterpret_cast<const float4*>(M + 2 * e);      // (re, im, -im, +im): one 128-bit constant load
+    return mel{q.x, pack2(q.z, q.w)};
+}
+__device__ __forceinline__ ramp rzero() { return 0ull; }
+__device__ __forceinline__ uint64_t swap2(uint64_t v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return pack2(hi, lo);
+}
+__device__ __forceinline__ void rmac(ramp& acc, const mel m, const ramp v) {
+    acc = fma2(pack2(m.re, m.re), v, acc);
+    acc = fma2(m.im2, swap2(v), acc);
+}
+__device__ __forceinline__ ramp rmul(const rq_cplx d, const ramp v) {
+    ramp acc = fma2(pack2(d.x, d.x), v, 0ull);
+    return fma2(pack2(-d.y, d.y), swap2(v), acc);
+}
+#endif
+
 // deposit the bits of g around the fixed positions fix[0..nfix) (ascending), leaving zeros there
 __device__ __forceinline__ uint32_t spread(uint32_t g, const rq_tile_op& o) {
     for (uint32_t f = 0; f < o.nfix; ++f) {
@@ -154,7 +198,7 @@ __device__ __forceinline__ void op_dense(rq_cplx* sm, const rq_tile_op& o, const
             cacc acc = czero();
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                const rq_cplx m = EXT ? ldg_cplx(M + i + j * D) : M[i + j * D];   // column-major, as the API
+                const rq_cplx m = EXT ? ldg_cplx(M + i + j * D) : M[(i + j * D) * RQ_MSLOTS];   // column-major, as the API
                 cmac(acc, m, a[j]);
             }
             sm[sidx<SWZ>(base | off[i])] = cget(acc);
@@ -199,66 +243,66 @@ __device__ __forceinline__ void op_perm(rq_cplx* sm, const rq_tile_op& o, uint32
 // registers, so the tile makes ONE shared-memory round trip per phase instead of one per op.  Window bits sit at
 // local positions >= 4: for a fixed register slot the lanes of a warp read consecutive amplitudes (no bank conflicts).
 template <int V, int W>
-__device__ __forceinline__ void win_dense1(rq_cplx (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
-    const rq_cplx m00 = M[0], m10 = M[1], m01 = M[2], m11 = M[3];          // column-major
+__device__ __forceinline__ void win_dense1(ramp (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
+    const mel m00 = mload(M, 0), m10 = mload(M, 1), m01 = mload(M, 2), m11 = mload(M, 3);          // column-major
 #pragma unroll
     for (int j = 0; j < (1 << V); ++j) {
         if (j & (1 << W)) continue;
         if ((j & cm_in) != cm_in) continue;
-        const cin a0 = cprep(a[j]), a1 = cprep(a[j | (1 << W)]);
-        cacc r0 = czero(), r1 = czero();
-        cmac(r0, m00, a0); cmac(r0, m01, a1);
-        cmac(r1, m10, a0); cmac(r1, m11, a1);
-        a[j] = cget(r0);
-        a[j | (1 << W)] = cget(r1);
+        const ramp a0 = a[j], a1 = a[j | (1 << W)];
+        ramp r0 = rzero(), r1 = rzero();
+        rmac(r0, m00, a0); rmac(r0, m01, a1);
+        rmac(r1, m10, a0); rmac(r1, m11, a1);
+        a[j] = r0;
+        a[j | (1 << W)] = r1;
     }
 }
 // matrix bit 0 <-> window bit W0, matrix bit 1 <-> window bit W1 (the host orders the targets ascending)
 template <int V, int W0, int W1>
-__device__ __forceinline__ void win_dense2(rq_cplx (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
-    rq_cplx m[16];
+__device__ __forceinline__ void win_dense2(ramp (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
+    mel m[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) m[e] = M[e];
+    for (int e = 0; e < 16; ++e) m[e] = mload(M, e);
 #pragma unroll
     for (int j = 0; j < (1 << V); ++j) {
         if (j & ((1 << W0) | (1 << W1))) continue;
         if ((j & cm_in) != cm_in) continue;
-        const cin x0 = cprep(a[j]), x1 = cprep(a[j | (1 << W0)]), x2 = cprep(a[j | (1 << W1)]), x3 = cprep(a[j | (1 << W0) | (1 << W1)]);
-        rq_cplx r[4];
+        const ramp x0 = a[j], x1 = a[j | (1 << W0)], x2 = a[j | (1 << W1)], x3 = a[j | (1 << W0) | (1 << W1)];
+        ramp r[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            cacc acc = czero();
-            cmac(acc, m[i], x0); cmac(acc, m[i + 4], x1); cmac(acc, m[i + 8], x2); cmac(acc, m[i + 12], x3);
-            r[i] = cget(acc);
+            ramp acc = rzero();
+            rmac(acc, m[i], x0); rmac(acc, m[i + 4], x1); rmac(acc, m[i + 8], x2); rmac(acc, m[i + 12], x3);
+            r[i] = acc;
         }
         a[j] = r[0]; a[j | (1 << W0)] = r[1]; a[j | (1 << W1)] = r[2]; a[j | (1 << W0) | (1 << W1)] = r[3];
     }
 }
 template <int V, int W>
-__device__ __forceinline__ void win_x(rq_cplx (&a)[1 << V], uint32_t cm_in) {
+__device__ __forceinline__ void win_x(ramp (&a)[1 << V], uint32_t cm_in) {
 #pragma unroll
     for (int j = 0; j < (1 << V); ++j) {
         if (j & (1 << W)) continue;
         if ((j & cm_in) != cm_in) continue;
-        const rq_cplx t = a[j];
+        const ramp t = a[j];
         a[j] = a[j | (1 << W)];
         a[j | (1 << W)] = t;
     }
 }
 template <int V, int W0, int W1>
-__device__ __forceinline__ void win_swap(rq_cplx (&a)[1 << V], uint32_t cm_in) {
+__device__ __forceinline__ void win_swap(ramp (&a)[1 << V], uint32_t cm_in) {
 #pragma unroll
     for (int j = 0; j < (1 << V); ++j) {
         if (j & ((1 << W0) | (1 << W1))) continue;
         if ((j & cm_in) != cm_in) continue;
-        const rq_cplx t = a[j | (1 << W0)];
+        const ramp t = a[j | (1 << W0)];
         a[j | (1 << W0)] = a[j | (1 << W1)];
         a[j | (1 << W1)] = t;
     }
 }
 
 template <int V>
-__device__ __forceinline__ void win_dispatch1(rq_cplx (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense) {
+__device__ __forceinline__ void win_dispatch1(ramp (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense) {
     const uint32_t w = o.wt[0], ci = o.cm_in;
     if (dense) {
         if (w == 0) win_dense1<V, 0>(a, M, ci);
@@ -273,7 +317,7 @@ __device__ __forceinline__ void win_dispatch1(rq_cplx (&a)[1 << V], const rq_til
     }
 }
 template <int V>
-__device__ __forceinline__ void win_dispatch2(rq_cplx (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense) {
+__device__ __forceinline__ void win_dispatch2(ramp (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense) {
     const uint32_t pair = o.wt[0] * 4u + o.wt[1], ci = o.cm_in;      // wt[0] < wt[1]
 #define RQ_PAIR(A, B)                                            \
     case (A) * 4 + (B):                                          \
@@ -309,13 +353,13 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
             const uint32_t p = ph.w[b];
             base = ((base >> p) << (p + 1)) | (base & ((1u << p) - 1u));
         }
-        rq_cplx a[D];
+        ramp a[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             uint32_t idx = base;
 #pragma unroll
             for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
-            a[j] = sm[sidx<SWZ>(idx)];
+            a[j] = ramp_load(sm, sidx<SWZ>(idx));
         }
         for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
             const rq_tile_op& o = prog.ops[oi];
@@ -335,7 +379,7 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
                     uint32_t sel = selbase;
                     for (uint32_t b = 0; b < o.k; ++b)
                         if (o.t[b] != 0xFF) sel |= ((idx >> o.t[b]) & 1u) << b;
-                    a[j] = cmul(M[sel], a[j]);
+                    a[j] = rmul(M[sel], a[j]);
                 }
             } else if (o.kind == RQ_OP_DENSE) {
                 if (o.k == 1) win_dispatch1<V>(a, o, M, true);
@@ -350,7 +394,7 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
             uint32_t idx = base;
 #pragma unroll
             for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
-            sm[sidx<SWZ>(idx)] = a[j];
+            ramp_store(sm, sidx<SWZ>(idx), a[j]);
         }
     }
 }
@@ -376,7 +420,7 @@ __device__ __forceinline__ void swizzle_pass(rq_cplx* sm, uint32_t T, uint32_t t
 }
 
 template <typename Prog, int MODE, bool SWZ>
-__global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? 2 : 1)) tile_sweep_kernel(rq_cplx* __restrict__ state, const __grid_constant__ Prog prog) {
+__global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN_BLOCKS : 1)) tile_sweep_kernel(rq_cplx* __restrict__ state, const __grid_constant__ Prog prog) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     rq_cplx* sm = reinterpret_cast<rq_cplx*>(smem_raw);
     __shared__ __align__(8) uint64_t bar_storage;

@@ -66,7 +66,8 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
         if (j > i) {
             std::vector<HostOp> seg(ops.begin() + i, ops.begin() + j);
             if (fused && seg.size() > 1) seg = rq::fuse_algebraic(seg, n, h->dist.active() ? h->dist.global_mask() : 0ull);
-            const bool large = seg.size() > 1;
+            // a lone op normally travels in the small program; a 4-qubit host matrix needs the large pool
+            const bool large = seg.size() > 1 || rq::pool_need(seg[0]) > sizeof(rq_program_small::pool) / sizeof(rq_cplx);
             const rq::PlanLimits L = limits_for(h, large);
             const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(seg, n, L);
             for (const rq::SweepPlan& sp : plans) {

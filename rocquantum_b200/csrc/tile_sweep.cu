@@ -242,13 +242,13 @@ __device__ __forceinline__ void op_perm(rq_cplx* sm, const rq_tile_op& o, uint32
 // Every thread owns the D = 2^V amplitudes that differ in the V window bits; all ops of the phase act on them in
 // registers, so the tile makes ONE shared-memory round trip per phase instead of one per op.  Window bits sit at
 // local positions >= 4: for a fixed register slot the lanes of a warp read consecutive amplitudes (no bank conflicts).
-template <int V, int W>
+template <int V, int W, bool CTRL>
 __device__ __forceinline__ void win_dense1(ramp (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
     const mel m00 = mload(M, 0), m10 = mload(M, 1), m01 = mload(M, 2), m11 = mload(M, 3);          // column-major
 #pragma unroll
     for (int j = 0; j < (1 << V); ++j) {
         if (j & (1 << W)) continue;
-        if ((j & cm_in) != cm_in) continue;
+        if (CTRL && (j & cm_in) != cm_in) continue;
         const ramp a0 = a[j], a1 = a[j | (1 << W)];
         ramp r0 = rzero(), r1 = rzero();
         rmac(r0, m00, a0); rmac(r0, m01, a1);
@@ -258,7 +258,7 @@ __device__ __forceinline__ void win_dense1(ramp (&a)[1 << V], const rq_cplx* M, 
     }
 }
 // matrix bit 0 <-> window bit W0, matrix bit 1 <-> window bit W1 (the host orders the targets ascending)
-template <int V, int W0, int W1>
+template <int V, int W0, int W1, bool CTRL>
 __device__ __forceinline__ void win_dense2(ramp (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
     mel m[16];
 #pragma unroll
@@ -266,7 +266,7 @@ __device__ __forceinline__ void win_dense2(ramp (&a)[1 << V], const rq_cplx* M, 
 #pragma unroll
     for (int j = 0; j < (1 << V); ++j) {
         if (j & ((1 << W0) | (1 << W1))) continue;
-        if ((j & cm_in) != cm_in) continue;
+        if (CTRL && (j & cm_in) != cm_in) continue;
         const ramp x0 = a[j], x1 = a[j | (1 << W0)], x2 = a[j | (1 << W1)], x3 = a[j | (1 << W0) | (1 << W1)];
         ramp r[4];
 #pragma unroll
@@ -304,11 +304,16 @@ __device__ __forceinline__ void win_swap(ramp (&a)[1 << V], uint32_t cm_in) {
 template <int V>
 __device__ __forceinline__ void win_dispatch1(ramp (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense) {
     const uint32_t w = o.wt[0], ci = o.cm_in;
-    if (dense) {
-        if (w == 0) win_dense1<V, 0>(a, M, ci);
-        else if (w == 1) win_dense1<V, 1>(a, M, ci);
-        else if (w == 2) win_dense1<V, 2>(a, M, ci);
-        else if (V > 3) win_dense1<V, (V > 3 ? 3 : 0)>(a, M, ci);
+    if (dense && ci == 0) {                                  // uncontrolled: straight-line code, matrix stays in registers
+        if (w == 0) win_dense1<V, 0, false>(a, M, 0);
+        else if (w == 1) win_dense1<V, 1, false>(a, M, 0);
+        else if (w == 2) win_dense1<V, 2, false>(a, M, 0);
+        else if (V > 3) win_dense1<V, (V > 3 ? 3 : 0), false>(a, M, 0);
+    } else if (dense) {
+        if (w == 0) win_dense1<V, 0, true>(a, M, ci);
+        else if (w == 1) win_dense1<V, 1, true>(a, M, ci);
+        else if (w == 2) win_dense1<V, 2, true>(a, M, ci);
+        else if (V > 3) win_dense1<V, (V > 3 ? 3 : 0), true>(a, M, ci);
     } else {
         if (w == 0) win_x<V, 0>(a, ci);
         else if (w == 1) win_x<V, 1>(a, ci);
@@ -321,7 +326,8 @@ __device__ __forceinline__ void win_dispatch2(ramp (&a)[1 << V], const rq_tile_o
     const uint32_t pair = o.wt[0] * 4u + o.wt[1], ci = o.cm_in;      // wt[0] < wt[1]
 #define RQ_PAIR(A, B)                                            \
     case (A) * 4 + (B):                                          \
-        if (dense) win_dense2<V, A, B>(a, M, ci);                \
+        if (dense && ci == 0) win_dense2<V, A, B, false>(a, M, 0); \
+        else if (dense) win_dense2<V, A, B, true>(a, M, ci);     \
         else win_swap<V, A, B>(a, ci);                           \
         break;
     switch (pair) {

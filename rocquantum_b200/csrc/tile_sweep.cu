@@ -373,19 +373,36 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
             if ((base & o.cm_out) != o.cm_out) continue;
             const rq_cplx* M = prog.pool + o.moff;
             if (o.kind == RQ_OP_DIAG) {
-                uint32_t selbase = 0;
-                for (uint32_t b = 0; b < o.k; ++b)
-                    if (o.t[b] == 0xFF) selbase |= (uint32_t)((gbase >> o.gq[b]) & 1ull) << b;
+                const uint32_t lc = o.setmask, k = o.k;
+                if (k == 0) {                                   // pure phase on "all controls set" (Z, S, T, CZ, CP, ...)
+                    const rq_cplx ph = M[0];
 #pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    uint32_t idx = base;
+                    for (int j = 0; j < D; ++j) {
+                        uint32_t idx = base;
 #pragma unroll
-                    for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
-                    if ((idx & o.setmask) != o.setmask) continue;
-                    uint32_t sel = selbase;
-                    for (uint32_t b = 0; b < o.k; ++b)
-                        if (o.t[b] != 0xFF) sel |= ((idx >> o.t[b]) & 1u) << b;
-                    a[j] = rmul(M[sel], a[j]);
+                        for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
+                        if ((idx & lc) == lc) a[j] = rmul(ph, a[j]);
+                    }
+                } else {
+                    // table bit b comes from local position tb[b], or (non-resident) is the tile constant in selbase
+                    uint32_t selbase = 0, tb[4] = {32, 32, 32, 32};
+#pragma unroll
+                    for (uint32_t b = 0; b < 4; ++b) {
+                        if (b >= k) continue;
+                        const uint32_t p = o.t[b];
+                        if (p == 0xFF) selbase |= (uint32_t)((gbase >> o.gq[b]) & 1ull) << b; else tb[b] = p;
+                    }
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        uint32_t idx = base;
+#pragma unroll
+                        for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
+                        if ((idx & lc) != lc) continue;
+                        uint32_t sel = selbase;
+#pragma unroll
+                        for (uint32_t b = 0; b < 4; ++b) sel |= (tb[b] < 32 ? ((idx >> tb[b]) & 1u) : 0u) << b;
+                        a[j] = rmul(M[sel], a[j]);
+                    }
                 }
             } else if (o.kind == RQ_OP_DENSE) {
                 if (o.k == 1) win_dispatch1<V>(a, o, M, true);

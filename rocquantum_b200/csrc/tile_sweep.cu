@@ -360,11 +360,13 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
             base = ((base >> p) << (p + 1)) | (base & ((1u << p) - 1u));
         }
         ramp a[D];
+        uint32_t lidx[D];                                   // logical local index of every register slot
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             uint32_t idx = base;
 #pragma unroll
             for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
+            lidx[j] = idx;
             a[j] = ramp_load(sm, sidx<SWZ>(idx));
         }
         for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
@@ -377,12 +379,8 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
                 if (k == 0) {                                   // pure phase on "all controls set" (Z, S, T, CZ, CP, ...)
                     const rq_cplx ph = M[0];
 #pragma unroll
-                    for (int j = 0; j < D; ++j) {
-                        uint32_t idx = base;
-#pragma unroll
-                        for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
-                        if ((idx & lc) == lc) a[j] = rmul(ph, a[j]);
-                    }
+                    for (int j = 0; j < D; ++j)
+                        if ((lidx[j] & lc) == lc) a[j] = rmul(ph, a[j]);
                 } else {
                     // table bit b comes from local position tb[b], or (non-resident) is the tile constant in selbase
                     uint32_t selbase = 0, tb[4] = {32, 32, 32, 32};
@@ -394,9 +392,7 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
                     }
 #pragma unroll
                     for (int j = 0; j < D; ++j) {
-                        uint32_t idx = base;
-#pragma unroll
-                        for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
+                        const uint32_t idx = lidx[j];
                         if ((idx & lc) != lc) continue;
                         uint32_t sel = selbase;
 #pragma unroll
@@ -413,12 +409,7 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
             }
         }
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            uint32_t idx = base;
-#pragma unroll
-            for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
-            ramp_store(sm, sidx<SWZ>(idx), a[j]);
-        }
+        for (int j = 0; j < D; ++j) ramp_store(sm, sidx<SWZ>(lidx[j]), a[j]);
     }
 }
 

@@ -174,6 +174,14 @@ typedef struct {
 rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits,
                                 const rocsvxGateOp* ops, size_t numOps);
 
+/* Tensor-core path (complex64 library only): apply one dense 6-qubit matrix (HOST, column-major 64x64, interleaved
+ * (re,im) doubles, index bit b <-> qubits[b]) to the whole state in one HBM pass with tcgen05 MMAs (bf16x3 split,
+ * fp32 accumulation in TMEM).  Needs numQubits >= 13.  rocsvxApplyCircuit uses the same kernel for the 6-qubit
+ * blocks its planner forms when rocsvxSetTensorCoreBlocks is on. */
+rocqStatus_t rocsvxApplyBlock6(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, const unsigned* qubits,
+                               const double* matrix);
+rocqStatus_t rocsvxSetTensorCoreBlocks(rocsvHandle_t handle, int enabled);
+
 /* ||psi||^2 of batch member 0 (one read sweep). */
 rocqStatus_t rocsvxGetNorm(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, double* result);
 

@@ -8,6 +8,7 @@
 // fails with ROCQ_STATUS_HIP_ERROR.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -55,6 +56,89 @@ rq::PlanLimits limits_for(const H* h, bool large) {
     return L;
 }
 
+rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsigned>& blk, const std::vector<cd>& U);
+rocqStatus_t launch_plan(H* h, rq_cplx* state, unsigned n, const rq::SweepPlan& sp, const std::vector<HostOp>& seg, bool large);
+
+rocqStatus_t launch_plan(H* h, rq_cplx* state, unsigned n, const rq::SweepPlan& sp, const std::vector<HostOp>& seg, bool large) {
+    int e;
+    if (large) {
+        static thread_local rq_program_large P;
+        if (!rq::build_program(P, sp, seg, n, h->batchSize, h->dist.high_base())) return ROCQ_STATUS_FAILURE;
+        e = rq_launch_sweep_large(state, &P, h->stream);
+        h->stats.h2dBytes += sizeof(P);
+    } else {
+        static thread_local rq_program_small P;
+        if (!rq::build_program(P, sp, seg, n, h->batchSize, h->dist.high_base())) return ROCQ_STATUS_FAILURE;
+        e = rq_launch_sweep_small(state, &P, h->stream);
+        h->stats.h2dBytes += sizeof(P);
+    }
+    RQ_CUDA(e, "tile sweep launch");
+    h->stats.kernelLaunches++;
+    h->stats.sweeps++;
+    h->stats.opsExecuted += sp.ops.size();
+    return ROCQ_STATUS_SUCCESS;
+}
+
+// Mixed execution of one fused op list: wherever >= RQ_BLOCK_MIN_COST worth of gates can be folded into six qubits
+// (positions >= 5, so that tile columns stay coalesced) they become ONE 64x64 unitary applied by the tensor-core block
+// sweep; everything else goes through ordinary tile sweeps.  Same in-order / blocked-qubit rule as plan_sweeps.
+rocqStatus_t run_ops_with_blocks(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>& seg) {
+    const double min_cost = h->blockMinCost;
+    std::vector<char> done(seg.size(), 0);
+    size_t remaining = seg.size();
+    const rq::PlanLimits L = limits_for(h, true);
+    while (remaining > 0) {
+        // ---- candidate block ----
+        uint64_t B = 0, blockedAny = 0, blockedND = 0;
+        std::vector<int> pick;
+        double cost = 0.0;
+        for (size_t i = 0; i < seg.size(); ++i) {
+            if (done[i]) continue;
+            const HostOp& o = seg[i];
+            const uint64_t Q = o.qubits(), nd = o.nondiag(), dg = Q & ~nd;
+            const bool free_ = !((nd & (blockedAny | blockedND)) || (dg & blockedAny));
+            if (free_ && !o.ext && !(Q & 31ull) && __builtin_popcountll(B | Q) <= RQ_BLOCK_QUBITS) {
+                B |= Q;
+                pick.push_back((int)i);
+                cost += o.cost();
+            } else {
+                blockedAny |= nd;
+                blockedND |= dg;
+            }
+        }
+        if (cost >= min_cost && !pick.empty()) {
+            for (unsigned p = n; p-- > 5 && __builtin_popcountll(B) < RQ_BLOCK_QUBITS;) if (!((B >> p) & 1ull)) B |= 1ull << p;
+            std::vector<unsigned> blk;
+            for (unsigned p = 0; p < n; ++p) if ((B >> p) & 1ull) blk.push_back(p);
+            if (blk.size() == RQ_BLOCK_QUBITS) {
+                std::vector<cd> U(64 * 64, cd(0.0, 0.0)), colv(64);
+                for (unsigned c = 0; c < 64; ++c) U[c + 64u * c] = cd(1.0, 0.0);
+                for (int idx : pick)                                   // U <- op * U, column by column
+                    for (unsigned c = 0; c < 64; ++c) {
+                        std::copy(U.begin() + 64u * c, U.begin() + 64u * (c + 1), colv.begin());
+                        rq::apply_small(seg[idx], blk, colv);
+                        std::copy(colv.begin(), colv.end(), U.begin() + 64u * c);
+                    }
+                const rocqStatus_t s = run_block(h, state, n, blk, U);
+                if (s != ROCQ_STATUS_SUCCESS) return s;
+                for (int idx : pick) { done[idx] = 1; --remaining; }
+                h->stats.opsExecuted += pick.size();
+                continue;
+            }
+        }
+        // ---- one ordinary sweep over what is left ----
+        std::vector<HostOp> rest;
+        std::vector<int> back;
+        for (size_t i = 0; i < seg.size(); ++i) if (!done[i]) { rest.push_back(seg[i]); back.push_back((int)i); }
+        const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(rest, n, L);
+        if (plans.empty()) return ROCQ_STATUS_FAILURE;
+        const rocqStatus_t s = launch_plan(h, state, n, plans[0], rest, true);
+        if (s != ROCQ_STATUS_SUCCESS) return s;
+        for (int k : plans[0].ops) { done[back[k]] = 1; --remaining; }
+    }
+    return ROCQ_STATUS_SUCCESS;
+}
+
 // run ops (already validated) on `state`: dense/diag ops wider than the tile kernel handles go through
 // the gather kernel, everything else through planned sweeps.
 rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>& ops, bool fused) {
@@ -66,27 +150,19 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
         if (j > i) {
             std::vector<HostOp> seg(ops.begin() + i, ops.begin() + j);
             if (fused && seg.size() > 1) seg = rq::fuse_algebraic(seg, n, h->dist.active() ? h->dist.global_mask() : 0ull);
+            if (fused && h->tcBlocks && sizeof(rq_real) == 4 && n >= 13 && !h->dist.active() && seg.size() > 1) {
+                const rocqStatus_t s = run_ops_with_blocks(h, state, n, seg);
+                if (s != ROCQ_STATUS_SUCCESS) return s;
+                i = j;
+                continue;
+            }
             // a lone op normally travels in the small program; a 4-qubit host matrix needs the large pool
             const bool large = seg.size() > 1 || rq::pool_need(seg[0]) > sizeof(rq_program_small::pool) / sizeof(rq_cplx);
             const rq::PlanLimits L = limits_for(h, large);
             const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(seg, n, L);
             for (const rq::SweepPlan& sp : plans) {
-                int e;
-                if (large) {
-                    static thread_local rq_program_large P;
-                    if (!rq::build_program(P, sp, seg, n, h->batchSize, h->dist.high_base())) return ROCQ_STATUS_FAILURE;
-                    e = rq_launch_sweep_large(state, &P, h->stream);
-                    h->stats.h2dBytes += sizeof(P);
-                } else {
-                    static thread_local rq_program_small P;
-                    if (!rq::build_program(P, sp, seg, n, h->batchSize, h->dist.high_base())) return ROCQ_STATUS_FAILURE;
-                    e = rq_launch_sweep_small(state, &P, h->stream);
-                    h->stats.h2dBytes += sizeof(P);
-                }
-                RQ_CUDA(e, "tile sweep launch");
-                h->stats.kernelLaunches++;
-                h->stats.sweeps++;
-                h->stats.opsExecuted += sp.ops.size();
+                const rocqStatus_t s = launch_plan(h, state, n, sp, seg, large);
+                if (s != ROCQ_STATUS_SUCCESS) return s;
             }
             i = j;
         }
@@ -118,6 +194,77 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
             ++i;
         }
     }
+    return ROCQ_STATUS_SUCCESS;
+}
+
+// ---- tensor-core 6-qubit blocks (block_sweep.cu) -------------------------------------------------------------------
+inline uint16_t f2bf(float f) {                      // round to nearest even
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+    return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+inline float bf2f(uint16_t h) {
+    const uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// U: 64x64 complex column-major, index bit b <-> b-th smallest block position.  Writes the three bf16 terms of the real
+// 128x128 matrix A' = [[Re U, -Im U], [Im U, Re U]] in the K-major core-matrix order the kernel's descriptors describe.
+void build_block_terms(const std::vector<cd>& U, std::vector<uint16_t>& out) {
+    out.assign(3 * (RQ_BLOCK_TERM_BYTES / 2), 0);
+    for (unsigned mo = 0; mo < 128; ++mo)
+        for (unsigned k = 0; k < 128; ++k) {
+            const cd u = U[(mo & 63u) + 64u * (k & 63u)];
+            float v;
+            if (mo < 64) v = k < 64 ? (float)u.real() : -(float)u.imag();
+            else v = k < 64 ? (float)u.imag() : (float)u.real();
+            const uint16_t hi = f2bf(v);
+            const float r = v - bf2f(hi);
+            const uint16_t mid = f2bf(r);
+            const uint16_t lo = f2bf(r - bf2f(mid));
+            const size_t off = ((mo & 7u) * 16u + (k >> 3) * 128u + (mo >> 3) * 2048u + (k & 7u) * 2u) / 2u;
+            out[off] = hi;
+            out[RQ_BLOCK_TERM_BYTES / 2 + off] = mid;
+            out[2 * (RQ_BLOCK_TERM_BYTES / 2) + off] = lo;
+        }
+}
+
+// launch one block sweep: block positions (ascending), matrix U over them
+rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsigned>& blk, const std::vector<cd>& U) {
+    if (sizeof(rq_real) != 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    if (n < 13 || blk.size() != RQ_BLOCK_QUBITS) return ROCQ_STATUS_INVALID_VALUE;
+    rq_block_params P{};
+    P.n = n; P.T = 13; P.ntiles = (uint64_t)h->batchSize << (n - 13);
+    uint64_t bm = 0;
+    for (unsigned b = 0; b < 6; ++b) { P.blk[b] = (uint8_t)blk[b]; bm |= 1ull << blk[b]; }
+    unsigned nc = 0;
+    uint64_t rm = bm;
+    for (unsigned p = 0; p < n && nc < RQ_BLOCK_COLBITS; ++p) if (!((bm >> p) & 1ull)) { P.col[nc++] = (uint8_t)p; rm |= 1ull << p; }
+    unsigned nr = 0;
+    for (unsigned p = 0; p < n; ++p) if ((rm >> p) & 1ull) P.res[nr++] = (uint8_t)p;
+    // unitary?  (then every tile column keeps its norm, which the kernel restores exactly)
+    double dev = 0.0;
+    for (unsigned a = 0; a < 64; ++a)
+        for (unsigned b = a; b < 64; ++b) {
+            cd s(0.0, 0.0);
+            for (unsigned r = 0; r < 64; ++r) s += std::conj(U[r + 64u * a]) * U[r + 64u * b];
+            dev = std::max(dev, std::abs(s - (a == b ? cd(1.0, 0.0) : cd(0.0, 0.0))));
+        }
+    P.renorm = dev < 1e-9 ? 1u : 0u;
+    std::vector<uint16_t> terms;
+    build_block_terms(U, terms);
+    void* d_terms = nullptr;
+    RQ_CUDA(cudaMallocAsync(&d_terms, 3 * RQ_BLOCK_TERM_BYTES, h->stream), "block terms alloc");
+    // pageable source: cudaMemcpyAsync stages it before returning, so `terms` may go out of scope
+    RQ_CUDA(cudaMemcpyAsync(d_terms, terms.data(), 3 * RQ_BLOCK_TERM_BYTES, cudaMemcpyHostToDevice, h->stream), "block terms upload");
+    RQ_CUDA(rq_launch_block_sweep(state, &P, d_terms, h->stream), "block sweep launch");
+    RQ_CUDA(cudaFreeAsync(d_terms, h->stream), "block terms free");
+    h->stats.kernelLaunches++;
+    h->stats.sweeps++;
+    h->stats.h2dBytes += 3 * RQ_BLOCK_TERM_BYTES;
     return ROCQ_STATUS_SUCCESS;
 }
 
@@ -241,7 +388,7 @@ rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
         return ROCQ_STATUS_HIP_ERROR;
     }
     const unsigned nb = rq_reduce_blocks();
-    if (rq_sweep_configure() != 0 || cudaMalloc(&h->d_partials, (nb + 8) * sizeof(double)) != cudaSuccess ||
+    if (rq_sweep_configure() != 0 || rq_block_configure() != 0 || cudaMalloc(&h->d_partials, (nb + 8) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_upartials, (4 * nb + 4) * sizeof(uint64_t)) != cudaSuccess ||
         cudaHostAlloc(&h->h_scratch, 4096, cudaHostAllocDefault) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
@@ -252,6 +399,8 @@ rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
     }
     if (const char* e = getenv("ROCQ_FUSION")) h->fusion = atoi(e) != 0;
     if (const char* e = getenv("ROCQ_TILE_BITS")) { const int t = atoi(e); if (t >= 6 && t <= RQ_MAX_TILE_BITS) h->tileBits = (unsigned)t; }
+    if (const char* e = getenv("ROCQ_TC")) h->tcBlocks = atoi(e) != 0 && sizeof(rq_real) == 4;
+    if (const char* e = getenv("ROCQ_TC_MIN_COST")) { const double b = atof(e); if (b > 0) h->blockMinCost = b; }
     if (const char* e = getenv("ROCQ_SWEEP_BUDGET")) { const double b = atof(e); if (b > 0) h->budget = b; }
     *handle = h;
     return ROCQ_STATUS_SUCCESS;
@@ -538,6 +687,39 @@ rocqStatus_t rocsvxGetExpectationPauliBatch(rocsvHandle_t h, rocComplex* d, unsi
     }
     return ROCQ_STATUS_SUCCESS;
 }
+rocqStatus_t rocsvxSetTensorCoreBlocks(rocsvHandle_t h, int enabled) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (enabled && sizeof(rq_real) != 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    h->tcBlocks = enabled != 0;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t rocsvxApplyBlock6(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* qubits, const double* matrix) {
+    if (!h || !qubits || !matrix) return ROCQ_STATUS_INVALID_VALUE;
+    rq_cplx* state = resolve(h, d);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    if (sizeof(rq_real) != 4 || h->dist.active()) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    if (n < 13) return ROCQ_STATUS_INVALID_VALUE;
+    uint64_t seen = 0;
+    for (unsigned b = 0; b < 6; ++b) {
+        if (qubits[b] >= n || ((seen >> qubits[b]) & 1ull)) return ROCQ_STATUS_INVALID_VALUE;
+        seen |= 1ull << qubits[b];
+    }
+    const rocqStatus_t s = flush(h);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    // reorder the matrix so that index bit b <-> b-th smallest qubit
+    std::vector<unsigned> blk(qubits, qubits + 6);
+    std::sort(blk.begin(), blk.end());
+    unsigned bitmap[6];                                    // API bit b -> sorted bit
+    for (unsigned b = 0; b < 6; ++b) bitmap[b] = (unsigned)(std::find(blk.begin(), blk.end(), qubits[b]) - blk.begin());
+    auto remap = [&](unsigned i) { unsigned o = 0; for (unsigned b = 0; b < 6; ++b) if ((i >> b) & 1u) o |= 1u << bitmap[b]; return o; };
+    std::vector<cd> U(64 * 64);
+    for (unsigned c = 0; c < 64; ++c)
+        for (unsigned r = 0; r < 64; ++r) U[remap(r) + 64u * remap(c)] = cd(matrix[2 * (r + 64u * c)], matrix[2 * (r + 64u * c) + 1]);
+    h->stats.gatesSubmitted++;
+    return run_block(h, state, n, blk, U);
+}
+
 rocqStatus_t rocsvxGetNorm(rocsvHandle_t h, rocComplex* d, unsigned n, double* r) { return expect_string(h, d, n, "", nullptr, 0, r); }
 
 // ---- measurement (hipStateVec.h:172-177; algorithm measurement_kernels.hip:37-77, MULTI_GPU_GUIDE.md:61-78) ----

@@ -31,6 +31,8 @@ struct rocsvInternalHandle {
     size_t pinnedSize = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     // tuning
+    bool tcBlocks = false;              // form 6-qubit tensor-core blocks in rocsvxApplyCircuit / fused flushes
+    double blockMinCost = 54.0;         // fold >= this much HostOp::cost() (3 dense 2q gates) or stay on the CUDA cores
     unsigned tileBits = RQ_MAX_TILE_BITS;
     double budget = 1e30;
     rocsvxStats stats{};

@@ -116,6 +116,22 @@ typedef rq_program<160, 2496> rq_program_large;     // ~31.6 KB
 #define RQ_MIN_ROW_BITS 5                            // rows >= 256 B
 #endif
 
+// ---- tensor-core block sweep (block_sweep.cu, complex64 only) ------------------------------------------------------
+// One 6-qubit dense block applied to the whole state: tile = 64 block values x 128 columns (13 resident positions).
+struct rq_block_params {
+    uint32_t n;                     // qubits per state vector
+    uint32_t T;                     // 13
+    uint32_t renorm;                // 1: the block is unitary -> restore every column's norm in the epilogue
+    uint32_t pad;
+    uint64_t ntiles;                // batch * 2^(n-13)
+    uint8_t res[16];                // ascending resident positions (block + column bits)
+    uint8_t blk[8];                 // 6 block positions, ascending: bit b of the block value <-> blk[b]
+    uint8_t col[8];                 // 7 column positions, ascending
+};
+#define RQ_BLOCK_QUBITS 6
+#define RQ_BLOCK_COLBITS 7
+#define RQ_BLOCK_TERM_BYTES 32768    // one bf16 term of the real 128x128 operand, in UMMA K-major core-matrix order
+
 // ---- thin C ABI to the launchers (all return a cudaError_t as int; stream is a cudaStream_t) --------
 extern "C" {
 int rq_launch_sweep_small(rq_cplx* state, const rq_program_small* prog, void* stream);
@@ -141,4 +157,7 @@ int rq_launch_sample(const rq_cplx* state, unsigned n, unsigned chunk_bits, cons
                      uint64_t win_hi, uint64_t win_lo, uint64_t seed, uint64_t call, unsigned shots,
                      uint64_t shot_offset, uint64_t* d_indices, void* stream);
 unsigned rq_reduce_blocks(void);
+int rq_block_configure(void);
+// d_uterms: 3 * RQ_BLOCK_TERM_BYTES device bytes (hi, mid, lo bf16 terms of the real 128x128 block matrix)
+int rq_launch_block_sweep(rq_cplx* state, const rq_block_params* P, const void* d_uterms, void* stream);
 }

@@ -140,6 +140,16 @@ class StateVector:
         self.sync()
         self._ck("rocsvApplyFusedSingleQubitMatrix", st)
 
+    def apply_block6(self, qubits, M):
+        """Dense 6-qubit matrix through the tensor-core block sweep (complex64 only).  M[i][j]: row i, column j."""
+        Mc = np.ascontiguousarray(np.asarray(M, dtype=np.complex128).reshape(64, 64).T).reshape(-1)   # column-major
+        buf = np.empty(2 * Mc.size, dtype=np.float64)
+        buf[0::2], buf[1::2] = Mc.real, Mc.imag
+        self._ck("rocsvxApplyBlock6", self.lib.rocsvxApplyBlock6(self.h, self.d, self.n, capi.uarr(qubits), buf.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def set_tensor_core_blocks(self, on: bool):
+        self._ck("rocsvxSetTensorCoreBlocks", self.lib.rocsvxSetTensorCoreBlocks(self.h, int(on)))
+
     def swap_index_bits(self, a, b):
         self._ck("rocsvSwapIndexBits", self.lib.rocsvSwapIndexBits(self.h, a, b))
 

@@ -269,3 +269,32 @@ def test_full_size_properties_30_qubits():
     s = g.sample(list(range(n)), 256)
     assert set(np.unique(s)) <= {0, (1 << n) - 1} and 0 < (s == 0).sum() < 256
     assert abs(g.expect_zprod([0, 29]) - 1) < 1e-5 and abs(g.expect_pauli("X" * n, list(range(n))) - 1) < 1e-4
+
+
+# ---- tensor-core 6-qubit blocks (complex64 only) ------------------------------------------------------------------
+def test_block6_tensor_core_matches_oracle():
+    rng = np.random.default_rng(11)
+    for n, qs in ((13, [5, 6, 7, 8, 9, 10]), (15, [14, 2, 9, 0, 6, 11]), (19, [13, 14, 15, 16, 17, 18])):
+        U = workloads.haar_unitary(rng, 64)
+        o, g = _pair(n, "c64", seed=n)
+        o.apply_matrix(qs, U); g.apply_block6(qs, U)
+        assert util.rel_err(g.state(), o.state) < 2e-6            # bf16x3 split + fp32 accumulation in TMEM
+    # a non-unitary matrix must not be renormalised
+    o, g = _pair(14, "c64", seed=2)
+    M = rng.standard_normal((64, 64)) + 1j * rng.standard_normal((64, 64))
+    o.apply_matrix([5, 7, 8, 10, 12, 13], M); g.apply_block6([5, 7, 8, 10, 12, 13], M)
+    assert util.rel_err(g.state(), o.state) < 5e-6
+    assert g.lib.rocsvxApplyBlock6(g.h, g.d, 14, capi.uarr([5, 5, 8, 10, 12, 13]), (C.c_double * 8192)()) == capi.INVALID_VALUE
+    d = StateVector(14, "c128")
+    assert d.lib.rocsvxSetTensorCoreBlocks(d.h, 1) == capi.NOT_IMPLEMENTED
+
+
+@pytest.mark.parametrize("n", [14, 22])
+def test_circuit_with_tensor_core_blocks(n):
+    gates = workloads.c2_random_unitary(n, 10, seed=30) + workloads.c1_ghz_random_layers(n, 4, seed=20)[n:]
+    o = so.Oracle(n, "c64"); util.run_on_oracle(o, gates)
+    g = StateVector(n, "c64"); g.set_tensor_core_blocks(True); g.apply_circuit(gates)
+    assert util.rel_err(g.state(), o.state) < TOL["c64"]
+    plain = StateVector(n, "c64"); plain.apply_circuit(gates)
+    assert g.stats().sweeps != plain.stats().sweeps                  # blocks were actually formed
+    assert abs(g.norm2() - 1) < 2e-5

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
         // ---- convert: 8 block values at a time -> one 16-byte row chunk per (term, re|im) ----
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+            if (P.pad & 2u) break;
             float h[16], m[16], l[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -203,7 +204,8 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
         __syncthreads();
 
         // ---- 48 MMAs: six term products x eight K steps, one issuing thread ----
-        if (tid == 0) {
+        const uint32_t dbg = P.pad;        // timing experiments only (ROCQ_BLOCK_DEBUG): 1 = no MMA, 2 = no convert, 4 = no stores
+        if (tid == 0 && !(dbg & 1u)) {
             tc_fence_after();
             const uint32_t xa = smem_u32(smem + SMEM_X), ua = smem_u32(smem + SMEM_U);
             // The tensor core truncates when it adds a K=16 partial sum to the fp32 accumulator, a bias that grows with the
@@ -230,8 +232,10 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             for (int j = 0; j < 16; ++j) raw[j] = g[boff[16 * qt + j]];
         }
 
-        mbar_wait(smem_u32(&bar_mma), phase);
-        phase ^= 1;
+        if (!(dbg & 1u)) {
+            mbar_wait(smem_u32(&bar_mma), phase);
+            phase ^= 1;
+        }
         tc_fence_after();
 
         // ---- epilogue: TMEM lane = column; this thread's 16 block values: re at column t, im at column 64 + t ----
@@ -262,8 +266,10 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             const float sout = (cnorm[512 + ncol] + cnorm[640 + ncol]) + (cnorm[768 + ncol] + cnorm[896 + ncol]);
             if (sout > 0.f && sin > 0.f) scale = sqrtf(sin / sout);
         }
+        if (!(dbg & 4u)) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) gt[boff[16 * qt + j]] = make_float2(out[j].x * scale, out[j].y * scale);
+            for (int j = 0; j < 16; ++j) gt[boff[16 * qt + j]] = make_float2(out[j].x * scale, out[j].y * scale);
+        }
         tc_fence_before();
         __syncthreads();            // D and the X terms are free again
     }

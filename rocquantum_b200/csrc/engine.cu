@@ -254,6 +254,7 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
             dev = std::max(dev, std::abs(s - (a == b ? cd(1.0, 0.0) : cd(0.0, 0.0))));
         }
     P.renorm = dev < 1e-9 ? 1u : 0u;
+    if (const char* dbgenv = getenv("ROCQ_BLOCK_DEBUG")) { P.pad = (uint32_t)atoi(dbgenv); if (P.pad & 8u) P.renorm = 0; }
     std::vector<uint16_t> terms;
     build_block_terms(U, terms);
     void* d_terms = nullptr;

@@ -1,0 +1,13 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from rocquantum_b200 import workloads
+from rocquantum_b200.statevec import StateVector
+n = 30
+g = StateVector(n, "c64"); g.gate("h", 0)
+U = workloads.haar_unitary(np.random.default_rng(1), 64)
+qs = [10, 11, 12, 13, 14, 15]
+g.apply_block6(qs, U); g.sync()
+g.timer_start()
+for _ in range(5): g.apply_block6(qs, U)
+print(os.environ.get("ROCQ_BLOCK_DEBUG", "0"), "ms per sweep", g.timer_stop() / 5, flush=True)

@@ -1,556 +1,28 @@
-// rocquantum_b200/csrc/tile_sweep.cu  --  the fused gate sweep, hand-written for sm_100a.
-//
-// One launch = one pass over HBM: 2 * 2^n * sizeof(amp) algorithmic bytes, however many gates the
-// program carries.  It replaces, for every gate of the reference's path, the one-kernel-per-gate
-// grid-stride loops of /root/reference/rocquantum/src/hipStateVec/{single,two,multi}_qubit_kernels.hip
-// (launched from hipStateVec.cpp:100-186, 431-687): same arithmetic per amplitude pair
-// (single_qubit_kernels.hip:64-67), but
-//   * a tile of 2^T amplitudes (T resident qubit positions) is staged in shared memory by the TMA
-//     engine: one cp.async.bulk (SASS UBLKCP) per contiguous row, completion on an mbarrier, so no
-//     thread spends registers or issue slots on the copy and several tiles per SM are in flight;
-//   * every op of the program is applied to the resident tile (dense 1..4-qubit matrices with
-//     controls, diagonal phases, pair permutations), with gate matrices read warp-uniformly from the
-//     constant bank of the __grid_constant__ program;
-//   * controls and diagonal factors on NON-resident qubits are resolved per tile from the tile's base
-//     index, so they never force a qubit to be resident;
-//   * the tile goes back with bulk async stores (smem -> global).
-#include <cuda_runtime.h>
-#include <stdint.h>
-
+// tile_sweep.cu -- dispatch of a sweep program to the instantiation that matches its size and tile layout.
+// The kernel itself is in tile_sweep.cuh; it is compiled in four translation units so that the build parallelises.
 #include "sv_internal.h"
 
-namespace {
+extern "C" {
+int rq_sweep_configure_small_lin(void);
+int rq_sweep_configure_small_swz(void);
+int rq_sweep_configure_large_lin(void);
+int rq_sweep_configure_large_swz(void);
+int rq_launch_sweep_small_lin(rq_cplx*, const rq_program_small*, void*);
+int rq_launch_sweep_small_swz(rq_cplx*, const rq_program_small*, void*);
+int rq_launch_sweep_large_lin(rq_cplx*, const rq_program_large*, void*);
+int rq_launch_sweep_large_swz(rq_cplx*, const rq_program_large*, void*);
 
-constexpr int NT = RQ_TILE_THREADS;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <bool SWZ>
-__device__ __forceinline__ uint32_t sidx(uint32_t idx) {
-    return SWZ ? (idx ^ ((idx >> RQ_SWZ_BITS) & ((1u << RQ_SWZ_BITS) - 1u))) : idx;
+int rq_sweep_configure(void) {
+    int e = rq_sweep_configure_small_lin();
+    if (!e) e = rq_sweep_configure_small_swz();
+    if (!e) e = rq_sweep_configure_large_lin();
+    if (!e) e = rq_sweep_configure_large_swz();
+    return e;
 }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+int rq_launch_sweep_small(rq_cplx* state, const rq_program_small* prog, void* stream) {
+    return prog->hdr.swz ? rq_launch_sweep_small_swz(state, prog, stream) : rq_launch_sweep_small_lin(state, prog, stream);
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+int rq_launch_sweep_large(rq_cplx* state, const rq_program_large* prog, void* stream) {
+    return prog->hdr.swz ? rq_launch_sweep_large_swz(state, prog, stream) : rq_launch_sweep_large_lin(state, prog, stream);
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(bar), "r"(phase) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit_wait_read() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ rq_cplx ldg_cplx(const rq_cplx* p) {
-#ifdef ROCQ_PRECISION_DOUBLE
-    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
-#else
-    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
-#endif
-    rq_cplx r;
-    r.x = v.x;
-    r.y = v.y;
-    return r;
-}
-// ---- complex multiply-accumulate -----------------------------------------------------------------------
-// complex64: Blackwell's packed fp32 FMA (PTX fma.rn.f32x2, SASS FFMA2) does one complex MAC in TWO instructions:
-//   acc(re,im) += m.re * (v.re, v.im);   acc(re,im) += m.im * (-v.im, v.re)
-// (scalar-broadcast and half-swap are operand modifiers of FFMA2), instead of the 6 (FMUL+FFMA+FADD per component)
-// that `acc += m*v` compiles to without reassociation.  complex128: explicit 4-FMA chains (DFMA).
-#ifdef ROCQ_PRECISION_DOUBLE
-struct cin { double x, y; };
-struct cacc { double x, y; };
-__device__ __forceinline__ cin cprep(const rq_cplx a) { return cin{a.x, a.y}; }
-__device__ __forceinline__ cacc czero() { return cacc{0.0, 0.0}; }
-__device__ __forceinline__ void cmac(cacc& acc, const rq_cplx m, const cin v) {
-    acc.x = fma(m.x, v.x, acc.x);
-    acc.x = fma(-m.y, v.y, acc.x);
-    acc.y = fma(m.x, v.y, acc.y);
-    acc.y = fma(m.y, v.x, acc.y);
-}
-__device__ __forceinline__ rq_cplx cget(const cacc a) { return rq_cplx{a.x, a.y}; }
-#else
-struct cin { uint64_t p, q; };            // (re, im) and (-im, re)
-typedef uint64_t cacc;
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ cin cprep(const rq_cplx a) { return cin{pack2(a.x, a.y), pack2(-a.y, a.x)}; }
-__device__ __forceinline__ cacc czero() { return 0ull; }
-__device__ __forceinline__ void cmac(cacc& acc, const rq_cplx m, const cin v) {
-    acc = fma2(pack2(m.x, m.x), v.p, acc);
-    acc = fma2(pack2(m.y, m.y), v.q, acc);
-}
-__device__ __forceinline__ rq_cplx cget(const cacc a) {
-    rq_cplx r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a));
-    return r;
-}
-#endif
-__device__ __forceinline__ rq_cplx cmul(rq_cplx a, rq_cplx b) {
-    cacc acc = czero();
-    cmac(acc, a, cprep(b));
-    return cget(acc);
-}
-
-// ---- register amplitudes of the window phases -------------------------------------------------------------------
-// complex64: an amplitude stays a packed 64-bit (re,im) register pair from LDS.64 to STS.64, and a complex MAC is
-//   acc += (m.re,m.re) * (v.re,v.im);  acc += (-m.im,+m.im) * (v.im,v.re)
-// i.e. two FFMA2 with no per-amplitude fix-up: the scalar broadcast and the half swap are FFMA2 operand modifiers and
-// the pair (-im,+im) is precomputed by the host in the second pool slot of every dense matrix element.
-#ifdef ROCQ_PRECISION_DOUBLE
-typedef rq_cplx ramp;
-struct mel { double re, im; };
-__device__ __forceinline__ ramp ramp_load(const rq_cplx* sm, uint32_t i) { return sm[i]; }
-__device__ __forceinline__ void ramp_store(rq_cplx* sm, uint32_t i, const ramp v) { sm[i] = v; }
-__device__ __forceinline__ mel mload(const rq_cplx* M, int e) { const rq_cplx m = M[e]; return mel{m.x, m.y}; }
-__device__ __forceinline__ ramp rzero() { return rq_cplx{0.0, 0.0}; }
-__device__ __forceinline__ void rmac(ramp& acc, const mel m, const ramp v) {
-    acc.x = fma(m.re, v.x, acc.x);
-    acc.x = fma(-m.im, v.y, acc.x);
-    acc.y = fma(m.re, v.y, acc.y);
-    acc.y = fma(m.im, v.x, acc.y);
-}
-__device__ __forceinline__ ramp rmul(const rq_cplx d, const ramp v) { return cmul(d, v); }
-#else
-typedef uint64_t ramp;
-struct mel { float re; uint64_t im2; };
-__device__ __forceinline__ ramp ramp_load(const rq_cplx* sm, uint32_t i) { return *reinterpret_cast<const uint64_t*>(sm + i); }
-__device__ __forceinline__ void ramp_store(rq_cplx* sm, uint32_t i, const ramp v) { *reinterpret_cast<uint64_t*>(sm + i) = v; }
-__device__ __forceinline__ mel mload(const rq_cplx* M, int e) {
-    const float4 q = *reinterpret_cast<const float4*>(M + 2 * e);      // (re, im, -im, +im): one 128-bit constant load
-    return mel{q.x, pack2(q.z, q.w)};
-}
-__device__ __forceinline__ ramp rzero() { return 0ull; }
-__device__ __forceinline__ uint64_t swap2(uint64_t v) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    return pack2(hi, lo);
-}
-__device__ __forceinline__ void rmac(ramp& acc, const mel m, const ramp v) {
-    acc = fma2(pack2(m.re, m.re), v, acc);
-    acc = fma2(m.im2, swap2(v), acc);
-}
-__device__ __forceinline__ ramp rmul(const rq_cplx d, const ramp v) {
-    ramp acc = fma2(pack2(d.x, d.x), v, 0ull);
-    return fma2(pack2(-d.y, d.y), swap2(v), acc);
-}
-#endif
-
-// deposit the bits of g around the fixed positions fix[0..nfix) (ascending), leaving zeros there
-__device__ __forceinline__ uint32_t spread(uint32_t g, const rq_tile_op& o) {
-    for (uint32_t f = 0; f < o.nfix; ++f) {
-        const uint32_t p = o.fix[f];
-        g = ((g >> p) << (p + 1)) | (g & ((1u << p) - 1u));
-    }
-    return g;
-}
-
-template <int K, bool EXT, bool SWZ>
-__device__ __forceinline__ void op_dense(rq_cplx* sm, const rq_tile_op& o, const rq_cplx* pool, const rq_cplx* ext,
-                                         uint32_t T, uint32_t tid) {
-    constexpr int D = 1 << K;
-    uint32_t off[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        uint32_t v = 0;
-#pragma unroll
-        for (int b = 0; b < K; ++b)
-            if ((j >> b) & 1) v |= 1u << o.t[b];
-        off[j] = v;
-    }
-    const uint32_t ngroups = 1u << (T - o.nfix);
-    const rq_cplx* M = EXT ? ext : (pool + o.moff);
-    for (uint32_t g = tid; g < ngroups; g += NT) {
-        const uint32_t base = spread(g, o) | o.setmask;
-        cin a[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) a[j] = cprep(sm[sidx<SWZ>(base | off[j])]);
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            cacc acc = czero();
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                const rq_cplx m = EXT ? ldg_cplx(M + i + j * D) : M[(i + j * D) * RQ_MSLOTS];   // column-major, as the API
-                cmac(acc, m, a[j]);
-            }
-            sm[sidx<SWZ>(base | off[i])] = cget(acc);
-        }
-    }
-}
-
-// diagonal: amp[idx] *= d[sel], sel bit b taken from the local index or, for a non-resident qubit,
-// from the tile base.  Qubits whose "0" entries are all 1 were turned into controls by the host.
-template <bool SWZ>
-__device__ __forceinline__ void op_diag(rq_cplx* sm, const rq_tile_op& o, const rq_cplx* pool, uint32_t T, uint32_t tid,
-                                        uint64_t gbase) {
-    uint32_t selbase = 0;
-    for (uint32_t b = 0; b < o.k; ++b)
-        if (o.t[b] == 0xFF) selbase |= (uint32_t)((gbase >> o.gq[b]) & 1ull) << b;
-    const uint32_t ngroups = 1u << (T - o.nfix);
-    const rq_cplx* D = pool + o.moff;
-    for (uint32_t g = tid; g < ngroups; g += NT) {
-        const uint32_t idx = spread(g, o) | o.setmask;
-        uint32_t sel = selbase;
-        for (uint32_t b = 0; b < o.k; ++b)
-            if (o.t[b] != 0xFF) sel |= ((idx >> o.t[b]) & 1u) << b;
-        const uint32_t pi = sidx<SWZ>(idx);
-        sm[pi] = cmul(D[sel], sm[pi]);
-    }
-}
-
-// pair permutation: swap(idx, idx ^ xm) over the idx whose fixed bits equal setmask
-template <bool SWZ>
-__device__ __forceinline__ void op_perm(rq_cplx* sm, const rq_tile_op& o, uint32_t T, uint32_t tid) {
-    const uint32_t ngroups = 1u << (T - o.nfix);
-    for (uint32_t g = tid; g < ngroups; g += NT) {
-        const uint32_t l0 = spread(g, o) | o.setmask, i0 = sidx<SWZ>(l0), i1 = sidx<SWZ>(l0 ^ o.xm);
-        const rq_cplx a = sm[i0], b = sm[i1];
-        sm[i0] = b;
-        sm[i1] = a;
-    }
-}
-
-// ---- register-window phases ---------------------------------------------------------------------------
-// Every thread owns the D = 2^V amplitudes that differ in the V window bits; all ops of the phase act on them in
-// registers, so the tile makes ONE shared-memory round trip per phase instead of one per op.  Window bits sit at
-// local positions >= 4: for a fixed register slot the lanes of a warp read consecutive amplitudes (no bank conflicts).
-template <int V, int W, bool CTRL>
-__device__ __forceinline__ void win_dense1(ramp (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
-    const mel m00 = mload(M, 0), m10 = mload(M, 1), m01 = mload(M, 2), m11 = mload(M, 3);          // column-major
-#pragma unroll
-    for (int j = 0; j < (1 << V); ++j) {
-        if (j & (1 << W)) continue;
-        if (CTRL && (j & cm_in) != cm_in) continue;
-        const ramp a0 = a[j], a1 = a[j | (1 << W)];
-        ramp r0 = rzero(), r1 = rzero();
-        rmac(r0, m00, a0); rmac(r0, m01, a1);
-        rmac(r1, m10, a0); rmac(r1, m11, a1);
-        a[j] = r0;
-        a[j | (1 << W)] = r1;
-    }
-}
-// matrix bit 0 <-> window bit W0, matrix bit 1 <-> window bit W1 (the host orders the targets ascending)
-template <int V, int W0, int W1, bool CTRL>
-__device__ __forceinline__ void win_dense2(ramp (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
-    mel m[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) m[e] = mload(M, e);
-#pragma unroll
-    for (int j = 0; j < (1 << V); ++j) {
-        if (j & ((1 << W0) | (1 << W1))) continue;
-        if (CTRL && (j & cm_in) != cm_in) continue;
-        const ramp x0 = a[j], x1 = a[j | (1 << W0)], x2 = a[j | (1 << W1)], x3 = a[j | (1 << W0) | (1 << W1)];
-        ramp r[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            ramp acc = rzero();
-            rmac(acc, m[i], x0); rmac(acc, m[i + 4], x1); rmac(acc, m[i + 8], x2); rmac(acc, m[i + 12], x3);
-            r[i] = acc;
-        }
-        a[j] = r[0]; a[j | (1 << W0)] = r[1]; a[j | (1 << W1)] = r[2]; a[j | (1 << W0) | (1 << W1)] = r[3];
-    }
-}
-template <int V, int W>
-__device__ __forceinline__ void win_x(ramp (&a)[1 << V], uint32_t cm_in) {
-#pragma unroll
-    for (int j = 0; j < (1 << V); ++j) {
-        if (j & (1 << W)) continue;
-        if ((j & cm_in) != cm_in) continue;
-        const ramp t = a[j];
-        a[j] = a[j | (1 << W)];
-        a[j | (1 << W)] = t;
-    }
-}
-template <int V, int W0, int W1>
-__device__ __forceinline__ void win_swap(ramp (&a)[1 << V], uint32_t cm_in) {
-#pragma unroll
-    for (int j = 0; j < (1 << V); ++j) {
-        if (j & ((1 << W0) | (1 << W1))) continue;
-        if ((j & cm_in) != cm_in) continue;
-        const ramp t = a[j | (1 << W0)];
-        a[j | (1 << W0)] = a[j | (1 << W1)];
-        a[j | (1 << W1)] = t;
-    }
-}
-
-template <int V>
-__device__ __forceinline__ void win_dispatch1(ramp (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense) {
-    const uint32_t w = o.wt[0], ci = o.cm_in;
-    if (dense && ci == 0) {                                  // uncontrolled: straight-line code, matrix stays in registers
-        if (w == 0) win_dense1<V, 0, false>(a, M, 0);
-        else if (w == 1) win_dense1<V, 1, false>(a, M, 0);
-        else if (w == 2) win_dense1<V, 2, false>(a, M, 0);
-        else if (V > 3) win_dense1<V, (V > 3 ? 3 : 0), false>(a, M, 0);
-    } else if (dense) {
-        if (w == 0) win_dense1<V, 0, true>(a, M, ci);
-        else if (w == 1) win_dense1<V, 1, true>(a, M, ci);
-        else if (w == 2) win_dense1<V, 2, true>(a, M, ci);
-        else if (V > 3) win_dense1<V, (V > 3 ? 3 : 0), true>(a, M, ci);
-    } else {
-        if (w == 0) win_x<V, 0>(a, ci);
-        else if (w == 1) win_x<V, 1>(a, ci);
-        else if (w == 2) win_x<V, 2>(a, ci);
-        else if (V > 3) win_x<V, (V > 3 ? 3 : 0)>(a, ci);
-    }
-}
-template <int V>
-__device__ __forceinline__ void win_dispatch2(ramp (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense) {
-    const uint32_t pair = o.wt[0] * 4u + o.wt[1], ci = o.cm_in;      // wt[0] < wt[1]
-#define RQ_PAIR(A, B)                                            \
-    case (A) * 4 + (B):                                          \
-        if (dense && ci == 0) win_dense2<V, A, B, false>(a, M, 0); \
-        else if (dense) win_dense2<V, A, B, true>(a, M, ci);     \
-        else win_swap<V, A, B>(a, ci);                           \
-        break;
-    switch (pair) {
-        RQ_PAIR(0, 1) RQ_PAIR(0, 2) RQ_PAIR(1, 2)
-        default:
-            if (V > 3) {
-                switch (pair) {
-                    RQ_PAIR(0, (V > 3 ? 3 : 1)) RQ_PAIR(1, (V > 3 ? 3 : 2)) RQ_PAIR(2, (V > 3 ? 3 : 2) + (V > 3 ? 0 : 1))
-                    default: break;
-                }
-            }
-            break;
-    }
-#undef RQ_PAIR
-}
-
-template <int V, bool SWZ, typename Prog>
-__device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint32_t tid,
-                                                 uint64_t gbase) {
-    constexpr int D = 1 << V;
-    uint32_t stride[V];
-#pragma unroll
-    for (int b = 0; b < V; ++b) stride[b] = 1u << ph.w[b];
-    const uint32_t ngroups = 1u << (T - V);
-    for (uint32_t g = tid; g < ngroups; g += NT) {
-        uint32_t base = g;
-#pragma unroll
-        for (int b = 0; b < V; ++b) {
-            const uint32_t p = ph.w[b];
-            base = ((base >> p) << (p + 1)) | (base & ((1u << p) - 1u));
-        }
-        ramp a[D];
-        uint32_t lidx[D];                                   // logical local index of every register slot
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            uint32_t idx = base;
-#pragma unroll
-            for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
-            lidx[j] = idx;
-            a[j] = ramp_load(sm, sidx<SWZ>(idx));
-        }
-        for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
-            const rq_tile_op& o = prog.ops[oi];
-            if ((gbase & o.gcmask) != o.gcmask) continue;
-            if ((base & o.cm_out) != o.cm_out) continue;
-            const rq_cplx* M = prog.pool + o.moff;
-            if (o.kind == RQ_OP_DIAG) {
-                const uint32_t lc = o.setmask, k = o.k;
-                if (k == 0) {                                   // pure phase on "all controls set" (Z, S, T, CZ, CP, ...)
-                    const rq_cplx ph = M[0];
-#pragma unroll
-                    for (int j = 0; j < D; ++j)
-                        if ((lidx[j] & lc) == lc) a[j] = rmul(ph, a[j]);
-                } else {
-                    // table bit b comes from local position tb[b], or (non-resident) is the tile constant in selbase
-                    uint32_t selbase = 0, tb[4] = {32, 32, 32, 32};
-#pragma unroll
-                    for (uint32_t b = 0; b < 4; ++b) {
-                        if (b >= k) continue;
-                        const uint32_t p = o.t[b];
-                        if (p == 0xFF) selbase |= (uint32_t)((gbase >> o.gq[b]) & 1ull) << b; else tb[b] = p;
-                    }
-#pragma unroll
-                    for (int j = 0; j < D; ++j) {
-                        const uint32_t idx = lidx[j];
-                        if ((idx & lc) != lc) continue;
-                        uint32_t sel = selbase;
-#pragma unroll
-                        for (uint32_t b = 0; b < 4; ++b) sel |= (tb[b] < 32 ? ((idx >> tb[b]) & 1u) : 0u) << b;
-                        a[j] = rmul(M[sel], a[j]);
-                    }
-                }
-            } else if (o.kind == RQ_OP_DENSE) {
-                if (o.k == 1) win_dispatch1<V>(a, o, M, true);
-                else win_dispatch2<V>(a, o, M, true);
-            } else {
-                if (o.k == 1) win_dispatch1<V>(a, o, M, false);
-                else win_dispatch2<V>(a, o, M, false);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < D; ++j) ramp_store(sm, sidx<SWZ>(lidx[j]), a[j]);
-    }
-}
-
-// MODE 0 (narrow): one op per shared-memory pass, dense ops of 1-2 qubits only, <= 64 registers so that 3+ tiles per SM
-//                  are in flight -- the variant for one-gate and lightly fused sweeps (HBM-bound).
-// MODE 1 (wide)  : also 3- and 4-qubit dense ops (16 amplitudes per thread in registers).
-// MODE 2 (phased): register-window phases for heavily fused sweeps (compute-bound): several ops per smem round trip.
-// SWZ: the tile is kept XOR-swizzled in shared memory (sv_internal.h) between a swizzle pass after the TMA load and
-//      an unswizzle pass before the TMA store; chosen for sweeps with ops on the lowest local bits.
-template <bool SWZ>
-__device__ __forceinline__ void swizzle_pass(rq_cplx* sm, uint32_t T, uint32_t tid) {
-    if (!SWZ) return;
-    for (uint32_t idx = tid; idx < (1u << T); idx += NT) {       // an involution inside each aligned group: swap pairs
-        const uint32_t p = sidx<true>(idx);
-        if (idx < p) {
-            const rq_cplx a = sm[idx], b = sm[p];
-            sm[idx] = b;
-            sm[p] = a;
-        }
-    }
-    __syncthreads();
-}
-
-template <typename Prog, int MODE, bool SWZ>
-__global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN_BLOCKS : 1)) tile_sweep_kernel(rq_cplx* __restrict__ state, const __grid_constant__ Prog prog) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    rq_cplx* sm = reinterpret_cast<rq_cplx*>(smem_raw);
-    __shared__ __align__(8) uint64_t bar_storage;
-
-    const uint32_t tid = threadIdx.x;
-    const uint32_t T = prog.hdr.T, n = prog.hdr.n, rowbits = prog.hdr.rowbits;
-    const uint32_t bar = smem_u32(&bar_storage);
-
-    // tile -> (batch member, base index with zeros at the resident positions)
-    const uint64_t tile = blockIdx.x;
-    const uint64_t member = tile >> (n - T);
-    uint64_t base = tile & ((1ull << (n - T)) - 1ull);
-    for (uint32_t j = 0; j < T; ++j) {
-        const uint32_t p = prog.hdr.res[j];
-        base = ((base >> p) << (p + 1)) | (base & ((1ull << p) - 1ull));
-    }
-    rq_cplx* gtile = state + (member << n) + base;
-    const uint64_t gbase = base | prog.hdr.high_base;
-
-    const uint32_t nrows = 1u << (T - rowbits);
-    const uint32_t rowbytes = (uint32_t)sizeof(rq_cplx) << rowbits;
-
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, rowbytes * nrows);
-    }
-    __syncthreads();
-    for (uint32_t r = tid; r < nrows; r += NT) {
-        uint64_t goff = 0;
-        for (uint32_t i = 0; i < T - rowbits; ++i) goff |= (uint64_t)((r >> i) & 1u) << prog.hdr.res[rowbits + i];
-        bulk_g2s(smem_u32(sm) + r * rowbytes, gtile + goff, rowbytes, bar);
-    }
-    mbar_wait(bar, 0);
-    swizzle_pass<SWZ>(sm, T, tid);
-
-    const rq_cplx* ext = reinterpret_cast<const rq_cplx*>(prog.hdr.ext_matrix);
-    constexpr bool WIDE = MODE != 0;
-    const uint32_t nsteps = MODE == 2 ? prog.hdr.nphases : prog.hdr.nops;
-    for (uint32_t step = 0; step < nsteps; ++step) {
-        uint32_t i = step;
-        if (MODE == 2) {
-            const rq_phase& ph = prog.phases[step];
-            if (ph.kind == 1) {
-                run_window_phase<RQ_WINDOW_BITS, SWZ>(sm, prog, ph, T, tid, gbase);
-                __syncthreads();
-                continue;
-            }
-            i = ph.first;
-        }
-        const rq_tile_op& o = prog.ops[i];
-        if ((gbase & o.gcmask) != o.gcmask) continue;          // uniform per tile: no divergent barrier
-        switch (o.kind) {
-            case RQ_OP_DENSE:
-                if (o.ext) {
-                    switch (o.k) {
-                        case 1: op_dense<1, true, SWZ>(sm, o, prog.pool, ext, T, tid); break;
-                        case 2: op_dense<2, true, SWZ>(sm, o, prog.pool, ext, T, tid); break;
-                        case 3: if (WIDE) op_dense<3, true, SWZ>(sm, o, prog.pool, ext, T, tid); break;
-                        default: if (WIDE) op_dense<4, true, SWZ>(sm, o, prog.pool, ext, T, tid); break;
-                    }
-                } else {
-                    switch (o.k) {
-                        case 1: op_dense<1, false, SWZ>(sm, o, prog.pool, ext, T, tid); break;
-                        case 2: op_dense<2, false, SWZ>(sm, o, prog.pool, ext, T, tid); break;
-                        case 3: if (WIDE) op_dense<3, false, SWZ>(sm, o, prog.pool, ext, T, tid); break;
-                        default: if (WIDE) op_dense<4, false, SWZ>(sm, o, prog.pool, ext, T, tid); break;
-                    }
-                }
-                break;
-            case RQ_OP_DIAG: op_diag<SWZ>(sm, o, prog.pool, T, tid, gbase); break;
-            default: op_perm<SWZ>(sm, o, T, tid); break;
-        }
-        __syncthreads();
-    }
-
-    swizzle_pass<SWZ>(sm, T, tid);      // back to the linear layout the bulk stores expect
-    fence_async_smem();       // generic-proxy writes to smem -> visible to the async (TMA) proxy
-    __syncthreads();
-    for (uint32_t r = tid; r < nrows; r += NT) {
-        uint64_t goff = 0;
-        for (uint32_t i = 0; i < T - rowbits; ++i) goff |= (uint64_t)((r >> i) & 1u) << prog.hdr.res[rowbits + i];
-        bulk_s2g(gtile + goff, smem_u32(sm) + r * rowbytes, rowbytes);
-    }
-    bulk_commit_wait_read();  // smem must stay valid until the TMA engine has read it
-}
-
-template <typename Prog>
-int launch(rq_cplx* state, const Prog* prog, void* stream) {
-    const size_t smem = sizeof(rq_cplx) << prog->hdr.T;
-    const unsigned grid = (unsigned)prog->hdr.ntiles;
-    bool wide = false;
-    for (uint32_t i = 0; i < prog->hdr.nops; ++i) wide |= (prog->ops[i].kind == RQ_OP_DENSE && prog->ops[i].k > 2);
-    const int mode = (prog->hdr.nphases > 0 && prog->hdr.max_phase_ops >= 2) ? 2 : (wide ? 1 : 0);
-    cudaStream_t st = (cudaStream_t)stream;
-#define RQ_LAUNCH(M, S) tile_sweep_kernel<Prog, M, S><<<grid, NT, smem, st>>>(state, *prog)
-    if (prog->hdr.swz) {
-        if (mode == 2) RQ_LAUNCH(2, true); else if (mode == 1) RQ_LAUNCH(1, true); else RQ_LAUNCH(0, true);
-    } else {
-        if (mode == 2) RQ_LAUNCH(2, false); else if (mode == 1) RQ_LAUNCH(1, false); else RQ_LAUNCH(0, false);
-    }
-#undef RQ_LAUNCH
-    return (int)cudaGetLastError();
-}
-
-}  // namespace
-
-extern "C" int rq_sweep_configure(void) {
-    const int bytes = (int)(sizeof(rq_cplx) << RQ_MAX_TILE_BITS);
-    cudaError_t e = cudaSuccess;
-#define RQ_ATTR(P, M, S) if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sweep_kernel<P, M, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
-    RQ_ATTR(rq_program_small, 0, false); RQ_ATTR(rq_program_small, 1, false); RQ_ATTR(rq_program_small, 2, false);
-    RQ_ATTR(rq_program_small, 0, true);  RQ_ATTR(rq_program_small, 1, true);  RQ_ATTR(rq_program_small, 2, true);
-    RQ_ATTR(rq_program_large, 0, false); RQ_ATTR(rq_program_large, 1, false); RQ_ATTR(rq_program_large, 2, false);
-    RQ_ATTR(rq_program_large, 0, true);  RQ_ATTR(rq_program_large, 1, true);  RQ_ATTR(rq_program_large, 2, true);
-#undef RQ_ATTR
-    return (int)e;
-}
-extern "C" int rq_launch_sweep_small(rq_cplx* state, const rq_program_small* prog, void* stream) { return launch(state, prog, stream); }
-extern "C" int rq_launch_sweep_large(rq_cplx* state, const rq_program_large* prog, void* stream) { return launch(state, prog, stream); }

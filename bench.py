@@ -287,7 +287,15 @@ def run_engine(args):
 
     peaks, peak_src = measured_peaks()
     sweep_bytes = 2.0 * (1 << n_local) * 8
-    avg_sweep_ms = dev_ms / max(1, st.sweeps)
+    exchange = None
+    if ngpus > 1:
+        # the step's device time contains the NCCL exchanges; they are timed separately (CUDA events around each)
+        exchange = {"per_step": st.exchanges / args.steps, "ms_per_step": st.exchangeMs / args.steps,
+                    "sent_bytes_per_rank_per_step": st.exchangeBytes / args.steps,
+                    "send_GBps_per_rank": (st.exchangeBytes / 1e9) / (st.exchangeMs * 1e-3) if st.exchangeMs > 0 else None,
+                    "what": "k rank bits <-> top-k local bits, ncclSend/ncclRecv per peer + staging->slice copy; rank 0's figures"}
+    sweep_ms = max(0.0, dev_ms - st.exchangeMs) if ngpus > 1 else dev_ms
+    avg_sweep_ms = sweep_ms / max(1, st.sweeps)
     achieved = sweep_bytes / (avg_sweep_ms * 1e-3) / 1e9 if avg_sweep_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "tile_sweep_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "frac_of_8TBs_spec": achieved / 8000.0, "peak_source": peak_src,
@@ -299,10 +307,7 @@ def run_engine(args):
         one_gate["frac"] = one_gate["achieved"] / peaks["hbm_gbs"]
         one_gate["frac_of_8TBs_spec"] = one_gate["achieved"] / 8000.0
         roofline["one_gate_sweep"] = one_gate
-    flops = 0.0
-    for g in gates:                                   # complex 2^k x 2^k mat-vec per 2^k amplitudes: 8 * 2^k flop per amplitude
-        flops += 8.0 * (1 << len(g[1])) * (1 << n_local) if g[0] == "matrix" else 0.0
-    roofline["fp32_tflops_unfused_equivalent"] = flops * args.steps / elapsed / 1e12
+    roofline["tile_ops_per_sweep"] = st.opsExecuted / max(1, st.sweeps)     # after algebraic fusion
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
@@ -341,6 +346,8 @@ def run_engine(args):
                     "what": "rocsvInitializeState + rocsvxApplyCircuit(host gate list) + <Z0> and 256 sampled bitstrings read back, every step; "
                             "the gate list reaches the device as sweep programs in kernel parameters"},
             "gpu_launches": int(st.kernelLaunches), "roofline": roofline, "cpu_baseline": cpu}
+    if exchange:
+        line["exchange"] = exchange
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

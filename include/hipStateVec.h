@@ -200,6 +200,9 @@ typedef struct {
     uint64_t opsExecuted;      /* tile ops after algebraic fusion */
     uint64_t h2dBytes;         /* host->device bytes the engine itself moved: sweep programs (kernel parameters), matrices */
     double   lastSweepMs;      /* device time of the most recent flush (CUDA events), 0 if none */
+    uint64_t exchanges;        /* multi-process: global<->local index-bit exchanges executed */
+    uint64_t exchangeBytes;    /* multi-process: bytes this rank sent to peers in those exchanges */
+    double   exchangeMs;       /* multi-process: device time of those exchanges (CUDA events around each) */
 } rocsvxStats;
 rocqStatus_t rocsvxGetStats(rocsvHandle_t handle, rocsvxStats* stats, int reset);
 

@@ -178,6 +178,10 @@ static rocqStatus_t exchange_data(rocsvInternalHandle* h, Dist& d, const std::ve
     const uint64_t run = 1ull << (d.n_local - k);
     const uint64_t chunk = std::min<uint64_t>(run, d.staging_amps / (uint64_t)std::max<size_t>(ns, 1));
     ncclComm_t comm = (ncclComm_t)d.comm;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    RQ_CU(cudaEventCreate(&e0));
+    RQ_CU(cudaEventCreate(&e1));
+    RQ_CU(cudaEventRecord(e0, h->stream));
     for (uint64_t c = 0; c < run; c += chunk) {
         const uint64_t len = std::min<uint64_t>(chunk, run - c);
         RQ_NCCL(g_nccl.GroupStart());
@@ -190,8 +194,12 @@ static rocqStatus_t exchange_data(rocsvInternalHandle* h, Dist& d, const std::ve
             RQ_CU(cudaMemcpyAsync(h->d_state + segs[i].recvOffset + c, d.staging + i * chunk, len * sizeof(rq_cplx),
                                   cudaMemcpyDeviceToDevice, h->stream));
     }
+    RQ_CU(cudaEventRecord(e1, h->stream));
+    d.timed.push_back({e0, e1});                       // resolved (and destroyed) by rocsvxGetStats
     d.exchanges++;
     d.exchanged_amps += run * ns;
+    h->stats.exchanges++;
+    h->stats.exchangeBytes += run * ns * sizeof(rq_cplx);
     return ROCQ_STATUS_SUCCESS;
 }
 

@@ -3,7 +3,10 @@
 // MULTI_GPU_GUIDE.md:19-24).  The engine keeps a logical->physical qubit map; gates on physical
 // positions >= n_local are made local by an index-bit exchange over NCCL (dist.cu).
 #pragma once
+#include <cuda_runtime.h>
+
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 #include "../../include/hipStateVec.h"
@@ -26,6 +29,7 @@ struct Dist {
     uint64_t* d_gather = nullptr;    // small device buffer for all-gathers
     uint64_t exchanges = 0;          // statistics
     uint64_t exchanged_amps = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;   // event pairs around exchanges not yet folded into stats
 
     bool active() const { return inited && n_total > 0; }
     unsigned num_local() const { return n_local; }

@@ -946,6 +946,14 @@ rocqStatus_t rocsvxGetStats(rocsvHandle_t h, rocsvxStats* stats, int reset) {
         cudaEventSynchronize(h->ev1);
         h->stats.lastSweepMs = cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess ? (double)ms : 0.0;
     }
+    for (auto& ev : h->dist.timed) {
+        float ms = 0.f;
+        cudaEventSynchronize(ev.second);
+        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) h->stats.exchangeMs += (double)ms;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    h->dist.timed.clear();
     if (stats) *stats = h->stats;
     if (reset) h->stats = rocsvxStats{};
     return ROCQ_STATUS_SUCCESS;

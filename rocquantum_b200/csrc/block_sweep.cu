@@ -9,27 +9,38 @@
 //   * tile = 64 block values x 128 columns.  D[column][out] = sum_k X'[column][k] * A'[out][k], k over (re|im, block
 //     value): tcgen05.mma.cta_group::1.kind::f16, M = 128 (tile columns), N = 128, K = 16 per instruction, operands in
 //     shared memory (K-major, no swizzle, 8x16B core matrices), accumulator in TMEM (128 lanes x 128 fp32 columns).
-//   * fp32 accuracy from bf16 tensor cores by splitting every operand in three bf16 terms (hi + mid + lo = 24 mantissa
-//     bits) and accumulating the six products of order <= 2 in the fp32 accumulator: 48 MMAs per tile.
+//   * fp32-class accuracy from fp16 tensor-core inputs: amplitudes are scaled by a power of two (|amp| <= 1 -> the fp16
+//     normal range), then both operands are split in two fp16 terms (hi + lo = 22 mantissa bits) and the three products
+//     of order <= 1 are accumulated in fp32: 24 MMAs per tile (the lo*lo product is 2^-22 relative and dropped).
+//   * the tensor core truncates when it adds a K = 16 partial sum into the accumulator; the correction products are
+//     therefore accumulated first and the dominant hi*hi product last, and for a unitary block the epilogue restores the
+//     norm of every tile column (which the block preserves exactly).
 //   * columns map to TMEM lanes, so that the 32 lanes of a warp read 32 consecutive amplitudes from global memory
 //     (one 256-byte segment per LDG.64) and the epilogue (tcgen05.ld -> float2 STG) writes them back the same way:
-//     the tile never needs an fp32 staging buffer, shared memory holds only the bf16 operand terms (96 KB + 96 KB).
-//   * persistent CTA per SM; the next tile's amplitudes are prefetched into registers while the tensor core works.
+//     the tile never needs an fp32 staging buffer; shared memory holds the fp16 operand terms only.
+//   * software pipeline in a persistent CTA per SM: operand buffers and accumulators are double-buffered, so that the
+//     MMAs of tile i run while the CUDA cores do the epilogue of tile i-1 and the split of tile i+1; global loads run
+//     two tiles ahead (128 KB in flight per SM).
 // complex64 only: there is no fp64 tensor path for this (complex128 stays on the CUDA-core sweep).
 #ifndef ROCQ_PRECISION_DOUBLE
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "sv_internal.h"
 
 namespace {
 
 constexpr int BT = 512;                        // threads per CTA: 4 warps per TMEM lane quarter, 16 block values per thread
-constexpr uint32_t TERM_BYTES = 32768;         // one bf16 term of a 128 x 128 operand
-constexpr uint32_t SMEM_U = 0, SMEM_X = 3 * TERM_BYTES, SMEM_TAB = 6 * TERM_BYTES;   // + 64 u64 block offsets
-constexpr uint32_t SMEM_NORM = SMEM_TAB + 64 * 8;                 // 2 x 4 x 128 floats: column norms in / out
-constexpr uint32_t SMEM_BYTES = SMEM_NORM + 8 * 128 * 4 + 64;
+constexpr uint32_t TERM_BYTES = 32768;         // one fp16 term of a 128 x 128 operand
+constexpr uint32_t SMEM_U = 0;                                    // 2 terms of A'
+constexpr uint32_t SMEM_X = 2 * TERM_BYTES;                       // 2 buffers x 2 terms of X'
+constexpr uint32_t SMEM_TAB = 6 * TERM_BYTES;                     // 64 u64 block offsets
+constexpr uint32_t SMEM_NIN = SMEM_TAB + 64 * 8;                  // column norms going in: [buffer][quarter][column]
+constexpr uint32_t SMEM_NOUT = SMEM_NIN + 2 * 4 * 128 * 4;        // column norms coming out: [quarter][column]
+constexpr uint32_t SMEM_BYTES = SMEM_NOUT + 4 * 128 * 4 + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -59,8 +70,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-// instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = 128, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor (kind::f16): D = F32, A = B = F16, both K-major, N = 128, M = 128
+constexpr uint32_t IDESC = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t accumulate) {
     asm volatile(
@@ -76,18 +87,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -97,16 +96,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr));
 }
 
-// x = hi + mid + lo with three bf16 values (round to nearest each time; the residuals are exact in fp32)
-__device__ __forceinline__ void split3(float x, float& hi, float& mid, float& lo) {
-    hi = __bfloat162float(__float2bfloat16_rn(x));
-    const float r = x - hi;
-    mid = __bfloat162float(__float2bfloat16_rn(r));
-    lo = (r - mid);
-}
-__device__ __forceinline__ uint32_t bf2(float a, float b) {           // a -> low half, b -> high half
-    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&v);
+// (a, b) scaled -> hi and lo fp16 pairs: a*s = hi + lo up to 2^-22 relative (the residual is exact in fp32)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __device__ __forceinline__ uint64_t tile_base(uint64_t tile, const rq_block_params& P, uint64_t& member) {
@@ -122,18 +118,21 @@ __device__ __forceinline__ uint64_t tile_base(uint64_t tile, const rq_block_para
 __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__ state, const unsigned char* __restrict__ uterms,
                                                              const __grid_constant__ rq_block_params P) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_u, bar_mma;
+    __shared__ __align__(8) uint64_t bar_u, bar_mma[2];
     __shared__ uint32_t tmem_slot;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ uint64_t tbase[8];      // ring: amplitude offset of the CTA's tile i at [i & 7], computed by one thread per tile
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
     uint64_t* boff = reinterpret_cast<uint64_t*>(smem + SMEM_TAB);
-    float* cnorm = reinterpret_cast<float*>(smem + SMEM_NORM);          // [in|out][half][column]
+    float* nin = reinterpret_cast<float*>(smem + SMEM_NIN);
+    float* nout = reinterpret_cast<float*>(smem + SMEM_NOUT);
 
     if (tid == 0) {
         mbar_init(smem_u32(&bar_u), 1);
-        mbar_init(smem_u32(&bar_mma), 1);
+        mbar_init(smem_u32(&bar_mma[0]), 1);
+        mbar_init(smem_u32(&bar_mma[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == 0) {                                         // two accumulator buffers x 128 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -147,133 +146,142 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
     tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
 
-    if (tid == 0) {                                          // the three bf16 terms of A' stay resident for all tiles
-        mbar_expect_tx(smem_u32(&bar_u), 3 * TERM_BYTES);
-        for (uint32_t j = 0; j < 3; ++j) bulk_g2s(smem_u32(smem + SMEM_U + j * TERM_BYTES), uterms + (size_t)j * TERM_BYTES, TERM_BYTES, smem_u32(&bar_u));
+    if (tid == 0) {                                          // the two fp16 terms of A' stay resident for all tiles
+        mbar_expect_tx(smem_u32(&bar_u), 2 * TERM_BYTES);
+        for (uint32_t j = 0; j < 2; ++j) bulk_g2s(smem_u32(smem + SMEM_U + j * TERM_BYTES), uterms + (size_t)j * TERM_BYTES, TERM_BYTES, smem_u32(&bar_u));
     }
 
-    // this thread: tile column n (= TMEM lane), block values [16*qt, 16*qt+16)
+    // this thread: tile column ncol (= TMEM lane), block values [16*qt, 16*qt+16)
     const uint32_t ncol = tid & 127, qt = tid >> 7;
     uint64_t coff = 0;
     for (uint32_t b = 0; b < 7; ++b) coff |= (uint64_t)((ncol >> b) & 1u) << P.col[b];
     const uint32_t xrow = (ncol & 7u) * 16u + (ncol >> 3) * 2048u;          // byte offset of row `ncol` in an operand term
+    const uint32_t dbg = P.pad;        // timing experiments only (ROCQ_BLOCK_DEBUG): 1 = no MMA, 2 = no split, 4 = no stores, 8 = no renorm
+    const float scale = P.scale, inv_scale = 1.f / P.scale;
+    const uint64_t first = blockIdx.x, stride = gridDim.x;
+    const uint64_t cnt = P.ntiles > first ? (P.ntiles - first + stride - 1) / stride : 0;     // tiles of this CTA
 
-    float2 raw[16];
-    uint64_t tile = blockIdx.x, member;
-    if (tile < P.ntiles) {
-        const uint64_t base = tile_base(tile, P, member);
-        const float2* g = state + (member << P.n) + base + coff;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) raw[j] = g[boff[16 * qt + j]];
-    }
-    mbar_wait(smem_u32(&bar_u), 0);
+    const uint64_t* off = boff + 16 * qt;                                   // block-value offsets of this thread (shared memory)
 
-    uint32_t phase = 0;
-    for (; tile < P.ntiles; tile += gridDim.x) {
-        const uint64_t base = tile_base(tile, P, member);
-        float2* gt = state + (member << P.n) + base + coff;
-
-        // ---- convert: 8 block values at a time -> one 16-byte row chunk per (term, re|im) ----
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            if (P.pad & 2u) break;
-            float h[16], m[16], l[16];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                split3(raw[8 * c + j].x, h[j], m[j], l[j]);
-                split3(raw[8 * c + j].y, h[8 + j], m[8 + j], l[8 + j]);
-            }
-            const uint32_t kg_re = 2 * qt + c, kg_im = 8 + 2 * qt + c;          // K group (8 values) of the re / im block
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {
-                const uint32_t o = xrow + (part ? kg_im : kg_re) * 128u;
-                const int s = 8 * part;
-                *reinterpret_cast<uint4*>(smem + SMEM_X + 0 * TERM_BYTES + o) = make_uint4(bf2(h[s], h[s + 1]), bf2(h[s + 2], h[s + 3]), bf2(h[s + 4], h[s + 5]), bf2(h[s + 6], h[s + 7]));
-                *reinterpret_cast<uint4*>(smem + SMEM_X + 1 * TERM_BYTES + o) = make_uint4(bf2(m[s], m[s + 1]), bf2(m[s + 2], m[s + 3]), bf2(m[s + 4], m[s + 5]), bf2(m[s + 6], m[s + 7]));
-                *reinterpret_cast<uint4*>(smem + SMEM_X + 2 * TERM_BYTES + o) = make_uint4(bf2(l[s], l[s + 1]), bf2(l[s + 2], l[s + 3]), bf2(l[s + 4], l[s + 5]), bf2(l[s + 6], l[s + 7]));
-            }
+    // the index deposit costs ~130 instructions: one thread does it per tile, two tiles ahead, and publishes the result
+    auto publish_tile = [&](uint64_t i) {
+        if (i < cnt) {
+            uint64_t member;
+            const uint64_t base = tile_base(first + i * stride, P, member);
+            tbase[i & 7u] = (member << P.n) + base;
         }
-        if (P.renorm) {                                                    // |column|^2 going in (this thread's 16 block values)
-            float s = 0.f;
+    };
+    auto tile_ptr = [&](uint64_t i) -> float2* { return state + tbase[i & 7u] + coff; };
+    auto load_tile = [&](uint64_t i, float2 (&raw)[16]) {
+        if (i < cnt) {
+            const float2* g = tile_ptr(i);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s = fmaf(raw[j].x, raw[j].x, fmaf(raw[j].y, raw[j].y, s));
-            cnorm[qt * 128 + ncol] = s;
+            for (int j = 0; j < 16; ++j) raw[j] = g[off[j]];
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> visible to the tensor core
-        tc_fence_before();
-        __syncthreads();
+    };
 
-        // ---- 48 MMAs: six term products x eight K steps, one issuing thread ----
-        const uint32_t dbg = P.pad;        // timing experiments only (ROCQ_BLOCK_DEBUG): 1 = no MMA, 2 = no convert, 4 = no stores
-        if (tid == 0 && !(dbg & 1u)) {
-            tc_fence_after();
-            const uint32_t xa = smem_u32(smem + SMEM_X), ua = smem_u32(smem + SMEM_U);
-            // The tensor core truncates when it adds a K=16 partial sum to the fp32 accumulator, a bias that grows with the
-            // number of accumulation steps.  So the dominant product hi*hi (8 steps) gets its own accumulator D0 and the five
-            // correction products (2^-8 .. 2^-16 smaller) go to D1; the epilogue adds D0 + D1 in fp32.
-            // (X term, U term): hi*hi | hi*mid, mid*hi, mid*mid, hi*lo, lo*hi
-            const uint32_t tx[6] = {0, 0, 1, 1, 0, 2}, tu[6] = {0, 1, 0, 1, 2, 0};
-#pragma unroll
-            for (int p = 0; p < 6; ++p)
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    umma(tmem_d + (p == 0 ? 0u : 128u), umma_desc(xa + tx[p] * TERM_BYTES + ks * 256u, 128u, 2048u),
-                         umma_desc(ua + tu[p] * TERM_BYTES + ks * 256u, 128u, 2048u), (p == 0 || p == 1) ? (ks != 0) : 1u);
-            umma_commit(smem_u32(&bar_mma));
-        }
-
-        // ---- prefetch the next tile while the tensor core runs ----
-        const uint64_t next = tile + gridDim.x;
-        if (next < P.ntiles) {
-            uint64_t nm;
-            const uint64_t nb = tile_base(next, P, nm);
-            const float2* g = state + (nm << P.n) + nb + coff;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) raw[j] = g[boff[16 * qt + j]];
-        }
-
-        if (!(dbg & 1u)) {
-            mbar_wait(smem_u32(&bar_mma), phase);
-            phase ^= 1;
-        }
+    // ---- epilogue of tile i from accumulator buffer B: TMEM lane = column; re at column t, im at column 64 + t ----
+    auto epilogue = [&](auto BC, uint64_t i) {
+        constexpr uint32_t B = decltype(BC)::value;
+        if (!(dbg & 1u)) mbar_wait(smem_u32(&bar_mma[B]), (uint32_t)(i >> 1) & 1u);
         tc_fence_after();
-
-        // ---- epilogue: TMEM lane = column; this thread's 16 block values: re at column t, im at column 64 + t ----
-        float2 out[16];
-        {
-            uint32_t re0[16], im0[16], re1[16], im1[16];
-            const uint32_t taddr = tmem_d + (((warp & 3u) * 32u) << 16) + 16u * qt;
-            tmem_ld16(taddr, re0);
-            tmem_ld16(taddr + 64u, im0);
-            tmem_ld16(taddr + 128u, re1);
-            tmem_ld16(taddr + 192u, im1);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                out[j] = make_float2(__uint_as_float(re0[j]) + __uint_as_float(re1[j]), __uint_as_float(im0[j]) + __uint_as_float(im1[j]));
-        }
-        float scale = 1.f;
+        // one accumulator per buffer: re at TMEM column t, im at column 64 + t (TMEM reads run at 64 B/clk per SM, so the
+        // accumulator is read exactly once)
+        const uint32_t taddr = tmem_d + (((warp & 3u) * 32u) << 16) + B * 128u + 16u * qt;
+        uint32_t re[16], im[16];
+        tmem_ld16(taddr, re);
+        tmem_ld16(taddr + 64u, im);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float f = inv_scale;
         if (P.renorm) {
             // A unitary block preserves the norm of every tile column (it only mixes the 64 block values of a column).
             // Restoring it removes the systematic shrink of the tensor core's truncating accumulation, which would
             // otherwise grow linearly with the number of sweeps.
             float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s = fmaf(out[j].x, out[j].x, fmaf(out[j].y, out[j].y, s));
-            cnorm[512 + qt * 128 + ncol] = s;
+            for (int j = 0; j < 16; ++j) s = fmaf(__uint_as_float(re[j]), __uint_as_float(re[j]), fmaf(__uint_as_float(im[j]), __uint_as_float(im[j]), s));
+            nout[qt * 128 + ncol] = s;
+            const float* ni = nin + B * 512;
+            const float sin = (ni[ncol] + ni[128 + ncol]) + (ni[256 + ncol] + ni[384 + ncol]);
             __syncthreads();
-            const float sin = (cnorm[ncol] + cnorm[128 + ncol]) + (cnorm[256 + ncol] + cnorm[384 + ncol]);
-            const float sout = (cnorm[512 + ncol] + cnorm[640 + ncol]) + (cnorm[768 + ncol] + cnorm[896 + ncol]);
-            if (sout > 0.f && sin > 0.f) scale = sqrtf(sin / sout);
+            const float sout = (nout[ncol] + nout[128 + ncol]) + (nout[256 + ncol] + nout[384 + ncol]);   // of the scaled outputs
+            if (sout > 0.f && sin > 0.f) f = sqrtf(sin / sout);
         }
         if (!(dbg & 4u)) {
+            float2* gt = tile_ptr(i);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) gt[boff[16 * qt + j]] = make_float2(out[j].x * scale, out[j].y * scale);
+            for (int j = 0; j < 16; ++j) gt[off[j]] = make_float2(__uint_as_float(re[j]) * f, __uint_as_float(im[j]) * f);
         }
         tc_fence_before();
-        __syncthreads();            // D and the X terms are free again
+    };
+
+    // ---- one pipeline step: split tile i into operand buffer B, start its MMAs, prefetch tile i+2, finish tile i-1 ----
+    auto step = [&](auto BC, uint64_t i, float2 (&raw)[16]) {
+        constexpr uint32_t B = decltype(BC)::value;
+        unsigned char* X = smem + SMEM_X + B * 2 * TERM_BYTES;
+        if (!(dbg & 2u)) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t hr[4], lr[4], hi[4], li[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    split2(raw[8 * c + 2 * j].x * scale, raw[8 * c + 2 * j + 1].x * scale, hr[j], lr[j]);
+                    split2(raw[8 * c + 2 * j].y * scale, raw[8 * c + 2 * j + 1].y * scale, hi[j], li[j]);
+                }
+                const uint32_t o_re = xrow + (2 * qt + c) * 128u, o_im = xrow + (8 + 2 * qt + c) * 128u;   // K groups of 8 values
+                *reinterpret_cast<uint4*>(X + o_re) = make_uint4(hr[0], hr[1], hr[2], hr[3]);
+                *reinterpret_cast<uint4*>(X + TERM_BYTES + o_re) = make_uint4(lr[0], lr[1], lr[2], lr[3]);
+                *reinterpret_cast<uint4*>(X + o_im) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(X + TERM_BYTES + o_im) = make_uint4(li[0], li[1], li[2], li[3]);
+            }
+        }
+        if (P.renorm) {                                                    // |column|^2 going in (this thread's 16 block values)
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s = fmaf(raw[j].x, raw[j].x, fmaf(raw[j].y, raw[j].y, s));
+            nin[B * 512 + qt * 128 + ncol] = s;
+        }
+        if (tid == 32) publish_tile(i + 2);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> visible to the tensor core
+        tc_fence_before();
+        __syncthreads();
+
+        if (tid == 0 && !(dbg & 1u)) {                                     // 24 MMAs, one issuing thread
+            tc_fence_after();
+            const uint32_t xh = smem_u32(X), xl = xh + TERM_BYTES, uh = smem_u32(smem + SMEM_U), ul = uh + TERM_BYTES;
+            const uint32_t d = tmem_d + B * 128u;
+            // The tensor core truncates when it adds a K = 16 partial sum into the fp32 accumulator.  The two correction
+            // products (2^-11 smaller) therefore go first, while the accumulator is small, and the dominant hi*hi product
+            // last: only its eight additions truncate at full magnitude.
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) umma(d, umma_desc(xh + ks * 256u, 128u, 2048u), umma_desc(ul + ks * 256u, 128u, 2048u), ks != 0);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) umma(d, umma_desc(xl + ks * 256u, 128u, 2048u), umma_desc(uh + ks * 256u, 128u, 2048u), 1u);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) umma(d, umma_desc(xh + ks * 256u, 128u, 2048u), umma_desc(uh + ks * 256u, 128u, 2048u), 1u);
+            umma_commit(smem_u32(&bar_mma[B]));
+        }
+        load_tile(i + 2, raw);                                             // two tiles ahead, into the registers just consumed
+        if (i >= 1) epilogue(std::integral_constant<uint32_t, B ^ 1u>{}, i - 1);
+    };
+
+    float2 raw0[16], raw1[16];
+    if (tid == 32) { publish_tile(0); publish_tile(1); }
+    __syncthreads();
+    load_tile(0, raw0);
+    load_tile(1, raw1);
+    mbar_wait(smem_u32(&bar_u), 0);
+
+    for (uint64_t i = 0; i < cnt; i += 2) {
+        step(std::integral_constant<uint32_t, 0u>{}, i, raw0);
+        if (i + 1 < cnt) step(std::integral_constant<uint32_t, 1u>{}, i + 1, raw1);
+    }
+    if (cnt > 0) {
+        if ((cnt - 1) & 1u) epilogue(std::integral_constant<uint32_t, 1u>{}, cnt - 1);
+        else epilogue(std::integral_constant<uint32_t, 0u>{}, cnt - 1);
     }
 
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256u) : "memory");
 }

@@ -122,7 +122,9 @@ struct rq_block_params {
     uint32_t n;                     // qubits per state vector
     uint32_t T;                     // 13
     uint32_t renorm;                // 1: the block is unitary -> restore every column's norm in the epilogue
-    uint32_t pad;
+    uint32_t pad;                   // debug switches (ROCQ_BLOCK_DEBUG), 0 in production
+    float scale;                    // power of two that brings amplitudes into the fp16 normal range
+    uint32_t pad2;
     uint64_t ntiles;                // batch * 2^(n-13)
     uint8_t res[16];                // ascending resident positions (block + column bits)
     uint8_t blk[8];                 // 6 block positions, ascending: bit b of the block value <-> blk[b]
@@ -130,7 +132,8 @@ struct rq_block_params {
 };
 #define RQ_BLOCK_QUBITS 6
 #define RQ_BLOCK_COLBITS 7
-#define RQ_BLOCK_TERM_BYTES 32768    // one bf16 term of the real 128x128 operand, in UMMA K-major core-matrix order
+#define RQ_BLOCK_TERM_BYTES 32768    // one fp16 term of the real 128x128 operand, in UMMA K-major core-matrix order
+#define RQ_BLOCK_TERMS 2
 
 // ---- thin C ABI to the launchers (all return a cudaError_t as int; stream is a cudaStream_t) --------
 extern "C" {
@@ -158,6 +161,6 @@ int rq_launch_sample(const rq_cplx* state, unsigned n, unsigned chunk_bits, cons
                      uint64_t shot_offset, uint64_t* d_indices, void* stream);
 unsigned rq_reduce_blocks(void);
 int rq_block_configure(void);
-// d_uterms: 3 * RQ_BLOCK_TERM_BYTES device bytes (hi, mid, lo bf16 terms of the real 128x128 block matrix)
+// d_uterms: RQ_BLOCK_TERMS * RQ_BLOCK_TERM_BYTES device bytes (hi, lo fp16 terms of the real 128x128 block matrix)
 int rq_launch_block_sweep(rq_cplx* state, const rq_block_params* P, const void* d_uterms, void* stream);
 }

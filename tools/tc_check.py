@@ -9,7 +9,7 @@ from rocquantum_b200.statevec import StateVector
 from tests import util
 
 rng = np.random.default_rng(7)
-for n, qs in ((13, [5, 6, 7, 8, 9, 10]), (16, [9, 5, 15, 7, 11, 12]), (18, [0, 3, 17, 8, 2, 12]), (20, [14, 15, 16, 17, 18, 19])):
+for n, qs in ((13, [5, 6, 7, 8, 9, 10]), (16, [9, 5, 15, 7, 11, 12]), (18, [0, 3, 17, 8, 2, 12]), (14, [0, 1, 2, 3, 4, 5]), (15, [2, 3, 4, 5, 6, 7]), (20, [14, 15, 16, 17, 18, 19])):
     U = workloads.haar_unitary(rng, 64)
     v = util.random_state(n, seed=n)
     o = so.Oracle(n, "c64"); o.set_state(v); o.apply_matrix(qs, U)
@@ -23,7 +23,7 @@ v = util.random_state(n, seed=3)
 o = so.Oracle(n, "c64"); o.set_state(v)
 g = StateVector(n, "c64"); g.set_state(v)
 for it in range(40):
-    qs = sorted(int(x) for x in rng.choice(np.arange(5, n), size=6, replace=False))
+    qs = sorted(int(x) for x in rng.choice(np.arange(0, n), size=6, replace=False))
     U = workloads.haar_unitary(rng, 64)
     o.apply_matrix(qs, U); g.apply_block6(qs, U)
     if it in (0, 9, 19, 39):
@@ -33,10 +33,12 @@ n = 30
 g = StateVector(n, "c64")
 g.gate("h", 0)
 U = workloads.haar_unitary(rng, 64)
-for qs in ([10, 11, 12, 13, 14, 15], [24, 25, 26, 27, 28, 29], [5, 9, 13, 17, 21, 25])[: (1 if "--quick" in sys.argv else 3)]:
-    g.apply_block6(qs, U); g.sync()
-    g.timer_start()
+for qs in ([10, 11, 12, 13, 14, 15], [24, 25, 26, 27, 28, 29], [5, 9, 13, 17, 21, 25], [0, 1, 2, 3, 4, 5], [3, 4, 5, 6, 7, 8], [1, 2, 3, 4, 5, 6])[: (1 if "--quick" in sys.argv else 6)]:
     for _ in range(5):
         g.apply_block6(qs, U)
-    ms = g.timer_stop() / 5
+    g.sync()
+    g.timer_start()
+    for _ in range(20):
+        g.apply_block6(qs, U)
+    ms = g.timer_stop() / 20
     print(f"n=30 block {qs}: {ms:.3f} ms per sweep = {2*(1<<n)*8/(ms*1e-3)/1e9:.0f} GB/s; norm {g.norm2():.6f}", flush=True)

@@ -35,12 +35,16 @@ namespace {
 
 constexpr int BT = 512;                        // threads per CTA: 4 warps per TMEM lane quarter, 16 block values per thread
 constexpr uint32_t TERM_BYTES = 32768;         // one fp16 term of a 128 x 128 operand
-constexpr uint32_t SMEM_U = 0;                                    // 2 terms of A'
-constexpr uint32_t SMEM_X = 2 * TERM_BYTES;                       // 2 buffers x 2 terms of X'
-constexpr uint32_t SMEM_TAB = 6 * TERM_BYTES;                     // 64 u64 block offsets
-constexpr uint32_t SMEM_NIN = SMEM_TAB + 64 * 8;                  // column norms going in: [buffer][quarter][column]
+constexpr uint32_t TILE_BYTES = 65536;         // 2^13 complex64 amplitudes
+constexpr uint32_t SMEM_U = 0;                                    // 2 terms of A' (the B operand of the MMA)
+constexpr uint32_t SMEM_S = 2 * TERM_BYTES;                       // 2 staging tiles (fp32 amplitudes, TMA destination)
+constexpr uint32_t SMEM_TAB = SMEM_S + 2 * TILE_BYTES;            // 64 u64 global block offsets
+constexpr uint32_t SMEM_ROW = SMEM_TAB + 64 * 8;                  // <= 256 u64 global row offsets
+constexpr uint32_t SMEM_NIN = SMEM_ROW + 256 * 8;                 // column norms going in: [buffer][quarter][column]
 constexpr uint32_t SMEM_NOUT = SMEM_NIN + 2 * 4 * 128 * 4;        // column norms coming out: [quarter][column]
 constexpr uint32_t SMEM_BYTES = SMEM_NOUT + 4 * 128 * 4 + 64;
+// TMEM columns, per pipeline buffer b (at 256 * b): [0,128) accumulator D, [128,192) hi term of X', [192,256) lo term of X'
+constexpr uint32_t TM_D = 0, TM_XH = 128, TM_XL = 192, TM_BUF = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -81,6 +85,19 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
         "}" ::"r"(tmem_d), "l"(a), "l"(b), "r"(IDESC), "r"(accumulate), "r"(0u) : "memory");
 }
+// A operand (X') from tensor memory, B operand (A' = block matrix) from shared memory
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(b), "r"(IDESC), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -118,28 +135,38 @@ __device__ __forceinline__ uint64_t tile_base(uint64_t tile, const rq_block_para
 __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__ state, const unsigned char* __restrict__ uterms,
                                                              const __grid_constant__ rq_block_params P) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_u, bar_mma[2];
+    __shared__ __align__(8) uint64_t bar_u, bar_mma[2], bar_full[2];
     __shared__ uint32_t tmem_slot;
     __shared__ uint64_t tbase[8];      // ring: amplitude offset of the CTA's tile i at [i & 7], computed by one thread per tile
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* boff = reinterpret_cast<uint64_t*>(smem + SMEM_TAB);
+    uint64_t* rowoff = reinterpret_cast<uint64_t*>(smem + SMEM_ROW);
     float* nin = reinterpret_cast<float*>(smem + SMEM_NIN);
     float* nout = reinterpret_cast<float*>(smem + SMEM_NOUT);
+    const uint32_t rowbits = P.rowbits, nrows = 1u << (13u - rowbits), rowbytes = 8u << rowbits;
 
     if (tid == 0) {
         mbar_init(smem_u32(&bar_u), 1);
         mbar_init(smem_u32(&bar_mma[0]), 1);
         mbar_init(smem_u32(&bar_mma[1]), 1);
+        mbar_init(smem_u32(&bar_full[0]), 1);
+        mbar_init(smem_u32(&bar_full[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {                                         // two accumulator buffers x 128 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+    if (warp == 0) {                                         // all 512 columns: two buffers x (D | X' hi | X' lo)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid < 64) {                                          // global offset of block value t
         uint64_t o = 0;
         for (uint32_t b = 0; b < 6; ++b) o |= (uint64_t)((tid >> b) & 1u) << P.blk[b];
         boff[tid] = o;
+    }
+    if (tid >= 64 && tid < 64 + nrows) {                     // global offset of staging row r: its bits go to the resident positions above the row
+        const uint32_t r = tid - 64;
+        uint64_t o = 0;
+        for (uint32_t j = rowbits; j < 13; ++j) o |= (uint64_t)((r >> (j - rowbits)) & 1u) << P.res[j];
+        rowoff[r] = o;
     }
     tc_fence_before();
     __syncthreads();
@@ -155,15 +182,39 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
     const uint32_t ncol = tid & 127, qt = tid >> 7;
     uint64_t coff = 0;
     for (uint32_t b = 0; b < 7; ++b) coff |= (uint64_t)((ncol >> b) & 1u) << P.col[b];
-    const uint32_t xrow = (ncol & 7u) * 16u + (ncol >> 3) * 2048u;          // byte offset of row `ncol` in an operand term
+    // the same thing inside a staging tile: local index = resident bits compacted in ascending order
+    uint32_t lpos_blk[6], lcol = 0, lqt = 0;
+    {
+        uint32_t lpos_col[7];
+        for (uint32_t j = 0, ib = 0, ic = 0; j < 13; ++j) {
+            if (ib < 6 && P.res[j] == P.blk[ib]) lpos_blk[ib++] = j;
+            else lpos_col[ic++] = j;
+        }
+        for (uint32_t b = 0; b < 7; ++b) lcol |= ((ncol >> b) & 1u) << lpos_col[b];
+        lqt = ((qt & 1u) << lpos_blk[4]) | ((qt >> 1) << lpos_blk[5]);
+    }
+    const uint32_t s0 = 8u << lpos_blk[0], s1 = 8u << lpos_blk[1], s2 = 8u << lpos_blk[2], s3 = 8u << lpos_blk[3];   // byte strides of value bits 0..3
+    const uint32_t sbase = (lcol | lqt) * 8u;
     const uint32_t dbg = P.pad;        // timing experiments only (ROCQ_BLOCK_DEBUG): 1 = no MMA, 2 = no split, 4 = no stores, 8 = no renorm
     const float scale = P.scale, inv_scale = 1.f / P.scale;
     const uint64_t first = blockIdx.x, stride = gridDim.x;
     const uint64_t cnt = P.ntiles > first ? (P.ntiles - first + stride - 1) / stride : 0;     // tiles of this CTA
-
     const uint64_t* off = boff + 16 * qt;                                   // block-value offsets of this thread (shared memory)
+    const uint32_t tlane = tmem_d + (((warp & 3u) * 32u) << 16);            // this warp's TMEM lane quarter
 
-    // the index deposit costs ~130 instructions: one thread does it per tile, two tiles ahead, and publishes the result
+    // phase timers (ROCQ_BLOCK_DEBUG & 16): threads 0 and 64 of CTA 0 accumulate clock deltas between marks
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+    const bool timed = (dbg & 16u) && blockIdx.x == 0 && (tid == 0 || tid == 64);
+    auto mark = [&](int k) {
+        if (timed) {
+            const long long t = clock64();
+            tacc[k] += t - tlast;
+            tlast = t;
+        }
+    };
+    if (timed) tlast = clock64();
+
+    // the index deposit costs ~130 instructions: one thread does it per tile, ahead of time, and publishes the result
     auto publish_tile = [&](uint64_t i) {
         if (i < cnt) {
             uint64_t member;
@@ -171,27 +222,32 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             tbase[i & 7u] = (member << P.n) + base;
         }
     };
-    auto tile_ptr = [&](uint64_t i) -> float2* { return state + tbase[i & 7u] + coff; };
-    auto load_tile = [&](uint64_t i, float2 (&raw)[16]) {
-        if (i < cnt) {
-            const float2* g = tile_ptr(i);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) raw[j] = g[off[j]];
+    // bulk-copy the rows of tile i into staging buffer i & 1 (tbase[i & 7] must be visible).  A bulk copy is issued from
+    // the uniform datapath, i.e. one at a time per warp (~60 clocks each): every warp issues its share of the rows.
+    auto load_tile = [&](uint64_t i) {
+        if (i < cnt && lane == 0) {
+            const uint32_t bar = smem_u32(&bar_full[i & 1u]);
+            if (warp == 0) mbar_expect_tx(bar, TILE_BYTES);
+            const float2* g = state + tbase[i & 7u];
+            const uint32_t dst = smem_u32(smem + SMEM_S + (uint32_t)(i & 1u) * TILE_BYTES);
+            for (uint32_t r = warp; r < nrows; r += BT / 32) bulk_g2s(dst + r * rowbytes, g + rowoff[r], rowbytes, bar);
         }
     };
 
-    // ---- epilogue of tile i from accumulator buffer B: TMEM lane = column; re at column t, im at column 64 + t ----
+    // ---- epilogue of tile i from pipeline buffer B: TMEM lane = column; re at column t, im at column 64 + t ----
     auto epilogue = [&](auto BC, uint64_t i) {
         constexpr uint32_t B = decltype(BC)::value;
+        mark(4);
         if (!(dbg & 1u)) mbar_wait(smem_u32(&bar_mma[B]), (uint32_t)(i >> 1) & 1u);
         tc_fence_after();
-        // one accumulator per buffer: re at TMEM column t, im at column 64 + t (TMEM reads run at 64 B/clk per SM, so the
-        // accumulator is read exactly once)
-        const uint32_t taddr = tmem_d + (((warp & 3u) * 32u) << 16) + B * 128u + 16u * qt;
+        mark(5);
+        // (TMEM reads run at 64 B/clk per SM, so the accumulator is read exactly once)
+        const uint32_t taddr = tlane + B * TM_BUF + TM_D + 16u * qt;
         uint32_t re[16], im[16];
         tmem_ld16(taddr, re);
         tmem_ld16(taddr + 64u, im);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        mark(6);
         float f = inv_scale;
         if (P.renorm) {
             // A unitary block preserves the norm of every tile column (it only mixes the 64 block values of a column).
@@ -207,83 +263,98 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             const float sout = (nout[ncol] + nout[128 + ncol]) + (nout[256 + ncol] + nout[384 + ncol]);   // of the scaled outputs
             if (sout > 0.f && sin > 0.f) f = sqrtf(sin / sout);
         }
+        mark(7);
         if (!(dbg & 4u)) {
-            float2* gt = tile_ptr(i);
+            float2* gt = state + tbase[i & 7u] + coff;
 #pragma unroll
             for (int j = 0; j < 16; ++j) gt[off[j]] = make_float2(__uint_as_float(re[j]) * f, __uint_as_float(im[j]) * f);
         }
         tc_fence_before();
+        mark(8);
     };
 
-    // ---- one pipeline step: split tile i into operand buffer B, start its MMAs, prefetch tile i+2, finish tile i-1 ----
-    auto step = [&](auto BC, uint64_t i, float2 (&raw)[16]) {
+    // ---- one pipeline step: split tile i (staging buffer B) into TMEM, start its MMAs, refill the staging buffer with tile i+2,
+    //      finish tile i-1 ----
+    auto step = [&](auto BC, uint64_t i) {
         constexpr uint32_t B = decltype(BC)::value;
-        unsigned char* X = smem + SMEM_X + B * 2 * TERM_BYTES;
-        if (!(dbg & 2u)) {
+        mbar_wait(smem_u32(&bar_full[B]), (uint32_t)(i >> 1) & 1u);
+        mark(0);
+        const unsigned char* S = smem + SMEM_S + B * TILE_BYTES + sbase;
+        float sin = 0.f;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t hr[4], lr[4], hi[4], li[4];
+        for (int c = 0; c < 2; ++c) {                                      // 8 block values -> 4 packed words per (term, re|im)
+            uint32_t hr[4], lr[4], hi[4], li[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    split2(raw[8 * c + 2 * j].x * scale, raw[8 * c + 2 * j + 1].x * scale, hr[j], lr[j]);
-                    split2(raw[8 * c + 2 * j].y * scale, raw[8 * c + 2 * j + 1].y * scale, hi[j], li[j]);
-                }
-                const uint32_t o_re = xrow + (2 * qt + c) * 128u, o_im = xrow + (8 + 2 * qt + c) * 128u;   // K groups of 8 values
-                *reinterpret_cast<uint4*>(X + o_re) = make_uint4(hr[0], hr[1], hr[2], hr[3]);
-                *reinterpret_cast<uint4*>(X + TERM_BYTES + o_re) = make_uint4(lr[0], lr[1], lr[2], lr[3]);
-                *reinterpret_cast<uint4*>(X + o_im) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(X + TERM_BYTES + o_im) = make_uint4(li[0], li[1], li[2], li[3]);
+            for (int j = 0; j < 4; ++j) {
+                const int v0 = 8 * c + 2 * j, v1 = v0 + 1;
+                const float2 a0 = *reinterpret_cast<const float2*>(S + ((v0 & 1) ? s0 : 0u) + ((v0 & 2) ? s1 : 0u) + ((v0 & 4) ? s2 : 0u) + ((v0 & 8) ? s3 : 0u));
+                const float2 a1 = *reinterpret_cast<const float2*>(S + ((v1 & 1) ? s0 : 0u) + ((v1 & 2) ? s1 : 0u) + ((v1 & 4) ? s2 : 0u) + ((v1 & 8) ? s3 : 0u));
+                sin = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, sin))));
+                split2(a0.x * scale, a1.x * scale, hr[j], lr[j]);
+                split2(a0.y * scale, a1.y * scale, hi[j], li[j]);
+            }
+            // packed words [8*qt + 4*c, +4) of the re half and [32 + 8*qt + 4*c, +4) of the im half of this thread's TMEM lane
+            const uint32_t wre = 8u * qt + 4u * c, wim = 32u + 8u * qt + 4u * c;
+            if (!(dbg & 2u)) {
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tlane + B * TM_BUF + TM_XH + wre), "r"(hr[0]), "r"(hr[1]), "r"(hr[2]), "r"(hr[3]) : "memory");
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tlane + B * TM_BUF + TM_XL + wre), "r"(lr[0]), "r"(lr[1]), "r"(lr[2]), "r"(lr[3]) : "memory");
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tlane + B * TM_BUF + TM_XH + wim), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tlane + B * TM_BUF + TM_XL + wim), "r"(li[0]), "r"(li[1]), "r"(li[2]), "r"(li[3]) : "memory");
             }
         }
-        if (P.renorm) {                                                    // |column|^2 going in (this thread's 16 block values)
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s = fmaf(raw[j].x, raw[j].x, fmaf(raw[j].y, raw[j].y, s));
-            nin[B * 512 + qt * 128 + ncol] = s;
-        }
-        if (tid == 32) publish_tile(i + 2);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> visible to the tensor core
+        if (P.renorm) nin[B * 512 + qt * 128 + ncol] = sin;                // |column|^2 going in (this thread's 16 block values)
+        if (tid == 32) publish_tile(i + 3);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        mark(1);
         tc_fence_before();
-        __syncthreads();
+        __syncthreads();                                                   // staging buffer B is consumed, X' of tile i is in TMEM
+        mark(2);
 
-        if (tid == 0 && !(dbg & 1u)) {                                     // 24 MMAs, one issuing thread
-            tc_fence_after();
-            const uint32_t xh = smem_u32(X), xl = xh + TERM_BYTES, uh = smem_u32(smem + SMEM_U), ul = uh + TERM_BYTES;
-            const uint32_t d = tmem_d + B * 128u;
-            // The tensor core truncates when it adds a K = 16 partial sum into the fp32 accumulator.  The two correction
-            // products (2^-11 smaller) therefore go first, while the accumulator is small, and the dominant hi*hi product
-            // last: only its eight additions truncate at full magnitude.
+        if (warp == 0) {
+            if (lane == 0 && !(dbg & 1u)) {                                // 24 MMAs, one issuing thread
+                tc_fence_after();
+                const uint32_t uh = smem_u32(smem + SMEM_U), ul = uh + TERM_BYTES;
+                const uint32_t d = tmem_d + B * TM_BUF + TM_D, xh = tmem_d + B * TM_BUF + TM_XH, xl = tmem_d + B * TM_BUF + TM_XL;
+                // The tensor core truncates when it adds a K = 16 partial sum into the fp32 accumulator.  The two correction
+                // products (2^-11 smaller) therefore go first, while the accumulator is small, and the dominant hi*hi product
+                // last: only its eight additions truncate at full magnitude.
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) umma(d, umma_desc(xh + ks * 256u, 128u, 2048u), umma_desc(ul + ks * 256u, 128u, 2048u), ks != 0);
+                for (int ks = 0; ks < 8; ++ks) umma_ts(d, xh + 8u * ks, umma_desc(ul + ks * 256u, 128u, 2048u), ks != 0);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) umma(d, umma_desc(xl + ks * 256u, 128u, 2048u), umma_desc(uh + ks * 256u, 128u, 2048u), 1u);
+                for (int ks = 0; ks < 8; ++ks) umma_ts(d, xl + 8u * ks, umma_desc(uh + ks * 256u, 128u, 2048u), 1u);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) umma(d, umma_desc(xh + ks * 256u, 128u, 2048u), umma_desc(uh + ks * 256u, 128u, 2048u), 1u);
-            umma_commit(smem_u32(&bar_mma[B]));
+                for (int ks = 0; ks < 8; ++ks) umma_ts(d, xh + 8u * ks, umma_desc(uh + ks * 256u, 128u, 2048u), 1u);
+                umma_commit(smem_u32(&bar_mma[B]));
+            }
         }
-        load_tile(i + 2, raw);                                             // two tiles ahead, into the registers just consumed
+        load_tile(i + 2);                                                  // two tiles ahead, into the buffer just consumed
+        mark(3);
         if (i >= 1) epilogue(std::integral_constant<uint32_t, B ^ 1u>{}, i - 1);
     };
 
-    float2 raw0[16], raw1[16];
-    if (tid == 32) { publish_tile(0); publish_tile(1); }
+    if (tid == 32) { publish_tile(0); publish_tile(1); publish_tile(2); }
     __syncthreads();
-    load_tile(0, raw0);
-    load_tile(1, raw1);
+    load_tile(0);
+    load_tile(1);
     mbar_wait(smem_u32(&bar_u), 0);
 
     for (uint64_t i = 0; i < cnt; i += 2) {
-        step(std::integral_constant<uint32_t, 0u>{}, i, raw0);
-        if (i + 1 < cnt) step(std::integral_constant<uint32_t, 1u>{}, i + 1, raw1);
+        step(std::integral_constant<uint32_t, 0u>{}, i);
+        if (i + 1 < cnt) step(std::integral_constant<uint32_t, 1u>{}, i + 1);
     }
     if (cnt > 0) {
         if ((cnt - 1) & 1u) epilogue(std::integral_constant<uint32_t, 1u>{}, cnt - 1);
         else epilogue(std::integral_constant<uint32_t, 0u>{}, cnt - 1);
     }
 
+    if (timed) {
+        long long* out = reinterpret_cast<long long*>(const_cast<unsigned char*>(uterms) + 2 * TERM_BYTES) + (tid ? 16 : 0);
+        for (int k = 0; k < 10; ++k) out[k] = tacc[k];
+        out[10] = (long long)cnt;
+    }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
 }
 
 }  // namespace

@@ -231,6 +231,8 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     for (unsigned p = 0; p < n && nc < RQ_BLOCK_COLBITS; ++p) if (!((bm >> p) & 1ull)) { P.col[nc++] = (uint8_t)p; rm |= 1ull << p; }
     unsigned nr = 0;
     for (unsigned p = 0; p < n; ++p) if ((rm >> p) & 1ull) P.res[nr++] = (uint8_t)p;
+    while (P.rowbits < 13 && P.res[P.rowbits] == P.rowbits) ++P.rowbits;       // tile rows are bulk-copied: >= 256 B each
+    if (P.rowbits < 5) return ROCQ_STATUS_NOT_IMPLEMENTED;
     // unitary?  (then every tile column keeps its norm, which the kernel restores exactly)
     double dev = 0.0;
     for (unsigned a = 0; a < 64; ++a)
@@ -246,10 +248,22 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     std::vector<uint16_t> terms;
     build_block_terms(U, terms);
     void* d_terms = nullptr;
-    RQ_CUDA(cudaMallocAsync(&d_terms, RQ_BLOCK_TERMS * RQ_BLOCK_TERM_BYTES, h->stream), "block terms alloc");
+    RQ_CUDA(cudaMallocAsync(&d_terms, RQ_BLOCK_TERMS * RQ_BLOCK_TERM_BYTES + 256, h->stream), "block terms alloc");   // + debug timers
     // pageable source: cudaMemcpyAsync stages it before returning, so `terms` may go out of scope
     RQ_CUDA(cudaMemcpyAsync(d_terms, terms.data(), RQ_BLOCK_TERMS * RQ_BLOCK_TERM_BYTES, cudaMemcpyHostToDevice, h->stream), "block terms upload");
     RQ_CUDA(rq_launch_block_sweep(state, &P, d_terms, h->stream), "block sweep launch");
+    if (P.pad & 16u) {                                   // ROCQ_BLOCK_DEBUG & 16: per-phase clock totals of CTA 0, threads 0 and 64
+        long long t[32];
+        cudaMemcpyAsync(t, (char*)d_terms + RQ_BLOCK_TERMS * RQ_BLOCK_TERM_BYTES, sizeof t, cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+        static int printed = 0;
+        if (printed++ < 2)
+            for (int w = 0; w < 2; ++w) {
+                fprintf(stderr, "[block timers, thread %d, %lld tiles] clocks per tile:", w ? 64 : 0, t[16 * w + 10]);
+                for (int k = 0; k < 9; ++k) fprintf(stderr, " %d:%.0f", k, (double)t[16 * w + k] / (double)std::max(1ll, t[16 * w + 10]));
+                fprintf(stderr, "\n");
+            }
+    }
     RQ_CUDA(cudaFreeAsync(d_terms, h->stream), "block terms free");
     h->stats.kernelLaunches++;
     h->stats.sweeps++;
@@ -706,6 +720,12 @@ rocqStatus_t rocsvxApplyBlock6(rocsvHandle_t h, rocComplex* d, unsigned n, const
     for (unsigned c = 0; c < 64; ++c)
         for (unsigned r = 0; r < 64; ++r) U[remap(r) + 64u * remap(c)] = cd(matrix[2 * (r + 64u * c)], matrix[2 * (r + 64u * c) + 1]);
     h->stats.gatesSubmitted++;
+    if (blk[0] < 5) {
+        // the tensor-core kernel stages tiles as rows of >= 32 consecutive amplitudes, i.e. block qubits >= 5;
+        // a block on the lowest qubits takes the generic dense path
+        std::vector<HostOp> one{rq::make_matrix(blk, 0ull, U)};
+        return run_ops(h, state, n, one, false);
+    }
     return run_block(h, state, n, blk, U);
 }
 

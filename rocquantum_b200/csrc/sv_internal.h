@@ -124,7 +124,7 @@ struct rq_block_params {
     uint32_t renorm;                // 1: the block is unitary -> restore every column's norm in the epilogue
     uint32_t pad;                   // debug switches (ROCQ_BLOCK_DEBUG), 0 in production
     float scale;                    // power of two that brings amplitudes into the fp16 normal range
-    uint32_t pad2;
+    uint32_t rowbits;               // log2(amplitudes per contiguous row of a tile): resident positions 0..rowbits-1 are 0..rowbits-1
     uint64_t ntiles;                // batch * 2^(n-13)
     uint8_t res[16];                // ascending resident positions (block + column bits)
     uint8_t blk[8];                 // 6 block positions, ascending: bit b of the block value <-> blk[b]

@@ -217,6 +217,12 @@ rocqStatus_t rocsvxTimerStop(rocsvHandle_t handle, double* milliseconds);
 rocqStatus_t rocsvxPlanCircuit(unsigned numQubits, unsigned tileBits, const rocsvxGateOp* ops, size_t numOps,
                                unsigned* numSweeps, char* buf, size_t bufSize);
 
+/* Host-only: the mixed plan the engine follows when tensor-core blocks are enabled (complex64).  Text: one line
+ * "B p0..p5" per 6-qubit block or "S ..." per ordinary sweep, each followed by its "O ..." op lines in execution order.
+ * minCost <= 0 selects the engine default. */
+rocqStatus_t rocsvxPlanCircuitBlocks(unsigned numQubits, const rocsvxGateOp* ops, size_t numOps, double minCost,
+                                     unsigned* numBlocks, unsigned* numSweeps, char* buf, size_t bufSize);
+
 /* ---- multi-process distribution (one process per GPU).  The 128-byte id is NCCL's unique id: rank 0
  *      obtains it and the host broadcasts it by any means (torch.distributed in bench.py). ---- */
 rocqStatus_t rocsvxDistGetUniqueId(void* id128);

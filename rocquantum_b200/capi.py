@@ -93,6 +93,7 @@ PROTOTYPES = {
     "rocsvxTimerStart": [_h],
     "rocsvxTimerStop": [_h, C.POINTER(_d)],
     "rocsvxPlanCircuit": [_u, _u, C.POINTER(GateOp), _sz, _up, C.c_char_p, _sz],
+    "rocsvxPlanCircuitBlocks": [_u, C.POINTER(GateOp), _sz, _d, _up, _up, C.c_char_p, _sz],
     "rocsvxDistGetUniqueId": [_p],
     "rocsvxDistInit": [_h, C.c_int, C.c_int, _p],
     "rocsvxDistGetInfo": [_h, C.POINTER(C.c_int), C.POINTER(C.c_int), _up, C.POINTER(_p)],

@@ -23,6 +23,7 @@
 //     two tiles ahead (128 KB in flight per SM).
 // complex64 only: there is no fp64 tensor path for this (complex128 stays on the CUDA-core sweep).
 #ifndef ROCQ_PRECISION_DOUBLE
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,17 +34,16 @@
 
 namespace {
 
-constexpr int BT = 512;                        // threads per CTA: 4 warps per TMEM lane quarter, 16 block values per thread
-constexpr uint32_t TERM_BYTES = 32768;         // one fp16 term of a 128 x 128 operand
+constexpr int NW = 512;                        // worker threads: 4 warps per TMEM lane quarter, 16 block values per thread
+constexpr int BT = NW + 32;                    // + one warp that only issues the MMAs
+constexpr uint32_t MAT_BYTES = 8192;           // one fp16 term of a 64 x 64 operand (Re U or Im U)
 constexpr uint32_t TILE_BYTES = 65536;         // 2^13 complex64 amplitudes
-constexpr uint32_t SMEM_U = 0;                                    // 2 terms of A' (the B operand of the MMA)
-constexpr uint32_t SMEM_S = 2 * TERM_BYTES;                       // 2 staging tiles (fp32 amplitudes, TMA destination)
-constexpr uint32_t SMEM_TAB = SMEM_S + 2 * TILE_BYTES;            // 64 u64 global block offsets
-constexpr uint32_t SMEM_ROW = SMEM_TAB + 64 * 8;                  // <= 256 u64 global row offsets
-constexpr uint32_t SMEM_NIN = SMEM_ROW + 256 * 8;                 // column norms going in: [buffer][quarter][column]
-constexpr uint32_t SMEM_NOUT = SMEM_NIN + 2 * 4 * 128 * 4;        // column norms coming out: [quarter][column]
-constexpr uint32_t SMEM_BYTES = SMEM_NOUT + 4 * 128 * 4 + 64;
-// TMEM columns, per pipeline buffer b (at 256 * b): [0,128) accumulator D, [128,192) hi term of X', [192,256) lo term of X'
+constexpr uint32_t SMEM_U = 0;                                    // Re U hi | Re U lo | Im U hi | Im U lo  (B operands, N = 64)
+constexpr uint32_t SMEM_S = 4 * MAT_BYTES;                        // 3 tiles (fp32 amplitudes): bulk-loaded, transformed in place, bulk-stored
+constexpr uint32_t SMEM_ROW = SMEM_S + 3 * TILE_BYTES;            // <= 256 u32 global row offsets, in rows
+constexpr uint32_t SMEM_BYTES = SMEM_ROW + 256 * 4;
+// TMEM columns, per pipeline buffer b (at 256 * b): [0,64) Re D, [64,128) Im D, then the packed fp16 pairs of X':
+// [128,160) Re hi, [160,192) Im hi, [192,224) Re lo, [224,256) Im lo
 constexpr uint32_t TM_D = 0, TM_XH = 128, TM_XL = 192, TM_BUF = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,8 +74,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-// instruction descriptor (kind::f16): D = F32, A = B = F16, both K-major, N = 128, M = 128
-constexpr uint32_t IDESC = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor (kind::f16): D = F32, A = B = F16, both K-major, N = 64, M = 128; bit 14 negates B
+constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_NEGB = IDESC | (1u << 14);
 
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t accumulate) {
     asm volatile(
@@ -86,14 +87,40 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, ui
         "}" ::"r"(tmem_d), "l"(a), "l"(b), "r"(IDESC), "r"(accumulate), "r"(0u) : "memory");
 }
 // A operand (X') from tensor memory, B operand (A' = block matrix) from shared memory
-__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b, uint32_t accumulate) {
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
-        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(b), "r"(IDESC), "r"(accumulate), "r"(0u) : "memory");
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+// whole-tile copies through a tensor map (rank 2..5; coordinates in elements of 8 bytes, innermost first)
+__device__ __forceinline__ void tensor_g2s(uint32_t dst, const CUtensorMap* tm, const int32_t (&c)[5], uint32_t rank, uint32_t bar) {
+    const uint64_t t = reinterpret_cast<uint64_t>(tm);
+    if (rank == 2) asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                ::"r"(dst), "l"(t), "r"(bar), "r"(c[0]), "r"(c[1]) : "memory");
+    else if (rank == 3) asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                     ::"r"(dst), "l"(t), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory");
+    else if (rank == 4) asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                                     ::"r"(dst), "l"(t), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory");
+    else asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                      ::"r"(dst), "l"(t), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+}
+__device__ __forceinline__ void tensor_s2g(const CUtensorMap* tm, const int32_t (&c)[5], uint32_t rank, uint32_t src) {
+    const uint64_t t = reinterpret_cast<uint64_t>(tm);
+    if (rank == 2) asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(t), "r"(src), "r"(c[0]), "r"(c[1]) : "memory");
+    else if (rank == 3) asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(t), "r"(src), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory");
+    else if (rank == 4) asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(t), "r"(src), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory");
+    else asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(t), "r"(src), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory"); }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                  "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
@@ -133,225 +160,288 @@ __device__ __forceinline__ uint64_t tile_base(uint64_t tile, const rq_block_para
 }
 
 __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__ state, const unsigned char* __restrict__ uterms,
-                                                             const __grid_constant__ rq_block_params P) {
+                                                             const __grid_constant__ rq_block_params P,
+                                                             const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_u, bar_mma[2], bar_full[2];
+    __shared__ __align__(8) uint64_t bar_u, bar_mma[2], bar_x[2], bar_full[3];
     __shared__ uint32_t tmem_slot;
     __shared__ uint64_t tbase[8];      // ring: amplitude offset of the CTA's tile i at [i & 7], computed by one thread per tile
+    __shared__ float2 red[2][16];      // per-warp (|in|^2, |out|^2) of a tile, double-buffered
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t* boff = reinterpret_cast<uint64_t*>(smem + SMEM_TAB);
-    uint64_t* rowoff = reinterpret_cast<uint64_t*>(smem + SMEM_ROW);
-    float* nin = reinterpret_cast<float*>(smem + SMEM_NIN);
-    float* nout = reinterpret_cast<float*>(smem + SMEM_NOUT);
+    uint32_t* rowoff = reinterpret_cast<uint32_t*>(smem + SMEM_ROW);
     const uint32_t rowbits = P.rowbits, nrows = 1u << (13u - rowbits), rowbytes = 8u << rowbits;
 
     if (tid == 0) {
         mbar_init(smem_u32(&bar_u), 1);
-        mbar_init(smem_u32(&bar_mma[0]), 1);
-        mbar_init(smem_u32(&bar_mma[1]), 1);
-        mbar_init(smem_u32(&bar_full[0]), 1);
-        mbar_init(smem_u32(&bar_full[1]), 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_mma[b]), 1); mbar_init(smem_u32(&bar_x[b]), NW / 32); }
+        for (int b = 0; b < 3; ++b) mbar_init(smem_u32(&bar_full[b]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {                                         // all 512 columns: two buffers x (D | X' hi | X' lo)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid < 64) {                                          // global offset of block value t
-        uint64_t o = 0;
-        for (uint32_t b = 0; b < 6; ++b) o |= (uint64_t)((tid >> b) & 1u) << P.blk[b];
-        boff[tid] = o;
-    }
-    if (tid >= 64 && tid < 64 + nrows) {                     // global offset of staging row r: its bits go to the resident positions above the row
+    if (tid >= 64 && tid < 64 + nrows) {                     // global offset of tile row r (in rows): its bits go to the resident positions above the row
         const uint32_t r = tid - 64;
         uint64_t o = 0;
         for (uint32_t j = rowbits; j < 13; ++j) o |= (uint64_t)((r >> (j - rowbits)) & 1u) << P.res[j];
-        rowoff[r] = o;
+        rowoff[r] = (uint32_t)(o >> rowbits);
     }
+    if (tid < 32) reinterpret_cast<float2*>(red)[tid] = make_float2(0.f, 0.f);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
-
-    if (tid == 0) {                                          // the two fp16 terms of A' stay resident for all tiles
-        mbar_expect_tx(smem_u32(&bar_u), 2 * TERM_BYTES);
-        for (uint32_t j = 0; j < 2; ++j) bulk_g2s(smem_u32(smem + SMEM_U + j * TERM_BYTES), uterms + (size_t)j * TERM_BYTES, TERM_BYTES, smem_u32(&bar_u));
-    }
-
-    // this thread: tile column ncol (= TMEM lane), block values [16*qt, 16*qt+16)
-    const uint32_t ncol = tid & 127, qt = tid >> 7;
-    uint64_t coff = 0;
-    for (uint32_t b = 0; b < 7; ++b) coff |= (uint64_t)((ncol >> b) & 1u) << P.col[b];
-    // the same thing inside a staging tile: local index = resident bits compacted in ascending order
-    uint32_t lpos_blk[6], lcol = 0, lqt = 0;
-    {
-        uint32_t lpos_col[7];
-        for (uint32_t j = 0, ib = 0, ic = 0; j < 13; ++j) {
-            if (ib < 6 && P.res[j] == P.blk[ib]) lpos_blk[ib++] = j;
-            else lpos_col[ic++] = j;
-        }
-        for (uint32_t b = 0; b < 7; ++b) lcol |= ((ncol >> b) & 1u) << lpos_col[b];
-        lqt = ((qt & 1u) << lpos_blk[4]) | ((qt >> 1) << lpos_blk[5]);
-    }
-    const uint32_t s0 = 8u << lpos_blk[0], s1 = 8u << lpos_blk[1], s2 = 8u << lpos_blk[2], s3 = 8u << lpos_blk[3];   // byte strides of value bits 0..3
-    const uint32_t sbase = (lcol | lqt) * 8u;
     const uint32_t dbg = P.pad;        // timing experiments only (ROCQ_BLOCK_DEBUG): 1 = no MMA, 2 = no split, 4 = no stores, 8 = no renorm
-    const float scale = P.scale, inv_scale = 1.f / P.scale;
     const uint64_t first = blockIdx.x, stride = gridDim.x;
     const uint64_t cnt = P.ntiles > first ? (P.ntiles - first + stride - 1) / stride : 0;     // tiles of this CTA
-    const uint64_t* off = boff + 16 * qt;                                   // block-value offsets of this thread (shared memory)
-    const uint32_t tlane = tmem_d + (((warp & 3u) * 32u) << 16);            // this warp's TMEM lane quarter
 
-    // phase timers (ROCQ_BLOCK_DEBUG & 16): threads 0 and 64 of CTA 0 accumulate clock deltas between marks
-    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
-    const bool timed = (dbg & 16u) && blockIdx.x == 0 && (tid == 0 || tid == 64);
-    auto mark = [&](int k) {
-        if (timed) {
-            const long long t = clock64();
-            tacc[k] += t - tlast;
-            tlast = t;
-        }
-    };
-    if (timed) tlast = clock64();
-
-    // the index deposit costs ~130 instructions: one thread does it per tile, ahead of time, and publishes the result
-    auto publish_tile = [&](uint64_t i) {
-        if (i < cnt) {
-            uint64_t member;
-            const uint64_t base = tile_base(first + i * stride, P, member);
-            tbase[i & 7u] = (member << P.n) + base;
-        }
-    };
-    // bulk-copy the rows of tile i into staging buffer i & 1 (tbase[i & 7] must be visible).  A bulk copy is issued from
-    // the uniform datapath, i.e. one at a time per warp (~60 clocks each): every warp issues its share of the rows.
-    auto load_tile = [&](uint64_t i) {
-        if (i < cnt && lane == 0) {
-            const uint32_t bar = smem_u32(&bar_full[i & 1u]);
-            if (warp == 0) mbar_expect_tx(bar, TILE_BYTES);
-            const float2* g = state + tbase[i & 7u];
-            const uint32_t dst = smem_u32(smem + SMEM_S + (uint32_t)(i & 1u) * TILE_BYTES);
-            for (uint32_t r = warp; r < nrows; r += BT / 32) bulk_g2s(dst + r * rowbytes, g + rowoff[r], rowbytes, bar);
-        }
-    };
-
-    // ---- epilogue of tile i from pipeline buffer B: TMEM lane = column; re at column t, im at column 64 + t ----
-    auto epilogue = [&](auto BC, uint64_t i) {
-        constexpr uint32_t B = decltype(BC)::value;
-        mark(4);
-        if (!(dbg & 1u)) mbar_wait(smem_u32(&bar_mma[B]), (uint32_t)(i >> 1) & 1u);
-        tc_fence_after();
-        mark(5);
-        // (TMEM reads run at 64 B/clk per SM, so the accumulator is read exactly once)
-        const uint32_t taddr = tlane + B * TM_BUF + TM_D + 16u * qt;
-        uint32_t re[16], im[16];
-        tmem_ld16(taddr, re);
-        tmem_ld16(taddr + 64u, im);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        mark(6);
-        float f = inv_scale;
-        if (P.renorm) {
-            // A unitary block preserves the norm of every tile column (it only mixes the 64 block values of a column).
-            // Restoring it removes the systematic shrink of the tensor core's truncating accumulation, which would
-            // otherwise grow linearly with the number of sweeps.
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s = fmaf(__uint_as_float(re[j]), __uint_as_float(re[j]), fmaf(__uint_as_float(im[j]), __uint_as_float(im[j]), s));
-            nout[qt * 128 + ncol] = s;
-            const float* ni = nin + B * 512;
-            const float sin = (ni[ncol] + ni[128 + ncol]) + (ni[256 + ncol] + ni[384 + ncol]);
-            __syncthreads();
-            const float sout = (nout[ncol] + nout[128 + ncol]) + (nout[256 + ncol] + nout[384 + ncol]);   // of the scaled outputs
-            if (sout > 0.f && sin > 0.f) f = sqrtf(sin / sout);
-        }
-        mark(7);
-        if (!(dbg & 4u)) {
-            float2* gt = state + tbase[i & 7u] + coff;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) gt[off[j]] = make_float2(__uint_as_float(re[j]) * f, __uint_as_float(im[j]) * f);
-        }
-        tc_fence_before();
-        mark(8);
-    };
-
-    // ---- one pipeline step: split tile i (staging buffer B) into TMEM, start its MMAs, refill the staging buffer with tile i+2,
-    //      finish tile i-1 ----
-    auto step = [&](auto BC, uint64_t i) {
-        constexpr uint32_t B = decltype(BC)::value;
-        mbar_wait(smem_u32(&bar_full[B]), (uint32_t)(i >> 1) & 1u);
-        mark(0);
-        const unsigned char* S = smem + SMEM_S + B * TILE_BYTES + sbase;
-        float sin = 0.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {                                      // 8 block values -> 4 packed words per (term, re|im)
-            uint32_t hr[4], lr[4], hi[4], li[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int v0 = 8 * c + 2 * j, v1 = v0 + 1;
-                const float2 a0 = *reinterpret_cast<const float2*>(S + ((v0 & 1) ? s0 : 0u) + ((v0 & 2) ? s1 : 0u) + ((v0 & 4) ? s2 : 0u) + ((v0 & 8) ? s3 : 0u));
-                const float2 a1 = *reinterpret_cast<const float2*>(S + ((v1 & 1) ? s0 : 0u) + ((v1 & 2) ? s1 : 0u) + ((v1 & 4) ? s2 : 0u) + ((v1 & 8) ? s3 : 0u));
-                sin = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, sin))));
-                split2(a0.x * scale, a1.x * scale, hr[j], lr[j]);
-                split2(a0.y * scale, a1.y * scale, hi[j], li[j]);
-            }
-            // packed words [8*qt + 4*c, +4) of the re half and [32 + 8*qt + 4*c, +4) of the im half of this thread's TMEM lane
-            const uint32_t wre = 8u * qt + 4u * c, wim = 32u + 8u * qt + 4u * c;
-            if (!(dbg & 2u)) {
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tlane + B * TM_BUF + TM_XH + wre), "r"(hr[0]), "r"(hr[1]), "r"(hr[2]), "r"(hr[3]) : "memory");
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tlane + B * TM_BUF + TM_XL + wre), "r"(lr[0]), "r"(lr[1]), "r"(lr[2]), "r"(lr[3]) : "memory");
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tlane + B * TM_BUF + TM_XH + wim), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tlane + B * TM_BUF + TM_XL + wim), "r"(li[0]), "r"(li[1]), "r"(li[2]), "r"(li[3]) : "memory");
-            }
-        }
-        if (P.renorm) nin[B * 512 + qt * 128 + ncol] = sin;                // |column|^2 going in (this thread's 16 block values)
-        if (tid == 32) publish_tile(i + 3);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        mark(1);
-        tc_fence_before();
-        __syncthreads();                                                   // staging buffer B is consumed, X' of tile i is in TMEM
-        mark(2);
-
-        if (warp == 0) {
-            if (lane == 0 && !(dbg & 1u)) {                                // 24 MMAs, one issuing thread
+    if (warp == NW / 32) {
+        // ================================ the MMA warp ================================
+        if (lane == 0) {
+            mbar_expect_tx(smem_u32(&bar_u), 4 * MAT_BYTES);          // the block matrix stays resident for all tiles
+            bulk_g2s(smem_u32(smem + SMEM_U), uterms, 4 * MAT_BYTES, smem_u32(&bar_u));
+            mbar_wait(smem_u32(&bar_u), 0);
+            const uint32_t urh = smem_u32(smem + SMEM_U), url = urh + MAT_BYTES, uih = urh + 2 * MAT_BYTES, uil = urh + 3 * MAT_BYTES;
+            for (uint64_t i = 0; i < cnt && !(dbg & 1u); ++i) {
+                const uint32_t b = (uint32_t)i & 1u;
+                mbar_wait(smem_u32(&bar_x[b]), (uint32_t)(i >> 1) & 1u);       // X' of tile i is in tensor memory
                 tc_fence_after();
-                const uint32_t uh = smem_u32(smem + SMEM_U), ul = uh + TERM_BYTES;
-                const uint32_t d = tmem_d + B * TM_BUF + TM_D, xh = tmem_d + B * TM_BUF + TM_XH, xl = tmem_d + B * TM_BUF + TM_XL;
-                // The tensor core truncates when it adds a K = 16 partial sum into the fp32 accumulator.  The two correction
-                // products (2^-11 smaller) therefore go first, while the accumulator is small, and the dominant hi*hi product
-                // last: only its eight additions truncate at full magnitude.
+                const uint32_t dre = tmem_d + b * TM_BUF + TM_D, dim = dre + 64u;
+                const uint32_t xrh = tmem_d + b * TM_BUF + TM_XH, xih = xrh + 32u, xrl = tmem_d + b * TM_BUF + TM_XL, xil = xrl + 32u;
+                // Re D = Xr Ur^T - Xi Ui^T, Im D = Xr Ui^T + Xi Ur^T, each as three fp16 products (hi*lo, lo*hi, hi*hi).
+                // The tensor core truncates when it adds a K = 16 partial sum into the fp32 accumulator, so the two correction
+                // products (2^-11 smaller) go first, while the accumulator is small, and the dominant hi*hi product last.
+                auto product = [&](uint32_t xr, uint32_t xi, uint32_t ur, uint32_t ui, bool first_product) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) umma_ts(d, xh + 8u * ks, umma_desc(ul + ks * 256u, 128u, 2048u), ks != 0);
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) umma_ts(d, xl + 8u * ks, umma_desc(uh + ks * 256u, 128u, 2048u), 1u);
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) umma_ts(d, xh + 8u * ks, umma_desc(uh + ks * 256u, 128u, 2048u), 1u);
-                umma_commit(smem_u32(&bar_mma[B]));
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t dur = umma_desc(ur + ks * 256u, 128u, 1024u), dui = umma_desc(ui + ks * 256u, 128u, 1024u);
+                        umma_ts(dre, xr + 8u * ks, dur, IDESC, !(first_product && ks == 0));
+                        umma_ts(dim, xr + 8u * ks, dui, IDESC, !(first_product && ks == 0));
+                        umma_ts(dre, xi + 8u * ks, dui, IDESC_NEGB, 1u);
+                        umma_ts(dim, xi + 8u * ks, dur, IDESC, 1u);
+                    }
+                };
+                product(xrh, xih, url, uil, true);
+                product(xrl, xil, urh, uih, false);
+                product(xrh, xih, urh, uih, false);
+                umma_commit(smem_u32(&bar_mma[b]));
             }
         }
-        load_tile(i + 2);                                                  // two tiles ahead, into the buffer just consumed
-        mark(3);
-        if (i >= 1) epilogue(std::integral_constant<uint32_t, B ^ 1u>{}, i - 1);
-    };
+    } else {
+        // ================================ 16 worker warps ================================
+        // this thread: tile column ncol (= TMEM lane), block values [16*qt, 16*qt+16)
+        const uint32_t ncol = tid & 127, qt = tid >> 7;
+        // position inside a staged tile: local index = resident bits compacted in ascending order
+        uint32_t lpos_blk[6], lcol = 0, lqt = 0;
+        {
+            uint32_t lpos_col[7];
+            for (uint32_t j = 0, ib = 0, ic = 0; j < 13; ++j) {
+                if (ib < 6 && P.res[j] == P.blk[ib]) lpos_blk[ib++] = j;
+                else lpos_col[ic++] = j;
+            }
+            for (uint32_t b = 0; b < 7; ++b) lcol |= ((ncol >> b) & 1u) << lpos_col[b];
+            lqt = ((qt & 1u) << lpos_blk[4]) | ((qt >> 1) << lpos_blk[5]);
+        }
+        const uint32_t s0 = 8u << lpos_blk[0], s1 = 8u << lpos_blk[1], s2 = 8u << lpos_blk[2], s3 = 8u << lpos_blk[3];   // byte strides of value bits 0..3
+        const uint32_t sbase = (lcol | lqt) * 8u;
+        const float scale = P.scale, inv_scale = 1.f / P.scale;
+        const uint32_t tlane = tmem_d + (((warp & 3u) * 32u) << 16);            // this warp's TMEM lane quarter
 
-    if (tid == 32) { publish_tile(0); publish_tile(1); publish_tile(2); }
-    __syncthreads();
-    load_tile(0);
-    load_tile(1);
-    mbar_wait(smem_u32(&bar_u), 0);
+        // phase timers (ROCQ_BLOCK_DEBUG & 16): threads 0 and 64 of CTA 0 accumulate clock deltas between marks
+        long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+        const bool timed = (dbg & 16u) && blockIdx.x == 0 && (tid == 0 || tid == 64);
+        auto mark = [&](int k) {
+            if (timed) {
+                const long long t = clock64();
+                tacc[k] += t - tlast;
+                tlast = t;
+            }
+        };
+        if (timed) tlast = clock64();
 
-    for (uint64_t i = 0; i < cnt; i += 2) {
-        step(std::integral_constant<uint32_t, 0u>{}, i);
-        if (i + 1 < cnt) step(std::integral_constant<uint32_t, 1u>{}, i + 1);
-    }
-    if (cnt > 0) {
-        if ((cnt - 1) & 1u) epilogue(std::integral_constant<uint32_t, 1u>{}, cnt - 1);
-        else epilogue(std::integral_constant<uint32_t, 0u>{}, cnt - 1);
+        // the index deposit costs ~130 instructions: one thread does it per tile, ahead of time, and publishes the result
+        auto publish_tile = [&](uint64_t i) {
+            if (i < cnt) {
+                uint64_t member;
+                const uint64_t base = tile_base(first + i * stride, P, member);
+                tbase[i & 7u] = (member << P.n) + base;
+            }
+        };
+        // A bulk copy is issued from the uniform datapath, one at a time per warp (~60 clocks each), so every worker warp
+        // moves its own share of the rows of a tile: rows warp, warp+16, ...  (tile i lives in buffer i % 3)
+        // Preferred: the tile is one box of a tensor map over the state (one instruction per tile, issued by thread 0).
+        const uint32_t trank = P.trank;
+        auto tile_coords = [&](uint64_t i, int32_t (&c)[5]) {
+            uint64_t t = first + i * stride;                                   // tile index: non-resident bits, compacted, member on top
+#pragma unroll
+            for (uint32_t d = 0; d < 5; ++d) {
+                const uint32_t len = P.tbits[d];
+                if (len == 0) c[d] = 0;
+                else if (len == 255u) c[d] = (int32_t)t;
+                else { c[d] = (int32_t)(t & ((1ull << len) - 1ull)); t >>= len; }
+            }
+        };
+        auto load_rows = [&](uint64_t i) {
+            if (trank) {
+                if (i < cnt && tid == 0) {
+                    const uint32_t bar = smem_u32(&bar_full[i % 3u]);
+                    int32_t c[5];
+                    tile_coords(i, c);
+                    mbar_expect_tx(bar, TILE_BYTES);
+                    tensor_g2s(smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES), &tmap, c, trank, bar);
+                }
+                return;
+            }
+            if (i < cnt && lane == 0) {
+                const uint32_t bar = smem_u32(&bar_full[i % 3u]);
+                if (warp == 0) mbar_expect_tx(bar, TILE_BYTES);
+                const float2* g = state + tbase[i & 7u];
+                const uint32_t dst = smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES);
+                for (uint32_t r = warp; r < nrows; r += NW / 32) bulk_g2s(dst + r * rowbytes, g + ((uint64_t)rowoff[r] << rowbits), rowbytes, bar);
+            }
+        };
+        auto store_rows = [&](uint64_t i) {
+            if (trank) {
+                if (tid == 0) {
+                    int32_t c[5];
+                    tile_coords(i, c);
+                    tensor_s2g(&tmap, c, trank, smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                return;
+            }
+            if (lane == 0) {
+                float2* g = state + tbase[i & 7u];
+                const uint32_t src = smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES);
+                for (uint32_t r = warp; r < nrows; r += NW / 32) bulk_s2g(g + ((uint64_t)rowoff[r] << rowbits), src + r * rowbytes, rowbytes);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        };
+        // shared-memory address of this thread's block value v of a tile
+        auto vaddr = [&](int v) -> uint32_t { return ((v & 1) ? s0 : 0u) + ((v & 2) ? s1 : 0u) + ((v & 4) ? s2 : 0u) + ((v & 8) ? s3 : 0u); };
+
+        // ---- epilogue of tile i from pipeline buffer B: TMEM lane = column; re at column t, im at column 64 + t.  The
+        //      thread overwrites exactly the amplitudes it read, so the tile is transformed in place without a barrier. ----
+        float my_in = 0.f;                                                     // |.|^2 of this thread's inputs of the tile in flight
+        float fcorr = inv_scale;                                               // output factor: 1/scale times the norm correction
+        auto epilogue = [&](auto BC, uint64_t i, float in2) {
+            constexpr uint32_t B = decltype(BC)::value;
+            mark(4);
+            if (!(dbg & 1u)) mbar_wait(smem_u32(&bar_mma[B]), (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            mark(5);
+            // (TMEM reads run at 64 B/clk per SM, so the accumulator is read exactly once)
+            const uint32_t taddr = tlane + B * TM_BUF + TM_D + 16u * qt;
+            uint32_t re[16], im[16];
+            tmem_ld16(taddr, re);
+            tmem_ld16(taddr + 64u, im);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mark(6);
+            // A unitary block preserves the norm of the tile.  The tensor core's truncating accumulation shrinks it
+            // systematically (~1e-7 per sweep); the ratio measured on the CTA's previous tile removes that bias.
+            if (P.renorm && i > 0) {
+                float2 v = red[(i - 1) & 1u][lane & 15u];
+#pragma unroll
+                for (int m = 8; m >= 1; m >>= 1) {
+                    v.x += __shfl_xor_sync(0xffffffffu, v.x, m);
+                    v.y += __shfl_xor_sync(0xffffffffu, v.y, m);
+                }
+                if (v.x > 0.f && v.y > 0.f) fcorr = sqrtf(v.x / v.y);          // an all-zero tile says nothing: keep the last ratio
+            }
+            const float f = fcorr;
+            unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES + sbase;
+            float out2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float a = __uint_as_float(re[j]), b = __uint_as_float(im[j]);
+                out2 = fmaf(a, a, fmaf(b, b, out2));
+                *reinterpret_cast<float2*>(S + vaddr(j)) = make_float2(a * f, b * f);
+            }
+            if (P.renorm) {
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) {
+                    in2 += __shfl_xor_sync(0xffffffffu, in2, m);
+                    out2 += __shfl_xor_sync(0xffffffffu, out2, m);
+                }
+                if (lane == 0) red[i & 1u][warp] = make_float2(in2, out2);
+            }
+            mark(7);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> visible to the bulk copy engine
+            workers_sync();
+            if (!(dbg & 4u)) store_rows(i);
+            mark(8);
+        };
+
+        // ---- one pipeline step: split tile i into tensor memory (buffer B), hand it to the MMA warp, refill the tile buffer freed by
+        //      the last store with tile i+1's successor, finish tile i-1 ----
+        auto step = [&](auto BC, uint64_t i) {
+            constexpr uint32_t B = decltype(BC)::value;
+            mbar_wait(smem_u32(&bar_full[i % 3u]), (uint32_t)(i / 3u) & 1u);
+            mark(0);
+            const unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES + sbase;
+            float in2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {                                      // 8 block values -> 4 packed words per (term, re|im)
+                uint32_t hr[4], lr[4], hi[4], li[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 a0 = *reinterpret_cast<const float2*>(S + vaddr(8 * c + 2 * j));
+                    const float2 a1 = *reinterpret_cast<const float2*>(S + vaddr(8 * c + 2 * j + 1));
+                    in2 = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, in2))));
+                    split2(a0.x * scale, a1.x * scale, hr[j], lr[j]);
+                    split2(a0.y * scale, a1.y * scale, hi[j], li[j]);
+                }
+                // packed words [8*qt + 4*c, +4) of the re part and of the im part of this thread's TMEM lane
+                const uint32_t w = 8u * qt + 4u * c, xh = tlane + B * TM_BUF + TM_XH, xl = tlane + B * TM_BUF + TM_XL;
+                if (!(dbg & 2u)) {
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xh + w), "r"(hr[0]), "r"(hr[1]), "r"(hr[2]), "r"(hr[3]) : "memory");
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xl + w), "r"(lr[0]), "r"(lr[1]), "r"(lr[2]), "r"(lr[3]) : "memory");
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xh + 32u + w), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xl + 32u + w), "r"(li[0]), "r"(li[1]), "r"(li[2]), "r"(li[3]) : "memory");
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_x[B]));                   // one arrival per worker warp
+            mark(1);
+            if (tid == 32 && !trank) publish_tile(i + 3);
+            // the buffer of tile i-2 (stored during the previous step) is free once the bulk stores have read it: refill it
+            // with tile i+1.  Each warp waits for, and re-uses, its own rows only.
+            if (i >= 1) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                load_rows(i + 1);
+            }
+            mark(2);
+            const float prev_in = my_in;
+            my_in = in2;
+            if (i >= 1) epilogue(std::integral_constant<uint32_t, B ^ 1u>{}, i - 1, prev_in);
+            mark(3);
+        };
+
+        if (tid == 32 && !trank) { publish_tile(0); publish_tile(1); publish_tile(2); }
+        workers_sync();
+        load_rows(0);
+        load_rows(1);
+
+        for (uint64_t i = 0; i < cnt; i += 2) {
+            step(std::integral_constant<uint32_t, 0u>{}, i);
+            if (i + 1 < cnt) step(std::integral_constant<uint32_t, 1u>{}, i + 1);
+        }
+        if (cnt > 0) {
+            if ((cnt - 1) & 1u) epilogue(std::integral_constant<uint32_t, 1u>{}, cnt - 1, my_in);
+            else epilogue(std::integral_constant<uint32_t, 0u>{}, cnt - 1, my_in);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last stores must be complete before the CTA exits
+        if (timed) {
+            long long* out = reinterpret_cast<long long*>(const_cast<unsigned char*>(uterms) + 4 * MAT_BYTES) + (tid ? 16 : 0);
+            for (int k = 0; k < 10; ++k) out[k] = tacc[k];
+            out[10] = (long long)cnt;
+        }
     }
 
-    if (timed) {
-        long long* out = reinterpret_cast<long long*>(const_cast<unsigned char*>(uterms) + 2 * TERM_BYTES) + (tid ? 16 : 0);
-        for (int k = 0; k < 10; ++k) out[k] = tacc[k];
-        out[10] = (long long)cnt;
-    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
@@ -363,17 +453,19 @@ extern "C" int rq_block_configure(void) {
     return (int)cudaFuncSetAttribute(block_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
 }
 
-extern "C" int rq_launch_block_sweep(rq_cplx* state, const rq_block_params* P, const void* d_uterms, void* stream) {
+extern "C" int rq_launch_block_sweep(rq_cplx* state, const rq_block_params* P, const void* d_uterms, const void* tensor_map, void* stream) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(P->ntiles < (uint64_t)sms ? P->ntiles : (uint64_t)sms);
+    CUtensorMap tm{};
+    if (tensor_map) tm = *reinterpret_cast<const CUtensorMap*>(tensor_map);
     block_sweep_kernel<<<grid, BT, SMEM_BYTES, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(state),
-                                                                       reinterpret_cast<const unsigned char*>(d_uterms), *P);
+                                                                       reinterpret_cast<const unsigned char*>(d_uterms), *P, tm);
     return (int)cudaGetLastError();
 }
 #else
 #include "sv_internal.h"
 extern "C" int rq_block_configure(void) { return 0; }
-extern "C" int rq_launch_block_sweep(rq_cplx*, const rq_block_params*, const void*, void*) { return 801; /* cudaErrorNotSupported */ }
+extern "C" int rq_launch_block_sweep(rq_cplx*, const rq_block_params*, const void*, const void*, void*) { return 801; /* cudaErrorNotSupported */ }
 #endif

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +18,7 @@
 #include <vector>
 
 #include "../../include/hipStateVec.h"
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "engine.h"
@@ -58,7 +60,7 @@ rq::PlanLimits limits_for(const H* h, bool large) {
     return L;
 }
 
-rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsigned>& blk, const std::vector<cd>& U);
+rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsigned>& blk, const std::vector<cd>& U, int unitary = -1);
 rocqStatus_t launch_plan(H* h, rq_cplx* state, unsigned n, const rq::SweepPlan& sp, const std::vector<HostOp>& seg, bool large);
 
 rocqStatus_t launch_plan(H* h, rq_cplx* state, unsigned n, const rq::SweepPlan& sp, const std::vector<HostOp>& seg, bool large) {
@@ -81,62 +83,58 @@ rocqStatus_t launch_plan(H* h, rq_cplx* state, unsigned n, const rq::SweepPlan& 
     return ROCQ_STATUS_SUCCESS;
 }
 
-// Mixed execution of one fused op list: wherever >= RQ_BLOCK_MIN_COST worth of gates can be folded into six qubits
-// (positions >= 5, so that tile columns stay coalesced) they become ONE 64x64 unitary applied by the tensor-core block
-// sweep; everything else goes through ordinary tile sweeps.  Same in-order / blocked-qubit rule as plan_sweeps.
+bool op_is_unitary(const HostOp& o) {
+    const unsigned k = (unsigned)o.targets.size(), D = 1u << k;
+    if (o.kind == HostOp::DIAG) {
+        for (const cd& d : o.data) if (std::abs(std::abs(d) - 1.0) > 1e-9) return false;
+        return true;
+    }
+    if (o.kind != HostOp::DENSE) return true;
+    if (o.ext || o.data.size() != (size_t)D * D) return false;
+    for (unsigned a = 0; a < D; ++a)
+        for (unsigned b = a; b < D; ++b) {
+            cd s(0.0, 0.0);
+            for (unsigned r = 0; r < D; ++r) s += std::conj(o.data[r + (size_t)D * a]) * o.data[r + (size_t)D * b];
+            if (std::abs(s - (a == b ? cd(1.0, 0.0) : cd(0.0, 0.0))) > 1e-9) return false;
+        }
+    return true;
+}
+
+// Mixed execution of one fused op list (rq::plan_mixed): wherever enough arithmetic can be folded into six qubits
+// (positions >= 5) it becomes ONE 64x64 unitary applied by the tensor-core block sweep; everything else goes through
+// ordinary tile sweeps.
 rocqStatus_t run_ops_with_blocks(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>& seg) {
-    const double min_cost = h->blockMinCost;
-    std::vector<char> done(seg.size(), 0);
-    size_t remaining = seg.size();
-    const rq::PlanLimits L = limits_for(h, true);
-    while (remaining > 0) {
-        // ---- candidate block ----
-        uint64_t B = 0, blockedAny = 0, blockedND = 0;
-        std::vector<int> pick;
-        double cost = 0.0;
-        for (size_t i = 0; i < seg.size(); ++i) {
-            if (done[i]) continue;
-            const HostOp& o = seg[i];
-            const uint64_t Q = o.qubits(), nd = o.nondiag(), dg = Q & ~nd;
-            const bool free_ = !((nd & (blockedAny | blockedND)) || (dg & blockedAny));
-            if (free_ && !o.ext && !(Q & 31ull) && __builtin_popcountll(B | Q) <= RQ_BLOCK_QUBITS) {
-                B |= Q;
-                pick.push_back((int)i);
-                cost += o.cost();
-            } else {
-                blockedAny |= nd;
-                blockedND |= dg;
-            }
+    rq::BlockLimits BL;
+    BL.min_cost = h->blockMinCost;
+    static const bool prof = getenv("ROCQ_HOST_PROFILE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    double t_sweep = 0, t_build = 0, t_launch = 0;
+    const auto tp0 = now();
+    const std::vector<rq::MixedStep> steps = rq::plan_mixed(seg, n, limits_for(h, true), BL);
+    const auto tp1 = now();
+    struct Report { bool on; double& a; double& b; double& c; double plan; ~Report() { if (on) fprintf(stderr, "[host profile] plan %.2f ms, sweeps %.2f ms, block build %.2f ms, block launch %.2f ms\n", plan, a, b, c); } } report{prof, t_sweep, t_build, t_launch, ms(tp0, tp1)};
+    for (const rq::MixedStep& st : steps) {
+        const auto t0 = now();
+        if (!st.block) {
+            const rocqStatus_t s = launch_plan(h, state, n, st.sweep, seg, true);
+            t_sweep += ms(t0, now());
+            if (s != ROCQ_STATUS_SUCCESS) return s;
+            continue;
         }
-        if (cost >= min_cost && !pick.empty()) {
-            for (unsigned p = n; p-- > 5 && __builtin_popcountll(B) < RQ_BLOCK_QUBITS;) if (!((B >> p) & 1ull)) B |= 1ull << p;
-            std::vector<unsigned> blk;
-            for (unsigned p = 0; p < n; ++p) if ((B >> p) & 1ull) blk.push_back(p);
-            if (blk.size() == RQ_BLOCK_QUBITS) {
-                std::vector<cd> U(64 * 64, cd(0.0, 0.0)), colv(64);
-                for (unsigned c = 0; c < 64; ++c) U[c + 64u * c] = cd(1.0, 0.0);
-                for (int idx : pick)                                   // U <- op * U, column by column
-                    for (unsigned c = 0; c < 64; ++c) {
-                        std::copy(U.begin() + 64u * c, U.begin() + 64u * (c + 1), colv.begin());
-                        rq::apply_small(seg[idx], blk, colv);
-                        std::copy(colv.begin(), colv.end(), U.begin() + 64u * c);
-                    }
-                const rocqStatus_t s = run_block(h, state, n, blk, U);
-                if (s != ROCQ_STATUS_SUCCESS) return s;
-                for (int idx : pick) { done[idx] = 1; --remaining; }
-                h->stats.opsExecuted += pick.size();
-                continue;
-            }
+        std::vector<cd> U(64 * 64, cd(0.0, 0.0));
+        for (unsigned c = 0; c < 64; ++c) U[c + 64u * c] = cd(1.0, 0.0);
+        bool unitary = true;
+        for (int idx : st.ops) {                               // U <- op * U
+            unitary = unitary && op_is_unitary(seg[idx]);
+            rq::apply_small_columns(seg[idx], st.blk, U.data(), 64);
         }
-        // ---- one ordinary sweep over what is left ----
-        std::vector<HostOp> rest;
-        std::vector<int> back;
-        for (size_t i = 0; i < seg.size(); ++i) if (!done[i]) { rest.push_back(seg[i]); back.push_back((int)i); }
-        const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(rest, n, L);
-        if (plans.empty()) return ROCQ_STATUS_FAILURE;
-        const rocqStatus_t s = launch_plan(h, state, n, plans[0], rest, true);
+        const auto t1 = now();
+        const rocqStatus_t s = run_block(h, state, n, st.blk, U, unitary ? 1 : 0);
+        t_build += ms(t0, t1);
+        t_launch += ms(t1, now());
         if (s != ROCQ_STATUS_SUCCESS) return s;
-        for (int k : plans[0].ops) { done[back[k]] = 1; --remaining; }
+        h->stats.opsExecuted += st.ops.size();
     }
     return ROCQ_STATUS_SUCCESS;
 }
@@ -200,26 +198,88 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
 }
 
 // ---- tensor-core 6-qubit blocks (block_sweep.cu) -------------------------------------------------------------------
-// U: 64x64 complex column-major, index bit b <-> b-th smallest block position.  Writes the two fp16 terms (hi, lo) of the
-// real 128x128 matrix A' = [[Re U, -Im U], [Im U, Re U]] in the K-major core-matrix order the kernel's descriptors describe.
+// U: 64x64 complex column-major, index bit b <-> b-th smallest block position.  Writes Re U and Im U, each split in two fp16
+// terms (hi, lo), as 64 x 64 K-major core-matrix operands in the order the kernel's descriptors expect:
+// Re hi | Re lo | Im hi | Im lo, 8 KB each.
 void build_block_terms(const std::vector<cd>& U, std::vector<uint16_t>& out) {
-    out.assign(RQ_BLOCK_TERMS * (RQ_BLOCK_TERM_BYTES / 2), 0);
-    for (unsigned mo = 0; mo < 128; ++mo)
-        for (unsigned k = 0; k < 128; ++k) {
-            const cd u = U[(mo & 63u) + 64u * (k & 63u)];
-            float v;
-            if (mo < 64) v = k < 64 ? (float)u.real() : -(float)u.imag();
-            else v = k < 64 ? (float)u.imag() : (float)u.real();
-            const __half hi = __float2half_rn(v);
-            const __half lo = __float2half_rn(v - __half2float(hi));
-            const size_t off = ((mo & 7u) * 16u + (k >> 3) * 128u + (mo >> 3) * 2048u + (k & 7u) * 2u) / 2u;
-            memcpy(&out[off], &hi, 2);
-            memcpy(&out[RQ_BLOCK_TERM_BYTES / 2 + off], &lo, 2);
+    out.assign(RQ_BLOCK_UBYTES / 2, 0);
+    for (unsigned o = 0; o < 64; ++o)
+        for (unsigned k = 0; k < 64; ++k) {
+            const cd u = U[o + 64u * k];
+            const size_t off = ((o & 7u) * 16u + (k >> 3) * 128u + (o >> 3) * 1024u + (k & 7u) * 2u) / 2u;
+            for (int part = 0; part < 2; ++part) {
+                const float v = (float)(part ? u.imag() : u.real());
+                const __half hi = __float2half_rn(v);
+                const __half lo = __float2half_rn(v - __half2float(hi));
+                memcpy(&out[(size_t)(2 * part) * 4096 + off], &hi, 2);
+                memcpy(&out[(size_t)(2 * part + 1) * 4096 + off], &lo, 2);
+            }
         }
 }
 
+// Tensor map over the state (elements = 8-byte amplitudes) whose box is exactly one tile of the block sweep: index bits are
+// grouped in runs of the same kind (column / block / not resident); every run is one dimension, resident runs are covered by
+// the box, the others are addressed by tile-index bits.  Returns false when it takes more than five dimensions (the kernel
+// then moves tiles row by row) or the driver entry point is unavailable.
+bool build_block_tensor_map(const rq_cplx* state, unsigned n, size_t batch, uint64_t blockmask, uint64_t colmask, CUtensorMap* tm,
+                            rq_block_params& P) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<encode_fn>(fn);
+    }
+    if (!encode) return false;
+    cuuint64_t dims[6], strides[6];
+    cuuint32_t box[6], estr[6];
+    unsigned rank = 0;
+    auto kind = [&](unsigned p) { return ((colmask >> p) & 1ull) ? 1 : ((blockmask >> p) & 1ull) ? 2 : 0; };
+    int last_free = -1;
+    for (unsigned p = 0; p < n;) {
+        const int k = kind(p);
+        unsigned q = p;
+        while (q < n && kind(q) == k) ++q;
+        if (rank >= 5) return false;
+        dims[rank] = 1ull << (q - p);
+        strides[rank] = (8ull << p);                      // bytes
+        box[rank] = k ? (cuuint32_t)(1u << (q - p)) : 1u;
+        estr[rank] = 1;
+        P.tbits[rank] = k ? 0 : (uint8_t)(q - p);
+        if (!k) last_free = (int)rank;
+        ++rank;
+        p = q;
+    }
+    if (batch > 1 || last_free < 0) {
+        if (last_free == (int)rank - 1 && last_free >= 0) dims[last_free] *= batch;          // the top run is free: it absorbs the batch
+        else {
+            if (rank >= 5) return false;
+            dims[rank] = batch;
+            strides[rank] = 8ull << n;
+            box[rank] = 1;
+            estr[rank] = 1;
+            P.tbits[rank] = 1;                             // placeholder, becomes "the rest" below
+            last_free = (int)rank++;
+        }
+    }
+    if (rank < 2 || last_free < 0) return false;
+    P.tbits[last_free] = 255;                              // the last free dimension takes every remaining tile-index bit (incl. the batch member)
+    for (unsigned d = 0; d < rank; ++d) if (dims[d] > 0xffffffffull || box[d] > 256) return false;
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<rq_cplx*>(state), dims, strides + 1, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    P.trank = rank;
+    return true;
+}
+
 // launch one block sweep: block positions (ascending), matrix U over them
-rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsigned>& blk, const std::vector<cd>& U) {
+// unitary: 1 / 0 when the caller knows, -1 = check U here
+rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsigned>& blk, const std::vector<cd>& U, int unitary) {
     if (sizeof(rq_real) != 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
     if (n < 13 || blk.size() != RQ_BLOCK_QUBITS) return ROCQ_STATUS_INVALID_VALUE;
     rq_block_params P{};
@@ -234,8 +294,8 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     while (P.rowbits < 13 && P.res[P.rowbits] == P.rowbits) ++P.rowbits;       // tile rows are bulk-copied: >= 256 B each
     if (P.rowbits < 5) return ROCQ_STATUS_NOT_IMPLEMENTED;
     // unitary?  (then every tile column keeps its norm, which the kernel restores exactly)
-    double dev = 0.0;
-    for (unsigned a = 0; a < 64; ++a)
+    double dev = unitary == 1 ? 0.0 : unitary == 0 ? 1.0 : 0.0;
+    for (unsigned a = 0; a < 64 && unitary < 0; ++a)
         for (unsigned b = a; b < 64; ++b) {
             cd s(0.0, 0.0);
             for (unsigned r = 0; r < 64; ++r) s += std::conj(U[r + 64u * a]) * U[r + 64u * b];
@@ -248,13 +308,18 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     std::vector<uint16_t> terms;
     build_block_terms(U, terms);
     void* d_terms = nullptr;
-    RQ_CUDA(cudaMallocAsync(&d_terms, RQ_BLOCK_TERMS * RQ_BLOCK_TERM_BYTES + 256, h->stream), "block terms alloc");   // + debug timers
+    RQ_CUDA(cudaMallocAsync(&d_terms, RQ_BLOCK_UBYTES + 256, h->stream), "block terms alloc");   // + debug timers
     // pageable source: cudaMemcpyAsync stages it before returning, so `terms` may go out of scope
-    RQ_CUDA(cudaMemcpyAsync(d_terms, terms.data(), RQ_BLOCK_TERMS * RQ_BLOCK_TERM_BYTES, cudaMemcpyHostToDevice, h->stream), "block terms upload");
-    RQ_CUDA(rq_launch_block_sweep(state, &P, d_terms, h->stream), "block sweep launch");
+    RQ_CUDA(cudaMemcpyAsync(d_terms, terms.data(), RQ_BLOCK_UBYTES, cudaMemcpyHostToDevice, h->stream), "block terms upload");
+    CUtensorMap tm;
+    uint64_t cm = 0;
+    for (unsigned c = 0; c < RQ_BLOCK_COLBITS; ++c) cm |= 1ull << P.col[c];
+    const bool have_tm = !(P.pad & 32u) && build_block_tensor_map(state, n, h->batchSize, bm, cm, &tm, P);
+    if (!have_tm) { P.trank = 0; memset(P.tbits, 0, sizeof P.tbits); }
+    RQ_CUDA(rq_launch_block_sweep(state, &P, d_terms, have_tm ? &tm : nullptr, h->stream), "block sweep launch");
     if (P.pad & 16u) {                                   // ROCQ_BLOCK_DEBUG & 16: per-phase clock totals of CTA 0, threads 0 and 64
         long long t[32];
-        cudaMemcpyAsync(t, (char*)d_terms + RQ_BLOCK_TERMS * RQ_BLOCK_TERM_BYTES, sizeof t, cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(t, (char*)d_terms + RQ_BLOCK_UBYTES, sizeof t, cudaMemcpyDeviceToHost, h->stream);
         cudaStreamSynchronize(h->stream);
         static int printed = 0;
         if (printed++ < 2)
@@ -267,7 +332,7 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     RQ_CUDA(cudaFreeAsync(d_terms, h->stream), "block terms free");
     h->stats.kernelLaunches++;
     h->stats.sweeps++;
-    h->stats.h2dBytes += RQ_BLOCK_TERMS * RQ_BLOCK_TERM_BYTES;
+    h->stats.h2dBytes += RQ_BLOCK_UBYTES;
     return ROCQ_STATUS_SUCCESS;
 }
 
@@ -964,6 +1029,48 @@ rocqStatus_t rocsvxGetStats(rocsvHandle_t h, rocsvxStats* stats, int reset) {
     h->dist.timed.clear();
     if (stats) *stats = h->stats;
     if (reset) h->stats = rocsvxStats{};
+    return ROCQ_STATUS_SUCCESS;
+}
+
+rocqStatus_t rocsvxPlanCircuitBlocks(unsigned n, const rocsvxGateOp* ops, size_t numOps, double minCost, unsigned* numBlocks,
+                                     unsigned* numSweeps, char* buf, size_t bufSize) {
+    if (!ops && numOps) return ROCQ_STATUS_INVALID_VALUE;
+    std::vector<HostOp> hops;
+    const rocqStatus_t s = convert_ops(n, ops, numOps, hops);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    for (const HostOp& o : hops) if (o.targets.size() > 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    std::vector<HostOp> fused = hops.size() > 1 ? rq::fuse_algebraic(hops, n) : hops;
+    rq::PlanLimits L;
+    L.max_ops = sizeof(rq_program_large::ops) / sizeof(rq_tile_op);
+    L.pool_cplx = sizeof(rq_program_large::pool) / sizeof(rq_cplx);
+    if (const char* e = getenv("ROCQ_SWEEP_BUDGET")) { const double b = atof(e); if (b > 0) L.budget = b; }
+    rq::BlockLimits BL;
+    if (minCost > 0.0) BL.min_cost = minCost;
+    const std::vector<rq::MixedStep> steps = rq::plan_mixed(fused, n, L, BL);
+    unsigned nb = 0, ns = 0;
+    std::string text;
+    char line[64];
+    for (const rq::MixedStep& st : steps) {
+        if (st.block) {
+            ++nb;
+            text += "B";
+            for (unsigned p : st.blk) { snprintf(line, sizeof line, " %u", p); text += line; }
+            text += "\n";
+            rq::SweepPlan sp;                       // ops in program order, dumped like a sweep's
+            sp.ops = st.ops;
+            text += rq::dump_ops(sp.ops, fused);
+        } else {
+            ++ns;
+            text += rq::dump_plan(std::vector<rq::SweepPlan>{st.sweep}, fused);
+        }
+    }
+    if (numBlocks) *numBlocks = nb;
+    if (numSweeps) *numSweeps = ns;
+    if (buf && bufSize) {
+        const size_t c = std::min(bufSize - 1, text.size());
+        memcpy(buf, text.data(), c);
+        buf[c] = 0;
+    }
     return ROCQ_STATUS_SUCCESS;
 }
 

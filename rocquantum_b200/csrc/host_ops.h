@@ -27,7 +27,8 @@ struct HostOp {
     uint64_t cmask = 0;              // control qubits: op acts where all are 1
     std::vector<cd> data;            // DENSE: 2^k x 2^k column-major.  DIAG: 2^k entries
     const void* ext = nullptr;       // DENSE only: matrix stays in device memory (eager rocsvApplyMatrix)
-    bool dead = false;
+    bool dead = false;               // fuse_algebraic: absorbed into another op
+    bool defer = false;              // plan_sweeps: leave this op to a later step (plan_mixed keeps dense ops for the tensor-core blocks)
 
     uint64_t tmask() const { uint64_t m = 0; for (unsigned t : targets) m |= 1ull << t; return m; }
     uint64_t qubits() const { return tmask() | cmask; }
@@ -142,6 +143,46 @@ inline void apply_small(const HostOp& o, const std::vector<unsigned>& qs, std::v
         }
     }
 }
+// The same for every column of a column-major 2^m x ncols matrix at once (M <- op * M), without per-group allocations
+// and with the complex products written out in real arithmetic: this is on the launch path of the tensor-core blocks.
+inline void apply_small_columns(const HostOp& o, const std::vector<unsigned>& qs, cd* M, unsigned ncols) {
+    const unsigned m = (unsigned)qs.size(), k = (unsigned)o.targets.size();
+    if (o.kind != HostOp::DENSE || k > 4) {
+        std::vector<cd> col(1u << m);
+        for (unsigned c = 0; c < ncols; ++c) {
+            std::copy(M + ((size_t)c << m), M + ((size_t)(c + 1) << m), col.begin());
+            apply_small(o, qs, col);
+            std::copy(col.begin(), col.end(), M + ((size_t)c << m));
+        }
+        return;
+    }
+    auto pos = [&](unsigned q) { for (unsigned i = 0; i < m; ++i) if (qs[i] == q) return i; return 0u; };
+    uint32_t cm = 0, tm = 0, off[16];
+    for (unsigned q = 0; q < 64; ++q) if ((o.cmask >> q) & 1ull) cm |= 1u << pos(q);
+    unsigned tp[4];
+    for (unsigned b = 0; b < k; ++b) { tp[b] = pos(o.targets[b]); tm |= 1u << tp[b]; }
+    const unsigned D = 1u << k, N = 1u << m;
+    for (unsigned j = 0; j < D; ++j) { uint32_t f = 0; for (unsigned b = 0; b < k; ++b) if ((j >> b) & 1u) f |= 1u << tp[b]; off[j] = f; }
+    double ur[256], ui[256], xr[16], xi[16];
+    for (unsigned e = 0; e < D * D; ++e) { ur[e] = o.data[e].real(); ui[e] = o.data[e].imag(); }
+    for (unsigned c = 0; c < ncols; ++c) {
+        cd* v = M + ((size_t)c << m);
+        for (uint32_t i = 0; i < N; ++i) {
+            if ((i & cm) != cm || (i & tm)) continue;
+            for (unsigned j = 0; j < D; ++j) { xr[j] = v[i | off[j]].real(); xi[j] = v[i | off[j]].imag(); }
+            for (unsigned r = 0; r < D; ++r) {
+                double ar = 0.0, ai = 0.0;
+                for (unsigned j = 0; j < D; ++j) {
+                    const double a = ur[r + j * D], b = ui[r + j * D];
+                    ar += a * xr[j] - b * xi[j];
+                    ai += a * xi[j] + b * xr[j];
+                }
+                v[i | off[r]] = cd(ar, ai);
+            }
+        }
+    }
+}
+
 // column-major matrix of op over the ordered qubit list qs
 inline std::vector<cd> to_matrix(const HostOp& o, const std::vector<unsigned>& qs) {
     const unsigned D = 1u << qs.size();
@@ -295,7 +336,7 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
             ++scanned;
             const HostOp& o = ops[i];
             const uint64_t nd = o.nondiag(), dg = o.qubits() & ~nd;
-            bool ok = !((nd & (blockedAny | blockedND)) || (dg & blockedAny));
+            bool ok = !o.defer && !((nd & (blockedAny | blockedND)) || (dg & blockedAny));
             if (ok) {
                 const uint64_t newR = R | nd;
                 ok = __builtin_popcountll(newR) <= (int)T && !(nd & L.never_resident) && nops < L.max_ops &&
@@ -331,6 +372,144 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
         plans.push_back(std::move(sp));
     }
     return plans;
+}
+
+// ---- mixed plan: tensor-core blocks + ordinary sweeps ----------------------------------------------------------------
+// A step is either one 6-qubit block (every op of `ops` folded into one 64x64 unitary, applied by block_sweep.cu in one HBM
+// pass) or one ordinary tile sweep.  Oldest first, which keeps the frontier of the circuit flat so that blocks stay full:
+// take the first op not yet executed; if it can live in a block, try several 6-qubit sets around it (grown along the
+// interactions of the ops that follow, biased to lower / higher qubits), fold into each every op that is free to run
+// inside it, and keep the set that absorbs the most arithmetic.  If that is below `min_cost` (FMA-equivalents per
+// amplitude, HostOp::cost), or the op cannot live in a block, run one ordinary sweep; that sweep leaves the dense ops a
+// block could take to the blocks.
+struct BlockLimits {
+    unsigned qubits = 6;
+    unsigned min_pos = 5;            // block positions must be >= min_pos (tile layout of block_sweep.cu)
+    double min_cost = 50.0;          // ~ three dense two-qubit matrices: below that the CUDA-core sweep is cheaper
+    size_t batch = 1;
+    bool (*supported)(uint64_t blockmask, unsigned n, size_t batch) = nullptr;   // can the kernel run this set? (null: any)
+};
+struct MixedStep {
+    bool block = false;
+    std::vector<unsigned> blk;       // block: six ascending positions
+    std::vector<int> ops;            // block: indices folded into it, program order
+    SweepPlan sweep;                 // otherwise
+};
+
+inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L);
+
+inline std::vector<MixedStep> plan_mixed(const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L, const BlockLimits& BL) {
+    std::vector<MixedStep> steps;
+    std::vector<char> done(ops.size(), 0);
+    size_t remaining = ops.size(), first = 0;
+    const uint64_t low = BL.min_pos >= 64 ? ~0ull : ((1ull << BL.min_pos) - 1ull);
+    const uint64_t all = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+    auto eligible = [&](const HostOp& o) {
+        const uint64_t Q = o.qubits();
+        return !o.ext && !(Q & low) && (unsigned)__builtin_popcountll(Q) <= BL.qubits && !(Q & L.never_resident) && !(Q & ~all);
+    };
+    const bool possible = n >= 13 && n >= BL.min_pos + BL.qubits;
+    // every op that is free to run (nothing deferred conflicts with it) and lies inside B, in program order
+    auto fold = [&](uint64_t B, std::vector<int>& pick) {
+        double cost = 0.0;
+        uint64_t bAny = 0, bND = 0;
+        size_t scanned = 0;
+        for (size_t i = first; i < ops.size() && scanned < 4096; ++i) {
+            if (done[i]) continue;
+            ++scanned;
+            const HostOp& o = ops[i];
+            const uint64_t Q = o.qubits(), nd = o.nondiag(), dg = Q & ~nd;
+            if (!(Q & ~B) && !o.ext && !((nd & (bAny | bND)) || (dg & bAny))) {
+                pick.push_back((int)i);
+                cost += o.cost();
+            } else {
+                bAny |= nd;
+                bND |= dg;
+            }
+        }
+        return cost;
+    };
+    // grow a qubit set from the seed along the ops that follow; bias 0: in program order, 1: lowest neighbour first,
+    // 2: highest first, 3 / 4: alternating starting low / high
+    auto grow = [&](size_t seed, int bias) {
+        uint64_t B = ops[seed].qubits();
+        for (unsigned round = 0; (unsigned)__builtin_popcountll(B) < BL.qubits && round < BL.qubits; ++round) {
+            uint64_t nb = 0;                                   // qubits that an upcoming eligible op connects to B
+            size_t scanned = 0;
+            for (size_t i = seed; i < ops.size() && scanned < 512; ++i) {
+                if (done[i]) continue;
+                ++scanned;
+                const uint64_t Q = ops[i].qubits();
+                if ((Q & B) && (Q & ~B) && eligible(ops[i])) {
+                    nb |= Q & ~B;
+                    if (bias == 0) break;
+                }
+            }
+            if (!nb) break;
+            const bool take_low = bias == 1 || (bias == 3 && !(round & 1)) || (bias == 4 && (round & 1));
+            const unsigned q = (bias == 0 || take_low) ? (unsigned)__builtin_ctzll(nb) : 63u - (unsigned)__builtin_clzll(nb);
+            B |= 1ull << q;
+        }
+        // pad with neighbouring positions (keeps the tile a short list of contiguous index-bit runs)
+        while ((unsigned)__builtin_popcountll(B) < BL.qubits) {
+            const unsigned hi = 63u - (unsigned)__builtin_clzll(B), lo = (unsigned)__builtin_ctzll(B);
+            bool added = false;
+            auto ok = [&](unsigned p) { return p < n && p >= BL.min_pos && !((B >> p) & 1ull) && !((L.never_resident >> p) & 1ull); };
+            for (unsigned p = lo; p <= hi && !added; ++p) if (ok(p)) { B |= 1ull << p; added = true; }
+            if (!added && ok(hi + 1)) { B |= 1ull << (hi + 1); added = true; }
+            if (!added && lo > 0 && ok(lo - 1)) { B |= 1ull << (lo - 1); added = true; }
+            if (!added) break;
+        }
+        return B;
+    };
+    while (remaining > 0) {
+        while (first < ops.size() && done[first]) ++first;
+        std::vector<int> best;
+        uint64_t bestB = 0;
+        double best_cost = -1.0;
+        if (possible && eligible(ops[first])) {
+            uint64_t tried[5];
+            unsigned ntried = 0;
+            for (int bias = 0; bias < 5; ++bias) {
+                const uint64_t B = grow(first, bias);
+                if ((unsigned)__builtin_popcountll(B) != BL.qubits) continue;
+                bool dup = false;
+                for (unsigned t = 0; t < ntried; ++t) dup |= tried[t] == B;
+                if (dup) continue;
+                tried[ntried++] = B;
+                if (BL.supported && !BL.supported(B, n, BL.batch)) continue;
+                std::vector<int> pick;
+                const double cost = fold(B, pick);
+                if (cost > best_cost) { best_cost = cost; best.swap(pick); bestB = B; }
+            }
+        }
+        if (best_cost >= BL.min_cost && !best.empty()) {
+            MixedStep st;
+            st.block = true;
+            for (unsigned p = 0; p < n; ++p) if ((bestB >> p) & 1ull) st.blk.push_back(p);
+            st.ops = best;
+            for (int i : best) { done[i] = 1; --remaining; }
+            steps.push_back(std::move(st));
+            continue;
+        }
+        // One ordinary sweep over what is left.  When blocks are possible it leaves the dense ops a block could take alone
+        // (marked `defer` in the copy), unless the oldest op is such an op itself.
+        std::vector<HostOp> rest;
+        std::vector<int> back;
+        const bool keep_for_blocks = possible && !eligible(ops[first]);
+        for (size_t i = first; i < ops.size(); ++i)
+            if (!done[i]) {
+                rest.push_back(ops[i]);
+                rest.back().defer = keep_for_blocks && ops[i].kind == HostOp::DENSE && eligible(ops[i]);
+                back.push_back((int)i);
+            }
+        std::vector<SweepPlan> plans = plan_sweeps(rest, n, L);
+        MixedStep st;
+        st.sweep = std::move(plans[0]);
+        for (int& k : st.sweep.ops) { k = back[k]; done[k] = 1; --remaining; }
+        steps.push_back(std::move(st));
+    }
+    return steps;
 }
 
 // ---- order of the ops inside one sweep ---------------------------------------------------------------------------
@@ -543,6 +722,21 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
 }
 
 // ---- text dump of a plan (rocsvxPlanCircuit): enough to re-simulate it independently --------------------
+inline std::string dump_ops(const std::vector<int>& order, const std::vector<HostOp>& ops) {
+    std::string s;
+    char buf[128];
+    for (int i : order) {
+        const HostOp& o = ops[i];
+        snprintf(buf, sizeof buf, "O %d cmask %llx targets", o.kind, (unsigned long long)o.cmask);
+        s += buf;
+        for (unsigned t : o.targets) { snprintf(buf, sizeof buf, " %u", t); s += buf; }
+        s += " data";
+        for (const cd& c : o.data) { snprintf(buf, sizeof buf, " %.17g %.17g", c.real(), c.imag()); s += buf; }
+        s += "\n";
+    }
+    return s;
+}
+
 inline std::string dump_plan(const std::vector<SweepPlan>& plans, const std::vector<HostOp>& ops) {
     std::string s;
     char buf[128];
@@ -551,15 +745,7 @@ inline std::string dump_plan(const std::vector<SweepPlan>& plans, const std::vec
         s += buf;
         for (unsigned r : sp.res) { snprintf(buf, sizeof buf, " %u", r); s += buf; }
         s += "\n";
-        for (int i : phase_friendly_order(sp, ops, RQ_WINDOW_BITS)) {      // the order the kernel executes
-            const HostOp& o = ops[i];
-            snprintf(buf, sizeof buf, "O %d cmask %llx targets", o.kind, (unsigned long long)o.cmask);
-            s += buf;
-            for (unsigned t : o.targets) { snprintf(buf, sizeof buf, " %u", t); s += buf; }
-            s += " data";
-            for (const cd& c : o.data) { snprintf(buf, sizeof buf, " %.17g %.17g", c.real(), c.imag()); s += buf; }
-            s += "\n";
-        }
+        s += dump_ops(phase_friendly_order(sp, ops, RQ_WINDOW_BITS), ops);      // the order the kernel executes
     }
     return s;
 }

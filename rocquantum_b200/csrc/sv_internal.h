@@ -129,11 +129,13 @@ struct rq_block_params {
     uint8_t res[16];                // ascending resident positions (block + column bits)
     uint8_t blk[8];                 // 6 block positions, ascending: bit b of the block value <-> blk[b]
     uint8_t col[8];                 // 7 column positions, ascending
+    uint32_t trank;                 // rank of the tensor map whose box is one tile (0: none, tiles move as per-row bulk copies)
+    uint8_t tbits[5];               // per tensor-map dimension: tile-index bits it consumes (0: resident, 255: all that remain)
+    uint8_t pad3[3];
 };
 #define RQ_BLOCK_QUBITS 6
 #define RQ_BLOCK_COLBITS 7
-#define RQ_BLOCK_TERM_BYTES 32768    // one fp16 term of the real 128x128 operand, in UMMA K-major core-matrix order
-#define RQ_BLOCK_TERMS 2
+#define RQ_BLOCK_UBYTES 32768        // Re U and Im U of the 64x64 block, two fp16 terms each, in UMMA K-major core-matrix order
 
 // ---- thin C ABI to the launchers (all return a cudaError_t as int; stream is a cudaStream_t) --------
 extern "C" {
@@ -161,6 +163,7 @@ int rq_launch_sample(const rq_cplx* state, unsigned n, unsigned chunk_bits, cons
                      uint64_t shot_offset, uint64_t* d_indices, void* stream);
 unsigned rq_reduce_blocks(void);
 int rq_block_configure(void);
-// d_uterms: RQ_BLOCK_TERMS * RQ_BLOCK_TERM_BYTES device bytes (hi, lo fp16 terms of the real 128x128 block matrix)
-int rq_launch_block_sweep(rq_cplx* state, const rq_block_params* P, const void* d_uterms, void* stream);
+// d_uterms: RQ_BLOCK_UBYTES device bytes (+ 256 bytes of debug counters)
+// tensor_map: host pointer to a 128-byte CUtensorMap (P->trank dims), or NULL
+int rq_launch_block_sweep(rq_cplx* state, const rq_block_params* P, const void* d_uterms, const void* tensor_map, void* stream);
 }

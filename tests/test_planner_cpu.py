@@ -50,3 +50,47 @@ def test_single_gate_plans_are_one_sweep():
     for g in util.random_gates(9, 60, seed=5, maxk=3):
         nsw, sweeps = util.plan(9, [g], 6)
         assert nsw == 1 and len(sweeps[0]["ops"]) == 1
+
+
+# ---- mixed plan: tensor-core blocks + ordinary sweeps (rocsvxPlanCircuitBlocks) ------------------------------------
+def _check_blocks(n, gates, min_cost=0.0, tol=1e-11):
+    nb, ns, steps = util.plan_blocks(n, gates, min_cost)
+    for st in steps:
+        if "blk" in st:                                   # a block: six positions >= 5, every op inside it
+            assert len(st["blk"]) == 6 and sorted(st["blk"]) == st["blk"] and min(st["blk"]) >= 5 and max(st["blk"]) < n
+            for op in st["ops"]:
+                qs = set(op["targets"]) | {q for q in range(64) if (op["cmask"] >> q) & 1}
+                assert qs <= set(st["blk"])
+            st.update(T=min(n, 13), rowbits=0, res=list(range(n)))      # simulate_plan: treat it as "everything resident"
+            st["T"] = len(st["res"])
+    v = util.random_state(n, seed=n + len(gates))
+    a = so.Oracle(n, "c128"); a.set_state(v); util.run_on_oracle(a, gates)
+    b = so.Oracle(n, "c128"); b.set_state(v); util.simulate_plan(b, steps)
+    assert util.rel_err(b.state, a.state) < tol
+    return nb, ns, steps
+
+
+@pytest.mark.parametrize("n", [13, 16, 18])
+def test_block_plan_is_equivalent_and_forms_blocks(n):
+    gates = workloads.c2_random_unitary(n, 10, seed=30)
+    nb, ns, steps = _check_blocks(n, gates)
+    assert nb >= 1                                         # the brick circuit above qubit 5 goes to blocks ...
+    low = [op for st in steps if "res" in st and "blk" not in st for op in st["ops"] if op["kind"] == 1]
+    # ... and the ordinary sweeps keep (almost) only what touches qubits 0-4
+    assert sum(1 for op in low if min(op["targets"]) < 5) >= 0.8 * len(low)
+
+
+def test_block_plan_mixed_bag_and_threshold():
+    n = 15
+    gates = util.random_gates(n, 250, seed=5, maxk=3)
+    _check_blocks(n, gates)
+    nb_hi, _, _ = _check_blocks(n, gates, min_cost=1e9)    # nothing reaches the threshold: ordinary sweeps only
+    assert nb_hi == 0
+
+
+def test_block_plan_large_brick_circuit_block_occupancy():
+    # 30 qubits, depth 40 (BASELINE configs[1]): host-only planning, no simulation
+    gates = workloads.c2_random_unitary(30, 40, seed=30)
+    nb, ns, steps = util.plan_blocks(30, gates)
+    in_blocks = sum(len(s["ops"]) for s in steps if "blk" in s)
+    assert nb <= 75 and in_blocks / nb >= 6.5              # blocks stay full (a brick diamond holds 9 two-qubit matrices)

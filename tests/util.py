@@ -83,6 +83,40 @@ def run_per_gate(sv, gates):
             raise ValueError(name)
 
 
+def plan_blocks(n, gates, min_cost=0.0):
+    """-> (num_blocks, num_sweeps, steps) via rocsvxPlanCircuitBlocks (host only); a step is a dict with 'blk' (6 positions) for a
+    tensor-core block or 'res' for an ordinary sweep, and its ops in execution order."""
+    lib = capi.load("c64")
+    arr, keep = capi.make_ops(gates)
+    nb, ns = C.c_uint(), C.c_uint()
+    size = 1 << 18
+    while True:
+        buf = C.create_string_buffer(size)
+        st = lib.rocsvxPlanCircuitBlocks(n, arr, len(gates), C.c_double(min_cost), C.byref(nb), C.byref(ns), buf, size)
+        assert st == 0, st
+        txt = buf.value.decode()
+        if len(txt) < size - 2:
+            break
+        size *= 4
+    steps = []
+    for line in txt.splitlines():
+        tok = line.split()
+        if tok[0] == "B":
+            steps.append(dict(blk=[int(x) for x in tok[1:]], ops=[]))
+        elif tok[0] == "S":
+            steps.append(dict(T=int(tok[1]), rowbits=int(tok[2]), res=[int(x) for x in tok[4:]], ops=[]))
+        else:
+            kind = int(tok[1])
+            cmask = int(tok[3], 16)
+            ti, di = tok.index("targets"), tok.index("data")
+            targets = [int(x) for x in tok[ti + 1:di]]
+            vals = [float(x) for x in tok[di + 1:]]
+            data = np.array(vals[0::2]) + 1j * np.array(vals[1::2])
+            steps[-1]["ops"].append(dict(kind=kind, cmask=cmask, targets=targets, data=data))
+    assert sum(1 for s in steps if "blk" in s) == nb.value and sum(1 for s in steps if "res" in s) == ns.value
+    return nb.value, ns.value, steps
+
+
 def plan(n, gates, tile_bits=0, prec="c64"):
     """-> (num_sweeps, [ {T,rowbits,res,ops:[{kind,cmask,targets,data}]} ])  via rocsvxPlanCircuit (host only)."""
     lib = capi.load(prec)

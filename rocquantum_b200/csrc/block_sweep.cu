@@ -40,8 +40,7 @@ constexpr uint32_t MAT_BYTES = 8192;           // one fp16 term of a 64 x 64 ope
 constexpr uint32_t TILE_BYTES = 65536;         // 2^13 complex64 amplitudes
 constexpr uint32_t SMEM_U = 0;                                    // Re U hi | Re U lo | Im U hi | Im U lo  (B operands, N = 64)
 constexpr uint32_t SMEM_S = 4 * MAT_BYTES;                        // 3 tiles (fp32 amplitudes): bulk-loaded, transformed in place, bulk-stored
-constexpr uint32_t SMEM_ROW = SMEM_S + 3 * TILE_BYTES;            // <= 256 u32 global row offsets, in rows
-constexpr uint32_t SMEM_BYTES = SMEM_ROW + 256 * 4;
+constexpr uint32_t SMEM_BYTES = SMEM_S + 3 * TILE_BYTES;
 // TMEM columns, per pipeline buffer b (at 256 * b): [0,64) Re D, [64,128) Im D, then the packed fp16 pairs of X':
 // [128,160) Re hi, [160,192) Im hi, [192,224) Re lo, [224,256) Im lo
 constexpr uint32_t TM_D = 0, TM_XH = 128, TM_XL = 192, TM_BUF = 256;
@@ -165,11 +164,8 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_u, bar_mma[2], bar_x[2], bar_full[3];
     __shared__ uint32_t tmem_slot;
-    __shared__ uint64_t tbase[8];      // ring: amplitude offset of the CTA's tile i at [i & 7], computed by one thread per tile
     __shared__ float2 red[2][16];      // per-warp (|in|^2, |out|^2) of a tile, double-buffered
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint32_t* rowoff = reinterpret_cast<uint32_t*>(smem + SMEM_ROW);
-    const uint32_t rowbits = P.rowbits, nrows = 1u << (13u - rowbits), rowbytes = 8u << rowbits;
 
     if (tid == 0) {
         mbar_init(smem_u32(&bar_u), 1);
@@ -180,12 +176,6 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
     if (warp == 0) {                                         // all 512 columns: two buffers x (D | X' hi | X' lo)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (tid >= 64 && tid < 64 + nrows) {                     // global offset of tile row r (in rows): its bits go to the resident positions above the row
-        const uint32_t r = tid - 64;
-        uint64_t o = 0;
-        for (uint32_t j = rowbits; j < 13; ++j) o |= (uint64_t)((r >> (j - rowbits)) & 1u) << P.res[j];
-        rowoff[r] = (uint32_t)(o >> rowbits);
     }
     if (tid < 32) reinterpret_cast<float2*>(red)[tid] = make_float2(0.f, 0.f);
     tc_fence_before();
@@ -232,19 +222,16 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
         // ================================ 16 worker warps ================================
         // this thread: tile column ncol (= TMEM lane), block values [16*qt, 16*qt+16)
         const uint32_t ncol = tid & 127, qt = tid >> 7;
-        // position inside a staged tile: local index = resident bits compacted in ascending order
-        uint32_t lpos_blk[6], lcol = 0, lqt = 0;
-        {
-            uint32_t lpos_col[7];
-            for (uint32_t j = 0, ib = 0, ic = 0; j < 13; ++j) {
-                if (ib < 6 && P.res[j] == P.blk[ib]) lpos_blk[ib++] = j;
-                else lpos_col[ic++] = j;
-            }
-            for (uint32_t b = 0; b < 7; ++b) lcol |= ((ncol >> b) & 1u) << lpos_col[b];
-            lqt = ((qt & 1u) << lpos_blk[4]) | ((qt >> 1) << lpos_blk[5]);
-        }
-        const uint32_t s0 = 8u << lpos_blk[0], s1 = 8u << lpos_blk[1], s2 = 8u << lpos_blk[2], s3 = 8u << lpos_blk[3];   // byte strides of value bits 0..3
-        const uint32_t sbase = (lcol | lqt) * 8u;
+        // Position inside a staged tile.  The tensor map lays a tile out as 512 rows of 16 amplitudes (index bits 0-3 of the
+        // state), then the other column bits, then the other block bits (P.lp_col / P.lp_blk: bit of the tile-local amplitude
+        // index that each column / block bit lands on), with the 128-byte swizzle: 16-byte chunk c of row r is stored at chunk
+        // c ^ (r & 7).  Local bits 4-6 are always column bits, so the swizzle is one XOR constant per thread, and lanes that
+        // differ in the lowest column bits hit different banks wherever the block sits -- also on index bits 0-4.
+        uint32_t lcol = 0;
+        for (uint32_t b = 0; b < 7; ++b) lcol |= ((ncol >> b) & 1u) << P.lp_col[b];
+        const uint32_t lbase = lcol | ((qt & 1u) << P.lp_blk[4]) | ((qt >> 1) << P.lp_blk[5]);
+        const uint32_t sbase = (lbase ^ (((lbase >> 4) & 7u) << 1)) * 8u;                      // bytes, swizzled
+        const uint32_t s0 = 8u << P.lp_blk[0], s1 = 8u << P.lp_blk[1], s2 = 8u << P.lp_blk[2], s3 = 8u << P.lp_blk[3];   // byte strides of value bits 0..3
         const float scale = P.scale, inv_scale = 1.f / P.scale;
         const uint32_t tlane = tmem_d + (((warp & 3u) * 32u) << 16);            // this warp's TMEM lane quarter
 
@@ -260,17 +247,7 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
         };
         if (timed) tlast = clock64();
 
-        // the index deposit costs ~130 instructions: one thread does it per tile, ahead of time, and publishes the result
-        auto publish_tile = [&](uint64_t i) {
-            if (i < cnt) {
-                uint64_t member;
-                const uint64_t base = tile_base(first + i * stride, P, member);
-                tbase[i & 7u] = (member << P.n) + base;
-            }
-        };
-        // A bulk copy is issued from the uniform datapath, one at a time per warp (~60 clocks each), so every worker warp
-        // moves its own share of the rows of a tile: rows warp, warp+16, ...  (tile i lives in buffer i % 3)
-        // Preferred: the tile is one box of a tensor map over the state (one instruction per tile, issued by thread 0).
+        // A tile is one box of a tensor map over the state: one bulk-tensor instruction per tile and direction, issued by thread 0.
         const uint32_t trank = P.trank;
         auto tile_coords = [&](uint64_t i, int32_t (&c)[5]) {
             uint64_t t = first + i * stride;                                   // tile index: non-resident bits, compacted, member on top
@@ -283,43 +260,25 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             }
         };
         auto load_rows = [&](uint64_t i) {
-            if (trank) {
-                if (i < cnt && tid == 0) {
-                    const uint32_t bar = smem_u32(&bar_full[i % 3u]);
-                    int32_t c[5];
-                    tile_coords(i, c);
-                    mbar_expect_tx(bar, TILE_BYTES);
-                    tensor_g2s(smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES), &tmap, c, trank, bar);
-                }
-                return;
-            }
-            if (i < cnt && lane == 0) {
+            if (i < cnt && tid == 0) {
                 const uint32_t bar = smem_u32(&bar_full[i % 3u]);
-                if (warp == 0) mbar_expect_tx(bar, TILE_BYTES);
-                const float2* g = state + tbase[i & 7u];
-                const uint32_t dst = smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES);
-                for (uint32_t r = warp; r < nrows; r += NW / 32) bulk_g2s(dst + r * rowbytes, g + ((uint64_t)rowoff[r] << rowbits), rowbytes, bar);
+                int32_t c[5];
+                tile_coords(i, c);
+                mbar_expect_tx(bar, TILE_BYTES);
+                tensor_g2s(smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES), &tmap, c, trank, bar);
             }
         };
         auto store_rows = [&](uint64_t i) {
-            if (trank) {
-                if (tid == 0) {
-                    int32_t c[5];
-                    tile_coords(i, c);
-                    tensor_s2g(&tmap, c, trank, smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES));
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                return;
-            }
-            if (lane == 0) {
-                float2* g = state + tbase[i & 7u];
-                const uint32_t src = smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES);
-                for (uint32_t r = warp; r < nrows; r += NW / 32) bulk_s2g(g + ((uint64_t)rowoff[r] << rowbits), src + r * rowbytes, rowbytes);
+            if (tid == 0) {
+                int32_t c[5];
+                tile_coords(i, c);
+                tensor_s2g(&tmap, c, trank, smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES));
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         };
         // shared-memory address of this thread's block value v of a tile
-        auto vaddr = [&](int v) -> uint32_t { return ((v & 1) ? s0 : 0u) + ((v & 2) ? s1 : 0u) + ((v & 4) ? s2 : 0u) + ((v & 8) ? s3 : 0u); };
+        // (value bits and the thread's own bits are disjoint, and the swizzle is an XOR: offsets combine with XOR)
+        auto vaddr = [&](int v) -> uint32_t { return ((v & 1) ? s0 : 0u) ^ ((v & 2) ? s1 : 0u) ^ ((v & 4) ? s2 : 0u) ^ ((v & 8) ? s3 : 0u); };
 
         // ---- epilogue of tile i from pipeline buffer B: TMEM lane = column; re at column t, im at column 64 + t.  The
         //      thread overwrites exactly the amplitudes it read, so the tile is transformed in place without a barrier. ----
@@ -351,13 +310,13 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                 if (v.x > 0.f && v.y > 0.f) fcorr = sqrtf(v.x / v.y);          // an all-zero tile says nothing: keep the last ratio
             }
             const float f = fcorr;
-            unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES + sbase;
+            unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES;
             float out2 = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const float a = __uint_as_float(re[j]), b = __uint_as_float(im[j]);
                 out2 = fmaf(a, a, fmaf(b, b, out2));
-                *reinterpret_cast<float2*>(S + vaddr(j)) = make_float2(a * f, b * f);
+                *reinterpret_cast<float2*>(S + (sbase ^ vaddr(j))) = make_float2(a * f, b * f);
             }
             if (P.renorm) {
 #pragma unroll
@@ -380,15 +339,15 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             constexpr uint32_t B = decltype(BC)::value;
             mbar_wait(smem_u32(&bar_full[i % 3u]), (uint32_t)(i / 3u) & 1u);
             mark(0);
-            const unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES + sbase;
+            const unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES;
             float in2 = 0.f;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {                                      // 8 block values -> 4 packed words per (term, re|im)
                 uint32_t hr[4], lr[4], hi[4], li[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float2 a0 = *reinterpret_cast<const float2*>(S + vaddr(8 * c + 2 * j));
-                    const float2 a1 = *reinterpret_cast<const float2*>(S + vaddr(8 * c + 2 * j + 1));
+                    const float2 a0 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j)));
+                    const float2 a1 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j + 1)));
                     in2 = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, in2))));
                     split2(a0.x * scale, a1.x * scale, hr[j], lr[j]);
                     split2(a0.y * scale, a1.y * scale, hi[j], li[j]);
@@ -407,7 +366,6 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_x[B]));                   // one arrival per worker warp
             mark(1);
-            if (tid == 32 && !trank) publish_tile(i + 3);
             // the buffer of tile i-2 (stored during the previous step) is free once the bulk stores have read it: refill it
             // with tile i+1.  Each warp waits for, and re-uses, its own rows only.
             if (i >= 1) {
@@ -421,8 +379,6 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             mark(3);
         };
 
-        if (tid == 32 && !trank) { publish_tile(0); publish_tile(1); publish_tile(2); }
-        workers_sync();
         load_rows(0);
         load_rows(1);
 

@@ -106,6 +106,7 @@ bool op_is_unitary(const HostOp& o) {
 rocqStatus_t run_ops_with_blocks(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>& seg) {
     rq::BlockLimits BL;
     BL.min_cost = h->blockMinCost;
+    BL.batch = h->batchSize;
     static const bool prof = getenv("ROCQ_HOST_PROFILE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
@@ -217,12 +218,9 @@ void build_block_terms(const std::vector<cd>& U, std::vector<uint16_t>& out) {
         }
 }
 
-// Tensor map over the state (elements = 8-byte amplitudes) whose box is exactly one tile of the block sweep: index bits are
-// grouped in runs of the same kind (column / block / not resident); every run is one dimension, resident runs are covered by
-// the box, the others are addressed by tile-index bits.  Returns false when it takes more than five dimensions (the kernel
-// then moves tiles row by row) or the driver entry point is unavailable.
-bool build_block_tensor_map(const rq_cplx* state, unsigned n, size_t batch, uint64_t blockmask, uint64_t colmask, CUtensorMap* tm,
-                            rq_block_params& P) {
+// Tensor map over the state (elements = 8-byte amplitudes) whose box is exactly one tile of the block sweep, in the
+// shared-memory order and with the 128-byte swizzle rq::block_layout describes.
+bool build_block_tensor_map(const rq_cplx* state, const rq::BlockLayout& L, CUtensorMap* tm) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static encode_fn encode = nullptr;
@@ -235,46 +233,12 @@ bool build_block_tensor_map(const rq_cplx* state, unsigned n, size_t batch, uint
             encode = reinterpret_cast<encode_fn>(fn);
     }
     if (!encode) return false;
-    cuuint64_t dims[6], strides[6];
-    cuuint32_t box[6], estr[6];
-    unsigned rank = 0;
-    auto kind = [&](unsigned p) { return ((colmask >> p) & 1ull) ? 1 : ((blockmask >> p) & 1ull) ? 2 : 0; };
-    int last_free = -1;
-    for (unsigned p = 0; p < n;) {
-        const int k = kind(p);
-        unsigned q = p;
-        while (q < n && kind(q) == k) ++q;
-        if (rank >= 5) return false;
-        dims[rank] = 1ull << (q - p);
-        strides[rank] = (8ull << p);                      // bytes
-        box[rank] = k ? (cuuint32_t)(1u << (q - p)) : 1u;
-        estr[rank] = 1;
-        P.tbits[rank] = k ? 0 : (uint8_t)(q - p);
-        if (!k) last_free = (int)rank;
-        ++rank;
-        p = q;
-    }
-    if (batch > 1 || last_free < 0) {
-        if (last_free == (int)rank - 1 && last_free >= 0) dims[last_free] *= batch;          // the top run is free: it absorbs the batch
-        else {
-            if (rank >= 5) return false;
-            dims[rank] = batch;
-            strides[rank] = 8ull << n;
-            box[rank] = 1;
-            estr[rank] = 1;
-            P.tbits[rank] = 1;                             // placeholder, becomes "the rest" below
-            last_free = (int)rank++;
-        }
-    }
-    if (rank < 2 || last_free < 0) return false;
-    P.tbits[last_free] = 255;                              // the last free dimension takes every remaining tile-index bit (incl. the batch member)
-    for (unsigned d = 0; d < rank; ++d) if (dims[d] > 0xffffffffull || box[d] > 256) return false;
-    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<rq_cplx*>(state), dims, strides + 1, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return false;
-    P.trank = rank;
-    return true;
+    cuuint64_t dims[5], strides[5];
+    cuuint32_t box[5], estr[5];
+    for (unsigned d = 0; d < L.rank; ++d) { dims[d] = L.dims[d]; strides[d] = L.strides[d]; box[d] = L.box[d]; estr[d] = 1; }
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, L.rank, const_cast<rq_cplx*>(state), dims, strides + 1, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // launch one block sweep: block positions (ascending), matrix U over them
@@ -286,13 +250,11 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     P.n = n; P.T = 13; P.ntiles = (uint64_t)h->batchSize << (n - 13);
     uint64_t bm = 0;
     for (unsigned b = 0; b < 6; ++b) { P.blk[b] = (uint8_t)blk[b]; bm |= 1ull << blk[b]; }
-    unsigned nc = 0;
-    uint64_t rm = bm;
-    for (unsigned p = 0; p < n && nc < RQ_BLOCK_COLBITS; ++p) if (!((bm >> p) & 1ull)) { P.col[nc++] = (uint8_t)p; rm |= 1ull << p; }
-    unsigned nr = 0;
-    for (unsigned p = 0; p < n; ++p) if ((rm >> p) & 1ull) P.res[nr++] = (uint8_t)p;
-    while (P.rowbits < 13 && P.res[P.rowbits] == P.rowbits) ++P.rowbits;       // tile rows are bulk-copied: >= 256 B each
-    if (P.rowbits < 5) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    rq::BlockLayout L;
+    CUtensorMap tm;
+    if (!rq::block_layout(bm, n, h->batchSize, L) || !build_block_tensor_map(state, L, &tm)) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    memcpy(P.col, L.col, 7); memcpy(P.res, L.res, 13); memcpy(P.tbits, L.tbits, 5); memcpy(P.lp_blk, L.lp_blk, 6); memcpy(P.lp_col, L.lp_col, 7);
+    P.trank = L.rank;
     // unitary?  (then every tile column keeps its norm, which the kernel restores exactly)
     double dev = unitary == 1 ? 0.0 : unitary == 0 ? 1.0 : 0.0;
     for (unsigned a = 0; a < 64 && unitary < 0; ++a)
@@ -311,12 +273,7 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     RQ_CUDA(cudaMallocAsync(&d_terms, RQ_BLOCK_UBYTES + 256, h->stream), "block terms alloc");   // + debug timers
     // pageable source: cudaMemcpyAsync stages it before returning, so `terms` may go out of scope
     RQ_CUDA(cudaMemcpyAsync(d_terms, terms.data(), RQ_BLOCK_UBYTES, cudaMemcpyHostToDevice, h->stream), "block terms upload");
-    CUtensorMap tm;
-    uint64_t cm = 0;
-    for (unsigned c = 0; c < RQ_BLOCK_COLBITS; ++c) cm |= 1ull << P.col[c];
-    const bool have_tm = !(P.pad & 32u) && build_block_tensor_map(state, n, h->batchSize, bm, cm, &tm, P);
-    if (!have_tm) { P.trank = 0; memset(P.tbits, 0, sizeof P.tbits); }
-    RQ_CUDA(rq_launch_block_sweep(state, &P, d_terms, have_tm ? &tm : nullptr, h->stream), "block sweep launch");
+    RQ_CUDA(rq_launch_block_sweep(state, &P, d_terms, &tm, h->stream), "block sweep launch");
     if (P.pad & 16u) {                                   // ROCQ_BLOCK_DEBUG & 16: per-phase clock totals of CTA 0, threads 0 and 64
         long long t[32];
         cudaMemcpyAsync(t, (char*)d_terms + RQ_BLOCK_UBYTES, sizeof t, cudaMemcpyDeviceToHost, h->stream);
@@ -785,9 +742,10 @@ rocqStatus_t rocsvxApplyBlock6(rocsvHandle_t h, rocComplex* d, unsigned n, const
     for (unsigned c = 0; c < 64; ++c)
         for (unsigned r = 0; r < 64; ++r) U[remap(r) + 64u * remap(c)] = cd(matrix[2 * (r + 64u * c)], matrix[2 * (r + 64u * c) + 1]);
     h->stats.gatesSubmitted++;
-    if (blk[0] < 5) {
-        // the tensor-core kernel stages tiles as rows of >= 32 consecutive amplitudes, i.e. block qubits >= 5;
-        // a block on the lowest qubits takes the generic dense path
+    uint64_t bm = 0;
+    for (unsigned q : blk) bm |= 1ull << q;
+    if (!rq::block_supported(bm, n, h->batchSize)) {
+        // the tile of a very scattered block does not fit one five-dimensional tensor map: generic dense path
         std::vector<HostOp> one{rq::make_matrix(blk, 0ull, U)};
         return run_ops(h, state, n, one, false);
     }

@@ -374,6 +374,84 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
     return plans;
 }
 
+// ---- tile geometry of the tensor-core block sweep (block_sweep.cu) -------------------------------------------------------
+// A tile = the 6 block bits + the 7 lowest other index bits ("columns").  It is moved by ONE tensor-map copy whose box lists,
+// in shared-memory order: index bits 0-3 (a 128-byte row), the remaining column bits, the remaining block bits; index bits
+// that are consecutive in that list AND in the state share a dimension.  Bits outside the tile form one box-1 dimension per
+// run (addressed by tile-index bits), the last of which also carries the batch member.  At most five dimensions.
+struct BlockLayout {
+    unsigned rank = 0;
+    uint64_t dims[5], strides[5];    // elements (8-byte amplitudes), bytes
+    uint32_t box[5];
+    uint8_t tbits[5];                // tile-index bits a dimension consumes (0: in the tile, 255: all that remain)
+    uint8_t col[7], lp_col[7], lp_blk[6];
+    uint8_t res[13];                 // tile bits, ascending
+};
+inline bool block_layout(uint64_t blockmask, unsigned n, size_t batch, BlockLayout& L) {
+    if (n < 13 || n > 40 || __builtin_popcountll(blockmask) != 6 || (blockmask >> n)) return false;
+    unsigned blk[6], nb = 0, nc = 0;
+    uint64_t colmask = 0;
+    for (unsigned p = 0; p < n; ++p) {
+        if ((blockmask >> p) & 1ull) blk[nb++] = p;
+        else if (nc < 7) { L.col[nc++] = (uint8_t)p; colmask |= 1ull << p; }
+    }
+    const uint64_t tile = blockmask | colmask;
+    for (unsigned p = 0, r = 0; p < n; ++p) if ((tile >> p) & 1ull) L.res[r++] = (uint8_t)p;
+    // shared-memory order of the tile bits
+    unsigned order[13], no = 0;
+    for (unsigned p = 0; p < 4; ++p) order[no++] = p;                       // bits 0-3 are always in the tile
+    for (unsigned c = 0; c < 7; ++c) if (L.col[c] >= 4) order[no++] = L.col[c];
+    for (unsigned b = 0; b < 6; ++b) if (blk[b] >= 4) order[no++] = blk[b];
+    for (unsigned l = 0; l < 13; ++l) {
+        const unsigned p = order[l];
+        bool is_blk = false;
+        for (unsigned b = 0; b < 6; ++b) if (blk[b] == p) { L.lp_blk[b] = (uint8_t)l; is_blk = true; }
+        if (!is_blk) for (unsigned c = 0; c < 7; ++c) if (L.col[c] == p) L.lp_col[c] = (uint8_t)l;
+    }
+    unsigned rank = 0;
+    auto add = [&](unsigned start, unsigned len, bool in_tile) {
+        if (rank >= 5) { rank = 99; return; }
+        L.dims[rank] = 1ull << len;
+        L.strides[rank] = 8ull << start;
+        L.box[rank] = in_tile ? (1u << len) : 1u;
+        L.tbits[rank] = in_tile ? 0 : (uint8_t)len;
+        ++rank;
+    };
+    add(0, 4, true);
+    for (unsigned l = 4; l < 13 && rank <= 5;) {                            // runs of the ordered list, at most 8 bits each (box <= 256)
+        unsigned m = l + 1;
+        while (m < 13 && order[m] == order[m - 1] + 1 && m - l < 8) ++m;
+        add(order[l], m - l, true);
+        l = m;
+    }
+    int last_free = -1;
+    for (unsigned p = 4; p < n && rank <= 5;) {                             // runs of bits outside the tile, ascending
+        if ((tile >> p) & 1ull) { ++p; continue; }
+        unsigned q = p;
+        while (q < n && !((tile >> q) & 1ull)) ++q;
+        add(p, q - p, false);
+        last_free = (int)rank - 1;
+        p = q;
+    }
+    if (rank > 5) return false;
+    if (last_free >= 0 && L.strides[last_free] * L.dims[last_free] == (8ull << n)) L.dims[last_free] *= batch;   // top run: absorbs the batch
+    else if (batch > 1 || last_free < 0) {
+        if (rank >= 5) return false;
+        L.dims[rank] = batch;
+        L.strides[rank] = 8ull << n;
+        L.box[rank] = 1;
+        last_free = (int)rank++;
+    }
+    L.tbits[last_free] = 255;
+    for (unsigned d = 0; d < rank; ++d) if (L.dims[d] > 0xffffffffull || L.box[d] > 256) return false;
+    L.rank = rank;
+    return true;
+}
+inline bool block_supported(uint64_t blockmask, unsigned n, size_t batch) {
+    BlockLayout L;
+    return block_layout(blockmask, n, batch, L);
+}
+
 // ---- mixed plan: tensor-core blocks + ordinary sweeps ----------------------------------------------------------------
 // A step is either one 6-qubit block (every op of `ops` folded into one 64x64 unitary, applied by block_sweep.cu in one HBM
 // pass) or one ordinary tile sweep.  Oldest first, which keeps the frontier of the circuit flat so that blocks stay full:
@@ -384,10 +462,10 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
 // block could take to the blocks.
 struct BlockLimits {
     unsigned qubits = 6;
-    unsigned min_pos = 5;            // block positions must be >= min_pos (tile layout of block_sweep.cu)
+    unsigned min_pos = 0;            // block positions must be >= min_pos
     double min_cost = 50.0;          // ~ three dense two-qubit matrices: below that the CUDA-core sweep is cheaper
     size_t batch = 1;
-    bool (*supported)(uint64_t blockmask, unsigned n, size_t batch) = nullptr;   // can the kernel run this set? (null: any)
+    bool (*supported)(uint64_t blockmask, unsigned n, size_t batch) = block_supported;   // can the kernel move this tile?
 };
 struct MixedStep {
     bool block = false;

@@ -124,14 +124,16 @@ struct rq_block_params {
     uint32_t renorm;                // 1: the block is unitary -> restore every column's norm in the epilogue
     uint32_t pad;                   // debug switches (ROCQ_BLOCK_DEBUG), 0 in production
     float scale;                    // power of two that brings amplitudes into the fp16 normal range
-    uint32_t rowbits;               // log2(amplitudes per contiguous row of a tile): resident positions 0..rowbits-1 are 0..rowbits-1
+    uint32_t pad2;
     uint64_t ntiles;                // batch * 2^(n-13)
     uint8_t res[16];                // ascending resident positions (block + column bits)
     uint8_t blk[8];                 // 6 block positions, ascending: bit b of the block value <-> blk[b]
     uint8_t col[8];                 // 7 column positions, ascending
-    uint32_t trank;                 // rank of the tensor map whose box is one tile (0: none, tiles move as per-row bulk copies)
+    uint32_t trank;                 // rank of the tensor map whose box is one tile
     uint8_t tbits[5];               // per tensor-map dimension: tile-index bits it consumes (0: resident, 255: all that remain)
-    uint8_t pad3[3];
+    uint8_t lp_blk[6];              // bit of the tile-local amplitude index (shared-memory layout) that block bit b lands on
+    uint8_t lp_col[7];              // ... and column bit b
+    uint8_t pad3[2];
 };
 #define RQ_BLOCK_QUBITS 6
 #define RQ_BLOCK_COLBITS 7

@@ -56,8 +56,8 @@ def test_single_gate_plans_are_one_sweep():
 def _check_blocks(n, gates, min_cost=0.0, tol=1e-11):
     nb, ns, steps = util.plan_blocks(n, gates, min_cost)
     for st in steps:
-        if "blk" in st:                                   # a block: six positions >= 5, every op inside it
-            assert len(st["blk"]) == 6 and sorted(st["blk"]) == st["blk"] and min(st["blk"]) >= 5 and max(st["blk"]) < n
+        if "blk" in st:                                   # a block: six positions, every op inside it
+            assert len(st["blk"]) == 6 and sorted(st["blk"]) == st["blk"] and max(st["blk"]) < n
             for op in st["ops"]:
                 qs = set(op["targets"]) | {q for q in range(64) if (op["cmask"] >> q) & 1}
                 assert qs <= set(st["blk"])
@@ -74,10 +74,9 @@ def _check_blocks(n, gates, min_cost=0.0, tol=1e-11):
 def test_block_plan_is_equivalent_and_forms_blocks(n):
     gates = workloads.c2_random_unitary(n, 10, seed=30)
     nb, ns, steps = _check_blocks(n, gates)
-    assert nb >= 1                                         # the brick circuit above qubit 5 goes to blocks ...
-    low = [op for st in steps if "res" in st and "blk" not in st for op in st["ops"] if op["kind"] == 1]
-    # ... and the ordinary sweeps keep (almost) only what touches qubits 0-4
-    assert sum(1 for op in low if min(op["targets"]) < 5) >= 0.8 * len(low)
+    in_blocks = sum(len(st["ops"]) for st in steps if "blk" in st)
+    total = sum(len(st["ops"]) for st in steps)
+    assert nb >= 1 and in_blocks >= 0.8 * total            # a brick circuit goes (almost) entirely to blocks, also on qubits 0-4
 
 
 def test_block_plan_mixed_bag_and_threshold():
@@ -93,4 +92,4 @@ def test_block_plan_large_brick_circuit_block_occupancy():
     gates = workloads.c2_random_unitary(30, 40, seed=30)
     nb, ns, steps = util.plan_blocks(30, gates)
     in_blocks = sum(len(s["ops"]) for s in steps if "blk" in s)
-    assert nb <= 75 and in_blocks / nb >= 6.5              # blocks stay full (a brick diamond holds 9 two-qubit matrices)
+    assert nb <= 90 and in_blocks / nb >= 6.5              # blocks stay full (a brick diamond holds 9 two-qubit matrices)

@@ -227,11 +227,12 @@ def run_engine(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    dev_ms = 0.0
+    # device time of the K steps: CUDA events on the engine's own stream (rocsvxTimerStart/Stop), no sync inside the region
+    sv.timer_start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
-        dev_ms += sv.stats().lastSweepMs          # CUDA events on the handle's stream around the step's sweeps
+    dev_ms = sv.timer_stop()
     barrier()
     elapsed = time.perf_counter() - t0
     clk = clocks.stop() if rank == 0 else None
@@ -256,6 +257,22 @@ def run_engine(args):
             sv.gate("h", (7 * r) % n)
         one_ms = sv.timer_stop() / reps
         one_gate = {"avg_launch_ms": one_ms, "achieved": 2.0 * (1 << n) * 8 / (one_ms * 1e-3) / 1e9, "gates": "H on 10 different qubits, one sweep each"}
+
+    # ---- the tensor-core block sweep alone: ten 6-qubit Haar blocks back to back -------------------------------------
+    block_alone = None
+    if ngpus == 1 and st.blockSweeps > 0:
+        import numpy as np
+        from rocquantum_b200 import workloads as wl_
+        U = wl_.haar_unitary(np.random.default_rng(5), 64)
+        qs = list(range(n // 2 - 3, n // 2 + 3))
+        sv.apply_block6(qs, U)
+        sv.sync()
+        sv.timer_start()
+        for r in range(10):
+            sv.apply_block6(qs, U)
+        blk_ms = sv.timer_stop() / 10
+        block_alone = {"avg_launch_ms": blk_ms, "achieved": 2.0 * (1 << n) * 8 / (blk_ms * 1e-3) / 1e9,
+                       "what": "block_sweep_kernel, one Haar 64x64 block on qubits %s, ten launches back to back" % qs}
 
     # ---- end to end through the public call: host gate list in, host result out, every step ----------
     e2e_t, d2h = 0.0, 0
@@ -297,12 +314,19 @@ def run_engine(args):
     sweep_ms = max(0.0, dev_ms - st.exchangeMs) if ngpus > 1 else dev_ms
     avg_sweep_ms = sweep_ms / max(1, st.sweeps)
     achieved = sweep_bytes / (avg_sweep_ms * 1e-3) / 1e9 if avg_sweep_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "tile_sweep_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    nblk = st.blockSweeps
+    kernel = "block_sweep_kernel (tcgen05, %d of %d launches) + tile_sweep_kernel" % (nblk, st.sweeps) if nblk else "tile_sweep_kernel"
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "frac_of_8TBs_spec": achieved / 8000.0, "peak_source": peak_src,
                 "traffic": None, "algorithmic_bytes_per_launch": sweep_bytes, "avg_launch_ms": avg_sweep_ms,
                 "launches_per_step": sweeps_per_step, "gates_per_sweep": ngates / max(1.0, sweeps_per_step),
-                "note": "fused sweeps of this circuit carry ~8 dense 2q matrices each and are FP32-bound, not HBM-bound; "
-                        "one_gate_sweep is the same kernel in its HBM-bound regime"}
+                "note": "every launch is one pass over the state (2 * 2^n * 8 B); avg_launch_ms = device time of the timed region "
+                        "/ launches, idle gaps included.  With tensor-core blocks most launches carry one fused 64x64 unitary "
+                        "(~8 two-qubit matrices) and run near the HBM roofline; block_sweep_alone / one_gate_sweep time the two "
+                        "kernels alone"}
+    if block_alone:
+        block_alone["frac"] = block_alone["achieved"] / peaks["hbm_gbs"]
+        roofline["block_sweep_alone"] = block_alone
     if one_gate:
         one_gate["frac"] = one_gate["achieved"] / peaks["hbm_gbs"]
         one_gate["frac_of_8TBs_spec"] = one_gate["achieved"] / 8000.0

@@ -175,9 +175,11 @@ rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t handle, rocComplex* d_state, unsig
                                 const rocsvxGateOp* ops, size_t numOps);
 
 /* Tensor-core path (complex64 library only): apply one dense 6-qubit matrix (HOST, column-major 64x64, interleaved
- * (re,im) doubles, index bit b <-> qubits[b]) to the whole state in one HBM pass with tcgen05 MMAs (bf16x3 split,
- * fp32 accumulation in TMEM).  Needs numQubits >= 13.  rocsvxApplyCircuit uses the same kernel for the 6-qubit
- * blocks its planner forms when rocsvxSetTensorCoreBlocks is on. */
+ * (re,im) doubles, index bit b <-> qubits[b], any six distinct qubits) to the whole state in one HBM pass with tcgen05
+ * MMAs (two-term fp16 split of both operands, fp32 accumulation in tensor memory; ~2e-7 relative error per block).
+ * Needs numQubits >= 13.  rocsvxApplyCircuit and fused flushes use the same kernel for the 6-qubit blocks their planner
+ * forms: rocsvxSetTensorCoreBlocks(h, 1) always, (h, 0) never, (h, -1) = default: from 24 qubits on.  Environment:
+ * ROCQ_TC=0|1|auto, ROCQ_TC_MIN_COST. */
 rocqStatus_t rocsvxApplyBlock6(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, const unsigned* qubits,
                                const double* matrix);
 rocqStatus_t rocsvxSetTensorCoreBlocks(rocsvHandle_t handle, int enabled);
@@ -203,6 +205,7 @@ typedef struct {
     uint64_t exchanges;        /* multi-process: global<->local index-bit exchanges executed */
     uint64_t exchangeBytes;    /* multi-process: bytes this rank sent to peers in those exchanges */
     double   exchangeMs;       /* multi-process: device time of those exchanges (CUDA events around each) */
+    uint64_t blockSweeps;      /* launches of the tensor-core block-sweep kernel (counted in `sweeps` too) */
 } rocsvxStats;
 rocqStatus_t rocsvxGetStats(rocsvHandle_t handle, rocsvxStats* stats, int reset);
 

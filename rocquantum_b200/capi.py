@@ -30,7 +30,7 @@ class Stats(C.Structure):
     """rocsvxStats"""
     _fields_ = [("kernelLaunches", C.c_uint64), ("sweeps", C.c_uint64), ("gatesSubmitted", C.c_uint64),
                 ("opsExecuted", C.c_uint64), ("h2dBytes", C.c_uint64), ("lastSweepMs", C.c_double),
-                ("exchanges", C.c_uint64), ("exchangeBytes", C.c_uint64), ("exchangeMs", C.c_double)]
+                ("exchanges", C.c_uint64), ("exchangeBytes", C.c_uint64), ("exchangeMs", C.c_double), ("blockSweeps", C.c_uint64)]
 
 
 class ExchangeSeg(C.Structure):

@@ -151,7 +151,8 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
         if (j > i) {
             std::vector<HostOp> seg(ops.begin() + i, ops.begin() + j);
             if (fused && seg.size() > 1) seg = rq::fuse_algebraic(seg, n, h->dist.active() ? h->dist.global_mask() : 0ull);
-            if (fused && h->tcBlocks && sizeof(rq_real) == 4 && n >= 13 && !h->dist.active() && seg.size() > 1) {
+            const bool tc = h->tcBlocks > 0 || (h->tcBlocks < 0 && n >= RQ_BLOCK_AUTO_QUBITS);
+            if (fused && tc && sizeof(rq_real) == 4 && n >= 13 && !h->dist.active() && seg.size() > 1) {
                 const rocqStatus_t s = run_ops_with_blocks(h, state, n, seg);
                 if (s != ROCQ_STATUS_SUCCESS) return s;
                 i = j;
@@ -289,6 +290,7 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     RQ_CUDA(cudaFreeAsync(d_terms, h->stream), "block terms free");
     h->stats.kernelLaunches++;
     h->stats.sweeps++;
+    h->stats.blockSweeps++;
     h->stats.h2dBytes += RQ_BLOCK_UBYTES;
     return ROCQ_STATUS_SUCCESS;
 }
@@ -424,7 +426,7 @@ rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
     }
     if (const char* e = getenv("ROCQ_FUSION")) h->fusion = atoi(e) != 0;
     if (const char* e = getenv("ROCQ_TILE_BITS")) { const int t = atoi(e); if (t >= 6 && t <= RQ_MAX_TILE_BITS) h->tileBits = (unsigned)t; }
-    if (const char* e = getenv("ROCQ_TC")) h->tcBlocks = atoi(e) != 0 && sizeof(rq_real) == 4;
+    if (const char* e = getenv("ROCQ_TC")) h->tcBlocks = (e[0] == 'a' || e[0] == '-') ? -1 : (atoi(e) != 0 && sizeof(rq_real) == 4) ? 1 : 0;
     if (const char* e = getenv("ROCQ_TC_MIN_COST")) { const double b = atof(e); if (b > 0) h->blockMinCost = b; }
     if (const char* e = getenv("ROCQ_SWEEP_BUDGET")) { const double b = atof(e); if (b > 0) h->budget = b; }
     *handle = h;
@@ -714,8 +716,8 @@ rocqStatus_t rocsvxGetExpectationPauliBatch(rocsvHandle_t h, rocComplex* d, unsi
 }
 rocqStatus_t rocsvxSetTensorCoreBlocks(rocsvHandle_t h, int enabled) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
-    if (enabled && sizeof(rq_real) != 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
-    h->tcBlocks = enabled != 0;
+    if (enabled > 0 && sizeof(rq_real) != 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
+    h->tcBlocks = enabled > 0 ? 1 : enabled < 0 ? -1 : 0;
     return ROCQ_STATUS_SUCCESS;
 }
 
@@ -941,6 +943,8 @@ rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t h, rocComplex* d, unsigned n, cons
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
     if (numOps == 0) return ROCQ_STATUS_SUCCESS;
     if (!ops) return ROCQ_STATUS_INVALID_VALUE;
+    static const bool prof = getenv("ROCQ_HOST_PROFILE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     std::vector<HostOp> hops;
     rocqStatus_t s = convert_ops(n, ops, numOps, hops);
     if (s != ROCQ_STATUS_SUCCESS) return s;
@@ -948,9 +952,13 @@ rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t h, rocComplex* d, unsigned n, cons
     if (s != ROCQ_STATUS_SUCCESS) return s;
     h->stats.gatesSubmitted += numOps;
     if (h->dist.active()) return h->dist.run_circuit(h, hops);
+    const auto t1 = std::chrono::steady_clock::now();
     cudaEventRecord(h->ev0, h->stream);
     s = run_ops(h, state, n, hops, true);
     cudaEventRecord(h->ev1, h->stream);
+    if (prof) fprintf(stderr, "[host profile] ApplyCircuit: convert %.2f ms, run_ops (fuse + plan + launches) %.2f ms\n",
+                      std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     h->stats.lastSweepMs = -1.0;
     return s;
 }

@@ -31,7 +31,7 @@ struct rocsvInternalHandle {
     size_t pinnedSize = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     // tuning
-    bool tcBlocks = false;              // form 6-qubit tensor-core blocks in rocsvxApplyCircuit / fused flushes
+    int tcBlocks = -1;                  // 6-qubit tensor-core blocks in rocsvxApplyCircuit / fused flushes: 0 off, 1 on, -1 auto (on from RQ_BLOCK_AUTO_QUBITS qubits)
     double blockMinCost = 54.0;         // fold >= this much HostOp::cost() (3 dense 2q gates) or stay on the CUDA cores
     unsigned tileBits = RQ_MAX_TILE_BITS;
     double budget = 1e30;

@@ -137,6 +137,7 @@ struct rq_block_params {
 };
 #define RQ_BLOCK_QUBITS 6
 #define RQ_BLOCK_COLBITS 7
+#define RQ_BLOCK_AUTO_QUBITS 24        // 'auto': tensor-core blocks from this many qubits (state beyond L2; below, launch overheads dominate)
 #define RQ_BLOCK_UBYTES 32768        // Re U and Im U of the 64x64 block, two fp16 terms each, in UMMA K-major core-matrix order
 
 // ---- thin C ABI to the launchers (all return a cudaError_t as int; stream is a cudaStream_t) --------

@@ -63,6 +63,14 @@ class DistStateVector:
         self._ck("rocsvxGetStats", self.lib.rocsvxGetStats(self.h, C.byref(s), int(reset)))
         return s
 
+    def timer_start(self):
+        self._ck("rocsvxTimerStart", self.lib.rocsvxTimerStart(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._ck("rocsvxTimerStop", self.lib.rocsvxTimerStop(self.h, C.byref(ms)))
+        return ms.value
+
     def apply_ops(self, arr, count):
         self._ck("rocsvxApplyCircuit", self.lib.rocsvxApplyCircuit(self.h, None, self.n, arr, count))
 

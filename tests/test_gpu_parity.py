@@ -298,3 +298,26 @@ def test_circuit_with_tensor_core_blocks(n):
     plain = StateVector(n, "c64"); plain.apply_circuit(gates)
     assert g.stats().sweeps != plain.stats().sweeps                  # blocks were actually formed
     assert abs(g.norm2() - 1) < 2e-5
+
+
+def test_block6_batch_and_low_qubits():
+    # blocks on index bits 0-4 (swizzled tile layout) and a batch of states (extra tensor-map dimension)
+    rng = np.random.default_rng(12)
+    for n, batch, qs in ((13, 3, [0, 1, 2, 3, 4, 5]), (15, 2, [1, 2, 3, 4, 5, 6]), (16, 2, [10, 11, 12, 13, 14, 15]), (17, 1, [3, 4, 5, 6, 7, 8])):
+        U = workloads.haar_unitary(rng, 64)
+        o, g = _pair(n, "c64", batch=batch, seed=n)
+        o.apply_matrix(qs, U); g.apply_block6(qs, U)
+        assert g.stats().blockSweeps == 1
+        assert util.rel_err(g.state(), o.state) < 2e-6
+
+
+def test_default_path_forms_blocks_from_24_qubits():
+    n = 24
+    gates = workloads.c2_random_unitary(n, 6, seed=30)
+    o = so.Oracle(n, "c64"); util.run_on_oracle(o, gates)
+    g = StateVector(n, "c64"); g.apply_circuit(gates)          # default = auto: tensor-core blocks on at >= 24 qubits
+    assert g.stats().blockSweeps > 0
+    assert util.rel_err(g.state(), o.state) < TOL["c64"]
+    off = StateVector(n, "c64"); off.set_tensor_core_blocks(False); off.apply_circuit(gates)
+    assert off.stats().blockSweeps == 0
+    assert util.rel_err(off.state(), o.state) < TOL["c64"]

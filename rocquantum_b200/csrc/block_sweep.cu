@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
         //      thread overwrites exactly the amplitudes it read, so the tile is transformed in place without a barrier. ----
         float my_in = 0.f;                                                     // |.|^2 of this thread's inputs of the tile in flight
         float fcorr = inv_scale;                                               // output factor: 1/scale times the norm correction
+        float acc_in = 0.f, acc_out = 0.f;                                     // |in|^2, |scaled out|^2 over the CTA's finished tiles
         auto epilogue = [&](auto BC, uint64_t i, float in2) {
             constexpr uint32_t B = decltype(BC)::value;
             mark(4);
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             tc_fence_before();
             mark(6);
             // A unitary block preserves the norm of the tile.  The tensor core's truncating accumulation shrinks it
-            // systematically (~1e-7 per sweep); the ratio measured on the CTA's previous tile removes that bias.
+            // systematically (~1e-7 per sweep); the ratio measured on the tiles this CTA has finished removes that bias.
             if (P.renorm && i > 0) {
                 float2 v = red[(i - 1) & 1u][lane & 15u];
 #pragma unroll
@@ -307,7 +308,14 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                     v.x += __shfl_xor_sync(0xffffffffu, v.x, m);
                     v.y += __shfl_xor_sync(0xffffffffu, v.y, m);
                 }
-                if (v.x > 0.f && v.y > 0.f) fcorr = sqrtf(v.x / v.y);          // an all-zero tile says nothing: keep the last ratio
+                // mass-weighted over all previous tiles of this CTA: an empty or nearly empty tile (whose ratio is rounding
+                // noise) must not set the factor of a tile that carries the state's weight
+                acc_in += v.x;
+                acc_out += v.y;
+                if (acc_in > 0.f && acc_out > 0.f) {
+                    const float r = sqrtf(acc_in / acc_out);
+                    if (fabsf(r * scale - 1.f) < 1e-4f) fcorr = r;
+                }
             }
             const float f = fcorr;
             unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES;

@@ -336,7 +336,8 @@ def run_engine(args):
     if os.path.exists(prof):
         try:
             tj = json.load(open(prof))
-            # ncu capture at a smaller state (see the file); DRAM bytes scale with the state, so report per launch of THIS run
+            tj = tj["block_sweep_kernel" if nblk * 2 > st.sweeps else "tile_sweep_kernel"]      # the dominant kernel of this run
+            # one ncu --set full capture (see the file); DRAM bytes scale with the state, so report per launch of THIS run
             roofline["traffic"] = tj["traffic_over_algorithmic"] * sweep_bytes
             roofline["traffic_source"] = tj["source"]
         except Exception:

@@ -184,6 +184,11 @@ rocqStatus_t rocsvxApplyBlock6(rocsvHandle_t handle, rocComplex* d_state, unsign
                                const double* matrix);
 rocqStatus_t rocsvxSetTensorCoreBlocks(rocsvHandle_t handle, int enabled);
 
+/* Fused execution merges runs of controlled phases / controlled one-qubit diagonals that share a control qubit (a QFT's
+ * CP ladder after each H) into ONE diagonal pass per run instead of one per gate.  On by default; 0 switches it off
+ * (environment: ROCQ_MERGE_DIAG=0). */
+rocqStatus_t rocsvxSetMergeDiagonals(rocsvHandle_t handle, int enabled);
+
 /* ||psi||^2 of batch member 0 (one read sweep). */
 rocqStatus_t rocsvxGetNorm(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, double* result);
 

@@ -24,7 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", HOSTCXX, "-Xcompiler", "-f
           "-I", os.path.join(HERE, "..", "include")]
 SOURCES = ["tile_sweep.cu", "tile_sweep_small.cu", "tile_sweep_small_swz.cu", "tile_sweep_large.cu", "tile_sweep_large_swz.cu",
            "block_sweep.cu", "sv_kernels.cu", "engine.cu", "dist.cu"]
-HEADERS = ["sv_internal.h", "host_ops.h", "dist.h", "dist_plan.h", "engine.h", "tile_sweep.cuh", os.path.join("..", "..", "include", "hipStateVec.h")]
+HEADERS = ["sv_internal.h", "host_ops.h", "gate_convert.h", "dist.h", "dist_plan.h", "engine.h", "tile_sweep.cuh", os.path.join("..", "..", "include", "hipStateVec.h")]
 VARIANTS = {"libhipStateVec.so": [], "libhipStateVec_f64.so": ["-DROCQ_PRECISION_DOUBLE"]}
 
 

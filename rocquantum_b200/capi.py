@@ -87,6 +87,7 @@ PROTOTYPES = {
     "rocsvxApplyCircuit": [_h, _p, _u, C.POINTER(GateOp), _sz],
     "rocsvxApplyBlock6": [_h, _p, _u, _up, C.POINTER(_d)],
     "rocsvxSetTensorCoreBlocks": [_h, C.c_int],
+    "rocsvxSetMergeDiagonals": [_h, C.c_int],
     "rocsvxGetNorm": [_h, _p, _u, C.POINTER(_d)],
     "rocsvxGetExpectationPauliBatch": [_h, _p, _u, C.c_char_p, _up, _up, _u, C.POINTER(_d)],
     "rocsvxGetStats": [_h, C.POINTER(Stats), C.c_int],

@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include "engine.h"
+#include "gate_convert.h"
 
 using rq::cd;
 using rq::HostOp;
@@ -85,7 +86,7 @@ rocqStatus_t launch_plan(H* h, rq_cplx* state, unsigned n, const rq::SweepPlan& 
 
 bool op_is_unitary(const HostOp& o) {
     const unsigned k = (unsigned)o.targets.size(), D = 1u << k;
-    if (o.kind == HostOp::DIAG) {
+    if (o.kind == HostOp::DIAG || o.kind == HostOp::DIAGP) {
         for (const cd& d : o.data) if (std::abs(std::abs(d) - 1.0) > 1e-9) return false;
         return true;
     }
@@ -150,7 +151,10 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
         while (j < ops.size() && ops[j].targets.size() <= 4) ++j;
         if (j > i) {
             std::vector<HostOp> seg(ops.begin() + i, ops.begin() + j);
-            if (fused && seg.size() > 1) seg = rq::fuse_algebraic(seg, n, h->dist.active() ? h->dist.global_mask() : 0ull);
+            if (fused && seg.size() > 1) {
+                seg = rq::fuse_algebraic(seg, n, h->dist.active() ? h->dist.global_mask() : 0ull);
+                if (h->mergeDiagonals) seg = rq::merge_diagonals(seg);
+            }
             const bool tc = h->tcBlocks > 0 || (h->tcBlocks < 0 && n >= RQ_BLOCK_AUTO_QUBITS);
             if (fused && tc && sizeof(rq_real) == 4 && n >= 13 && !h->dist.active() && seg.size() > 1) {
                 const rocqStatus_t s = run_ops_with_blocks(h, state, n, seg);
@@ -427,6 +431,7 @@ rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
     if (const char* e = getenv("ROCQ_FUSION")) h->fusion = atoi(e) != 0;
     if (const char* e = getenv("ROCQ_TILE_BITS")) { const int t = atoi(e); if (t >= 6 && t <= RQ_MAX_TILE_BITS) h->tileBits = (unsigned)t; }
     if (const char* e = getenv("ROCQ_TC")) h->tcBlocks = (e[0] == 'a' || e[0] == '-') ? -1 : (atoi(e) != 0 && sizeof(rq_real) == 4) ? 1 : 0;
+    if (const char* e = getenv("ROCQ_MERGE_DIAG")) h->mergeDiagonals = atoi(e) != 0;
     if (const char* e = getenv("ROCQ_TC_MIN_COST")) { const double b = atof(e); if (b > 0) h->blockMinCost = b; }
     if (const char* e = getenv("ROCQ_SWEEP_BUDGET")) { const double b = atof(e); if (b > 0) h->budget = b; }
     *handle = h;
@@ -721,6 +726,13 @@ rocqStatus_t rocsvxSetTensorCoreBlocks(rocsvHandle_t h, int enabled) {
     return ROCQ_STATUS_SUCCESS;
 }
 
+rocqStatus_t rocsvxSetMergeDiagonals(rocsvHandle_t h, int enabled) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    const rocqStatus_t s = flush(h);                     // queued gates keep the setting they were submitted under
+    h->mergeDiagonals = enabled != 0;
+    return s;
+}
+
 rocqStatus_t rocsvxApplyBlock6(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* qubits, const double* matrix) {
     if (!h || !qubits || !matrix) return ROCQ_STATUS_INVALID_VALUE;
     rq_cplx* state = resolve(h, d);
@@ -872,70 +884,7 @@ rocqStatus_t rocsvxSetFusion(rocsvHandle_t h, int enabled) {
 }
 rocqStatus_t rocsvxFlush(rocsvHandle_t h) { return h ? flush(h) : ROCQ_STATUS_INVALID_VALUE; }
 
-static rocqStatus_t convert_ops(unsigned n, const rocsvxGateOp* ops, size_t numOps, std::vector<HostOp>& out) {
-    out.reserve(numOps);
-    for (size_t i = 0; i < numOps; ++i) {
-        const rocsvxGateOp& g = ops[i];
-        const unsigned t0 = g.targets[0], t1 = g.targets[1];
-        const uint64_t cm = g.controlMask;
-        auto okq = [&](unsigned q) { return q < n; };
-        if (n < 64 && (cm >> n)) return ROCQ_STATUS_INVALID_VALUE;
-        const double c = std::cos(g.theta / 2.0), s = std::sin(g.theta / 2.0), r = 1.0 / std::sqrt(2.0);
-        const bool one_ctrl = __builtin_popcountll(cm) == 1;
-        switch (g.kind) {
-            case ROCSVX_H: case ROCSVX_X: case ROCSVX_Y: case ROCSVX_Z: case ROCSVX_S: case ROCSVX_SDG: case ROCSVX_T:
-            case ROCSVX_RX: case ROCSVX_RY: case ROCSVX_RZ:
-                if (!okq(t0) || cm) return ROCQ_STATUS_INVALID_VALUE;
-                break;
-            case ROCSVX_CNOT: case ROCSVX_CRX: case ROCSVX_CRY: case ROCSVX_CRZ:
-                if (!okq(t0) || !one_ctrl || ((cm >> t0) & 1ull)) return ROCQ_STATUS_INVALID_VALUE;
-                break;
-            case ROCSVX_MCX:
-                if (!okq(t0) || cm == 0 || ((cm >> t0) & 1ull)) return ROCQ_STATUS_INVALID_VALUE;
-                break;
-            case ROCSVX_CZ: case ROCSVX_SWAP:
-                if (!okq(t0) || !okq(t1) || t0 == t1 || cm) return ROCQ_STATUS_INVALID_VALUE;
-                break;
-            case ROCSVX_CSWAP:
-                if (!okq(t0) || !okq(t1) || t0 == t1 || !one_ctrl || ((cm >> t0) & 1ull) || ((cm >> t1) & 1ull)) return ROCQ_STATUS_INVALID_VALUE;
-                break;
-            case ROCSVX_MATRIX: break;
-            default: return ROCQ_STATUS_INVALID_VALUE;
-        }
-        switch (g.kind) {
-            case ROCSVX_H: out.push_back(rq::make_dense1(t0, r, r, r, -r)); break;
-            case ROCSVX_X: out.push_back(rq::make_x(t0)); break;
-            case ROCSVX_Y: out.push_back(rq::make_dense1(t0, 0.0, -I1, I1, 0.0)); break;
-            case ROCSVX_Z: out.push_back(rq::make_phase(1ull << t0, -1.0)); break;
-            case ROCSVX_S: out.push_back(rq::make_phase(1ull << t0, I1)); break;
-            case ROCSVX_SDG: out.push_back(rq::make_phase(1ull << t0, -I1)); break;
-            case ROCSVX_T: { const double ph = 3.14159265358979323846 / 4.0; out.push_back(rq::make_phase(1ull << t0, cd(std::cos(ph), std::sin(ph)))); break; }
-            case ROCSVX_RX: out.push_back(rq::make_dense1(t0, c, cd(0, -s), cd(0, -s), c)); break;
-            case ROCSVX_RY: out.push_back(rq::make_dense1(t0, c, -s, s, c)); break;
-            case ROCSVX_RZ: out.push_back(rq::make_diag1(t0, cd(c, -s), cd(c, s))); break;
-            case ROCSVX_CNOT: case ROCSVX_MCX: out.push_back(rq::make_x(t0, cm)); break;
-            case ROCSVX_CZ: out.push_back(rq::make_phase((1ull << t0) | (1ull << t1), -1.0)); break;
-            case ROCSVX_SWAP: out.push_back(rq::make_swap(t0, t1)); break;
-            case ROCSVX_CRX: out.push_back(rq::make_dense1(t0, c, cd(0, -s), cd(0, -s), c, cm)); break;
-            case ROCSVX_CRY: out.push_back(rq::make_dense1(t0, c, -s, s, c, cm)); break;
-            case ROCSVX_CRZ: out.push_back(rq::make_diag1(t0, cd(c, -s), cd(c, s), cm)); break;
-            case ROCSVX_CSWAP: out.push_back(rq::make_swap(t0, t1, cm)); break;
-            case ROCSVX_MATRIX: {
-                const unsigned k = g.numTargets;
-                if (k == 0 || k > 8 || !g.matrix) return ROCQ_STATUS_INVALID_VALUE;
-                uint64_t seen = cm;
-                std::vector<unsigned> ts(g.targets, g.targets + k);
-                for (unsigned q : ts) { if (!okq(q) || ((seen >> q) & 1ull)) return ROCQ_STATUS_INVALID_VALUE; seen |= 1ull << q; }
-                const size_t D = (size_t)1 << k;
-                std::vector<cd> m(D * D);
-                for (size_t e = 0; e < D * D; ++e) m[e] = cd(g.matrix[2 * e], g.matrix[2 * e + 1]);
-                out.push_back(rq::make_matrix(ts, cm, m));
-                break;
-            }
-        }
-    }
-    return ROCQ_STATUS_SUCCESS;
-}
+using rq::convert_ops;      // gate_convert.h
 
 rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t h, rocComplex* d, unsigned n, const rocsvxGateOp* ops, size_t numOps) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
@@ -1005,7 +954,7 @@ rocqStatus_t rocsvxPlanCircuitBlocks(unsigned n, const rocsvxGateOp* ops, size_t
     const rocqStatus_t s = convert_ops(n, ops, numOps, hops);
     if (s != ROCQ_STATUS_SUCCESS) return s;
     for (const HostOp& o : hops) if (o.targets.size() > 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
-    std::vector<HostOp> fused = hops.size() > 1 ? rq::fuse_algebraic(hops, n) : hops;
+    std::vector<HostOp> fused = hops.size() > 1 ? rq::merge_diagonals(rq::fuse_algebraic(hops, n)) : hops;
     rq::PlanLimits L;
     L.max_ops = sizeof(rq_program_large::ops) / sizeof(rq_tile_op);
     L.pool_cplx = sizeof(rq_program_large::pool) / sizeof(rq_cplx);
@@ -1047,7 +996,7 @@ rocqStatus_t rocsvxPlanCircuit(unsigned n, unsigned tileBits, const rocsvxGateOp
     const rocqStatus_t s = convert_ops(n, ops, numOps, hops);
     if (s != ROCQ_STATUS_SUCCESS) return s;
     for (const HostOp& o : hops) if (o.targets.size() > 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
-    std::vector<HostOp> fused = hops.size() > 1 ? rq::fuse_algebraic(hops, n) : hops;
+    std::vector<HostOp> fused = hops.size() > 1 ? rq::merge_diagonals(rq::fuse_algebraic(hops, n)) : hops;
     rq::PlanLimits L;
     if (tileBits >= 1 && tileBits <= RQ_MAX_TILE_BITS) L.tile_bits = tileBits;
     L.max_ops = sizeof(rq_program_large::ops) / sizeof(rq_tile_op);
@@ -1105,7 +1054,7 @@ rocqStatus_t rocsvxDistPlanCircuit(unsigned n, int numRanks, const rocsvxGateOp*
                 }
                 txt += "R\n";
                 for (const HostOp& o : st.ops) if (o.targets.size() > 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
-                std::vector<HostOp> fused = st.ops.size() > 1 ? rq::fuse_algebraic(st.ops, n - M, P.global_mask()) : st.ops;
+                std::vector<HostOp> fused = st.ops.size() > 1 ? rq::merge_diagonals(rq::fuse_algebraic(st.ops, n - M, P.global_mask())) : st.ops;
                 const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(fused, n - M, L);
                 for (const rq::SweepPlan& sp : plans)
                     if (!rq::build_program(prog, sp, fused, n - M, 1, 0)) return ROCQ_STATUS_FAILURE;

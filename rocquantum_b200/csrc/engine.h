@@ -33,6 +33,7 @@ struct rocsvInternalHandle {
     // tuning
     int tcBlocks = -1;                  // 6-qubit tensor-core blocks in rocsvxApplyCircuit / fused flushes: 0 off, 1 on, -1 auto (on from RQ_BLOCK_AUTO_QUBITS qubits)
     double blockMinCost = 54.0;         // fold >= this much HostOp::cost() (3 dense 2q gates) or stay on the CUDA cores
+    bool mergeDiagonals = true;         // runs of controlled phases on one hub qubit become one RQ_OP_DIAGP (ROCQ_MERGE_DIAG=0: off)
     unsigned tileBits = RQ_MAX_TILE_BITS;
     double budget = 1e30;
     rocsvxStats stats{};

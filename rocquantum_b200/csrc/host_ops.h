@@ -11,6 +11,7 @@
 #include <complex>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -21,11 +22,14 @@ namespace rq {
 typedef std::complex<double> cd;
 
 struct HostOp {
-    enum Kind { DENSE = 1, DIAG = 2, PERM_X = 3, PERM_SWAP = 4 };
+    enum Kind { DENSE = 1, DIAG = 2, PERM_X = 3, PERM_SWAP = 4, DIAGP = 5 };
     int kind = DENSE;
     std::vector<unsigned> targets;   // DENSE: matrix bit b <-> targets[b].  DIAG: table bit b.  PERM_X: {t}.  PERM_SWAP: {a,b}
+                                     // DIAGP: any number of qubits, each contributing its own factor
     uint64_t cmask = 0;              // control qubits: op acts where all are 1
     std::vector<cd> data;            // DENSE: 2^k x 2^k column-major.  DIAG: 2^k entries
+                                     // DIAGP (product of one-qubit diagonals under common controls, merge_diagonals):
+                                     //   amp *= data[0] * prod over b with bit targets[b] set of data[1 + b]
     const void* ext = nullptr;       // DENSE only: matrix stays in device memory (eager rocsvApplyMatrix)
     bool dead = false;               // fuse_algebraic: absorbed into another op
     bool defer = false;              // plan_sweeps: leave this op to a later step (plan_mixed keeps dense ops for the tensor-core blocks)
@@ -33,12 +37,13 @@ struct HostOp {
     uint64_t tmask() const { uint64_t m = 0; for (unsigned t : targets) m |= 1ull << t; return m; }
     uint64_t qubits() const { return tmask() | cmask; }
     // qubits that must be resident in the tile: everything the op does not act on diagonally
-    uint64_t nondiag() const { return kind == DIAG ? 0ull : tmask(); }
+    uint64_t nondiag() const { return (kind == DIAG || kind == DIAGP) ? 0ull : tmask(); }
     bool host_dense_uncontrolled() const { return kind == DENSE && cmask == 0 && ext == nullptr; }
     double cost() const {            // rough FMA-equivalents per amplitude, for the sweep budget
         const double frac = 1.0 / (double)(1ull << std::min(8, __builtin_popcountll(cmask)));
         if (kind == DENSE) return 4.0 * (double)(1u << targets.size()) * frac + 2.0;
         if (kind == DIAG) return 6.0 * frac + 1.0;
+        if (kind == DIAGP) return 10.0 * frac + 2.0;
         return 2.0 * frac + 1.0;
     }
 };
@@ -119,6 +124,13 @@ inline void apply_small(const HostOp& o, const std::vector<unsigned>& qs, std::v
             unsigned s = 0;
             for (unsigned b = 0; b < k; ++b) s |= ((i >> tp[b]) & 1u) << b;
             v[i] *= o.data[s];
+        }
+    } else if (o.kind == HostOp::DIAGP) {
+        for (uint32_t i = 0; i < N; ++i) {
+            if ((i & cm) != cm) continue;
+            cd f = o.data[0];
+            for (unsigned b = 0; b < k; ++b) if ((i >> tp[b]) & 1u) f *= o.data[1 + b];
+            v[i] *= f;
         }
     } else if (o.kind == HostOp::PERM_X) {
         for (uint32_t i = 0; i < N; ++i)
@@ -289,6 +301,99 @@ inline std::vector<HostOp> fuse_algebraic(const std::vector<HostOp>& in, unsigne
     return live;
 }
 
+
+// ---- merging runs of controlled phases -----------------------------------------------------------------
+// A QFT-class circuit applies, after every H(i), the controlled phases CP(j, i) for all j > i: n(n-1)/2 diagonal ops, each
+// of which would touch a quarter of the tile.  Diagonal ops sharing one control qubit h ("hub") multiply to
+//     amp *= C * prod_{k : bit k set} f_k        wherever bit h is set,
+// ONE pass over half of the tile (HostOp::DIAGP, device op RQ_OP_DIAGP).  Members: a pure phase on {h} or {h, k}
+// (P, CZ, CP) and a one-qubit diagonal on k controlled by h (CRZ).  A later member may be moved back to the group's
+// first member when nothing in between acts non-diagonally on its qubits (`nd_since`).  Groups of fewer than
+// `min_members` stay as they were.
+inline std::vector<HostOp> merge_diagonals(const std::vector<HostOp>& in, unsigned min_members = 3) {
+    struct Group { uint64_t cand; uint64_t nd_since = 0; std::vector<int> members; bool open = true; };
+    std::vector<Group> groups;
+    std::vector<int> active;
+    auto candidates = [](const HostOp& o) -> uint64_t {
+        if (o.kind != HostOp::DIAG || o.ext) return 0ull;
+        for (const cd& d : o.data) if (!(std::abs(d) > 0.5 && std::abs(d) < 2.0)) return 0ull;
+        const int nc = __builtin_popcountll(o.cmask);
+        if (o.targets.empty() && (nc == 1 || nc == 2)) return o.cmask;
+        if (o.targets.size() == 1 && nc == 1) return o.cmask;
+        return 0ull;
+    };
+    for (size_t i = 0; i < in.size(); ++i) {
+        const HostOp& o = in[i];
+        const uint64_t cand = candidates(o), Q = o.qubits();
+        bool joined = false;
+        if (cand) {
+            for (int gi : active) {
+                Group& g = groups[gi];
+                if (!(Q & g.nd_since) && (cand & g.cand)) { g.cand &= cand; g.members.push_back((int)i); joined = true; break; }
+            }
+            if (!joined) {
+                Group g;
+                g.cand = cand;
+                g.members.push_back((int)i);
+                groups.push_back(std::move(g));
+                active.push_back((int)groups.size() - 1);
+                if (active.size() > 96) active.erase(active.begin());
+            }
+        }
+        const uint64_t nd = o.nondiag();
+        if (nd) {
+            size_t w = 0;
+            for (size_t a = 0; a < active.size(); ++a) {
+                Group& g = groups[active[a]];
+                g.nd_since |= nd;
+                if ((g.cand & ~g.nd_since) != 0) active[w++] = active[a];      // a hub is still reachable
+            }
+            active.resize(w);
+        }
+    }
+    std::vector<int> role(in.size(), -1);            // -1: keep, -2: dropped (merged), g >= 0: first member of group g
+    bool any = false;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        const Group& g = groups[gi];
+        if (g.members.size() < min_members) continue;
+        any = true;
+        role[g.members[0]] = (int)gi;
+        for (size_t m = 1; m < g.members.size(); ++m) role[g.members[m]] = -2;
+    }
+    if (!any) return in;
+    std::vector<HostOp> out;
+    out.reserve(in.size());
+    for (size_t i = 0; i < in.size(); ++i) {
+        if (role[i] == -1) { out.push_back(in[i]); continue; }
+        if (role[i] == -2) continue;
+        const Group& g = groups[role[i]];
+        const unsigned hub = (unsigned)__builtin_ctzll(g.cand);
+        HostOp P;
+        P.kind = HostOp::DIAGP;
+        P.cmask = 1ull << hub;
+        P.data.push_back(cd(1.0, 0.0));
+        auto factor = [&](unsigned q) -> cd& {
+            for (size_t b = 0; b < P.targets.size(); ++b) if (P.targets[b] == q) return P.data[1 + b];
+            P.targets.push_back(q);
+            P.data.push_back(cd(1.0, 0.0));
+            return P.data.back();
+        };
+        for (int mi : g.members) {
+            const HostOp& m = in[mi];
+            if (m.targets.empty()) {
+                const uint64_t other = m.cmask & ~(1ull << hub);
+                if (!other) P.data[0] *= m.data[0];
+                else factor((unsigned)__builtin_ctzll(other)) *= m.data[0];
+            } else {                                   // diag(d0, d1) on targets[0], controlled by the hub
+                P.data[0] *= m.data[0];
+                factor(m.targets[0]) *= m.data[1] / m.data[0];
+            }
+        }
+        out.push_back(std::move(P));
+    }
+    return out;
+}
+
 // ---- sweep planner ----------------------------------------------------------------------------------
 struct SweepPlan {
     std::vector<unsigned> res;       // ascending resident positions, size T
@@ -305,10 +410,14 @@ struct PlanLimits {
     uint64_t never_resident = 0;     // positions that may not be resident (global qubits of a distributed state)
 };
 
-inline unsigned pool_need(const HostOp& o) {
+inline unsigned pool_need(const HostOp& o, unsigned T = RQ_MAX_TILE_BITS) {
     if (o.ext) return 0;
     if (o.kind == HostOp::DENSE) return RQ_MSLOTS * (1u << (2 * o.targets.size())) + 1u;     // +1: slot alignment
     if (o.kind == HostOp::DIAG) return 1u << o.targets.size();
+    if (o.kind == HostOp::DIAGP) {                  // upper bound of build_program's layout (no resident control)
+        const unsigned k = (unsigned)o.targets.size();
+        return 1u + std::min(T, 8u) + (1u << (T > 8 ? T - 8 : 0)) + k + (k + (unsigned)sizeof(rq_cplx) - 1u) / (unsigned)sizeof(rq_cplx);
+    }
     return 0;
 }
 
@@ -340,7 +449,7 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
             if (ok) {
                 const uint64_t newR = R | nd;
                 ok = __builtin_popcountll(newR) <= (int)T && !(nd & L.never_resident) && nops < L.max_ops &&
-                     pool + pool_need(o) <= L.pool_cplx && (nops == 0 || cost + o.cost() <= L.budget) &&
+                     pool + pool_need(o, T) <= L.pool_cplx && (nops == 0 || cost + o.cost() <= L.budget) &&
                      (o.kind != HostOp::DENSE || o.targets.size() <= 4) && (o.kind != HostOp::DIAG || o.targets.size() <= 4) &&
                      !(o.ext && nops > 0);
                 if (ok) {
@@ -349,7 +458,7 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
                     done[i] = 1;
                     --remaining;
                     ++nops;
-                    pool += pool_need(o);
+                    pool += pool_need(o, T);
                     cost += o.cost();
                     if (o.ext) break;            // a device-matrix op travels alone (one ext pointer per program)
                     continue;
@@ -646,6 +755,7 @@ inline void build_phases(Prog& P, unsigned T) {
     auto need_of = [&](const rq_tile_op& o, uint32_t& need) -> bool {
         need = 0;
         if (o.kind == RQ_OP_DIAG) return true;
+        if (o.kind == RQ_OP_DIAGP) return false;           // its own pass over the tile
         if (o.kind == RQ_OP_DENSE) {
             if (o.ext || o.k > 2) return false;
             for (unsigned b = 0; b < o.k; ++b) { if (o.t[b] < MINP) return false; need |= 1u << o.t[b]; }
@@ -768,6 +878,44 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
             t.moff = pool;
             for (unsigned e = 0; e < need; ++e) { P.pool[pool + e].x = (rq_real)o.data[e].real(); P.pool[pool + e].y = (rq_real)o.data[e].imag(); }
             pool += need;
+        } else if (o.kind == HostOp::DIAGP) {
+            // pool: C | A[na]: factor of group-index bit i < na (i-th free local position) | B[2^nb]: product over the
+            // remaining free positions, indexed by the group-index bits above na | G[ng]: factors of non-resident
+            // qubits | ng bytes: which bit of the tile's "outer" word (tile_sweep.cuh) each of them reads
+            t.kind = RQ_OP_DIAGP;
+            std::vector<cd> floc(T, cd(1.0, 0.0)), G;
+            std::vector<uint8_t> gbit;
+            for (unsigned b = 0; b < k; ++b) {
+                const unsigned q = o.targets[b];
+                if (local[q] >= 0) { floc[local[q]] *= o.data[1 + b]; continue; }
+                unsigned bit;
+                if (q < n) { bit = q; for (unsigned j = 0; j < T; ++j) if (sp.res[j] < q) --bit; }     // rank among the non-resident positions
+                else bit = (n - T) + (q - n);                                                        // rank bit of a distributed state
+                if (bit >= 64) return false;
+                G.push_back(o.data[1 + b]);
+                gbit.push_back((uint8_t)bit);
+            }
+            std::vector<unsigned> nf;
+            for (unsigned j = 0; j < T; ++j) if (!((fixmask >> j) & 1u)) nf.push_back(j);
+            const unsigned nfree = (unsigned)nf.size(), na = std::min(nfree, 8u), nb = nfree - na, ng = (unsigned)G.size();
+            const unsigned need = 1u + na + (1u << nb) + ng + (ng + (unsigned)sizeof(rq_cplx) - 1u) / (unsigned)sizeof(rq_cplx);
+            if (pool + need > maxpool || ng > 255) return false;
+            t.moff = pool; t.k = (uint8_t)ng; t.t[0] = (uint8_t)na; t.t[1] = (uint8_t)nb;
+            auto put = [&](const cd& c) { P.pool[pool].x = (rq_real)c.real(); P.pool[pool].y = (rq_real)c.imag(); ++pool; };
+            put(o.data[0]);
+            for (unsigned i = 0; i < na; ++i) put(floc[nf[i]]);
+            for (unsigned m = 0; m < (1u << nb); ++m) {
+                cd f(1.0, 0.0);
+                for (unsigned i = 0; i < nb; ++i) if ((m >> i) & 1u) f *= floc[nf[na + i]];
+                put(f);
+            }
+            for (const cd& g : G) put(g);
+            const unsigned nbytes_cplx = (ng + (unsigned)sizeof(rq_cplx) - 1u) / (unsigned)sizeof(rq_cplx);
+            if (nbytes_cplx) {
+                memset(&P.pool[pool], 0, nbytes_cplx * sizeof(rq_cplx));
+                memcpy(&P.pool[pool], gbit.data(), ng);
+                pool += nbytes_cplx;
+            }
         } else if (o.kind == HostOp::PERM_X) {
             t.kind = RQ_OP_PERM;
             if (local[o.targets[0]] < 0) return false;

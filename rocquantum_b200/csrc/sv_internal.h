@@ -18,14 +18,15 @@ struct rq_cplx { rq_real x, y; };
 // position res[j]) and one tile per assignment of the other n-T bits.  A tile is staged in shared
 // memory with 1-D bulk async copies (one per contiguous row of 2^rowbits amplitudes), every op of the
 // program is applied to it in order, and it is written back with bulk async stores.
-enum : uint8_t { RQ_OP_DENSE = 1, RQ_OP_DIAG = 2, RQ_OP_PERM = 3 };
+enum : uint8_t { RQ_OP_DENSE = 1, RQ_OP_DIAG = 2, RQ_OP_PERM = 3, RQ_OP_DIAGP = 4 };
 
 struct rq_tile_op {                 // 64 bytes
     uint8_t kind;                   // RQ_OP_*
-    uint8_t k;                      // DENSE: number of targets (1..4).  DIAG: number of table bits (0..3)
+    uint8_t k;                      // DENSE: number of targets (1..4).  DIAG: number of table bits (0..3).  DIAGP: non-resident factors
     uint8_t nfix;                   // entries of fix[]: local positions held fixed while enumerating
     uint8_t ext;                    // DENSE: 1 => matrix is read from hdr.ext_matrix (device pointer)
     uint8_t t[4];                   // DENSE: local position of matrix bit b.  DIAG: local position of table bit b, 0xFF = non-resident
+                                    // DIAGP: t[0] = per-thread factors (group-index bits 0..t[0]-1), t[1] = log2 of the table over the bits above
     uint8_t gq[4];                  // DIAG: global position of table bit b when non-resident
     uint8_t fix[16];                // ascending local positions (targets of DENSE/PERM and local controls)
     uint32_t setmask;               // OR-ed into the enumerated local index (controls = 1; PERM select value)

@@ -228,6 +228,32 @@ __device__ __forceinline__ void op_diag(rq_cplx* sm, const rq_tile_op& o, const 
     }
 }
 
+// product of one-qubit diagonals under common controls (host: merge_diagonals, a QFT's ladder of controlled phases):
+//   amp[idx] *= C * prod_{bit set} f_bit.   With 2^8 threads the low 8 bits of the group index are the thread's own, so their
+// factors and those of the non-resident qubits (bits of the tile's `outer` word) collapse into one per-thread constant;
+// the group-index bits above are warp-uniform and read a small host-built table: two complex multiplies per amplitude.
+template <bool SWZ>
+__device__ __forceinline__ void op_diagp(rq_cplx* sm, const rq_tile_op& o, const rq_cplx* pool, uint32_t T, uint32_t tid,
+                                         uint64_t outer) {
+    static_assert(NT == 256, "the per-thread factor covers group-index bits 0-7");
+    const rq_cplx* P = pool + o.moff;
+    const uint32_t na = o.t[0], nb = o.t[1], ng = o.k;
+    const rq_cplx* A = P + 1;
+    const rq_cplx* B = A + na;
+    const rq_cplx* G = B + (1u << nb);
+    const uint8_t* gbit = reinterpret_cast<const uint8_t*>(G + ng);
+    rq_cplx f = P[0];
+    for (uint32_t j = 0; j < ng; ++j)
+        if ((outer >> gbit[j]) & 1ull) f = cmul(G[j], f);
+    for (uint32_t i = 0; i < na; ++i)
+        if ((tid >> i) & 1u) f = cmul(A[i], f);
+    const uint32_t ngroups = 1u << (T - o.nfix);
+    for (uint32_t g = tid, m = 0; g < ngroups; g += NT, ++m) {
+        const uint32_t pi = sidx<SWZ>(spread(g, o) | o.setmask);
+        sm[pi] = cmul(cmul(B[m], f), sm[pi]);
+    }
+}
+
 // pair permutation: swap(idx, idx ^ xm) over the idx whose fixed bits equal setmask
 template <bool SWZ>
 __device__ __forceinline__ void op_perm(rq_cplx* sm, const rq_tile_op& o, uint32_t T, uint32_t tid) {
@@ -455,6 +481,8 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
     }
     rq_cplx* gtile = state + (member << n) + base;
     const uint64_t gbase = base | prog.hdr.high_base;
+    // bit j = value of the j-th non-resident position, then the rank bits of a distributed state (RQ_OP_DIAGP)
+    const uint64_t outer = (tile & ((1ull << (n - T)) - 1ull)) | ((prog.hdr.high_base >> n) << (n - T));
 
     const uint32_t nrows = 1u << (T - rowbits);
     const uint32_t rowbytes = (uint32_t)sizeof(rq_cplx) << rowbits;
@@ -507,6 +535,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
                 }
                 break;
             case RQ_OP_DIAG: op_diag<SWZ>(sm, o, prog.pool, T, tid, gbase); break;
+            case RQ_OP_DIAGP: op_diagp<SWZ>(sm, o, prog.pool, T, tid, outer); break;
             default: op_perm<SWZ>(sm, o, T, tid); break;
         }
         __syncthreads();

@@ -150,6 +150,9 @@ class StateVector:
     def set_tensor_core_blocks(self, on: bool):
         self._ck("rocsvxSetTensorCoreBlocks", self.lib.rocsvxSetTensorCoreBlocks(self.h, int(on)))
 
+    def set_merge_diagonals(self, on: bool):
+        self._ck("rocsvxSetMergeDiagonals", self.lib.rocsvxSetMergeDiagonals(self.h, int(on)))
+
     def swap_index_bits(self, a, b):
         self._ck("rocsvSwapIndexBits", self.lib.rocsvSwapIndexBits(self.h, a, b))
 

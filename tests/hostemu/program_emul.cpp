@@ -1,0 +1,269 @@
+// tests/hostemu/program_emul.cpp -- TEST INFRASTRUCTURE ONLY (built and loaded by tests/test_program_emul_cpu.py).
+//
+// A host interpreter of the sweep programs that rocquantum_b200/csrc/host_ops.h emits for the tile-sweep kernel.  It
+// lets the CPU suite check the whole host pipeline -- gate conversion, algebraic fusion, merging of controlled phases,
+// sweep partition, phase building and the bit-level program encoding (fix / setmask / gcmask / window fields / pool
+// layout) -- without a GPU, by following tile_sweep.cuh loop for loop (same group enumeration, same per-thread /
+// per-iteration decomposition of RQ_OP_DIAGP).  It is not part of the product: nothing under rocquantum_b200/ links or
+// loads it, and it is compiled from the product's headers so that it can never drift from what the engine launches.
+//
+// Arithmetic is done in double on the (rq_real-rounded) pool values.
+#include <complex>
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+
+#include "../../rocquantum_b200/csrc/gate_convert.h"
+#include "../../rocquantum_b200/csrc/host_ops.h"
+
+namespace {
+
+typedef std::complex<double> cd;
+constexpr uint32_t NT = RQ_TILE_THREADS;
+
+inline cd pc(const rq_cplx& c) { return cd((double)c.x, (double)c.y); }
+inline uint32_t sidx(bool swz, uint32_t idx) { return swz ? (idx ^ ((idx >> RQ_SWZ_BITS) & ((1u << RQ_SWZ_BITS) - 1u))) : idx; }
+
+inline uint32_t spread(uint32_t g, const rq_tile_op& o) {
+    for (uint32_t f = 0; f < o.nfix; ++f) {
+        const uint32_t p = o.fix[f];
+        g = ((g >> p) << (p + 1)) | (g & ((1u << p) - 1u));
+    }
+    return g;
+}
+
+template <typename Prog>
+bool emulate_window_phase(std::vector<cd>& sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint64_t gbase, bool swz) {
+    const uint32_t V = ph.v, D = 1u << V;
+    const uint32_t ngroups = 1u << (T - V);
+    std::vector<cd> a(D);
+    std::vector<uint32_t> lidx(D);
+    for (uint32_t g = 0; g < ngroups; ++g) {
+        uint32_t base = g;
+        for (uint32_t b = 0; b < V; ++b) {
+            const uint32_t p = ph.w[b];
+            base = ((base >> p) << (p + 1)) | (base & ((1u << p) - 1u));
+        }
+        for (uint32_t j = 0; j < D; ++j) {
+            uint32_t idx = base;
+            for (uint32_t b = 0; b < V; ++b) if (j & (1u << b)) idx |= 1u << ph.w[b];
+            lidx[j] = idx;
+            a[j] = sm[sidx(swz, idx)];
+        }
+        for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
+            const rq_tile_op& o = prog.ops[oi];
+            if ((gbase & o.gcmask) != o.gcmask) continue;
+            if ((base & o.cm_out) != o.cm_out) continue;
+            const rq_cplx* M = prog.pool + o.moff;
+            const uint32_t ci = o.cm_in;
+            if (o.kind == RQ_OP_DIAG) {
+                const uint32_t lc = o.setmask, k = o.k;
+                for (uint32_t j = 0; j < D; ++j) {
+                    if ((lidx[j] & lc) != lc) continue;
+                    uint32_t sel = 0;
+                    for (uint32_t b = 0; b < k; ++b) {
+                        const uint32_t p = o.t[b];
+                        sel |= (p == 0xFF ? (uint32_t)((gbase >> o.gq[b]) & 1ull) : ((lidx[j] >> p) & 1u)) << b;
+                    }
+                    a[j] *= pc(M[sel]);
+                }
+            } else if (o.kind == RQ_OP_DENSE) {
+                if (o.ext || o.k > 2) return false;
+                if (o.k == 1) {
+                    const uint32_t W = o.wt[0];
+                    const cd m00 = pc(M[0 * RQ_MSLOTS]), m10 = pc(M[1 * RQ_MSLOTS]), m01 = pc(M[2 * RQ_MSLOTS]), m11 = pc(M[3 * RQ_MSLOTS]);
+                    for (uint32_t j = 0; j < D; ++j) {
+                        if (j & (1u << W)) continue;
+                        if ((j & ci) != ci) continue;
+                        const cd a0 = a[j], a1 = a[j | (1u << W)];
+                        a[j] = m00 * a0 + m01 * a1;
+                        a[j | (1u << W)] = m10 * a0 + m11 * a1;
+                    }
+                } else {
+                    const uint32_t W0 = o.wt[0], W1 = o.wt[1];
+                    if (!(W0 < W1)) return false;
+                    for (uint32_t j = 0; j < D; ++j) {
+                        if (j & ((1u << W0) | (1u << W1))) continue;
+                        if ((j & ci) != ci) continue;
+                        const uint32_t s[4] = {j, j | (1u << W0), j | (1u << W1), j | (1u << W0) | (1u << W1)};
+                        const cd x[4] = {a[s[0]], a[s[1]], a[s[2]], a[s[3]]};
+                        for (uint32_t i = 0; i < 4; ++i) {
+                            cd acc(0.0, 0.0);
+                            for (uint32_t c = 0; c < 4; ++c) acc += pc(M[(i + 4 * c) * RQ_MSLOTS]) * x[c];
+                            a[s[i]] = acc;
+                        }
+                    }
+                }
+            } else if (o.kind == RQ_OP_PERM) {
+                if (o.k == 1) {
+                    const uint32_t W = o.wt[0];
+                    for (uint32_t j = 0; j < D; ++j) {
+                        if (j & (1u << W)) continue;
+                        if ((j & ci) != ci) continue;
+                        std::swap(a[j], a[j | (1u << W)]);
+                    }
+                } else {
+                    const uint32_t W0 = o.wt[0], W1 = o.wt[1];
+                    for (uint32_t j = 0; j < D; ++j) {
+                        if (j & ((1u << W0) | (1u << W1))) continue;
+                        if ((j & ci) != ci) continue;
+                        std::swap(a[j | (1u << W0)], a[j | (1u << W1)]);
+                    }
+                }
+            } else {
+                return false;
+            }
+        }
+        for (uint32_t j = 0; j < D; ++j) sm[sidx(swz, lidx[j])] = a[j];
+    }
+    return true;
+}
+
+template <typename Prog>
+bool emulate_op(std::vector<cd>& sm, const Prog& prog, const rq_tile_op& o, uint32_t T, uint64_t gbase, uint64_t outer, bool swz) {
+    const uint32_t ngroups = 1u << (T - o.nfix);
+    if (o.kind == RQ_OP_DENSE) {
+        if (o.ext) return false;
+        const uint32_t K = o.k, D = 1u << K;
+        std::vector<uint32_t> off(D);
+        for (uint32_t j = 0; j < D; ++j) {
+            uint32_t v = 0;
+            for (uint32_t b = 0; b < K; ++b) if ((j >> b) & 1u) v |= 1u << o.t[b];
+            off[j] = v;
+        }
+        const rq_cplx* M = prog.pool + o.moff;
+        std::vector<cd> a(D);
+        for (uint32_t g = 0; g < ngroups; ++g) {
+            const uint32_t base = spread(g, o) | o.setmask;
+            for (uint32_t j = 0; j < D; ++j) a[j] = sm[sidx(swz, base | off[j])];
+            for (uint32_t i = 0; i < D; ++i) {
+                cd acc(0.0, 0.0);
+                for (uint32_t j = 0; j < D; ++j) acc += pc(M[(i + j * D) * RQ_MSLOTS]) * a[j];
+                sm[sidx(swz, base | off[i])] = acc;
+            }
+        }
+    } else if (o.kind == RQ_OP_DIAG) {
+        uint32_t selbase = 0;
+        for (uint32_t b = 0; b < o.k; ++b)
+            if (o.t[b] == 0xFF) selbase |= (uint32_t)((gbase >> o.gq[b]) & 1ull) << b;
+        const rq_cplx* Dg = prog.pool + o.moff;
+        for (uint32_t g = 0; g < ngroups; ++g) {
+            const uint32_t idx = spread(g, o) | o.setmask;
+            uint32_t sel = selbase;
+            for (uint32_t b = 0; b < o.k; ++b)
+                if (o.t[b] != 0xFF) sel |= ((idx >> o.t[b]) & 1u) << b;
+            sm[sidx(swz, idx)] *= pc(Dg[sel]);
+        }
+    } else if (o.kind == RQ_OP_DIAGP) {
+        const rq_cplx* P = prog.pool + o.moff;
+        const uint32_t na = o.t[0], nb = o.t[1], ng = o.k;
+        const rq_cplx* A = P + 1;
+        const rq_cplx* B = A + na;
+        const rq_cplx* G = B + (1u << nb);
+        const uint8_t* gbit = reinterpret_cast<const uint8_t*>(G + ng);
+        for (uint32_t tid = 0; tid < NT; ++tid) {                   // one "thread" at a time, as the kernel decomposes it
+            cd f = pc(P[0]);
+            for (uint32_t j = 0; j < ng; ++j)
+                if ((outer >> gbit[j]) & 1ull) f *= pc(G[j]);
+            for (uint32_t i = 0; i < na; ++i)
+                if ((tid >> i) & 1u) f *= pc(A[i]);
+            for (uint32_t g = tid, m = 0; g < ngroups; g += NT, ++m) {
+                if (m >= (1u << nb)) return false;                  // table overrun
+                const uint32_t pi = sidx(swz, spread(g, o) | o.setmask);
+                sm[pi] *= pc(B[m]) * f;
+            }
+        }
+    } else if (o.kind == RQ_OP_PERM) {
+        for (uint32_t g = 0; g < ngroups; ++g) {
+            const uint32_t l0 = spread(g, o) | o.setmask;
+            std::swap(sm[sidx(swz, l0)], sm[sidx(swz, l0 ^ o.xm)]);
+        }
+    } else {
+        return false;
+    }
+    return true;
+}
+
+template <typename Prog>
+bool emulate_program(const Prog& prog, cd* state) {
+    const uint32_t T = prog.hdr.T, n = prog.hdr.n;
+    const bool swz = prog.hdr.swz != 0;
+    // the launcher's choice of kernel variant (tile_sweep.cuh: launch)
+    const bool phased = prog.hdr.nphases > 0 && prog.hdr.max_phase_ops >= 2;
+    std::vector<cd> sm((size_t)1 << T);
+    for (uint64_t tile = 0; tile < prog.hdr.ntiles; ++tile) {
+        const uint64_t member = tile >> (n - T);
+        uint64_t base = tile & ((1ull << (n - T)) - 1ull);
+        for (uint32_t j = 0; j < T; ++j) {
+            const uint32_t p = prog.hdr.res[j];
+            base = ((base >> p) << (p + 1)) | (base & ((1ull << p) - 1ull));
+        }
+        cd* gtile = state + (member << n) + base;
+        const uint64_t gbase = base | prog.hdr.high_base;
+        const uint64_t outer = (tile & ((1ull << (n - T)) - 1ull)) | ((prog.hdr.high_base >> n) << (n - T));
+        auto goff = [&](uint32_t l) {
+            uint64_t o = 0;
+            for (uint32_t j = 0; j < T; ++j) o |= (uint64_t)((l >> j) & 1u) << prog.hdr.res[j];
+            return o;
+        };
+        for (uint32_t j = 0; j < prog.hdr.rowbits; ++j) if (prog.hdr.res[j] != j) return false;     // rows must be contiguous
+        for (uint32_t l = 0; l < (1u << T); ++l) sm[sidx(swz, l)] = gtile[goff(l)];                 // bulk load + swizzle pass
+        const uint32_t nsteps = phased ? prog.hdr.nphases : prog.hdr.nops;
+        for (uint32_t step = 0; step < nsteps; ++step) {
+            uint32_t i = step;
+            if (phased) {
+                const rq_phase& ph = prog.phases[step];
+                if (ph.kind == 1) {
+                    if (!emulate_window_phase(sm, prog, ph, T, gbase, swz)) return false;
+                    continue;
+                }
+                i = ph.first;
+            }
+            const rq_tile_op& o = prog.ops[i];
+            if ((gbase & o.gcmask) != o.gcmask) continue;
+            if (!emulate_op(sm, prog, o, T, gbase, outer, swz)) return false;
+        }
+        for (uint32_t l = 0; l < (1u << T); ++l) gtile[goff(l)] = sm[sidx(swz, l)];
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+unsigned hostemu_precision_bytes(void) { return (unsigned)sizeof(rq_real); }
+
+// state: 2 * 2^n doubles (re, im interleaved), updated in place.  rankBits/rank: emulate the slice of one rank of a
+// distributed state (state then holds 2^(n - rankBits) amplitudes and ops may control / act diagonally on rank bits).
+// flags bit 0: skip merge_diagonals.  Returns 0, or a negative code naming the stage that failed.
+int hostemu_run_circuit(unsigned n, unsigned tileBits, const rocsvxGateOp* ops, size_t numOps, double* state, unsigned rankBits,
+                        unsigned rank, unsigned flags, unsigned* numSweeps, unsigned* numMerged) {
+    std::vector<rq::HostOp> hops;
+    if (rq::convert_ops(n, ops, numOps, hops) != ROCQ_STATUS_SUCCESS) return -1;
+    for (const rq::HostOp& o : hops) if (o.targets.size() > 4) return -2;
+    const unsigned nl = n - rankBits;
+    const uint64_t gmask = rankBits ? (((1ull << rankBits) - 1ull) << nl) : 0ull;
+    for (const rq::HostOp& o : hops) if (o.nondiag() & gmask) return -3;
+    std::vector<rq::HostOp> fused = hops.size() > 1 ? rq::fuse_algebraic(hops, nl, gmask) : hops;
+    if (!(flags & 1u) && fused.size() > 1) fused = rq::merge_diagonals(fused);
+    unsigned merged = 0;
+    for (const rq::HostOp& o : fused) merged += o.kind == rq::HostOp::DIAGP;
+    if (numMerged) *numMerged = merged;
+    rq::PlanLimits L;
+    if (tileBits >= 1 && tileBits <= RQ_MAX_TILE_BITS) L.tile_bits = tileBits;
+    L.max_ops = sizeof(rq_program_large::ops) / sizeof(rq_tile_op);
+    L.pool_cplx = sizeof(rq_program_large::pool) / sizeof(rq_cplx);
+    L.never_resident = gmask;
+    const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(fused, nl, L);
+    if (numSweeps) *numSweeps = (unsigned)plans.size();
+    static thread_local rq_program_large P;
+    cd* st = reinterpret_cast<cd*>(state);
+    for (const rq::SweepPlan& sp : plans) {
+        if (!rq::build_program(P, sp, fused, nl, 1, (uint64_t)rank << nl)) return -4;
+        if (!emulate_program(P, st)) return -5;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -153,6 +153,29 @@ def test_c2_and_qft_configs_reduced(prec):
         assert util.rel_err(g.state(), o.state) < TOL[prec] * 10
 
 
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("n,batch,seed", [(4, 2, 1), (7, 1, 2), (9, 3, 3), (13, 1, 4), (14, 2, 5), (17, 1, 6), (20, 1, 7)])
+def test_merged_controlled_phase_ladders(prec, n, batch, seed):
+    """Runs of CP / CZ / CRZ / P sharing a control become one RQ_OP_DIAGP pass (host_ops.h: merge_diagonals); same result
+    as the gate-by-gate oracle and as the engine with merging off, in fewer executed ops."""
+    from tests.test_program_emul_cpu import diag_heavy_gates
+    gates = diag_heavy_gates(n, 200, seed) + workloads.c3_qft(n, seed=seed)
+    v = util.random_state(n, batch, seed=seed)
+    o = so.Oracle(n, prec, batch=batch); o.set_state(v); util.run_on_oracle(o, gates)
+    m = StateVector(n, prec, batch=batch); m.set_state(v); m.apply_circuit(gates)
+    assert util.rel_err(m.state(), o.state) < TOL[prec] * 4
+    p = StateVector(n, prec, batch=batch); p.set_merge_diagonals(False); p.set_state(v); p.apply_circuit(gates)
+    assert util.rel_err(p.state(), o.state) < TOL[prec] * 4
+    assert m.stats().opsExecuted < p.stats().opsExecuted
+    # deferred rocsvApply* calls (named gates only: a device-matrix call flushes the queue)
+    named = diag_heavy_gates(n, 200, seed, named_only=True)
+    o = so.Oracle(n, prec, batch=batch); o.set_state(v); util.run_on_oracle(o, named)
+    d = StateVector(n, prec, batch=batch, fusion=True); d.set_state(v); util.run_per_gate(d, named)
+    q = StateVector(n, prec, batch=batch, fusion=True); q.set_merge_diagonals(False); q.set_state(v); util.run_per_gate(q, named)
+    assert util.rel_err(d.state(), o.state) < TOL[prec] * 4 and util.rel_err(q.state(), o.state) < TOL[prec] * 4
+    assert d.stats().opsExecuted < q.stats().opsExecuted
+
+
 def test_qft_analytic():
     """QFT of a basis state |x> has amplitudes exp(2 pi i x k / 2^n)/sqrt(2^n) (bit-reversed by the final swaps)."""
     n = 16

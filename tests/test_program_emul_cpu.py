@@ -1,0 +1,156 @@
+"""Host pipeline down to the bits of the sweep program, without a GPU.
+
+tests/hostemu/program_emul.cpp interprets the programs that host_ops.h emits for the tile-sweep kernel, loop for loop
+like tile_sweep.cuh (group enumeration, register-window phases, swizzle, RQ_OP_DIAGP's per-thread / per-iteration split).
+Gate list -> convert -> fuse -> merge controlled phases -> sweeps -> programs -> interpreted state must equal the oracle
+running the gate list.  Test infrastructure only: the interpreter is compiled here from the product's headers."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import sv_oracle as so
+from rocquantum_b200 import capi, workloads
+from tests import util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostemu", "program_emul.cpp")
+OUT = os.path.join(HERE, "hostemu", "_build")
+_LIBS = {}
+
+
+def emu(prec):
+    if prec not in _LIBS:
+        os.makedirs(OUT, exist_ok=True)
+        so_path = os.path.join(OUT, f"libprogram_emul_{prec}.so")
+        deps = [SRC] + [os.path.join(HERE, "..", "rocquantum_b200", "csrc", f) for f in ("host_ops.h", "gate_convert.h", "sv_internal.h")]
+        if not os.path.exists(so_path) or any(os.path.getmtime(d) > os.path.getmtime(so_path) for d in deps):
+            cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so_path, SRC]
+            if prec == "c128":
+                cmd.insert(1, "-DROCQ_PRECISION_DOUBLE")
+            subprocess.check_call(cmd)
+        lib = C.CDLL(so_path)
+        lib.hostemu_run_circuit.argtypes = [C.c_uint, C.c_uint, C.POINTER(capi.GateOp), C.c_size_t, C.c_void_p, C.c_uint, C.c_uint,
+                                            C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+        lib.hostemu_run_circuit.restype = C.c_int
+        assert lib.hostemu_precision_bytes() == (4 if prec == "c64" else 8)
+        _LIBS[prec] = lib
+    return _LIBS[prec]
+
+
+def run_emu(prec, n, gates, state, tile_bits=0, rank_bits=0, rank=0, flags=0):
+    arr, keep = capi.make_ops(gates)
+    v = np.ascontiguousarray(state, dtype=np.complex128).copy()
+    nsw, nmerged = C.c_uint(), C.c_uint()
+    st = emu(prec).hostemu_run_circuit(n, tile_bits, arr, len(gates), v.ctypes.data, rank_bits, rank, flags, C.byref(nsw), C.byref(nmerged))
+    assert st == 0, st
+    return v, nsw.value, nmerged.value
+
+
+def oracle_run(n, gates, state):
+    o = so.Oracle(n, "c128")
+    o.set_state(state)
+    util.run_on_oracle(o, gates)
+    return o.state
+
+
+def cp(j, i, theta):
+    return ("matrix", [j], [i], 0.0, np.array([[1, 0], [0, np.exp(1j * theta)]]))
+
+
+def diag_heavy_gates(n, count, seed, named_only=False):
+    """Mostly controlled phases / CRZ / CZ / P fanned out from a few hub qubits, broken up by H, X, CNOT, SWAP and dense 2q."""
+    rng = np.random.default_rng(seed)
+    g = []
+    while len(g) < count:
+        r = rng.random()
+        q = [int(x) for x in rng.permutation(n)]
+        th = float(rng.uniform(0, 2 * math.pi))
+        if r < 0.55:
+            hub = q[0]
+            for t in q[1:1 + int(rng.integers(1, n))]:
+                kind = int(rng.integers(5))
+                if kind == 0:
+                    g.append(("cz", [hub, t], [], 0.0))
+                elif kind == 1:
+                    g.append(("crz", [t], [hub], float(rng.uniform(0, 2 * math.pi))))
+                elif kind == 2:
+                    g.append(("t", [hub], [], 0.0))
+                elif named_only:
+                    g.append(("crz", [hub], [t], float(rng.uniform(0, 2 * math.pi))))
+                else:
+                    g.append(cp(t, hub, float(rng.uniform(0, 2 * math.pi))) if rng.integers(2) else cp(hub, t, float(rng.uniform(0, 2 * math.pi))))
+        elif r < 0.7:
+            g.append(("h", [q[0]], [], 0.0))
+        elif r < 0.8:
+            g.append(("cnot", [q[1]], [q[0]], 0.0))
+        elif r < 0.85:
+            g.append(("swap", [q[0], q[1]], [], 0.0))
+        elif r < 0.9:
+            g.append(("rz", [q[0]], [], th))
+        elif named_only:
+            g.append(("ry", [q[0]], [], th))
+        else:
+            g.append(("matrix", [q[0], q[1]], [], 0.0, workloads.haar_unitary(rng, 4)))
+    return g[:count]
+
+
+@pytest.mark.parametrize("prec,tol", [("c128", 1e-12), ("c64", 2e-6)])
+@pytest.mark.parametrize("n,tile_bits", [(5, 0), (9, 6), (12, 8), (14, 0)])
+def test_qft_programs(prec, tol, n, tile_bits):
+    gates = workloads.c3_qft(n, seed=33)
+    v = util.random_state(n, seed=n)
+    out, nsw, nmerged = run_emu(prec, n, gates, v, tile_bits)
+    assert util.rel_err(out, oracle_run(n, gates, v)) < tol
+    assert nmerged >= n - 4                                   # one merged ladder per H(i) that keeps >= 3 controlled phases
+    plain, nsw0, nm0 = run_emu(prec, n, gates, v, tile_bits, flags=1)
+    assert nm0 == 0 and util.rel_err(plain, oracle_run(n, gates, v)) < tol
+
+
+@pytest.mark.parametrize("prec,tol", [("c128", 1e-12), ("c64", 2e-6)])
+@pytest.mark.parametrize("n,tile_bits,seed", [(4, 0, 1), (8, 5, 2), (11, 7, 3), (13, 0, 4), (14, 9, 5)])
+def test_diagonal_heavy_programs(prec, tol, n, tile_bits, seed):
+    gates = diag_heavy_gates(n, 160, seed)
+    v = util.random_state(n, seed=seed)
+    out, nsw, nmerged = run_emu(prec, n, gates, v, tile_bits)
+    assert util.rel_err(out, oracle_run(n, gates, v)) < tol
+    assert nmerged >= 1
+
+
+@pytest.mark.parametrize("prec,tol", [("c128", 1e-12), ("c64", 2e-6)])
+@pytest.mark.parametrize("n,tile_bits", [(3, 0), (7, 5), (10, 6), (13, 0), (14, 8)])
+def test_mixed_bag_programs(prec, tol, n, tile_bits):
+    """Every gate family of the ABI (k <= 3 matrices, controls, MCX, CSWAP): exercises window phases, swizzle, gcmask."""
+    gates = util.random_gates(n, 220, seed=n, maxk=min(3, n))
+    v = util.random_state(n, seed=n + 7)
+    out, nsw, _ = run_emu(prec, n, gates, v, tile_bits)
+    assert util.rel_err(out, oracle_run(n, gates, v)) < tol
+    gates = workloads.c2_random_unitary(n, 6, seed=30) if n >= 2 else gates
+    out, nsw, _ = run_emu(prec, n, gates, v, tile_bits)
+    assert util.rel_err(out, oracle_run(n, gates, v)) < tol
+
+
+def test_rank_slices_with_diagonals_on_rank_bits():
+    """A distributed slice: controls and merged diagonal factors on rank bits come from hdr.high_base."""
+    n, rb = 12, 2
+    nl = n - rb
+    rng = np.random.default_rng(9)
+    gates = []
+    for i in range(nl):
+        gates.append(("h", [i], [], 0.0))
+        for j in range(i + 1, n):                               # ladders that reach into the rank bits
+            gates.append(cp(j, i, math.pi / (1 << (j - i))))
+    for hub in range(nl, n):                                    # a rank bit as hub: the op exists on half of the ranks
+        for t in range(0, nl, 2):
+            gates.append(cp(t, hub, float(rng.uniform(0, 6))))
+        gates.append(("cnot", [int(rng.integers(nl))], [hub], 0.0))
+    v = util.random_state(n, seed=3)
+    want = oracle_run(n, gates, v)
+    for rank in range(1 << rb):
+        sl = v[rank << nl:(rank + 1) << nl]
+        out, nsw, nmerged = run_emu("c128", n, gates, sl, 7, rank_bits=rb, rank=rank)
+        assert nmerged >= nl - 4
+        assert util.rel_err(out, want[rank << nl:(rank + 1) << nl]) < 1e-12

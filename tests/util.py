@@ -172,6 +172,16 @@ def simulate_plan(o: so.Oracle, sweeps):
                     st[:, m] = (st[:, m] * op["data"][0]).astype(o.dtype)
                 else:
                     o.apply_matrix(t, np.diag(op["data"]), controls)
+            elif op["kind"] == 5:    # DIAGP: data[0] * prod of data[1 + b] over the set bits targets[b], where all controls are 1
+                idx = np.arange(1 << n)
+                m = np.ones(1 << n, dtype=bool)
+                for c in controls:
+                    m &= ((idx >> c) & 1).astype(bool)
+                f = np.full(1 << n, op["data"][0], dtype=np.complex128)
+                for b, q in enumerate(t):
+                    f = np.where((idx >> q) & 1, f * op["data"][1 + b], f)
+                st = o.state.reshape(o.batch, 1 << n)
+                st[:, m] = (st[:, m] * f[m]).astype(o.dtype)
             elif op["kind"] == 3:    # PERM_X
                 assert set(t) <= res
                 if controls:
@@ -292,6 +302,6 @@ def simulate_dist_plan(o: so.Oracle, n_local, steps):
                 o.swap_index_bits(n_local - k + i, g)
         else:
             for op in payload:
-                if op["kind"] != 2:
+                if op["kind"] not in (2, 5):
                     assert all(t < n_local for t in op["targets"]), "non-diagonal target on a rank bit"
             simulate_plan(o, [dict(T=n, rowbits=n, res=list(range(n)), ops=payload)])

@@ -152,8 +152,10 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
         if (j > i) {
             std::vector<HostOp> seg(ops.begin() + i, ops.begin() + j);
             if (fused && seg.size() > 1) {
+                // ladders of controlled phases are merged BEFORE algebraic fusion, which would otherwise promote their first
+                // member to a dense 4x4 to absorb the preceding one-qubit gate
+                if (h->mergeDiagonals) seg = rq::merge_diagonals(rq::push_x_forward(seg));
                 seg = rq::fuse_algebraic(seg, n, h->dist.active() ? h->dist.global_mask() : 0ull);
-                if (h->mergeDiagonals) seg = rq::merge_diagonals(seg);
             }
             const bool tc = h->tcBlocks > 0 || (h->tcBlocks < 0 && n >= RQ_BLOCK_AUTO_QUBITS);
             if (fused && tc && sizeof(rq_real) == 4 && n >= 13 && !h->dist.active() && seg.size() > 1) {
@@ -954,7 +956,7 @@ rocqStatus_t rocsvxPlanCircuitBlocks(unsigned n, const rocsvxGateOp* ops, size_t
     const rocqStatus_t s = convert_ops(n, ops, numOps, hops);
     if (s != ROCQ_STATUS_SUCCESS) return s;
     for (const HostOp& o : hops) if (o.targets.size() > 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
-    std::vector<HostOp> fused = hops.size() > 1 ? rq::merge_diagonals(rq::fuse_algebraic(hops, n)) : hops;
+    std::vector<HostOp> fused = hops.size() > 1 ? rq::fuse_algebraic(rq::merge_diagonals(rq::push_x_forward(hops)), n) : hops;
     rq::PlanLimits L;
     L.max_ops = sizeof(rq_program_large::ops) / sizeof(rq_tile_op);
     L.pool_cplx = sizeof(rq_program_large::pool) / sizeof(rq_cplx);
@@ -996,7 +998,7 @@ rocqStatus_t rocsvxPlanCircuit(unsigned n, unsigned tileBits, const rocsvxGateOp
     const rocqStatus_t s = convert_ops(n, ops, numOps, hops);
     if (s != ROCQ_STATUS_SUCCESS) return s;
     for (const HostOp& o : hops) if (o.targets.size() > 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
-    std::vector<HostOp> fused = hops.size() > 1 ? rq::merge_diagonals(rq::fuse_algebraic(hops, n)) : hops;
+    std::vector<HostOp> fused = hops.size() > 1 ? rq::fuse_algebraic(rq::merge_diagonals(rq::push_x_forward(hops)), n) : hops;
     rq::PlanLimits L;
     if (tileBits >= 1 && tileBits <= RQ_MAX_TILE_BITS) L.tile_bits = tileBits;
     L.max_ops = sizeof(rq_program_large::ops) / sizeof(rq_tile_op);
@@ -1054,7 +1056,7 @@ rocqStatus_t rocsvxDistPlanCircuit(unsigned n, int numRanks, const rocsvxGateOp*
                 }
                 txt += "R\n";
                 for (const HostOp& o : st.ops) if (o.targets.size() > 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
-                std::vector<HostOp> fused = st.ops.size() > 1 ? rq::merge_diagonals(rq::fuse_algebraic(st.ops, n - M, P.global_mask())) : st.ops;
+                std::vector<HostOp> fused = st.ops.size() > 1 ? rq::fuse_algebraic(rq::merge_diagonals(rq::push_x_forward(st.ops)), n - M, P.global_mask()) : st.ops;
                 const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(fused, n - M, L);
                 for (const rq::SweepPlan& sp : plans)
                     if (!rq::build_program(prog, sp, fused, n - M, 1, 0)) return ROCQ_STATUS_FAILURE;

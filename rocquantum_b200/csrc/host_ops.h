@@ -218,6 +218,68 @@ inline std::vector<cd> matmul(const std::vector<cd>& A, const std::vector<cd>& B
     return C;
 }
 
+
+// ---- pushing X gates forward through diagonal ops --------------------------------------------------------
+// An uncontrolled X(q) followed by ops that act diagonally on q (controlled phases, Rz, controls of diagonal ops) and then
+// by a dense gate on q forces q to be resident twice (and blocks every merged diagonal run that touches q until it has
+// run).  Since  D X_q = X_q (X_q D X_q)  and X_q D X_q is again diagonal (the table with bit q flipped), the X can be
+// carried forward and folded into the dense gate:  M X_q = M with its columns permuted.  Exact algebra, fewer ops.
+inline void conjugate_diag_by_x(HostOp& o, unsigned q) {
+    unsigned b = 0;
+    const unsigned k = (unsigned)o.targets.size();
+    for (; b < k; ++b) if (o.targets[b] == q) break;
+    if (b == k) {                                         // q is a control: make it a table bit first ("0" half = 1)
+        o.cmask &= ~(1ull << q);
+        o.targets.push_back(q);
+        std::vector<cd> nd((size_t)2 << k, cd(1.0, 0.0));
+        for (unsigned s = 0; s < (1u << k); ++s) nd[s | (1u << k)] = o.data[s];
+        o.data.swap(nd);
+    }
+    const unsigned K = (unsigned)o.targets.size();
+    std::vector<cd> fl((size_t)1 << K);
+    for (unsigned s = 0; s < (1u << K); ++s) fl[s] = o.data[s ^ (1u << b)];
+    o.data.swap(fl);
+    canonicalize_diag(o);
+}
+inline std::vector<HostOp> push_x_forward(const std::vector<HostOp>& in) {
+    std::vector<HostOp> ops = in;
+    bool changed = false;
+    for (size_t p = 0; p < ops.size(); ++p) {
+        if (ops[p].dead || ops[p].kind != HostOp::PERM_X || ops[p].cmask != 0) continue;
+        const unsigned q = ops[p].targets[0];
+        const uint64_t qb = 1ull << q;
+        size_t stop = ops.size();
+        bool ok = true, crossed = false;
+        for (size_t j = p + 1; j < ops.size(); ++j) {
+            const HostOp& o = ops[j];
+            if (o.dead || !(o.qubits() & qb)) continue;
+            if (o.kind == HostOp::DIAG && !o.ext && (((o.tmask() & qb) != 0) || o.targets.size() < 4)) { crossed = true; continue; }
+            stop = j;
+            break;
+        }
+        if (stop == ops.size() || !crossed) continue;
+        HostOp& M = ops[stop];
+        if (!(M.kind == HostOp::DENSE && M.cmask == 0 && !M.ext && (M.tmask() & qb) && M.targets.size() <= 4)) ok = false;
+        if (!ok) continue;
+        for (size_t j = p + 1; j < stop; ++j)
+            if (!ops[j].dead && (ops[j].qubits() & qb)) conjugate_diag_by_x(ops[j], q);
+        unsigned b = 0;
+        while (M.targets[b] != q) ++b;
+        const unsigned D = 1u << M.targets.size();
+        std::vector<cd> nm((size_t)D * D);
+        for (unsigned c = 0; c < D; ++c)
+            for (unsigned r = 0; r < D; ++r) nm[r + (size_t)c * D] = M.data[r + (size_t)(c ^ (1u << b)) * D];      // M * X_q
+        M.data.swap(nm);
+        ops[p].dead = true;
+        changed = true;
+    }
+    if (!changed) return in;
+    std::vector<HostOp> out;
+    out.reserve(ops.size());
+    for (HostOp& o : ops) if (!o.dead) out.push_back(std::move(o));
+    return out;
+}
+
 // ---- algebraic fusion -------------------------------------------------------------------------------
 // Rule 1: an uncontrolled op on <= 2 qubits folds (left-multiplies) into the last op touching all of
 //         its qubits when that op is an uncontrolled host DENSE whose targets contain them.
@@ -414,9 +476,9 @@ inline unsigned pool_need(const HostOp& o, unsigned T = RQ_MAX_TILE_BITS) {
     if (o.ext) return 0;
     if (o.kind == HostOp::DENSE) return RQ_MSLOTS * (1u << (2 * o.targets.size())) + 1u;     // +1: slot alignment
     if (o.kind == HostOp::DIAG) return 1u << o.targets.size();
-    if (o.kind == HostOp::DIAGP) {                  // upper bound of build_program's layout (no resident control)
+    if (o.kind == HostOp::DIAGP) {                  // upper bound of build_program's layouts (pass of its own without resident control / window phase)
         const unsigned k = (unsigned)o.targets.size();
-        return 1u + std::min(T, 8u) + (1u << (T > 8 ? T - 8 : 0)) + k + (k + (unsigned)sizeof(rq_cplx) - 1u) / (unsigned)sizeof(rq_cplx);
+        return 1u + std::min(T, 8u) + (1u << (T > 8 ? T - 8 : 0)) + (1u << RQ_WINDOW_BITS) + k + (k + (unsigned)sizeof(rq_cplx) - 1u) / (unsigned)sizeof(rq_cplx);
     }
     return 0;
 }
@@ -436,7 +498,7 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
         const unsigned lowbits = std::min(std::min(L.min_row_bits, T), n);
         for (unsigned p = 0; p < lowbits; ++p) R |= 1ull << p;
         uint64_t blockedAny = 0, blockedND = 0;
-        unsigned nops = 0, pool = 0;
+        unsigned nops = 0, pool = 0, ndiagp = 0;
         double cost = 0.0;
         SweepPlan sp;
         size_t scanned = 0;
@@ -451,9 +513,10 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
                 ok = __builtin_popcountll(newR) <= (int)T && !(nd & L.never_resident) && nops < L.max_ops &&
                      pool + pool_need(o, T) <= L.pool_cplx && (nops == 0 || cost + o.cost() <= L.budget) &&
                      (o.kind != HostOp::DENSE || o.targets.size() <= 4) && (o.kind != HostOp::DIAG || o.targets.size() <= 4) &&
-                     !(o.ext && nops > 0);
+                     !(o.ext && nops > 0) && !(o.kind == HostOp::DIAGP && ndiagp >= RQ_MAX_DIAGP);
                 if (ok) {
                     R = newR;
+                    ndiagp += o.kind == HostOp::DIAGP;
                     sp.ops.push_back((int)i);
                     done[i] = 1;
                     --remaining;
@@ -713,7 +776,7 @@ inline std::vector<int> phase_friendly_order(const SweepPlan& sp, const std::vec
         for (int idx : rest) {
             const HostOp& o = ops[idx];
             const uint64_t nd = o.nondiag(), dg = o.qubits() & ~nd;
-            const bool eligible = o.kind == HostOp::DIAG || o.kind == HostOp::PERM_X || o.kind == HostOp::PERM_SWAP ||
+            const bool eligible = o.kind == HostOp::DIAG || o.kind == HostOp::DIAGP || o.kind == HostOp::PERM_X || o.kind == HostOp::PERM_SWAP ||
                                   (o.kind == HostOp::DENSE && o.targets.size() <= 2 && !o.ext);
             const bool free_ = !((nd & (blockedAny | blockedND)) || (dg & blockedAny));
             if (free_ && eligible && (unsigned)__builtin_popcountll(W | nd) <= V) {
@@ -750,12 +813,12 @@ inline void build_phases(Prog& P, unsigned T) {
         ph = rq_phase{};
         ph.kind = 0; ph.first = (uint8_t)i; ph.count = 1;
         if (P.hdr.max_phase_ops < 1) P.hdr.max_phase_ops = 1;
+        if (P.ops[i].kind == RQ_OP_DIAGP) P.ops[i].t[3] = 0xFF;
     };
     // window-eligible: DIAG (needs nothing); DENSE k<=2 from the pool and PERM with every target at a position >= MINP
     auto need_of = [&](const rq_tile_op& o, uint32_t& need) -> bool {
         need = 0;
-        if (o.kind == RQ_OP_DIAG) return true;
-        if (o.kind == RQ_OP_DIAGP) return false;           // its own pass over the tile
+        if (o.kind == RQ_OP_DIAG || o.kind == RQ_OP_DIAGP) return true;
         if (o.kind == RQ_OP_DENSE) {
             if (o.ext || o.k > 2) return false;
             for (unsigned b = 0; b < o.k; ++b) { if (o.t[b] < MINP) return false; need |= 1u << o.t[b]; }
@@ -772,10 +835,13 @@ inline void build_phases(Prog& P, unsigned T) {
         if (!need_of(P.ops[i], need)) { legacy(i++); continue; }
         uint32_t W = 0;
         const unsigned first = i;
+        unsigned ndp = 0;                                  // RQ_OP_DIAGP ops of the phase: their thread factors live in registers
         while (i < nops) {
             uint32_t nd = 0;
             if (!need_of(P.ops[i], nd)) break;
             if ((unsigned)__builtin_popcount(W | nd) > V) break;
+            if (P.ops[i].kind == RQ_OP_DIAGP && ndp >= RQ_PHASE_MAX_DIAGP) break;
+            ndp += P.ops[i].kind == RQ_OP_DIAGP;
             W |= nd;
             ++i;
         }
@@ -791,9 +857,14 @@ inline void build_phases(Prog& P, unsigned T) {
         unsigned nb = 0;
         for (unsigned p = 0; p < T; ++p) { widx[p] = -1; if ((W >> p) & 1u) { ph.w[nb] = (uint8_t)p; widx[p] = (int)nb++; } }
         if (ph.count > P.hdr.max_phase_ops) P.hdr.max_phase_ops = ph.count;
+        ndp = 0;
         for (unsigned j = first; j < i; ++j) {
             rq_tile_op& o = P.ops[j];
-            if (o.kind == RQ_OP_DIAG) { o.cm_in = 0; o.cm_out = 0; continue; }      // controls are evaluated per amplitude
+            if (o.kind == RQ_OP_DIAG || o.kind == RQ_OP_DIAGP) {                    // controls are evaluated per amplitude
+                o.cm_in = 0; o.cm_out = 0;
+                if (o.kind == RQ_OP_DIAGP) o.t[3] = (uint8_t)ndp++;
+                continue;
+            }
             uint32_t lc = o.setmask;                       // local controls (+ for SWAP the select bit, removed below)
             if (o.kind == RQ_OP_DENSE) {
                 for (unsigned b = 0; b < o.k; ++b) o.wt[b] = (uint8_t)widx[o.t[b]];
@@ -823,11 +894,14 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
     P.hdr.ntiles = (uint64_t)batch << (n - T);
     P.hdr.high_base = high_base;
     P.hdr.ext_matrix = nullptr;
+    P.hdr.ndiagp = 0;
     int local[64];
     uint64_t R = 0;
     for (int q = 0; q < 64; ++q) local[q] = -1;
     for (unsigned j = 0; j < T; ++j) { P.hdr.res[j] = (uint8_t)sp.res[j]; local[sp.res[j]] = (int)j; R |= 1ull << sp.res[j]; }
     unsigned pool = 0;
+    struct PendingDiagp { unsigned op; cd C; std::vector<cd> floc, G; std::vector<uint8_t> gbit; };
+    std::vector<PendingDiagp> pending;
     const unsigned maxops = (unsigned)(sizeof(P.ops) / sizeof(P.ops[0])), maxpool = (unsigned)(sizeof(P.pool) / sizeof(P.pool[0]));
     const std::vector<int> order = phase_friendly_order(sp, ops, RQ_WINDOW_BITS);
     for (int idx : order) {
@@ -879,43 +953,26 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
             for (unsigned e = 0; e < need; ++e) { P.pool[pool + e].x = (rq_real)o.data[e].real(); P.pool[pool + e].y = (rq_real)o.data[e].imag(); }
             pool += need;
         } else if (o.kind == HostOp::DIAGP) {
-            // pool: C | A[na]: factor of group-index bit i < na (i-th free local position) | B[2^nb]: product over the
-            // remaining free positions, indexed by the group-index bits above na | G[ng]: factors of non-resident
-            // qubits | ng bytes: which bit of the tile's "outer" word (tile_sweep.cuh) each of them reads
+            // the pool layout depends on the phase the op lands in: emitted by emit_diagp below, after build_phases
             t.kind = RQ_OP_DIAGP;
-            std::vector<cd> floc(T, cd(1.0, 0.0)), G;
-            std::vector<uint8_t> gbit;
+            if (P.hdr.ndiagp >= RQ_MAX_DIAGP) return false;
+            t.t[2] = P.hdr.ndiagp;
+            P.hdr.diagp_op[P.hdr.ndiagp++] = (uint8_t)(P.hdr.nops - 1);
+            PendingDiagp pd;
+            pd.op = P.hdr.nops - 1;
+            pd.C = o.data[0];
+            pd.floc.assign(T, cd(1.0, 0.0));
             for (unsigned b = 0; b < k; ++b) {
                 const unsigned q = o.targets[b];
-                if (local[q] >= 0) { floc[local[q]] *= o.data[1 + b]; continue; }
+                if (local[q] >= 0) { pd.floc[local[q]] *= o.data[1 + b]; continue; }
                 unsigned bit;
                 if (q < n) { bit = q; for (unsigned j = 0; j < T; ++j) if (sp.res[j] < q) --bit; }     // rank among the non-resident positions
                 else bit = (n - T) + (q - n);                                                        // rank bit of a distributed state
                 if (bit >= 64) return false;
-                G.push_back(o.data[1 + b]);
-                gbit.push_back((uint8_t)bit);
+                pd.G.push_back(o.data[1 + b]);
+                pd.gbit.push_back((uint8_t)bit);
             }
-            std::vector<unsigned> nf;
-            for (unsigned j = 0; j < T; ++j) if (!((fixmask >> j) & 1u)) nf.push_back(j);
-            const unsigned nfree = (unsigned)nf.size(), na = std::min(nfree, 8u), nb = nfree - na, ng = (unsigned)G.size();
-            const unsigned need = 1u + na + (1u << nb) + ng + (ng + (unsigned)sizeof(rq_cplx) - 1u) / (unsigned)sizeof(rq_cplx);
-            if (pool + need > maxpool || ng > 255) return false;
-            t.moff = pool; t.k = (uint8_t)ng; t.t[0] = (uint8_t)na; t.t[1] = (uint8_t)nb;
-            auto put = [&](const cd& c) { P.pool[pool].x = (rq_real)c.real(); P.pool[pool].y = (rq_real)c.imag(); ++pool; };
-            put(o.data[0]);
-            for (unsigned i = 0; i < na; ++i) put(floc[nf[i]]);
-            for (unsigned m = 0; m < (1u << nb); ++m) {
-                cd f(1.0, 0.0);
-                for (unsigned i = 0; i < nb; ++i) if ((m >> i) & 1u) f *= floc[nf[na + i]];
-                put(f);
-            }
-            for (const cd& g : G) put(g);
-            const unsigned nbytes_cplx = (ng + (unsigned)sizeof(rq_cplx) - 1u) / (unsigned)sizeof(rq_cplx);
-            if (nbytes_cplx) {
-                memset(&P.pool[pool], 0, nbytes_cplx * sizeof(rq_cplx));
-                memcpy(&P.pool[pool], gbit.data(), ng);
-                pool += nbytes_cplx;
-            }
+            pending.push_back(std::move(pd));
         } else if (o.kind == HostOp::PERM_X) {
             t.kind = RQ_OP_PERM;
             if (local[o.targets[0]] < 0) return false;
@@ -944,6 +1001,49 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
         }
     }
     build_phases(P, T);
+    // RQ_OP_DIAGP tables.  pool: C | A[na]: factor of group-index bit i < na | B[2^nb]: product over the group-index bits
+    // above na | (register-window phase only) W[2^V]: product over the window bits | G[ng]: factors of non-resident qubits |
+    // ng bytes: which bit of the tile's "outer" word (tile_sweep.cuh) each of them reads.
+    // Group-index bit i <-> i-th "free" local position: in a pass of its own every position that is not a control (controls
+    // are fixed by the enumeration); in a window phase every non-window position (controls are checked per amplitude).
+    for (const PendingDiagp& pd : pending) {
+        rq_tile_op& t = P.ops[pd.op];
+        const rq_phase* ph = nullptr;
+        for (unsigned i = 0; i < P.hdr.nphases; ++i)
+            if (P.phases[i].first <= pd.op && pd.op < (unsigned)P.phases[i].first + P.phases[i].count) ph = &P.phases[i];
+        if (!ph) return false;
+        const bool win = ph->kind == 1;
+        uint32_t skip = 0;
+        if (win) for (unsigned b = 0; b < ph->v; ++b) skip |= 1u << ph->w[b];
+        else for (unsigned f = 0; f < t.nfix; ++f) skip |= 1u << t.fix[f];
+        std::vector<unsigned> nf;
+        for (unsigned j = 0; j < T; ++j) if (!((skip >> j) & 1u)) nf.push_back(j);
+        const unsigned nfree = (unsigned)nf.size(), na = std::min(nfree, 8u), nb = nfree - na, ng = (unsigned)pd.G.size();
+        const unsigned nw = win ? (1u << ph->v) : 0u, nbytes_cplx = (ng + (unsigned)sizeof(rq_cplx) - 1u) / (unsigned)sizeof(rq_cplx);
+        const unsigned need = 1u + na + (1u << nb) + nw + ng + nbytes_cplx;
+        if (pool + need > maxpool || ng > 255) return false;
+        t.moff = pool; t.k = (uint8_t)ng; t.t[0] = (uint8_t)na; t.t[1] = (uint8_t)nb;
+        t.xm = 1u + na + (1u << nb) + nw;
+        auto put = [&](const cd& c) { P.pool[pool].x = (rq_real)c.real(); P.pool[pool].y = (rq_real)c.imag(); ++pool; };
+        put(pd.C);
+        for (unsigned i = 0; i < na; ++i) put(pd.floc[nf[i]]);
+        for (unsigned m = 0; m < (1u << nb); ++m) {
+            cd f(1.0, 0.0);
+            for (unsigned i = 0; i < nb; ++i) if ((m >> i) & 1u) f *= pd.floc[nf[na + i]];
+            put(f);
+        }
+        for (unsigned jw = 0; jw < nw; ++jw) {
+            cd f(1.0, 0.0);
+            for (unsigned b = 0; b < ph->v; ++b) if ((jw >> b) & 1u) f *= pd.floc[ph->w[b]];
+            put(f);
+        }
+        for (const cd& g : pd.G) put(g);
+        if (nbytes_cplx) {
+            memset(&P.pool[pool], 0, nbytes_cplx * sizeof(rq_cplx));
+            memcpy(&P.pool[pool], pd.gbit.data(), ng);
+            pool += nbytes_cplx;
+        }
+    }
     return true;
 }
 

@@ -18,6 +18,7 @@ struct rq_cplx { rq_real x, y; };
 // position res[j]) and one tile per assignment of the other n-T bits.  A tile is staged in shared
 // memory with 1-D bulk async copies (one per contiguous row of 2^rowbits amplitudes), every op of the
 // program is applied to it in order, and it is written back with bulk async stores.
+#define RQ_MAX_DIAGP 32
 enum : uint8_t { RQ_OP_DENSE = 1, RQ_OP_DIAG = 2, RQ_OP_PERM = 3, RQ_OP_DIAGP = 4 };
 
 struct rq_tile_op {                 // 64 bytes
@@ -26,11 +27,13 @@ struct rq_tile_op {                 // 64 bytes
     uint8_t nfix;                   // entries of fix[]: local positions held fixed while enumerating
     uint8_t ext;                    // DENSE: 1 => matrix is read from hdr.ext_matrix (device pointer)
     uint8_t t[4];                   // DENSE: local position of matrix bit b.  DIAG: local position of table bit b, 0xFF = non-resident
-                                    // DIAGP: t[0] = per-thread factors (group-index bits 0..t[0]-1), t[1] = log2 of the table over the bits above
+                                    // DIAGP: t[0] = per-thread factors (group-index bits 0..t[0]-1), t[1] = log2 of the table over the bits above,
+                                    //        t[2] = slot of its per-tile factor (hdr.diagp_op[]), t[3] = index among the DIAGP ops of
+                                    //        its register-window phase (0xFF: it has a pass of its own)
     uint8_t gq[4];                  // DIAG: global position of table bit b when non-resident
     uint8_t fix[16];                // ascending local positions (targets of DENSE/PERM and local controls)
     uint32_t setmask;               // OR-ed into the enumerated local index (controls = 1; PERM select value)
-    uint32_t xm;                    // PERM: partner = idx ^ xm
+    uint32_t xm;                    // PERM: partner = idx ^ xm.  DIAGP: offset (from moff) of the non-resident factors
     uint32_t moff;                  // offset into pool[], in complex elements
     uint32_t cm_out;                // register phases: local controls outside the phase window (checked on the group base)
     uint64_t gcmask;                // controls on non-resident positions: op is skipped for tiles whose base lacks a bit
@@ -62,6 +65,9 @@ struct rq_sweep_hdr {
     uint64_t high_base;             // OR-ed into every tile's base index for predicates (rank << n_local)
     const void* ext_matrix;         // device matrix of an op with ext = 1 (column-major, rq_cplx)
     uint8_t res[16];                // ascending resident global positions
+    uint8_t ndiagp;                 // RQ_OP_DIAGP ops of the program; their per-tile factors are computed while the tile loads
+    uint8_t diagp_op[RQ_MAX_DIAGP]; // op index of slot s
+    uint8_t pad2[7];
 };
 
 template <int MAXOPS, int POOL_CPLX>
@@ -106,6 +112,7 @@ typedef rq_program<160, 2496> rq_program_large;     // ~31.6 KB
 #define RQ_WINDOW_BITS 4                             // 16 amplitudes = 32 registers per thread
 #endif
 #endif
+#define RQ_PHASE_MAX_DIAGP RQ_WINDOW_BITS             // RQ_OP_DIAGP ops per register-window phase (their thread factors stay in registers)
 #ifndef RQ_PHASED_MIN_BLOCKS
 #define RQ_PHASED_MIN_BLOCKS 2                       // resident CTAs per SM the phased variant is compiled for
 #endif

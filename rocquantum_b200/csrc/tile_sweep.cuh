@@ -166,9 +166,21 @@ __device__ __forceinline__ ramp rmul(const rq_cplx d, const ramp v) {
 }
 #endif
 
-// deposit the bits of g around the fixed positions fix[0..nfix) (ascending), leaving zeros there
-__device__ __forceinline__ uint32_t spread(uint32_t g, const rq_tile_op& o) {
-    for (uint32_t f = 0; f < o.nfix; ++f) {
+// deposit the bits of g around the fixed positions fix[0..nfix) (ascending), leaving zeros there.
+// Opening a zero at position p is  g + (g & ~(2^p - 1)); the masks of the first four positions are loaded once per op
+// (0xffffffff = "no position": a no-op), so that the per-group cost is two ALU instructions per position and no loop.
+struct fixmasks { uint32_t m[4]; uint32_t nfix; };
+__device__ __forceinline__ fixmasks load_fix(const rq_tile_op& o) {
+    fixmasks F;
+    F.nfix = o.nfix;
+#pragma unroll
+    for (uint32_t f = 0; f < 4; ++f) F.m[f] = f < F.nfix ? ((1u << o.fix[f]) - 1u) : 0xffffffffu;
+    return F;
+}
+__device__ __forceinline__ uint32_t spread(uint32_t g, const rq_tile_op& o, const fixmasks& F) {
+#pragma unroll
+    for (uint32_t f = 0; f < 4; ++f) g += g & ~F.m[f];
+    for (uint32_t f = 4; f < F.nfix; ++f) {
         const uint32_t p = o.fix[f];
         g = ((g >> p) << (p + 1)) | (g & ((1u << p) - 1u));
     }
@@ -190,8 +202,10 @@ __device__ __forceinline__ void op_dense(rq_cplx* sm, const rq_tile_op& o, const
     }
     const uint32_t ngroups = 1u << (T - o.nfix);
     const rq_cplx* M = EXT ? ext : (pool + o.moff);
+    const fixmasks F = load_fix(o);
+    const uint32_t setmask = o.setmask;
     for (uint32_t g = tid; g < ngroups; g += NT) {
-        const uint32_t base = spread(g, o) | o.setmask;
+        const uint32_t base = spread(g, o, F) | setmask;
         cin a[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) a[j] = cprep(sm[sidx<SWZ>(base | off[j])]);
@@ -218,8 +232,10 @@ __device__ __forceinline__ void op_diag(rq_cplx* sm, const rq_tile_op& o, const 
         if (o.t[b] == 0xFF) selbase |= (uint32_t)((gbase >> o.gq[b]) & 1ull) << b;
     const uint32_t ngroups = 1u << (T - o.nfix);
     const rq_cplx* D = pool + o.moff;
+    const fixmasks F = load_fix(o);
+    const uint32_t setmask = o.setmask;
     for (uint32_t g = tid; g < ngroups; g += NT) {
-        const uint32_t idx = spread(g, o) | o.setmask;
+        const uint32_t idx = spread(g, o, F) | setmask;
         uint32_t sel = selbase;
         for (uint32_t b = 0; b < o.k; ++b)
             if (o.t[b] != 0xFF) sel |= ((idx >> o.t[b]) & 1u) << b;
@@ -229,27 +245,55 @@ __device__ __forceinline__ void op_diag(rq_cplx* sm, const rq_tile_op& o, const 
 }
 
 // product of one-qubit diagonals under common controls (host: merge_diagonals, a QFT's ladder of controlled phases):
-//   amp[idx] *= C * prod_{bit set} f_bit.   With 2^8 threads the low 8 bits of the group index are the thread's own, so their
-// factors and those of the non-resident qubits (bits of the tile's `outer` word) collapse into one per-thread constant;
-// the group-index bits above are warp-uniform and read a small host-built table: two complex multiplies per amplitude.
-template <bool SWZ>
-__device__ __forceinline__ void op_diagp(rq_cplx* sm, const rq_tile_op& o, const rq_cplx* pool, uint32_t T, uint32_t tid,
-                                         uint64_t outer) {
+//   amp[idx] *= C * prod_{bit set} f_bit.
+// The factors of the NON-resident qubits (bits of the tile's `outer` word) and C are the same for the whole tile:
+// diagp_tile_factors computes them, one warp per op, while the bulk loads of the tile are in flight.  With 2^8 threads the
+// low 8 bits of the group index are the thread's own, so their factors fold into one per-thread constant; the group-index
+// bits above are warp-uniform and read a small host-built table: two complex multiplies per amplitude.
+template <typename Prog>
+__device__ __forceinline__ void diagp_tile_factors(const Prog& prog, rq_cplx* gfac, uint32_t tid, uint64_t outer) {
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    for (uint32_t s = warp; s < prog.hdr.ndiagp; s += NT / 32) {
+        const rq_tile_op& o = prog.ops[prog.hdr.diagp_op[s]];
+        const rq_cplx* P = prog.pool + o.moff;
+        const uint32_t ng = o.k;
+        const rq_cplx* G = P + o.xm;
+        const uint8_t* gbit = reinterpret_cast<const uint8_t*>(G + ng);
+        rq_cplx f = lane == 0 ? P[0] : rq_cplx{(rq_real)1, (rq_real)0};
+        for (uint32_t j = lane; j < ng; j += 32)
+            if ((outer >> gbit[j]) & 1ull) f = cmul(G[j], f);
+#pragma unroll
+        for (uint32_t d = 16; d > 0; d >>= 1) {
+            rq_cplx g;
+            g.x = __shfl_xor_sync(0xffffffffu, f.x, d);
+            g.y = __shfl_xor_sync(0xffffffffu, f.y, d);
+            f = cmul(g, f);
+        }
+        if (lane == 0) gfac[s] = f;
+    }
+}
+
+// tile factor x the factors of the thread's own group-index bits
+__device__ __forceinline__ rq_cplx diagp_thread_factor(const rq_tile_op& o, const rq_cplx* pool, uint32_t tid, const rq_cplx* gfac) {
     static_assert(NT == 256, "the per-thread factor covers group-index bits 0-7");
-    const rq_cplx* P = pool + o.moff;
-    const uint32_t na = o.t[0], nb = o.t[1], ng = o.k;
-    const rq_cplx* A = P + 1;
-    const rq_cplx* B = A + na;
-    const rq_cplx* G = B + (1u << nb);
-    const uint8_t* gbit = reinterpret_cast<const uint8_t*>(G + ng);
-    rq_cplx f = P[0];
-    for (uint32_t j = 0; j < ng; ++j)
-        if ((outer >> gbit[j]) & 1ull) f = cmul(G[j], f);
+    const rq_cplx* A = pool + o.moff + 1;
+    const uint32_t na = o.t[0];
+    rq_cplx f = gfac[o.t[2]];
     for (uint32_t i = 0; i < na; ++i)
         if ((tid >> i) & 1u) f = cmul(A[i], f);
+    return f;
+}
+
+template <bool SWZ>
+__device__ __forceinline__ void op_diagp(rq_cplx* sm, const rq_tile_op& o, const rq_cplx* pool, uint32_t T, uint32_t tid,
+                                         const rq_cplx* gfac) {
+    const rq_cplx* B = pool + o.moff + 1 + o.t[0];
+    const rq_cplx f = diagp_thread_factor(o, pool, tid, gfac);
     const uint32_t ngroups = 1u << (T - o.nfix);
+    const fixmasks F = load_fix(o);
+    const uint32_t setmask = o.setmask;
     for (uint32_t g = tid, m = 0; g < ngroups; g += NT, ++m) {
-        const uint32_t pi = sidx<SWZ>(spread(g, o) | o.setmask);
+        const uint32_t pi = sidx<SWZ>(spread(g, o, F) | setmask);
         sm[pi] = cmul(cmul(B[m], f), sm[pi]);
     }
 }
@@ -258,8 +302,10 @@ __device__ __forceinline__ void op_diagp(rq_cplx* sm, const rq_tile_op& o, const
 template <bool SWZ>
 __device__ __forceinline__ void op_perm(rq_cplx* sm, const rq_tile_op& o, uint32_t T, uint32_t tid) {
     const uint32_t ngroups = 1u << (T - o.nfix);
+    const fixmasks F = load_fix(o);
+    const uint32_t setmask = o.setmask, xm = o.xm;
     for (uint32_t g = tid; g < ngroups; g += NT) {
-        const uint32_t l0 = spread(g, o) | o.setmask, i0 = sidx<SWZ>(l0), i1 = sidx<SWZ>(l0 ^ o.xm);
+        const uint32_t l0 = spread(g, o, F) | setmask, i0 = sidx<SWZ>(l0), i1 = sidx<SWZ>(l0 ^ xm);
         const rq_cplx a = sm[i0], b = sm[i1];
         sm[i0] = b;
         sm[i1] = a;
@@ -374,12 +420,26 @@ __device__ __forceinline__ void win_dispatch2(ramp (&a)[1 << V], const rq_tile_o
 
 template <int V, bool SWZ, typename Prog>
 __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint32_t tid,
-                                                 uint64_t gbase) {
+                                                 uint64_t gbase, const rq_cplx* gfac) {
     constexpr int D = 1 << V;
     uint32_t stride[V];
 #pragma unroll
     for (int b = 0; b < V; ++b) stride[b] = 1u << ph.w[b];
     const uint32_t ngroups = 1u << (T - V);
+    // RQ_OP_DIAGP ops of the phase: tile factor x thread factor, once per phase (the group loop only adds the table
+    // over the group-index bits above the thread's and the table over the window bits)
+    rq_cplx fA[RQ_PHASE_MAX_DIAGP];
+#pragma unroll
+    for (int d = 0; d < RQ_PHASE_MAX_DIAGP; ++d) fA[d] = rq_cplx{(rq_real)1, (rq_real)0};
+    if (prog.hdr.ndiagp) {
+        for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
+            const rq_tile_op& o = prog.ops[oi];
+            if (o.kind != RQ_OP_DIAGP) continue;
+            const rq_cplx f = diagp_thread_factor(o, prog.pool, tid, gfac);
+#pragma unroll
+            for (int d = 0; d < RQ_PHASE_MAX_DIAGP; ++d) if (o.t[3] == d) fA[d] = f;
+        }
+    }
     for (uint32_t g = tid; g < ngroups; g += NT) {
         uint32_t base = g;
 #pragma unroll
@@ -428,6 +488,17 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
                         a[j] = rmul(M[sel], a[j]);
                     }
                 }
+            } else if (o.kind == RQ_OP_DIAGP) {
+                const uint32_t lc = o.setmask;
+                const rq_cplx* B = M + 1 + o.t[0];
+                const rq_cplx* Wt = B + (1u << o.t[1]);
+                rq_cplx fs = fA[0];
+#pragma unroll
+                for (int d = 1; d < RQ_PHASE_MAX_DIAGP; ++d) if (o.t[3] == d) fs = fA[d];
+                const rq_cplx ft = cmul(B[g >> 8], fs);          // NT = 2^8: g >> 8 = the group-index bits above the thread's
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    if ((lidx[j] & lc) == lc) a[j] = rmul(cmul(Wt[j], ft), a[j]);
             } else if (o.kind == RQ_OP_DENSE) {
                 if (o.k == 1) win_dispatch1<V>(a, o, M, true);
                 else win_dispatch2<V>(a, o, M, true);
@@ -466,6 +537,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
     extern __shared__ __align__(128) unsigned char smem_raw[];
     rq_cplx* sm = reinterpret_cast<rq_cplx*>(smem_raw);
     __shared__ __align__(8) uint64_t bar_storage;
+    __shared__ __align__(16) rq_cplx gfac[RQ_MAX_DIAGP];        // per-tile factors of the RQ_OP_DIAGP ops
 
     const uint32_t tid = threadIdx.x;
     const uint32_t T = prog.hdr.T, n = prog.hdr.n, rowbits = prog.hdr.rowbits;
@@ -497,6 +569,10 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
         for (uint32_t i = 0; i < T - rowbits; ++i) goff |= (uint64_t)((r >> i) & 1u) << prog.hdr.res[rowbits + i];
         bulk_g2s(smem_u32(sm) + r * rowbytes, gtile + goff, rowbytes, bar);
     }
+    if (prog.hdr.ndiagp) {                                       // while the tile is in flight
+        diagp_tile_factors(prog, gfac, tid, outer);
+        __syncthreads();
+    }
     mbar_wait(bar, 0);
     swizzle_pass<SWZ>(sm, T, tid);
 
@@ -508,7 +584,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
         if (MODE == 2) {
             const rq_phase& ph = prog.phases[step];
             if (ph.kind == 1) {
-                run_window_phase<RQ_WINDOW_BITS, SWZ>(sm, prog, ph, T, tid, gbase);
+                run_window_phase<RQ_WINDOW_BITS, SWZ>(sm, prog, ph, T, tid, gbase, gfac);
                 __syncthreads();
                 continue;
             }
@@ -535,7 +611,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
                 }
                 break;
             case RQ_OP_DIAG: op_diag<SWZ>(sm, o, prog.pool, T, tid, gbase); break;
-            case RQ_OP_DIAGP: op_diagp<SWZ>(sm, o, prog.pool, T, tid, outer); break;
+            case RQ_OP_DIAGP: op_diagp<SWZ>(sm, o, prog.pool, T, tid, gfac); break;
             default: op_perm<SWZ>(sm, o, T, tid); break;
         }
         __syncthreads();

@@ -33,12 +33,23 @@ inline uint32_t spread(uint32_t g, const rq_tile_op& o) {
 }
 
 template <typename Prog>
-bool emulate_window_phase(std::vector<cd>& sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint64_t gbase, bool swz) {
+bool emulate_window_phase(std::vector<cd>& sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint64_t gbase, const cd* gfac, bool swz) {
     const uint32_t V = ph.v, D = 1u << V;
     const uint32_t ngroups = 1u << (T - V);
     std::vector<cd> a(D);
     std::vector<uint32_t> lidx(D);
-    for (uint32_t g = 0; g < ngroups; ++g) {
+    for (uint32_t tid = 0; tid < NT; ++tid)
+    for (uint32_t g = tid; g < ngroups; g += NT) {
+        cd fA[RQ_PHASE_MAX_DIAGP];                                  // per thread, once per phase in the kernel
+        for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
+            const rq_tile_op& o = prog.ops[oi];
+            if (o.kind != RQ_OP_DIAGP) continue;
+            if (o.t[3] >= RQ_PHASE_MAX_DIAGP || o.t[2] >= prog.hdr.ndiagp) return false;
+            const rq_cplx* A = prog.pool + o.moff + 1;
+            cd f = gfac[o.t[2]];
+            for (uint32_t i = 0; i < o.t[0]; ++i) if ((tid >> i) & 1u) f *= pc(A[i]);
+            fA[o.t[3]] = f;
+        }
         uint32_t base = g;
         for (uint32_t b = 0; b < V; ++b) {
             const uint32_t p = ph.w[b];
@@ -67,6 +78,14 @@ bool emulate_window_phase(std::vector<cd>& sm, const Prog& prog, const rq_phase&
                     }
                     a[j] *= pc(M[sel]);
                 }
+            } else if (o.kind == RQ_OP_DIAGP) {
+                const uint32_t lc = o.setmask;
+                const rq_cplx* B = M + 1 + o.t[0];
+                const rq_cplx* Wt = B + (1u << o.t[1]);
+                if ((g >> 8) >= (1u << o.t[1])) return false;
+                const cd ft = pc(B[g >> 8]) * fA[o.t[3]];
+                for (uint32_t j = 0; j < D; ++j)
+                    if ((lidx[j] & lc) == lc) a[j] *= pc(Wt[j]) * ft;
             } else if (o.kind == RQ_OP_DENSE) {
                 if (o.ext || o.k > 2) return false;
                 if (o.k == 1) {
@@ -120,7 +139,7 @@ bool emulate_window_phase(std::vector<cd>& sm, const Prog& prog, const rq_phase&
 }
 
 template <typename Prog>
-bool emulate_op(std::vector<cd>& sm, const Prog& prog, const rq_tile_op& o, uint32_t T, uint64_t gbase, uint64_t outer, bool swz) {
+bool emulate_op(std::vector<cd>& sm, const Prog& prog, const rq_tile_op& o, uint32_t T, uint64_t gbase, const cd* gfac, bool swz) {
     const uint32_t ngroups = 1u << (T - o.nfix);
     if (o.kind == RQ_OP_DENSE) {
         if (o.ext) return false;
@@ -156,15 +175,12 @@ bool emulate_op(std::vector<cd>& sm, const Prog& prog, const rq_tile_op& o, uint
         }
     } else if (o.kind == RQ_OP_DIAGP) {
         const rq_cplx* P = prog.pool + o.moff;
-        const uint32_t na = o.t[0], nb = o.t[1], ng = o.k;
+        const uint32_t na = o.t[0], nb = o.t[1];
         const rq_cplx* A = P + 1;
         const rq_cplx* B = A + na;
-        const rq_cplx* G = B + (1u << nb);
-        const uint8_t* gbit = reinterpret_cast<const uint8_t*>(G + ng);
+        if (o.t[2] >= prog.hdr.ndiagp || &prog.ops[prog.hdr.diagp_op[o.t[2]]] != &o || o.t[3] != 0xFF) return false;
         for (uint32_t tid = 0; tid < NT; ++tid) {                   // one "thread" at a time, as the kernel decomposes it
-            cd f = pc(P[0]);
-            for (uint32_t j = 0; j < ng; ++j)
-                if ((outer >> gbit[j]) & 1ull) f *= pc(G[j]);
+            cd f = gfac[o.t[2]];
             for (uint32_t i = 0; i < na; ++i)
                 if ((tid >> i) & 1u) f *= pc(A[i]);
             for (uint32_t g = tid, m = 0; g < ngroups; g += NT, ++m) {
@@ -208,20 +224,33 @@ bool emulate_program(const Prog& prog, cd* state) {
         };
         for (uint32_t j = 0; j < prog.hdr.rowbits; ++j) if (prog.hdr.res[j] != j) return false;     // rows must be contiguous
         for (uint32_t l = 0; l < (1u << T); ++l) sm[sidx(swz, l)] = gtile[goff(l)];                 // bulk load + swizzle pass
+        cd gfac[RQ_MAX_DIAGP];                                       // diagp_tile_factors
+        for (uint32_t s = 0; s < prog.hdr.ndiagp; ++s) {
+            const rq_tile_op& o = prog.ops[prog.hdr.diagp_op[s]];
+            if (o.kind != RQ_OP_DIAGP) return false;
+            const rq_cplx* P = prog.pool + o.moff;
+            const uint32_t ng = o.k;
+            const rq_cplx* G = P + o.xm;
+            const uint8_t* gbit = reinterpret_cast<const uint8_t*>(G + ng);
+            cd f = pc(P[0]);
+            for (uint32_t j = 0; j < ng; ++j)
+                if ((outer >> gbit[j]) & 1ull) f *= pc(G[j]);
+            gfac[s] = f;
+        }
         const uint32_t nsteps = phased ? prog.hdr.nphases : prog.hdr.nops;
         for (uint32_t step = 0; step < nsteps; ++step) {
             uint32_t i = step;
             if (phased) {
                 const rq_phase& ph = prog.phases[step];
                 if (ph.kind == 1) {
-                    if (!emulate_window_phase(sm, prog, ph, T, gbase, swz)) return false;
+                    if (!emulate_window_phase(sm, prog, ph, T, gbase, gfac, swz)) return false;
                     continue;
                 }
                 i = ph.first;
             }
             const rq_tile_op& o = prog.ops[i];
             if ((gbase & o.gcmask) != o.gcmask) continue;
-            if (!emulate_op(sm, prog, o, T, gbase, outer, swz)) return false;
+            if (!emulate_op(sm, prog, o, T, gbase, gfac, swz)) return false;
         }
         for (uint32_t l = 0; l < (1u << T); ++l) gtile[goff(l)] = sm[sidx(swz, l)];
     }
@@ -245,8 +274,8 @@ int hostemu_run_circuit(unsigned n, unsigned tileBits, const rocsvxGateOp* ops, 
     const unsigned nl = n - rankBits;
     const uint64_t gmask = rankBits ? (((1ull << rankBits) - 1ull) << nl) : 0ull;
     for (const rq::HostOp& o : hops) if (o.nondiag() & gmask) return -3;
+    if (!(flags & 1u) && hops.size() > 1) hops = rq::merge_diagonals(rq::push_x_forward(hops));
     std::vector<rq::HostOp> fused = hops.size() > 1 ? rq::fuse_algebraic(hops, nl, gmask) : hops;
-    if (!(flags & 1u) && fused.size() > 1) fused = rq::merge_diagonals(fused);
     unsigned merged = 0;
     for (const rq::HostOp& o : fused) merged += o.kind == rq::HostOp::DIAGP;
     if (numMerged) *numMerged = merged;

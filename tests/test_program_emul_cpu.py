@@ -83,6 +83,11 @@ def diag_heavy_gates(n, count, seed, named_only=False):
                     g.append(("crz", [hub], [t], float(rng.uniform(0, 2 * math.pi))))
                 else:
                     g.append(cp(t, hub, float(rng.uniform(0, 2 * math.pi))) if rng.integers(2) else cp(hub, t, float(rng.uniform(0, 2 * math.pi))))
+        elif r < 0.62:
+            g.append(("x", [q[0]], [], 0.0))                   # carried forward through the diagonals (push_x_forward)
+        elif r < 0.64:
+            k = min(3, n)
+            g.append(("matrix", q[:k], q[k:k + 1], 0.0, np.diag(np.exp(1j * rng.uniform(0, 2 * math.pi, size=1 << k)))))
         elif r < 0.7:
             g.append(("h", [q[0]], [], 0.0))
         elif r < 0.8:

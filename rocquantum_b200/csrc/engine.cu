@@ -158,7 +158,8 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
                 seg = rq::fuse_algebraic(seg, n, h->dist.active() ? h->dist.global_mask() : 0ull);
             }
             const bool tc = h->tcBlocks > 0 || (h->tcBlocks < 0 && n >= RQ_BLOCK_AUTO_QUBITS);
-            if (fused && tc && sizeof(rq_real) == 4 && n >= 13 && !h->dist.active() && seg.size() > 1) {
+            // (a distributed slice forms blocks on its local qubits; ops that touch rank bits stay in the ordinary sweeps)
+            if (fused && tc && sizeof(rq_real) == 4 && n >= 13 && seg.size() > 1) {
                 const rocqStatus_t s = run_ops_with_blocks(h, state, n, seg);
                 if (s != ROCQ_STATUS_SUCCESS) return s;
                 i = j;
@@ -1057,6 +1058,21 @@ rocqStatus_t rocsvxDistPlanCircuit(unsigned n, int numRanks, const rocsvxGateOp*
                 txt += "R\n";
                 for (const HostOp& o : st.ops) if (o.targets.size() > 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
                 std::vector<HostOp> fused = st.ops.size() > 1 ? rq::fuse_algebraic(rq::merge_diagonals(rq::push_x_forward(st.ops)), n - M, P.global_mask()) : st.ops;
+                if (mode & 4) {                              // with tensor-core blocks on the local qubits (complex64 engine)
+                    rq::BlockLimits BL;
+                    BL.min_cost = 0.0;
+                    for (const rq::MixedStep& ms : rq::plan_mixed(fused, n - M, L, BL)) {
+                        if (ms.block) {
+                            txt += "B";
+                            for (unsigned p : ms.blk) txt += " " + std::to_string(p);
+                            txt += "\n" + rq::dump_ops(ms.ops, fused);
+                        } else {
+                            if (!rq::build_program(prog, ms.sweep, fused, n - M, 1, 0)) return ROCQ_STATUS_FAILURE;
+                            txt += rq::dump_plan(std::vector<rq::SweepPlan>{ms.sweep}, fused);
+                        }
+                    }
+                    continue;
+                }
                 const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(fused, n - M, L);
                 for (const rq::SweepPlan& sp : plans)
                     if (!rq::build_program(prog, sp, fused, n - M, 1, 0)) return ROCQ_STATUS_FAILURE;

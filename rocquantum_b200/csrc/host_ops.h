@@ -828,7 +828,8 @@ inline void build_phases(Prog& P, unsigned T) {
         for (unsigned j = 0; j < T; ++j) if ((o.xm >> j) & 1u) { if (j < MINP) return false; need |= 1u << j; }
         return true;
     };
-    if (T < MINP + V) { for (unsigned i = 0; i < nops; ++i) legacy(i); return; }
+    // the kernel's window loop has a warp-uniform trip count: 2^(T-V) groups must fill the 2^8 threads
+    if (T < MINP + V || T < V + 8) { for (unsigned i = 0; i < nops; ++i) legacy(i); return; }
     unsigned i = 0;
     while (i < nops) {
         uint32_t need = 0;
@@ -860,13 +861,11 @@ inline void build_phases(Prog& P, unsigned T) {
         ndp = 0;
         for (unsigned j = first; j < i; ++j) {
             rq_tile_op& o = P.ops[j];
-            if (o.kind == RQ_OP_DIAG || o.kind == RQ_OP_DIAGP) {                    // controls are evaluated per amplitude
-                o.cm_in = 0; o.cm_out = 0;
-                if (o.kind == RQ_OP_DIAGP) o.t[3] = (uint8_t)ndp++;
-                continue;
-            }
+            if (o.kind == RQ_OP_DIAG) { o.cm_in = 0; o.cm_out = 0; continue; }      // controls are evaluated per amplitude
             uint32_t lc = o.setmask;                       // local controls (+ for SWAP the select bit, removed below)
-            if (o.kind == RQ_OP_DENSE) {
+            if (o.kind == RQ_OP_DIAGP) {
+                o.t[3] = (uint8_t)ndp++;
+            } else if (o.kind == RQ_OP_DENSE) {
                 for (unsigned b = 0; b < o.k; ++b) o.wt[b] = (uint8_t)widx[o.t[b]];
             } else {
                 unsigned b = 0;

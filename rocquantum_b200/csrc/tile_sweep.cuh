@@ -141,6 +141,7 @@ __device__ __forceinline__ void rmac(ramp& acc, const mel m, const ramp v) {
     acc.y = fma(m.im, v.x, acc.y);
 }
 __device__ __forceinline__ ramp rmul(const rq_cplx d, const ramp v) { return cmul(d, v); }
+__device__ __forceinline__ ramp rsel(bool on, const ramp r, const ramp a) { return rq_cplx{on ? r.x : a.x, on ? r.y : a.y}; }
 #else
 typedef uint64_t ramp;
 struct mel { float re; uint64_t im2; };
@@ -164,6 +165,7 @@ __device__ __forceinline__ ramp rmul(const rq_cplx d, const ramp v) {
     ramp acc = fma2(pack2(d.x, d.x), v, 0ull);
     return fma2(pack2(-d.y, d.y), swap2(v), acc);
 }
+__device__ __forceinline__ ramp rsel(bool on, const ramp r, const ramp a) { return on ? r : a; }
 #endif
 
 // deposit the bits of g around the fixed positions fix[0..nfix) (ascending), leaving zeros there.
@@ -187,6 +189,22 @@ __device__ __forceinline__ uint32_t spread(uint32_t g, const rq_tile_op& o, cons
     return g;
 }
 
+// f(g, it) for every group g = tid + 2^8 * it of the thread.  Tiles of >= 2^8 groups take a loop with a warp-uniform trip
+// count (no divergent control flow: op fields, matrices and tables are then read through the uniform datapath).
+template <typename F>
+__device__ __forceinline__ void for_groups(uint32_t ngroups, uint32_t tid, F&& f) {
+    static_assert(NT == 256, "group index = tid + 2^8 * it");
+#ifdef RQ_DIVERGENT_LOOPS
+    for (uint32_t g = tid, it = 0; g < ngroups; g += NT, ++it) f(g, it);
+    return;
+#endif
+    if (ngroups >= NT) {
+        for (uint32_t it = 0; it < (ngroups >> 8); ++it) f(tid + (it << 8), it);
+    } else if (tid < ngroups) {
+        f(tid, 0u);
+    }
+}
+
 template <int K, bool EXT, bool SWZ>
 __device__ __forceinline__ void op_dense(rq_cplx* sm, const rq_tile_op& o, const rq_cplx* pool, const rq_cplx* ext,
                                          uint32_t T, uint32_t tid) {
@@ -204,7 +222,7 @@ __device__ __forceinline__ void op_dense(rq_cplx* sm, const rq_tile_op& o, const
     const rq_cplx* M = EXT ? ext : (pool + o.moff);
     const fixmasks F = load_fix(o);
     const uint32_t setmask = o.setmask;
-    for (uint32_t g = tid; g < ngroups; g += NT) {
+    for_groups(ngroups, tid, [&](uint32_t g, uint32_t) {
         const uint32_t base = spread(g, o, F) | setmask;
         cin a[D];
 #pragma unroll
@@ -219,7 +237,7 @@ __device__ __forceinline__ void op_dense(rq_cplx* sm, const rq_tile_op& o, const
             }
             sm[sidx<SWZ>(base | off[i])] = cget(acc);
         }
-    }
+    });
 }
 
 // diagonal: amp[idx] *= d[sel], sel bit b taken from the local index or, for a non-resident qubit,
@@ -234,14 +252,14 @@ __device__ __forceinline__ void op_diag(rq_cplx* sm, const rq_tile_op& o, const 
     const rq_cplx* D = pool + o.moff;
     const fixmasks F = load_fix(o);
     const uint32_t setmask = o.setmask;
-    for (uint32_t g = tid; g < ngroups; g += NT) {
+    for_groups(ngroups, tid, [&](uint32_t g, uint32_t) {
         const uint32_t idx = spread(g, o, F) | setmask;
         uint32_t sel = selbase;
         for (uint32_t b = 0; b < o.k; ++b)
             if (o.t[b] != 0xFF) sel |= ((idx >> o.t[b]) & 1u) << b;
         const uint32_t pi = sidx<SWZ>(idx);
         sm[pi] = cmul(D[sel], sm[pi]);
-    }
+    });
 }
 
 // product of one-qubit diagonals under common controls (host: merge_diagonals, a QFT's ladder of controlled phases):
@@ -279,8 +297,12 @@ __device__ __forceinline__ rq_cplx diagp_thread_factor(const rq_tile_op& o, cons
     const rq_cplx* A = pool + o.moff + 1;
     const uint32_t na = o.t[0];
     rq_cplx f = gfac[o.t[2]];
-    for (uint32_t i = 0; i < na; ++i)
-        if ((tid >> i) & 1u) f = cmul(A[i], f);
+    for (uint32_t i = 0; i < na; ++i) {                      // select, not branch: A[i] stays a uniform load
+        const rq_cplx fm = cmul(A[i], f);
+        const bool bit = (tid >> i) & 1u;
+        f.x = bit ? fm.x : f.x;
+        f.y = bit ? fm.y : f.y;
+    }
     return f;
 }
 
@@ -292,10 +314,10 @@ __device__ __forceinline__ void op_diagp(rq_cplx* sm, const rq_tile_op& o, const
     const uint32_t ngroups = 1u << (T - o.nfix);
     const fixmasks F = load_fix(o);
     const uint32_t setmask = o.setmask;
-    for (uint32_t g = tid, m = 0; g < ngroups; g += NT, ++m) {
+    for_groups(ngroups, tid, [&](uint32_t g, uint32_t m) {
         const uint32_t pi = sidx<SWZ>(spread(g, o, F) | setmask);
         sm[pi] = cmul(cmul(B[m], f), sm[pi]);
-    }
+    });
 }
 
 // pair permutation: swap(idx, idx ^ xm) over the idx whose fixed bits equal setmask
@@ -304,20 +326,23 @@ __device__ __forceinline__ void op_perm(rq_cplx* sm, const rq_tile_op& o, uint32
     const uint32_t ngroups = 1u << (T - o.nfix);
     const fixmasks F = load_fix(o);
     const uint32_t setmask = o.setmask, xm = o.xm;
-    for (uint32_t g = tid; g < ngroups; g += NT) {
+    for_groups(ngroups, tid, [&](uint32_t g, uint32_t) {
         const uint32_t l0 = spread(g, o, F) | setmask, i0 = sidx<SWZ>(l0), i1 = sidx<SWZ>(l0 ^ xm);
         const rq_cplx a = sm[i0], b = sm[i1];
         sm[i0] = b;
         sm[i1] = a;
-    }
+    });
 }
 
 // ---- register-window phases ---------------------------------------------------------------------------
 // Every thread owns the D = 2^V amplitudes that differ in the V window bits; all ops of the phase act on them in
 // registers, so the tile makes ONE shared-memory round trip per phase instead of one per op.  Window bits sit at
 // local positions >= 4: for a fixed register slot the lanes of a warp read consecutive amplitudes (no bank conflicts).
+// `on`: the thread's group satisfies the op's controls OUTSIDE the window.  Results are selected, not branched around: a
+// phase without divergent control flow lets every op header / matrix / table load go through the uniform datapath
+// (a divergent region turns them into vector-indexed LDC, which the address-divergence unit serialises).
 template <int V, int W, bool CTRL>
-__device__ __forceinline__ void win_dense1(ramp (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
+__device__ __forceinline__ void win_dense1(ramp (&a)[1 << V], const rq_cplx* M, uint32_t cm_in, bool on = true) {
     const mel m00 = mload(M, 0), m10 = mload(M, 1), m01 = mload(M, 2), m11 = mload(M, 3);          // column-major
 #pragma unroll
     for (int j = 0; j < (1 << V); ++j) {
@@ -327,13 +352,13 @@ __device__ __forceinline__ void win_dense1(ramp (&a)[1 << V], const rq_cplx* M, 
         ramp r0 = rzero(), r1 = rzero();
         rmac(r0, m00, a0); rmac(r0, m01, a1);
         rmac(r1, m10, a0); rmac(r1, m11, a1);
-        a[j] = r0;
-        a[j | (1 << W)] = r1;
+        a[j] = CTRL ? rsel(on, r0, a0) : r0;
+        a[j | (1 << W)] = CTRL ? rsel(on, r1, a1) : r1;
     }
 }
 // matrix bit 0 <-> window bit W0, matrix bit 1 <-> window bit W1 (the host orders the targets ascending)
 template <int V, int W0, int W1, bool CTRL>
-__device__ __forceinline__ void win_dense2(ramp (&a)[1 << V], const rq_cplx* M, uint32_t cm_in) {
+__device__ __forceinline__ void win_dense2(ramp (&a)[1 << V], const rq_cplx* M, uint32_t cm_in, bool on = true) {
     mel m[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) m[e] = mload(M, e);
@@ -349,60 +374,62 @@ __device__ __forceinline__ void win_dense2(ramp (&a)[1 << V], const rq_cplx* M, 
             rmac(acc, m[i], x0); rmac(acc, m[i + 4], x1); rmac(acc, m[i + 8], x2); rmac(acc, m[i + 12], x3);
             r[i] = acc;
         }
+        if (CTRL) { r[0] = rsel(on, r[0], x0); r[1] = rsel(on, r[1], x1); r[2] = rsel(on, r[2], x2); r[3] = rsel(on, r[3], x3); }
         a[j] = r[0]; a[j | (1 << W0)] = r[1]; a[j | (1 << W1)] = r[2]; a[j | (1 << W0) | (1 << W1)] = r[3];
     }
 }
 template <int V, int W>
-__device__ __forceinline__ void win_x(ramp (&a)[1 << V], uint32_t cm_in) {
+__device__ __forceinline__ void win_x(ramp (&a)[1 << V], uint32_t cm_in, bool on) {
 #pragma unroll
     for (int j = 0; j < (1 << V); ++j) {
         if (j & (1 << W)) continue;
         if ((j & cm_in) != cm_in) continue;
-        const ramp t = a[j];
-        a[j] = a[j | (1 << W)];
-        a[j | (1 << W)] = t;
+        const ramp t = a[j], u = a[j | (1 << W)];
+        a[j] = rsel(on, u, t);
+        a[j | (1 << W)] = rsel(on, t, u);
     }
 }
 template <int V, int W0, int W1>
-__device__ __forceinline__ void win_swap(ramp (&a)[1 << V], uint32_t cm_in) {
+__device__ __forceinline__ void win_swap(ramp (&a)[1 << V], uint32_t cm_in, bool on) {
 #pragma unroll
     for (int j = 0; j < (1 << V); ++j) {
         if (j & ((1 << W0) | (1 << W1))) continue;
         if ((j & cm_in) != cm_in) continue;
-        const ramp t = a[j | (1 << W0)];
-        a[j | (1 << W0)] = a[j | (1 << W1)];
-        a[j | (1 << W1)] = t;
+        const ramp t = a[j | (1 << W0)], u = a[j | (1 << W1)];
+        a[j | (1 << W0)] = rsel(on, u, t);
+        a[j | (1 << W1)] = rsel(on, t, u);
     }
 }
 
 template <int V>
-__device__ __forceinline__ void win_dispatch1(ramp (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense) {
+__device__ __forceinline__ void win_dispatch1(ramp (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense, bool on) {
     const uint32_t w = o.wt[0], ci = o.cm_in;
-    if (dense && ci == 0) {                                  // uncontrolled: straight-line code, matrix stays in registers
+    if (dense && ci == 0 && o.cm_out == 0) {                                  // uncontrolled: straight-line code, matrix stays in registers
         if (w == 0) win_dense1<V, 0, false>(a, M, 0);
         else if (w == 1) win_dense1<V, 1, false>(a, M, 0);
         else if (w == 2) win_dense1<V, 2, false>(a, M, 0);
         else if (V > 3) win_dense1<V, (V > 3 ? 3 : 0), false>(a, M, 0);
     } else if (dense) {
-        if (w == 0) win_dense1<V, 0, true>(a, M, ci);
-        else if (w == 1) win_dense1<V, 1, true>(a, M, ci);
-        else if (w == 2) win_dense1<V, 2, true>(a, M, ci);
-        else if (V > 3) win_dense1<V, (V > 3 ? 3 : 0), true>(a, M, ci);
+        if (w == 0) win_dense1<V, 0, true>(a, M, ci, on);
+        else if (w == 1) win_dense1<V, 1, true>(a, M, ci, on);
+        else if (w == 2) win_dense1<V, 2, true>(a, M, ci, on);
+        else if (V > 3) win_dense1<V, (V > 3 ? 3 : 0), true>(a, M, ci, on);
     } else {
-        if (w == 0) win_x<V, 0>(a, ci);
-        else if (w == 1) win_x<V, 1>(a, ci);
-        else if (w == 2) win_x<V, 2>(a, ci);
-        else if (V > 3) win_x<V, (V > 3 ? 3 : 0)>(a, ci);
+        if (w == 0) win_x<V, 0>(a, ci, on);
+        else if (w == 1) win_x<V, 1>(a, ci, on);
+        else if (w == 2) win_x<V, 2>(a, ci, on);
+        else if (V > 3) win_x<V, (V > 3 ? 3 : 0)>(a, ci, on);
     }
 }
 template <int V>
-__device__ __forceinline__ void win_dispatch2(ramp (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense) {
+__device__ __forceinline__ void win_dispatch2(ramp (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense, bool on) {
     const uint32_t pair = o.wt[0] * 4u + o.wt[1], ci = o.cm_in;      // wt[0] < wt[1]
+    const bool plain = ci == 0 && o.cm_out == 0;
 #define RQ_PAIR(A, B)                                            \
     case (A) * 4 + (B):                                          \
-        if (dense && ci == 0) win_dense2<V, A, B, false>(a, M, 0); \
-        else if (dense) win_dense2<V, A, B, true>(a, M, ci);     \
-        else win_swap<V, A, B>(a, ci);                           \
+        if (dense && plain) win_dense2<V, A, B, false>(a, M, 0); \
+        else if (dense) win_dense2<V, A, B, true>(a, M, ci, on); \
+        else win_swap<V, A, B>(a, ci, on);                       \
         break;
     switch (pair) {
         RQ_PAIR(0, 1) RQ_PAIR(0, 2) RQ_PAIR(1, 2)
@@ -440,7 +467,14 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
             for (int d = 0; d < RQ_PHASE_MAX_DIAGP; ++d) if (o.t[3] == d) fA[d] = f;
         }
     }
-    for (uint32_t g = tid; g < ngroups; g += NT) {
+    // the host only builds window phases for tiles of >= 2^(V+8) amplitudes: a warp-uniform trip count, so that op
+    // headers, matrices and tables are fetched through the uniform datapath
+#ifdef RQ_DIVERGENT_LOOPS
+    for (uint32_t g = tid, it = 0; g < ngroups; g += NT, ++it) {
+#else
+    for (uint32_t it = 0; it < (ngroups >> 8); ++it) {
+        const uint32_t g = tid + (it << 8);
+#endif
         uint32_t base = g;
 #pragma unroll
         for (int b = 0; b < V; ++b) {
@@ -459,8 +493,13 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
         }
         for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
             const rq_tile_op& o = prog.ops[oi];
-            if ((gbase & o.gcmask) != o.gcmask) continue;
+            if ((gbase & o.gcmask) != o.gcmask) continue;       // uniform per tile
+#ifdef RQ_BRANCH_PRED
             if ((base & o.cm_out) != o.cm_out) continue;
+            const bool on = true;
+#else
+            const bool on = (base & o.cm_out) == o.cm_out;       // per thread: selected, never branched on
+#endif
             const rq_cplx* M = prog.pool + o.moff;
             if (o.kind == RQ_OP_DIAG) {
                 const uint32_t lc = o.setmask, k = o.k;
@@ -489,22 +528,24 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
                     }
                 }
             } else if (o.kind == RQ_OP_DIAGP) {
-                const uint32_t lc = o.setmask;
+                const uint32_t ci = o.cm_in;
                 const rq_cplx* B = M + 1 + o.t[0];
                 const rq_cplx* Wt = B + (1u << o.t[1]);
                 rq_cplx fs = fA[0];
 #pragma unroll
                 for (int d = 1; d < RQ_PHASE_MAX_DIAGP; ++d) if (o.t[3] == d) fs = fA[d];
-                const rq_cplx ft = cmul(B[g >> 8], fs);          // NT = 2^8: g >> 8 = the group-index bits above the thread's
+                const rq_cplx ft = cmul(B[it], fs);              // NT = 2^8: `it` = the group-index bits above the thread's
 #pragma unroll
-                for (int j = 0; j < D; ++j)
-                    if ((lidx[j] & lc) == lc) a[j] = rmul(cmul(Wt[j], ft), a[j]);
+                for (int j = 0; j < D; ++j) {
+                    if ((j & ci) != ci) continue;                // controls inside the window: uniform
+                    a[j] = rsel(on, rmul(cmul(Wt[j], ft), a[j]), a[j]);
+                }
             } else if (o.kind == RQ_OP_DENSE) {
-                if (o.k == 1) win_dispatch1<V>(a, o, M, true);
-                else win_dispatch2<V>(a, o, M, true);
+                if (o.k == 1) win_dispatch1<V>(a, o, M, true, on);
+                else win_dispatch2<V>(a, o, M, true, on);
             } else {
-                if (o.k == 1) win_dispatch1<V>(a, o, M, false);
-                else win_dispatch2<V>(a, o, M, false);
+                if (o.k == 1) win_dispatch1<V>(a, o, M, false, on);
+                else win_dispatch2<V>(a, o, M, false, on);
             }
         }
 #pragma unroll

@@ -79,13 +79,12 @@ bool emulate_window_phase(std::vector<cd>& sm, const Prog& prog, const rq_phase&
                     a[j] *= pc(M[sel]);
                 }
             } else if (o.kind == RQ_OP_DIAGP) {
-                const uint32_t lc = o.setmask;
                 const rq_cplx* B = M + 1 + o.t[0];
                 const rq_cplx* Wt = B + (1u << o.t[1]);
                 if ((g >> 8) >= (1u << o.t[1])) return false;
                 const cd ft = pc(B[g >> 8]) * fA[o.t[3]];
                 for (uint32_t j = 0; j < D; ++j)
-                    if ((lidx[j] & lc) == lc) a[j] *= pc(Wt[j]) * ft;
+                    if ((j & ci) == ci) a[j] *= pc(Wt[j]) * ft;
             } else if (o.kind == RQ_OP_DENSE) {
                 if (o.ext || o.k > 2) return false;
                 if (o.k == 1) {

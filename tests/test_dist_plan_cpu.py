@@ -45,3 +45,20 @@ def test_diagonal_and_controlled_gates_on_rank_bits_need_no_exchange():
     nx, steps, fmap = util.dist_plan(n, nranks, gates, 0, canonicalize=True)
     assert nx == 0
     _check(n, nranks, gates, 0)
+
+
+@pytest.mark.parametrize("nranks", [2, 8])
+def test_distributed_slices_form_blocks_on_local_qubits_only(nranks):
+    """mode bit 2: every RUN step planned with tensor-core blocks (what the complex64 engine does on a slice): blocks lie on
+    local positions, hold only ops inside them, and the plan still equals the circuit."""
+    n = 17
+    m = nranks.bit_length() - 1
+    for gates in (workloads.c4_global_layers(n, 8, seed=36, top=3), workloads.c2_random_unitary(n, 6, seed=30),
+                  workloads.c3_qft(n, seed=33) + util.random_gates(n, 80, seed=3, maxk=3)):
+        nx, steps, fmap = util.dist_plan(n, nranks, gates, 2 | 4, canonicalize=True)
+        assert fmap == list(range(n))
+        v = util.random_state(n, seed=nranks)
+        a = so.Oracle(n, "c128"); a.set_state(v); util.run_on_oracle(a, gates)
+        b = so.Oracle(n, "c128"); b.set_state(v); util.simulate_dist_plan(b, n - m, steps)
+        assert util.rel_err(b.state, a.state) < 1e-11
+    assert util.dist_plan.blocks > 0

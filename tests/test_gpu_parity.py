@@ -358,3 +358,24 @@ def test_blocks_on_sparse_states_circuit_and_inverse():
         assert g.stats().blockSweeps > 0
         assert abs(g.norm2() - 1) < 2e-5 and abs(g.expect_zprod([0]) - 1) < 2e-5 and abs(g.expect_zprod([n - 1]) - 1) < 2e-5
         assert not g.sample(list(range(n)), 64).any()
+
+
+def test_distributed_entry_points_on_one_rank_form_blocks():
+    """rocsvAllocateDistributedState without rocsvxDistInit = one rank: the distributed code path (planner, RUN steps) on
+    a single GPU, which now forms tensor-core blocks on the local qubits like the plain path."""
+    n = 24
+    lib = capi.load("c64")
+    gates = workloads.c4_global_layers(n, 6, seed=36, top=3) + workloads.c2_random_unitary(n, 4, seed=30)
+    o = so.Oracle(n, "c64"); util.run_on_oracle(o, gates)
+    h = C.c_void_p()
+    assert lib.rocsvCreate(C.byref(h)) == 0
+    assert lib.rocsvAllocateDistributedState(h, n) == 0 and lib.rocsvInitializeDistributedState(h) == 0
+    arr, keep = capi.make_ops(gates)
+    assert lib.rocsvxApplyCircuit(h, None, n, arr, len(gates)) == 0
+    out = np.empty(1 << n, dtype=np.complex64)
+    assert lib.rocsvGetStateVectorFull(h, None, out.ctypes.data_as(C.c_void_p)) == 0
+    st = capi.Stats()
+    assert lib.rocsvxGetStats(h, C.byref(st), 0) == 0
+    assert st.blockSweeps > 0
+    assert util.rel_err(out, o.state) < TOL["c64"]
+    assert lib.rocsvDestroy(h) == 0

@@ -271,13 +271,19 @@ def dist_plan(n, nranks, gates, mode=0, canonicalize=True, prec="c64"):
         if len(txt) < size - 2:
             break
         size *= 4
-    steps, fmap = [], None
+    steps, fmap, block, nblocks = [], None, None, [0]
     for line in txt.splitlines():
         tok = line.split()
         if tok[0] == "R":
+            block = None
             steps.append(("R", []))
         elif tok[0] == "S":
             assert all(int(x) < n - (nranks.bit_length() - 1) for x in tok[4:]), "rank bit made resident"
+            block = None
+        elif tok[0] == "B":                      # tensor-core block on six LOCAL positions; its ops follow
+            block = [int(x) for x in tok[1:]]
+            assert len(block) == 6 and all(x < n - (nranks.bit_length() - 1) for x in block), "block on a rank bit"
+            nblocks[0] += 1
         elif tok[0] == "X":
             steps.append(("X", [int(x) for x in tok[1:]]))
         elif tok[0] == "M":
@@ -286,8 +292,11 @@ def dist_plan(n, nranks, gates, mode=0, canonicalize=True, prec="c64"):
             kind, cmask = int(tok[1]), int(tok[3], 16)
             ti, di = tok.index("targets"), tok.index("data")
             vals = [float(x) for x in tok[di + 1:]]
-            steps[-1][1].append(dict(kind=kind, cmask=cmask, targets=[int(x) for x in tok[ti + 1:di]],
-                                     data=np.array(vals[0::2]) + 1j * np.array(vals[1::2])))
+            op = dict(kind=kind, cmask=cmask, targets=[int(x) for x in tok[ti + 1:di]], data=np.array(vals[0::2]) + 1j * np.array(vals[1::2]))
+            if block is not None:                # every op folded into a block lies inside it
+                assert set(op["targets"]) | {q for q in range(64) if (cmask >> q) & 1} <= set(block)
+            steps[-1][1].append(op)
+    dist_plan.blocks = nblocks[0]
     return nx.value, steps, fmap
 
 

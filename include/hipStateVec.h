@@ -211,8 +211,13 @@ typedef struct {
     uint64_t exchangeBytes;    /* multi-process: bytes this rank sent to peers in those exchanges */
     double   exchangeMs;       /* multi-process: device time of those exchanges (CUDA events around each) */
     uint64_t blockSweeps;      /* launches of the tensor-core block-sweep kernel (counted in `sweeps` too) */
+    uint64_t planCacheHits;    /* rocsvxApplyCircuit calls that replayed the recorded launches of an identical earlier call */
 } rocsvxStats;
 rocqStatus_t rocsvxGetStats(rocsvHandle_t handle, rocsvxStats* stats, int reset);
+/* rocsvxApplyCircuit keeps the launches it planned for the most recent circuit: resubmitting the identical gate list (same
+ * gates, matrices, state buffer and settings; compared by a 128-bit hash of the whole list) replays them and skips fusion,
+ * planning and the host-side matrix products.  Every kernel runs again; only host work is saved.  ROCQ_PLAN_CACHE=0 turns
+ * it off. */
 
 /* Device timer on the handle's stream (CUDA events): Start records, Stop records, flushes nothing and
  * returns the elapsed milliseconds after synchronising on the stop event. */

@@ -30,7 +30,8 @@ class Stats(C.Structure):
     """rocsvxStats"""
     _fields_ = [("kernelLaunches", C.c_uint64), ("sweeps", C.c_uint64), ("gatesSubmitted", C.c_uint64),
                 ("opsExecuted", C.c_uint64), ("h2dBytes", C.c_uint64), ("lastSweepMs", C.c_double),
-                ("exchanges", C.c_uint64), ("exchangeBytes", C.c_uint64), ("exchangeMs", C.c_double), ("blockSweeps", C.c_uint64)]
+                ("exchanges", C.c_uint64), ("exchangeBytes", C.c_uint64), ("exchangeMs", C.c_double), ("blockSweeps", C.c_uint64),
+                ("planCacheHits", C.c_uint64)]
 
 
 class ExchangeSeg(C.Structure):
@@ -119,7 +120,12 @@ def load(prec: str = "c64") -> C.CDLL:
                               "rocquantum_b200 has no CPU or PyTorch fallback")
         lib = C.CDLL(path)
         for name, args in PROTOTYPES.items():
-            fn = getattr(lib, name)
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                if "ROCQ_LIB_DIR" in os.environ:      # an older tuning variant built elsewhere: it may lack newer extensions
+                    continue
+                raise
             fn.argtypes = args
             fn.restype = C.c_int
         lib.rocsvGetPinnedBufferPointer.restype = C.c_void_p

@@ -66,21 +66,34 @@ rocqStatus_t launch_plan(H* h, rq_cplx* state, unsigned n, const rq::SweepPlan& 
 
 rocqStatus_t launch_plan(H* h, rq_cplx* state, unsigned n, const rq::SweepPlan& sp, const std::vector<HostOp>& seg, bool large) {
     int e;
+    const void* prog = nullptr;
+    size_t prog_bytes = 0;
     if (large) {
         static thread_local rq_program_large P;
         if (!rq::build_program(P, sp, seg, n, h->batchSize, h->dist.high_base())) return ROCQ_STATUS_FAILURE;
         e = rq_launch_sweep_large(state, &P, h->stream);
-        h->stats.h2dBytes += sizeof(P);
+        prog = &P; prog_bytes = sizeof(P);
     } else {
         static thread_local rq_program_small P;
         if (!rq::build_program(P, sp, seg, n, h->batchSize, h->dist.high_base())) return ROCQ_STATUS_FAILURE;
         e = rq_launch_sweep_small(state, &P, h->stream);
-        h->stats.h2dBytes += sizeof(P);
+        prog = &P; prog_bytes = sizeof(P);
     }
     RQ_CUDA(e, "tile sweep launch");
+    h->stats.h2dBytes += prog_bytes;
     h->stats.kernelLaunches++;
     h->stats.sweeps++;
     h->stats.opsExecuted += sp.ops.size();
+    if (h->recording) {                                  // plan cache: keep the program (it has no device pointers unless ext)
+        const bool ext = large ? static_cast<const rq_program_large*>(prog)->hdr.ext_matrix != nullptr
+                               : static_cast<const rq_program_small*>(prog)->hdr.ext_matrix != nullptr;
+        if (ext) h->recordingValid = false;
+        rocsvCachedStep st;
+        st.large = large;
+        st.ops = (unsigned)sp.ops.size();
+        st.prog.assign(static_cast<const unsigned char*>(prog), static_cast<const unsigned char*>(prog) + prog_bytes);
+        h->recording->push_back(std::move(st));
+    }
     return ROCQ_STATUS_SUCCESS;
 }
 
@@ -143,7 +156,11 @@ rocqStatus_t run_ops_with_blocks(H* h, rq_cplx* state, unsigned n, const std::ve
 
 // run ops (already validated) on `state`: dense/diag ops wider than the tile kernel handles go through
 // the gather kernel, everything else through planned sweeps.
-rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>& ops, bool fused) {
+rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>& ops_in, bool fused) {
+    // a slice of a distributed state: controls and diagonal factors on rank bits are constants of this rank
+    std::vector<HostOp> resolved;
+    if (h->dist.active() && h->dist.global_mask()) resolved = rq::specialize_for_rank(ops_in, n, h->dist.high_base());
+    const std::vector<HostOp>& ops = (h->dist.active() && h->dist.global_mask()) ? resolved : ops_in;
     size_t i = 0;
     while (i < ops.size()) {
         // segment of tile-capable ops
@@ -179,6 +196,7 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
             const HostOp& o = ops[i];
             const unsigned k = (unsigned)o.targets.size();
             if (k > 10) return ROCQ_STATUS_NOT_IMPLEMENTED;
+            h->recordingValid = false;                   // the gather kernel's matrix upload is not replayable
             const rq_cplx* dm = reinterpret_cast<const rq_cplx*>(o.ext);
             rq_cplx* tmp = nullptr;
             if (!dm) {                        // host matrix (or diagonal): upload, stream-ordered
@@ -278,7 +296,9 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     std::vector<uint16_t> terms;
     build_block_terms(U, terms);
     void* d_terms = nullptr;
-    RQ_CUDA(cudaMallocAsync(&d_terms, RQ_BLOCK_UBYTES + 256, h->stream), "block terms alloc");   // + debug timers
+    const bool keep = h->recording != nullptr && P.pad == 0;                                     // plan cache: the entry owns the buffer
+    if (keep) RQ_CUDA(cudaMalloc(&d_terms, RQ_BLOCK_UBYTES + 256), "block terms alloc (cached)");
+    else RQ_CUDA(cudaMallocAsync(&d_terms, RQ_BLOCK_UBYTES + 256, h->stream), "block terms alloc");   // + debug timers
     // pageable source: cudaMemcpyAsync stages it before returning, so `terms` may go out of scope
     RQ_CUDA(cudaMemcpyAsync(d_terms, terms.data(), RQ_BLOCK_UBYTES, cudaMemcpyHostToDevice, h->stream), "block terms upload");
     RQ_CUDA(rq_launch_block_sweep(state, &P, d_terms, &tm, h->stream), "block sweep launch");
@@ -294,11 +314,80 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
                 fprintf(stderr, "\n");
             }
     }
-    RQ_CUDA(cudaFreeAsync(d_terms, h->stream), "block terms free");
+    if (keep) {
+        rocsvCachedStep st;
+        st.block = true;
+        st.bp = P;
+        memcpy(st.tmap, &tm, sizeof st.tmap);
+        st.d_terms = d_terms;
+        h->recording->push_back(std::move(st));
+    } else {
+        if (h->recording) h->recordingValid = false;
+        RQ_CUDA(cudaFreeAsync(d_terms, h->stream), "block terms free");
+    }
     h->stats.kernelLaunches++;
     h->stats.sweeps++;
     h->stats.blockSweeps++;
     h->stats.h2dBytes += RQ_BLOCK_UBYTES;
+    return ROCQ_STATUS_SUCCESS;
+}
+
+// ---- plan cache of rocsvxApplyCircuit -------------------------------------------------------------------------------
+void free_steps(H* h, std::vector<rocsvCachedStep>& steps) {
+    bool any = false;
+    for (rocsvCachedStep& st : steps) any = any || st.d_terms;
+    if (any && h->stream) cudaStreamSynchronize(h->stream);       // a launch may still read the operand terms
+    for (rocsvCachedStep& st : steps) if (st.d_terms) { cudaFree(st.d_terms); st.d_terms = nullptr; }
+    steps.clear();
+}
+void drop_cache(H* h) {
+    free_steps(h, h->cache.steps);
+    h->cache.valid = false;
+}
+// two independent 64-bit word hashes over everything that determines the launches
+struct Hash2 {
+    uint64_t a = 0xcbf29ce484222325ull, b = 0x9e3779b97f4a7c15ull;
+    size_t bytes = 0;
+    void word(uint64_t w) {
+        a = (a ^ w) * 0x100000001b3ull; a ^= a >> 29;
+        b = (b + w) * 0xff51afd7ed558ccdull; b ^= b >> 32;
+    }
+    void mem(const void* p, size_t n) {
+        const unsigned char* c = static_cast<const unsigned char*>(p);
+        bytes += n;
+        for (; n >= 8; n -= 8, c += 8) { uint64_t w; memcpy(&w, c, 8); word(w); }
+        if (n) { uint64_t w = 0; memcpy(&w, c, n); word(w ^ ((uint64_t)n << 56)); }
+    }
+};
+Hash2 circuit_key(const H* h, const rq_cplx* state, unsigned n, const rocsvxGateOp* ops, size_t numOps) {
+    Hash2 k;
+    k.word((uint64_t)(uintptr_t)state); k.word(n); k.word(h->batchSize); k.word((uint64_t)(int64_t)h->tcBlocks); k.word(h->mergeDiagonals);
+    k.word(h->tileBits); k.mem(&h->blockMinCost, sizeof(double)); k.mem(&h->budget, sizeof(double)); k.word(numOps);
+    for (size_t i = 0; i < numOps; ++i) {
+        const rocsvxGateOp& g = ops[i];
+        k.word(((uint64_t)(uint32_t)g.kind << 32) | g.numTargets);
+        k.mem(g.targets, sizeof g.targets);
+        k.word(g.controlMask);
+        k.mem(&g.theta, sizeof(double));
+        if (g.kind == ROCSVX_MATRIX && g.matrix && g.numTargets <= 8) k.mem(g.matrix, sizeof(double) * 2 * ((size_t)1 << (2 * g.numTargets)));
+    }
+    return k;
+}
+rocqStatus_t replay_cache(H* h, rq_cplx* state) {
+    for (const rocsvCachedStep& st : h->cache.steps) {
+        if (st.block) {
+            RQ_CUDA(rq_launch_block_sweep(state, &st.bp, st.d_terms, st.tmap, h->stream), "block sweep launch (cached)");
+            h->stats.blockSweeps++;
+        } else {
+            const int e = st.large ? rq_launch_sweep_large(state, reinterpret_cast<const rq_program_large*>(st.prog.data()), h->stream)
+                                   : rq_launch_sweep_small(state, reinterpret_cast<const rq_program_small*>(st.prog.data()), h->stream);
+            RQ_CUDA(e, "tile sweep launch (cached)");
+            h->stats.h2dBytes += st.prog.size();
+            h->stats.opsExecuted += st.ops;
+        }
+        h->stats.kernelLaunches++;
+        h->stats.sweeps++;
+    }
     return ROCQ_STATUS_SUCCESS;
 }
 
@@ -435,6 +524,7 @@ rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
     if (const char* e = getenv("ROCQ_TILE_BITS")) { const int t = atoi(e); if (t >= 6 && t <= RQ_MAX_TILE_BITS) h->tileBits = (unsigned)t; }
     if (const char* e = getenv("ROCQ_TC")) h->tcBlocks = (e[0] == 'a' || e[0] == '-') ? -1 : (atoi(e) != 0 && sizeof(rq_real) == 4) ? 1 : 0;
     if (const char* e = getenv("ROCQ_MERGE_DIAG")) h->mergeDiagonals = atoi(e) != 0;
+    if (const char* e = getenv("ROCQ_PLAN_CACHE")) h->planCache = atoi(e) != 0;
     if (const char* e = getenv("ROCQ_TC_MIN_COST")) { const double b = atof(e); if (b > 0) h->blockMinCost = b; }
     if (const char* e = getenv("ROCQ_SWEEP_BUDGET")) { const double b = atof(e); if (b > 0) h->budget = b; }
     *handle = h;
@@ -464,6 +554,7 @@ rocqStatus_t rocsvAllocateState(rocsvHandle_t h, unsigned numQubits, rocComplex*
     if (numQubits > 40) return ROCQ_STATUS_ALLOCATION_FAILED;
     flush(h);
     cudaStreamSynchronize(h->stream);
+    drop_cache(h);
     h->batchSize = batchSize > 0 ? batchSize : 1;
     h->numQubits = numQubits;
     if (h->d_state && h->ownsState) { cudaFree(h->d_state); h->d_state = nullptr; h->ownsState = false; }
@@ -480,6 +571,7 @@ rocqStatus_t rocsvAllocateState(rocsvHandle_t h, unsigned numQubits, rocComplex*
 rocqStatus_t rocsvFreeState(rocsvHandle_t h) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     if (h->stream) { flush(h); cudaStreamSynchronize(h->stream); }
+    drop_cache(h);
     if (h->d_state && h->ownsState) cudaFree(h->d_state);
     h->d_state = nullptr;
     h->ownsState = false;
@@ -905,9 +997,37 @@ rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t h, rocComplex* d, unsigned n, cons
     h->stats.gatesSubmitted += numOps;
     if (h->dist.active()) return h->dist.run_circuit(h, hops);
     const auto t1 = std::chrono::steady_clock::now();
+    // Plan cache: the identical circuit on the identical state buffer and settings replays the recorded launches (all the
+    // device work is done again; what is skipped is fusion, planning and the host-side products of the block matrices).
+    const bool cacheable = h->planCache && !getenv("ROCQ_BLOCK_DEBUG");
+    Hash2 key;
+    if (cacheable) {
+        key = circuit_key(h, state, n, ops, numOps);
+        if (h->cache.valid && h->cache.key[0] == key.a && h->cache.key[1] == key.b && h->cache.bytes == key.bytes) {
+            cudaEventRecord(h->ev0, h->stream);
+            s = replay_cache(h, state);
+            cudaEventRecord(h->ev1, h->stream);
+            h->stats.lastSweepMs = -1.0;
+            h->stats.planCacheHits++;
+            return s;
+        }
+    }
+    std::vector<rocsvCachedStep> rec;
+    if (cacheable) { h->recording = &rec; h->recordingValid = true; }
     cudaEventRecord(h->ev0, h->stream);
     s = run_ops(h, state, n, hops, true);
     cudaEventRecord(h->ev1, h->stream);
+    h->recording = nullptr;
+    if (cacheable) {
+        if (s == ROCQ_STATUS_SUCCESS && h->recordingValid) {
+            drop_cache(h);
+            h->cache.steps = std::move(rec);
+            h->cache.key[0] = key.a; h->cache.key[1] = key.b; h->cache.bytes = key.bytes;
+            h->cache.valid = true;
+        } else {
+            free_steps(h, rec);
+        }
+    }
     if (prof) fprintf(stderr, "[host profile] ApplyCircuit: convert %.2f ms, run_ops (fuse + plan + launches) %.2f ms\n",
                       std::chrono::duration<double, std::milli>(t1 - t0).count(),
                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());

@@ -9,6 +9,24 @@
 #include "host_ops.h"
 #include "sv_internal.h"
 
+// One launch of a planned circuit, kept so that resubmitting the identical circuit skips fusion, planning and the host-side
+// matrix products (rocsvxApplyCircuit's plan cache): a block sweep (parameters, tensor map, its operand terms in a device
+// buffer the entry owns) or a tile sweep (the program that travels in the kernel parameters).
+struct rocsvCachedStep {
+    bool block = false, large = false;
+    rq_block_params bp{};
+    alignas(64) unsigned char tmap[128];
+    void* d_terms = nullptr;
+    std::vector<unsigned char> prog;
+    unsigned ops = 0;
+};
+struct rocsvPlanCache {
+    bool valid = false;
+    uint64_t key[2] = {0, 0};
+    size_t bytes = 0;
+    std::vector<rocsvCachedStep> steps;
+};
+
 // Reference handle: hipStateVec.cpp:62-68 {stream, batchSize, numQubits, d_state, ownsState}.
 struct rocsvInternalHandle {
     cudaStream_t stream = nullptr;
@@ -37,6 +55,11 @@ struct rocsvInternalHandle {
     unsigned tileBits = RQ_MAX_TILE_BITS;
     double budget = 1e30;
     rocsvxStats stats{};
+    // plan cache of rocsvxApplyCircuit (ROCQ_PLAN_CACHE=0: off)
+    bool planCache = true;
+    rocsvPlanCache cache;
+    std::vector<rocsvCachedStep>* recording = nullptr;   // non-null while a circuit is being planned for the cache
+    bool recordingValid = true;
     rq::Dist dist;
 };
 

@@ -219,6 +219,67 @@ inline std::vector<cd> matmul(const std::vector<cd>& A, const std::vector<cd>& B
 }
 
 
+
+// ---- a distributed slice sees rank bits as constants ---------------------------------------------------------------
+// On the rank whose index bits >= n_local read `high_base`, a control on a rank bit is either always satisfied (drop the
+// control) or never (drop the op), and a diagonal factor on a rank bit is a constant.  Resolving them per rank BEFORE
+// fusion and planning leaves purely local ops: CZ / CP across the slice boundary become one-qubit diagonals that fuse
+// into their neighbours and into tensor-core blocks instead of forcing an ordinary sweep of their own.  (Non-diagonal
+// targets never sit on rank bits: the distributed planner exchanges index bits first.)
+inline std::vector<HostOp> specialize_for_rank(const std::vector<HostOp>& in, unsigned n_local, uint64_t high_base) {
+    const uint64_t lmask = n_local >= 64 ? ~0ull : ((1ull << n_local) - 1ull);
+    bool touched = false;
+    for (const HostOp& o : in) if (o.qubits() & ~lmask) { touched = true; break; }
+    if (!touched) return in;
+    std::vector<HostOp> out;
+    out.reserve(in.size());
+    for (const HostOp& o : in) {
+        if (!(o.qubits() & ~lmask)) { out.push_back(o); continue; }
+        const uint64_t gc = o.cmask & ~lmask;
+        if ((high_base & gc) != gc) continue;                       // a control on a rank bit that is 0 here: identity
+        HostOp r = o;
+        r.cmask &= lmask;
+        if (o.kind == HostOp::DIAG) {
+            std::vector<unsigned> keep;                              // table bits that stay
+            uint32_t fixed_mask = 0, fixed_val = 0;
+            for (unsigned b = 0; b < o.targets.size(); ++b) {
+                if (o.targets[b] < n_local) { keep.push_back(b); continue; }
+                fixed_mask |= 1u << b;
+                if ((high_base >> o.targets[b]) & 1ull) fixed_val |= 1u << b;
+            }
+            if (fixed_mask) {
+                r.targets.clear();
+                for (unsigned b : keep) r.targets.push_back(o.targets[b]);
+                r.data.assign((size_t)1 << keep.size(), cd(1.0, 0.0));
+                for (unsigned s2 = 0; s2 < (1u << keep.size()); ++s2) {
+                    uint32_t full = fixed_val;
+                    for (unsigned i = 0; i < keep.size(); ++i) if ((s2 >> i) & 1u) full |= 1u << keep[i];
+                    r.data[s2] = o.data[full];
+                }
+                canonicalize_diag(r);
+            }
+            if (r.targets.empty() && r.cmask == 0) {                 // a phase on the whole slice: keep it as a 1q diagonal
+                if (r.data[0] == cd(1.0, 0.0)) continue;
+                r.targets = {0u};
+                r.data = {r.data[0], r.data[0]};
+            }
+        } else if (o.kind == HostOp::DIAGP) {
+            r.targets.clear();
+            r.data.assign(1, o.data[0]);
+            for (unsigned b = 0; b < o.targets.size(); ++b) {
+                if (o.targets[b] < n_local) { r.targets.push_back(o.targets[b]); r.data.push_back(o.data[1 + b]); }
+                else if ((high_base >> o.targets[b]) & 1ull) r.data[0] *= o.data[1 + b];
+            }
+            if (r.cmask == 0 && r.targets.empty()) { r.kind = HostOp::DIAG; r.targets = {0u}; r.data = {r.data[0], r.data[0]}; }
+        } else if (o.tmask() & ~lmask) {
+            out.push_back(o);                                        // not expected; leave it to the planner to reject
+            continue;
+        }
+        out.push_back(std::move(r));
+    }
+    return out;
+}
+
 // ---- pushing X gates forward through diagonal ops --------------------------------------------------------
 // An uncontrolled X(q) followed by ops that act diagonally on q (controlled phases, Rz, controls of diagonal ops) and then
 // by a dense gate on q forces q to be resident twice (and blocks every merged diagonal run that touches q until it has
@@ -987,17 +1048,21 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
         }
         for (unsigned j = 0; j < T; ++j) if ((fixmask >> j) & 1u) t.fix[t.nfix++] = (uint8_t)j;
     }
-    // ops with a non-diagonal target on one of the bank-selecting bits would serialise on shared-memory banks:
-    // such sweeps keep the tile XOR-swizzled (needs 2*RQ_SWZ_BITS local bits)
+    // Register windows over the bank-selecting bits would serialise 2^RQ_SWZ_BITS-fold on shared-memory banks: sweeps with
+    // several ops on those bits keep the tile XOR-swizzled (needs 2*RQ_SWZ_BITS local bits).  The swizzle costs two extra
+    // passes over the tile, more than the two-way conflicts of ONE op applied in place, so a lone low-bit op (every eager
+    // rocsvApply* call on qubits 0-3) stays on the linear layout and remains HBM-bound.
     P.hdr.swz = 0;
     if (T >= 2 * RQ_SWZ_BITS) {
+        unsigned low_ops = 0;
         for (unsigned i = 0; i < P.hdr.nops; ++i) {
             const rq_tile_op& t = P.ops[i];
             uint32_t tm = 0;
             if (t.kind == RQ_OP_DENSE) for (unsigned b = 0; b < t.k; ++b) tm |= 1u << t.t[b];
             else if (t.kind == RQ_OP_PERM) tm = t.xm;
-            if (tm & ((1u << RQ_SWZ_BITS) - 1u)) P.hdr.swz = 1;
+            if (tm & ((1u << RQ_SWZ_BITS) - 1u)) ++low_ops;
         }
+        P.hdr.swz = low_ops >= 2 ? 1 : 0;
     }
     build_phases(P, T);
     // RQ_OP_DIAGP tables.  pool: C | A[na]: factor of group-index bit i < na | B[2^nb]: product over the group-index bits

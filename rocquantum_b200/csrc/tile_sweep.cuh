@@ -180,6 +180,13 @@ __device__ __forceinline__ fixmasks load_fix(const rq_tile_op& o) {
     return F;
 }
 __device__ __forceinline__ uint32_t spread(uint32_t g, const rq_tile_op& o, const fixmasks& F) {
+#ifdef RQ_OLD_SPREAD
+    for (uint32_t f = 0; f < o.nfix; ++f) {
+        const uint32_t p = o.fix[f];
+        g = ((g >> p) << (p + 1)) | (g & ((1u << p) - 1u));
+    }
+    return g;
+#endif
 #pragma unroll
     for (uint32_t f = 0; f < 4; ++f) g += g & ~F.m[f];
     for (uint32_t f = 4; f < F.nfix; ++f) {
@@ -189,12 +196,17 @@ __device__ __forceinline__ uint32_t spread(uint32_t g, const rq_tile_op& o, cons
     return g;
 }
 
-// f(g, it) for every group g = tid + 2^8 * it of the thread.  Tiles of >= 2^8 groups take a loop with a warp-uniform trip
-// count (no divergent control flow: op fields, matrices and tables are then read through the uniform datapath).
+// f(g, it) for every group g = tid + 2^8 * it of the thread.
+// Build switches, measured on B200 (profiles/r01_loop_variants.log).  Window phases SELECT results on controls outside the
+// window instead of branching (-DRQ_BRANCH_PRED restores the branch): without the divergent region the phase's matrices
+// and tables are fetched through the uniform datapath (LDCU) instead of vector-indexed LDC; VQE ansatz 24.3 -> 22.7 ms,
+// QFT-30 complex128 108 -> 103 ms.  -DRQ_UNIFORM_LOOPS additionally gives tiles of >= 2^8 groups a warp-uniform trip
+// count: 8 % faster on heavily fused complex64 sweeps (678 -> 623 ms on configs[1] without tensor-core blocks) but the
+// longer uniform-datapath instruction stream costs 60 % on CNOT-heavy phases, so the default keeps thread-indexed loops.
 template <typename F>
 __device__ __forceinline__ void for_groups(uint32_t ngroups, uint32_t tid, F&& f) {
     static_assert(NT == 256, "group index = tid + 2^8 * it");
-#ifdef RQ_DIVERGENT_LOOPS
+#ifndef RQ_UNIFORM_LOOPS
     for (uint32_t g = tid, it = 0; g < ngroups; g += NT, ++it) f(g, it);
     return;
 #endif
@@ -469,7 +481,7 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
     }
     // the host only builds window phases for tiles of >= 2^(V+8) amplitudes: a warp-uniform trip count, so that op
     // headers, matrices and tables are fetched through the uniform datapath
-#ifdef RQ_DIVERGENT_LOOPS
+#ifndef RQ_UNIFORM_LOOPS
     for (uint32_t g = tid, it = 0; g < ngroups; g += NT, ++it) {
 #else
     for (uint32_t it = 0; it < (ngroups >> 8); ++it) {
@@ -578,7 +590,11 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
     extern __shared__ __align__(128) unsigned char smem_raw[];
     rq_cplx* sm = reinterpret_cast<rq_cplx*>(smem_raw);
     __shared__ __align__(8) uint64_t bar_storage;
+#ifdef RQ_NO_GFAC
+    rq_cplx* gfac = nullptr;
+#else
     __shared__ __align__(16) rq_cplx gfac[RQ_MAX_DIAGP];        // per-tile factors of the RQ_OP_DIAGP ops
+#endif
 
     const uint32_t tid = threadIdx.x;
     const uint32_t T = prog.hdr.T, n = prog.hdr.n, rowbits = prog.hdr.rowbits;
@@ -610,10 +626,12 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
         for (uint32_t i = 0; i < T - rowbits; ++i) goff |= (uint64_t)((r >> i) & 1u) << prog.hdr.res[rowbits + i];
         bulk_g2s(smem_u32(sm) + r * rowbytes, gtile + goff, rowbytes, bar);
     }
+#ifndef RQ_NO_GFAC
     if (prog.hdr.ndiagp) {                                       // while the tile is in flight
         diagp_tile_factors(prog, gfac, tid, outer);
         __syncthreads();
     }
+#endif
     mbar_wait(bar, 0);
     swizzle_pass<SWZ>(sm, T, tid);
 

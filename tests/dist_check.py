@@ -94,6 +94,19 @@ def main():
             if rank == 0:
                 print(f"{prec} n={n} world={world}: circuit sweeps={st.sweeps} launches={st.kernelLaunches} ok so far, fails={len(fails)}", flush=True)
             d.close()
+    # (f) tensor-core blocks on the local qubits of each slice (complex64), exchanges in between
+    n = 22
+    gates = workloads.c4_global_layers(n, 10, seed=36, top=3) + workloads.c2_random_unitary(n, 4, seed=30)
+    o = so.Oracle(n, "c64"); util.run_on_oracle(o, gates)
+    d = DistStateVector(n, "c64")
+    assert d.lib.rocsvxSetTensorCoreBlocks(d.h, 1) == 0
+    d.apply_circuit(gates)
+    st = d.stats()
+    err = util.rel_err(gather_full(d, d.local_slice()), o.state)
+    if err > 1e-5 or st.blockSweeps == 0 or (world > 1 and st.exchanges == 0): fails.append(("blocks", n, err, int(st.blockSweeps), int(st.exchanges)))
+    if rank == 0:
+        print(f"c64 n={n} world={world}: blocks={st.blockSweeps} sweeps={st.sweeps} exchanges={st.exchanges} err={err:.2e}", flush=True)
+    d.close()
     t = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(t)
     if rank == 0:

@@ -264,7 +264,7 @@ unsigned hostemu_precision_bytes(void) { return (unsigned)sizeof(rq_real); }
 
 // state: 2 * 2^n doubles (re, im interleaved), updated in place.  rankBits/rank: emulate the slice of one rank of a
 // distributed state (state then holds 2^(n - rankBits) amplitudes and ops may control / act diagonally on rank bits).
-// flags bit 0: skip merge_diagonals.  Returns 0, or a negative code naming the stage that failed.
+// flags bit 0: skip merge_diagonals / push_x_forward, bit 1: resolve rank bits first (specialize_for_rank).  Returns 0, or a negative code naming the stage that failed.
 int hostemu_run_circuit(unsigned n, unsigned tileBits, const rocsvxGateOp* ops, size_t numOps, double* state, unsigned rankBits,
                         unsigned rank, unsigned flags, unsigned* numSweeps, unsigned* numMerged) {
     std::vector<rq::HostOp> hops;
@@ -273,6 +273,7 @@ int hostemu_run_circuit(unsigned n, unsigned tileBits, const rocsvxGateOp* ops, 
     const unsigned nl = n - rankBits;
     const uint64_t gmask = rankBits ? (((1ull << rankBits) - 1ull) << nl) : 0ull;
     for (const rq::HostOp& o : hops) if (o.nondiag() & gmask) return -3;
+    if ((flags & 2u) && rankBits) hops = rq::specialize_for_rank(hops, nl, (uint64_t)rank << nl);      // as the engine does on a slice
     if (!(flags & 1u) && hops.size() > 1) hops = rq::merge_diagonals(rq::push_x_forward(hops));
     std::vector<rq::HostOp> fused = hops.size() > 1 ? rq::fuse_algebraic(hops, nl, gmask) : hops;
     unsigned merged = 0;

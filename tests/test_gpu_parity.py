@@ -379,3 +379,36 @@ def test_distributed_entry_points_on_one_rank_form_blocks():
     assert st.blockSweeps > 0
     assert util.rel_err(out, o.state) < TOL["c64"]
     assert lib.rocsvDestroy(h) == 0
+
+
+@pytest.mark.parametrize("n", [14, 24])
+def test_plan_cache_replays_identical_circuits_only(n):
+    """rocsvxApplyCircuit keeps the launches of the last circuit: the identical gate list replays them (bit-identical state,
+    planCacheHits counts), anything else -- other matrices, other settings -- is planned afresh."""
+    gates = workloads.c2_random_unitary(n, 5, seed=30) + workloads.c1_ghz_random_layers(n, 3, seed=20)[n:]
+    other = workloads.c2_random_unitary(n, 5, seed=31) + workloads.c1_ghz_random_layers(n, 3, seed=20)[n:]
+    g = StateVector(n, "c64")
+    g.apply_circuit(gates); first = g.state()
+    assert g.stats().planCacheHits == 0
+    g.init(); g.apply_circuit(gates)
+    assert g.stats().planCacheHits == 1
+    assert np.array_equal(g.state(), first)                          # same launches, same bits
+    g.apply_circuit(gates)                                           # a third time on top: still the cached launches
+    assert g.stats().planCacheHits == 2
+    twice = g.state()
+    g.init(); g.apply_circuit(other)                                 # same shape, other matrices: a miss
+    assert g.stats().planCacheHits == 2
+    o = so.Oracle(n, "c64"); util.run_on_oracle(o, other)
+    assert util.rel_err(g.state(), o.state) < TOL["c64"]
+    g.init(); g.apply_circuit(gates); g.apply_circuit(gates)         # back to the first circuit: miss, then hit
+    assert g.stats().planCacheHits == 3
+    assert np.array_equal(g.state(), twice)
+    o = so.Oracle(n, "c64"); util.run_on_oracle(o, gates); util.run_on_oracle(o, gates)
+    assert util.rel_err(twice, o.state) < TOL["c64"]
+    g.set_tensor_core_blocks(n < 20)                                 # a setting changes the plan: miss
+    g.init(); g.apply_circuit(gates)
+    assert g.stats().planCacheHits == 3
+    assert util.rel_err(g.state(), first) < TOL["c64"]
+    d = StateVector(12, "c128"); q = workloads.c3_qft(12, seed=33)
+    d.apply_circuit(q); a = d.state(); d.init(); d.apply_circuit(q)
+    assert d.stats().planCacheHits == 1 and np.array_equal(d.state(), a)

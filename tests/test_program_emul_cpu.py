@@ -159,3 +159,31 @@ def test_rank_slices_with_diagonals_on_rank_bits():
         out, nsw, nmerged = run_emu("c128", n, gates, sl, 7, rank_bits=rb, rank=rank)
         assert nmerged >= nl - 4
         assert util.rel_err(out, want[rank << nl:(rank + 1) << nl]) < 1e-12
+        # the engine's path: rank bits resolved to constants before fusion (specialize_for_rank) -> purely local ops
+        out, nsw2, _ = run_emu("c128", n, gates, sl, 7, rank_bits=rb, rank=rank, flags=2)
+        assert util.rel_err(out, want[rank << nl:(rank + 1) << nl]) < 1e-12
+
+
+@pytest.mark.parametrize("prec,tol", [("c128", 1e-12), ("c64", 2e-6)])
+@pytest.mark.parametrize("n,rb,seed", [(9, 1, 1), (12, 2, 2), (13, 3, 3)])
+def test_rank_specialised_mixed_bags(prec, tol, n, rb, seed):
+    """Every gate family with controls / diagonal targets reaching into the rank bits, resolved per rank."""
+    nl = n - rb
+    rng = np.random.default_rng(seed)
+    gates = []
+    for g in util.random_gates(n, 260, seed=seed, maxk=3) + diag_heavy_gates(n, 120, seed):
+        name, targets, controls = g[0], list(g[1]), list(g[2])
+        diagonal = name in ("z", "s", "sdg", "t", "rz", "cz", "crz") or (name == "matrix" and np.count_nonzero(g[4] - np.diag(np.diagonal(g[4]))) == 0)
+        if name == "cz":
+            diagonal = True
+        if not diagonal and any(t >= nl for t in targets):
+            continue                                            # non-diagonal targets stay local (the planner exchanges first)
+        gates.append(g)
+    v = util.random_state(n, seed=seed)
+    want = oracle_run(n, gates, v)
+    for rank in range(1 << rb):
+        sl = v[rank << nl:(rank + 1) << nl]
+        out, _, _ = run_emu(prec, n, gates, sl, 6, rank_bits=rb, rank=rank, flags=2)
+        assert util.rel_err(out, want[rank << nl:(rank + 1) << nl]) < tol
+        out, _, _ = run_emu(prec, n, gates, sl, 6, rank_bits=rb, rank=rank)
+        assert util.rel_err(out, want[rank << nl:(rank + 1) << nl]) < tol

@@ -150,6 +150,7 @@ rocqStatus_t run_ops_with_blocks(H* h, rq_cplx* state, unsigned n, const std::ve
         t_launch += ms(t1, now());
         if (s != ROCQ_STATUS_SUCCESS) return s;
         h->stats.opsExecuted += st.ops.size();
+        if (h->recording && !h->recording->empty() && h->recording->back().block) h->recording->back().ops = (unsigned)st.ops.size();
     }
     return ROCQ_STATUS_SUCCESS;
 }
@@ -378,6 +379,7 @@ rocqStatus_t replay_cache(H* h, rq_cplx* state) {
         if (st.block) {
             RQ_CUDA(rq_launch_block_sweep(state, &st.bp, st.d_terms, st.tmap, h->stream), "block sweep launch (cached)");
             h->stats.blockSweeps++;
+            h->stats.opsExecuted += st.ops;
         } else {
             const int e = st.large ? rq_launch_sweep_large(state, reinterpret_cast<const rq_program_large*>(st.prog.data()), h->stream)
                                    : rq_launch_sweep_small(state, reinterpret_cast<const rq_program_small*>(st.prog.data()), h->stream);

@@ -253,9 +253,12 @@ rocqStatus_t rocsvxDistPlanExchange(unsigned numLocalQubits, int numRanks, int r
 /* Host-only plan of a whole distributed circuit (no GPU, no NCCL): the steps the engine would execute on numRanks
  * ranks -- "R" blocks of ops in PHYSICAL qubit positions (positions >= numLocalQubits are rank bits) and "X g.."
  * lines (exchange the listed rank bits with the top local bits) -- followed by the final logical->physical map "M ..".
- * mode bit 0: 0 = rocsvxApplyCircuit (look-ahead eviction), 1 = one rocsvApply* call per gate.  mode bit 1: also run
- * algebraic fusion + sweep partition on every "R" block, as the engine does per slice ("S T rowbits res: .." lines
- * precede the ops of each sweep).  canonicalize != 0 appends the steps that restore the identity layout. */
+ * mode bit 0: 0 = rocsvxApplyCircuit (ops that need a rank bit are deferred together with what depends on them while the
+ * rest of the circuit runs; exchanges evict the qubits whose next use is farthest), 1 = one rocsvApply* call per gate.
+ * mode bit 1: also run algebraic fusion + sweep partition on every "R" block, as the engine does per slice ("S T
+ * rowbits res: .." lines precede the ops of each sweep); with bit 2 the partition includes tensor-core blocks ("B p0..p5"
+ * lines).  mode bit 3: rocsvxApplyCircuit strictly in program order (the engine with ROCQ_DIST_INORDER=1).
+ * canonicalize != 0 appends the steps that restore the identity layout. */
 rocqStatus_t rocsvxDistPlanCircuit(unsigned totalNumQubits, int numRanks, const rocsvxGateOp* ops, size_t numOps, int mode,
                                    int canonicalize, unsigned* numExchanges, char* buf, size_t bufSize);
 

@@ -11,6 +11,8 @@
 //   * controls and diagonal gates on rank bits need no communication (the tile base carries the rank);
 //   * scalars (probability masses, expectation values) are exact all-gathers / fp64 all-reduces.
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -231,7 +233,8 @@ rocqStatus_t Dist::localize(rocsvInternalHandle* h, HostOp& op) {
 rocqStatus_t Dist::run_circuit(rocsvInternalHandle* h, std::vector<HostOp>& ops) {
     plan.steps.clear();
     plan.pending.clear();
-    if (!plan.add_circuit(ops)) return ROCQ_STATUS_FAILURE;
+    static const bool inorder = getenv("ROCQ_DIST_INORDER") != nullptr && atoi(getenv("ROCQ_DIST_INORDER")) != 0;
+    if (!(inorder ? plan.add_circuit_inorder(ops) : plan.add_circuit(ops))) return ROCQ_STATUS_FAILURE;
     plan.flush_pending();
     cudaEventRecord(h->ev0, h->stream);
     RQ_OK(execute_steps(h, *this));

@@ -100,9 +100,66 @@ struct DistPlanner {
         return true;
     }
 
-    // whole circuit: on a global non-diagonal target trade ALL rank bits for the local qubits whose next
-    // non-diagonal use is farthest (Belady), so one exchange is amortised over as many gates as possible
+    // Whole circuit with deferral ("cache blocking" over the rank bits).  An op whose non-diagonal targets sit on a rank bit
+    // is DEFERRED instead of forcing an exchange at once, and so is every later op that does not commute past a deferred
+    // one (same rule as plan_sweeps: a non-diagonal target may not meet any deferred qubit, a diagonal/control qubit may
+    // not meet a deferred non-diagonal target).  Everything else in the REST OF THE CIRCUIT runs in the current layout: in
+    // a brick circuit the dependency cone of a parked qubit widens by one qubit per layer, so the far side of the register
+    // advances many layers per residency.  Only when nothing more can run are rank bits traded -- for the local qubits
+    // whose next non-diagonal use among the deferred ops is farthest (Belady) -- and the deferred list is rescanned.
+    // A depth-20 brick circuit on 34 qubits needs 2 exchanges this way instead of 20.
     bool add_circuit(const std::vector<HostOp>& ops) {
+        const uint64_t gm = global_mask();
+        std::vector<size_t> remaining(ops.size());
+        for (size_t i = 0; i < ops.size(); ++i) remaining[i] = i;
+        while (!remaining.empty()) {
+            uint64_t blockedAny = 0, blockedND = 0;
+            std::vector<size_t> deferred;
+            for (size_t idx : remaining) {
+                const HostOp& o = ops[idx];
+                const uint64_t nd = o.nondiag(), dg = o.qubits() & ~nd;
+                const bool free_ = !((nd & (blockedAny | blockedND)) || (dg & blockedAny));
+                HostOp phys;
+                to_physical(o, phys);
+                if (free_ && !(phys.nondiag() & gm)) { pending.push_back(std::move(phys)); continue; }
+                deferred.push_back(idx);
+                blockedAny |= nd;
+                blockedND |= dg;
+            }
+            remaining.swap(deferred);
+            if (remaining.empty()) break;
+            // next non-diagonal use of every logical qubit among the deferred ops
+            const size_t never = remaining.size() + n_total;
+            std::vector<size_t> next(n_total, never);
+            for (size_t j = 0; j < remaining.size(); ++j) {
+                const uint64_t nd = ops[remaining[j]].nondiag();
+                for (unsigned q = 0; q < n_total; ++q)
+                    if (((nd >> q) & 1ull) && next[q] == never) next[q] = j;
+            }
+            for (unsigned q = 0; q < n_total; ++q) if (next[q] == never) next[q] = remaining.size() + q;
+            std::vector<unsigned> order(n_total);
+            for (unsigned q = 0; q < n_total; ++q) order[q] = q;
+            std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return next[a] > next[b]; });
+            std::vector<char> want_global(n_total, 0);
+            for (unsigned r = 0; r < n_global; ++r) want_global[order[r]] = 1;
+            std::vector<unsigned> bring, evict;
+            for (unsigned q = 0; q < n_total; ++q) {
+                const bool is_global = map[q] >= n_local;
+                if (is_global && !want_global[q]) bring.push_back(q);
+                if (!is_global && want_global[q]) evict.push_back(q);
+            }
+            if (bring.size() != evict.size() || bring.empty()) return false;
+            trade(bring, evict);
+            HostOp phys;
+            to_physical(ops[remaining[0]], phys);                     // progress: the oldest deferred op can run now
+            if (phys.nondiag() & gm) return false;
+        }
+        return true;
+    }
+
+    // whole circuit, strictly in program order: on a global non-diagonal target trade ALL rank bits for the local qubits whose next
+    // non-diagonal use is farthest (Belady), so one exchange is amortised over as many gates as possible
+    bool add_circuit_inorder(const std::vector<HostOp>& ops) {
         const uint64_t gm = global_mask();
         for (size_t i = 0; i < ops.size(); ++i) {
             HostOp phys;

@@ -1153,7 +1153,7 @@ rocqStatus_t rocsvxDistPlanCircuit(unsigned n, int numRanks, const rocsvxGateOp*
     if (s != ROCQ_STATUS_SUCCESS) return s;
     rq::DistPlanner P;
     P.reset(n, n - M);
-    if ((mode & 1) == 0) { if (!P.add_circuit(hops)) return ROCQ_STATUS_FAILURE; }
+    if ((mode & 1) == 0) { if (!((mode & 8) ? P.add_circuit_inorder(hops) : P.add_circuit(hops))) return ROCQ_STATUS_FAILURE; }
     else for (const HostOp& o : hops) if (!P.add_op(o)) return ROCQ_STATUS_NOT_IMPLEMENTED;
     P.flush_pending();
     if (canonicalize) P.canonicalize();

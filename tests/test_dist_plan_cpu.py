@@ -20,7 +20,7 @@ def _check(n, nranks, gates, mode):
 
 
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 8])
 @pytest.mark.parametrize("n", [8, 11, 14])
 def test_random_bags(n, nranks, mode):
     for seed in range(3):
@@ -34,6 +34,8 @@ def test_c4_and_qft(nranks):
     nx = _check(n, nranks, workloads.c4_global_layers(n, 8, seed=36, top=3), 0)
     nx1 = _check(n, nranks, workloads.c4_global_layers(n, 8, seed=36, top=3), 1)
     assert nx <= nx1                                                # look-ahead never needs more exchanges than per-gate
+    nx8 = _check(n, nranks, workloads.c4_global_layers(n, 8, seed=36, top=3), 8)    # strictly in program order
+    assert nx <= nx8
     _check(n, nranks, workloads.c3_qft(n, seed=33), 0)
     _check(n, nranks, workloads.c2_random_unitary(n, 6, seed=30), 0)
 
@@ -62,3 +64,18 @@ def test_distributed_slices_form_blocks_on_local_qubits_only(nranks):
         b = so.Oracle(n, "c128"); b.set_state(v); util.simulate_dist_plan(b, n - m, steps)
         assert util.rel_err(b.state, a.state) < 1e-11
     assert util.dist_plan.blocks > 0
+
+
+@pytest.mark.parametrize("nranks", [2, 8])
+def test_deferral_cuts_the_exchanges_of_a_brick_circuit(nranks):
+    """Every layer of configs[3] puts a dense gate on every qubit: in program order the parked qubits come back once per
+    layer; with deferral the far side of the register runs ahead and a handful of exchanges is enough."""
+    n, depth = 16, 12
+    gates = workloads.c4_global_layers(n, depth, seed=36, top=3)
+    nx_deferred = _check(n, nranks, gates, 0)
+    nx_inorder = _check(n, nranks, gates, 8)
+    assert nx_inorder >= depth - 1
+    assert nx_deferred <= 4 and nx_deferred * 3 <= nx_inorder
+    # canonicalize=False: the exchanges of the circuit proper
+    nx_raw, _, _ = util.dist_plan(n, nranks, gates, 0, canonicalize=False)
+    assert nx_raw <= 3

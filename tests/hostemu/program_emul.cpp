@@ -264,7 +264,8 @@ unsigned hostemu_precision_bytes(void) { return (unsigned)sizeof(rq_real); }
 
 // state: 2 * 2^n doubles (re, im interleaved), updated in place.  rankBits/rank: emulate the slice of one rank of a
 // distributed state (state then holds 2^(n - rankBits) amplitudes and ops may control / act diagonally on rank bits).
-// flags bit 0: skip merge_diagonals / push_x_forward, bit 1: resolve rank bits first (specialize_for_rank).  Returns 0, or a negative code naming the stage that failed.
+// flags bit 0: skip merge_diagonals / push_x_forward, bit 1: resolve rank bits first (specialize_for_rank),
+// bit 2: the mixed plan with 6-qubit blocks (*numMerged then returns the number of blocks).  Returns 0, or a negative code naming the stage that failed.
 int hostemu_run_circuit(unsigned n, unsigned tileBits, const rocsvxGateOp* ops, size_t numOps, double* state, unsigned rankBits,
                         unsigned rank, unsigned flags, unsigned* numSweeps, unsigned* numMerged) {
     std::vector<rq::HostOp> hops;
@@ -284,10 +285,57 @@ int hostemu_run_circuit(unsigned n, unsigned tileBits, const rocsvxGateOp* ops, 
     L.max_ops = sizeof(rq_program_large::ops) / sizeof(rq_tile_op);
     L.pool_cplx = sizeof(rq_program_large::pool) / sizeof(rq_cplx);
     L.never_resident = gmask;
-    const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(fused, nl, L);
-    if (numSweeps) *numSweeps = (unsigned)plans.size();
     static thread_local rq_program_large P;
     cd* st = reinterpret_cast<cd*>(state);
+    if (flags & 4u) {
+        // the mixed plan of the complex64 engine: 6-qubit blocks (their ops folded into ONE 64x64 matrix exactly as
+        // engine.cu does, applied here as a plain matrix product -- the tensor-core kernel's arithmetic is not modelled)
+        // interleaved with ordinary sweeps
+        rq::BlockLimits BL;
+        BL.min_cost = 0.0;
+        unsigned launches = 0, nblocks = 0;
+        for (const rq::MixedStep& ms : rq::plan_mixed(fused, nl, L, BL)) {
+            ++launches;
+            if (!ms.block) {
+                if (!rq::build_program(P, ms.sweep, fused, nl, 1, (uint64_t)rank << nl)) return -4;
+                if (!emulate_program(P, st)) return -5;
+                continue;
+            }
+            ++nblocks;
+            std::vector<cd> U(64 * 64, cd(0.0, 0.0));
+            for (unsigned c = 0; c < 64; ++c) U[c + 64u * c] = cd(1.0, 0.0);
+            for (int idx : ms.ops) {
+                if ((fused[idx].qubits() >> nl) != 0) return -6;      // a block may only hold local ops
+                rq::apply_small_columns(fused[idx], ms.blk, U.data(), 64);
+            }
+            uint64_t bm = 0;
+            for (unsigned p : ms.blk) bm |= 1ull << p;
+            std::vector<cd> in(64), out(64);
+            for (uint64_t base = 0; base < (1ull << nl); ++base) {
+                if (base & bm) continue;
+                for (unsigned j = 0; j < 64; ++j) {
+                    uint64_t off = 0;
+                    for (unsigned b = 0; b < 6; ++b) if ((j >> b) & 1u) off |= 1ull << ms.blk[b];
+                    in[j] = st[base | off];
+                }
+                for (unsigned r = 0; r < 64; ++r) {
+                    cd acc(0.0, 0.0);
+                    for (unsigned j = 0; j < 64; ++j) acc += U[r + 64u * j] * in[j];
+                    out[r] = acc;
+                }
+                for (unsigned j = 0; j < 64; ++j) {
+                    uint64_t off = 0;
+                    for (unsigned b = 0; b < 6; ++b) if ((j >> b) & 1u) off |= 1ull << ms.blk[b];
+                    st[base | off] = out[j];
+                }
+            }
+        }
+        if (numSweeps) *numSweeps = launches;
+        if (numMerged) *numMerged = nblocks;
+        return 0;
+    }
+    const std::vector<rq::SweepPlan> plans = rq::plan_sweeps(fused, nl, L);
+    if (numSweeps) *numSweeps = (unsigned)plans.size();
     for (const rq::SweepPlan& sp : plans) {
         if (!rq::build_program(P, sp, fused, nl, 1, (uint64_t)rank << nl)) return -4;
         if (!emulate_program(P, st)) return -5;

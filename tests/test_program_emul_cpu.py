@@ -187,3 +187,21 @@ def test_rank_specialised_mixed_bags(prec, tol, n, rb, seed):
         assert util.rel_err(out, want[rank << nl:(rank + 1) << nl]) < tol
         out, _, _ = run_emu(prec, n, gates, sl, 6, rank_bits=rb, rank=rank)
         assert util.rel_err(out, want[rank << nl:(rank + 1) << nl]) < tol
+
+
+@pytest.mark.parametrize("rb", [0, 1, 2])
+def test_mixed_plan_with_blocks_on_rank_slices(rb):
+    """The complex64 engine's plan on a slice: rank bits resolved, ops folded into 6-qubit blocks (applied here as plain
+    64x64 products) and ordinary sweeps.  Blocks must hold local ops only and the result must equal the oracle."""
+    n = 14 + rb
+    nl = n - rb
+    gates = [g for g in workloads.c4_global_layers(n, 5, seed=36, top=3) + workloads.c2_random_unitary(n, 3, seed=30)
+             + diag_heavy_gates(n, 60, 7) if g[0] in ("cz", "crz", "t", "rz") or (g[0] == "matrix" and len(g[1]) == 1 and len(g[2]) == 1)
+             or all(t < nl for t in g[1])]
+    v = util.random_state(n, seed=rb)
+    want = oracle_run(n, gates, v)
+    for rank in range(1 << rb):
+        sl = v[rank << nl:(rank + 1) << nl]
+        out, launches, nblocks = run_emu("c64", n, gates, sl, 0, rank_bits=rb, rank=rank, flags=2 | 4)
+        assert nblocks >= 3
+        assert util.rel_err(out, want[rank << nl:(rank + 1) << nl]) < 2e-6

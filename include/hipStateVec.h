@@ -171,6 +171,10 @@ typedef struct {
     const double* matrix;      /* ROCSVX_MATRIX only: HOST, column-major 2^k x 2^k, interleaved (re,im) doubles */
 } rocsvxGateOp;
 
+/* rocsvxApplyCircuit keeps the launches it planned for the most recent circuit: resubmitting the identical gate list (same
+ * gates, matrices, state buffer and settings; compared by a 128-bit hash of the whole list) replays them and skips fusion,
+ * planning and the host-side matrix products.  Every kernel runs again; only host work is saved.  ROCQ_PLAN_CACHE=0 turns
+ * it off. */
 rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits,
                                 const rocsvxGateOp* ops, size_t numOps);
 
@@ -214,10 +218,6 @@ typedef struct {
     uint64_t planCacheHits;    /* rocsvxApplyCircuit calls that replayed the recorded launches of an identical earlier call */
 } rocsvxStats;
 rocqStatus_t rocsvxGetStats(rocsvHandle_t handle, rocsvxStats* stats, int reset);
-/* rocsvxApplyCircuit keeps the launches it planned for the most recent circuit: resubmitting the identical gate list (same
- * gates, matrices, state buffer and settings; compared by a 128-bit hash of the whole list) replays them and skips fusion,
- * planning and the host-side matrix products.  Every kernel runs again; only host work is saved.  ROCQ_PLAN_CACHE=0 turns
- * it off. */
 
 /* Device timer on the handle's stream (CUDA events): Start records, Stop records, flushes nothing and
  * returns the elapsed milliseconds after synchronising on the stop event. */

@@ -234,7 +234,15 @@ rocqStatus_t Dist::run_circuit(rocsvInternalHandle* h, std::vector<HostOp>& ops)
     plan.steps.clear();
     plan.pending.clear();
     static const bool inorder = getenv("ROCQ_DIST_INORDER") != nullptr && atoi(getenv("ROCQ_DIST_INORDER")) != 0;
-    if (!(inorder ? plan.add_circuit_inorder(ops) : plan.add_circuit(ops))) return ROCQ_STATUS_FAILURE;
+    const std::vector<unsigned> saved = plan.map;      // nothing has been executed yet: a failed plan must not move the map
+    bool planned = !inorder && plan.add_circuit(ops);
+    if (!planned) {                                   // program order (also the fallback if the deferring planner gives up)
+        plan.map = saved;
+        plan.steps.clear();
+        plan.pending.clear();
+        planned = plan.add_circuit_inorder(ops);
+        if (!planned) { plan.map = saved; plan.steps.clear(); plan.pending.clear(); return ROCQ_STATUS_FAILURE; }
+    }
     plan.flush_pending();
     cudaEventRecord(h->ev0, h->stream);
     RQ_OK(execute_steps(h, *this));

@@ -360,6 +360,34 @@ def run_engine(args):
         except Exception as ex:                      # the baseline must not take the bench down
             cpu = {"value": None, "unit": "gates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 
+    # ---- second headline of BASELINE.json's metric: HBM GB/s per sweep on the 33-qubit complex128 QFT (configs[2]) ------
+    qft = None
+    if ngpus == 1 and not args.no_qft:
+        try:
+            from rocquantum_b200 import workloads as wl_
+            sv.close()                                           # 8.6 GB back before the 137 GB state
+            nq = env_int("ROCQ_BENCH_QFT_QUBITS", 33)
+            qg = wl_.c3_qft(nq, seed=33)
+            qarr, qkeep = capi.make_ops(qg)
+            q = StateVector(nq, "c128")
+            best = None
+            for rep in range(2):                                 # first pass: warm-up (plans, allocations)
+                q.init(); q.sync(); q.stats(reset=True)
+                assert q.lib.rocsvxApplyCircuit(q.h, q.d, nq, qarr, len(qg)) == 0
+                q.sync()
+                qs = q.stats()
+                best = qs
+            ms = best.lastSweepMs
+            gbs = 2.0 * (1 << nq) * 16 * best.sweeps / (ms * 1e-3) / 1e9
+            qft = {"workload": f"C3: {nq}-qubit QFT (benchmarks/run_benchmark.py:60-69) on a seeded basis state, complex128, {(1 << nq) * 16 / 1e9:.1f} GB state",
+                   "gates": len(qg), "device_ms": ms, "gates_per_s": len(qg) / (ms * 1e-3), "sweeps": int(best.sweeps),
+                   "GBps_per_sweep": gbs, "frac_of_measured_peak": gbs / peaks["hbm_gbs"], "frac_of_8TBs_spec": gbs / 8000.0,
+                   "norm": q.norm2(), "note": "H + merged controlled-phase ladders in register windows are FP64/issue-bound "
+                   "(DESIGN.md section 8); the swap sweeps of the same circuit run at the HBM roofline"}
+            q.close()
+        except Exception as ex:                                  # never take the bench line down
+            qft = {"error": str(ex)[:200]}
+
     line = {"metric": "gates_per_sec", "value": value, "unit": unit_for(n),
             "n_gpus": ngpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
@@ -373,6 +401,8 @@ def run_engine(args):
             "gpu_launches": int(st.kernelLaunches), "roofline": roofline, "cpu_baseline": cpu}
     if exchange:
         line["exchange"] = exchange
+    if qft:
+        line["qft33_c128"] = qft
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -385,6 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-qft", action="store_true", help="skip the 33-qubit complex128 QFT leg (137 GB)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

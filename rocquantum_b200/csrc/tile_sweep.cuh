@@ -180,13 +180,6 @@ __device__ __forceinline__ fixmasks load_fix(const rq_tile_op& o) {
     return F;
 }
 __device__ __forceinline__ uint32_t spread(uint32_t g, const rq_tile_op& o, const fixmasks& F) {
-#ifdef RQ_OLD_SPREAD
-    for (uint32_t f = 0; f < o.nfix; ++f) {
-        const uint32_t p = o.fix[f];
-        g = ((g >> p) << (p + 1)) | (g & ((1u << p) - 1u));
-    }
-    return g;
-#endif
 #pragma unroll
     for (uint32_t f = 0; f < 4; ++f) g += g & ~F.m[f];
     for (uint32_t f = 4; f < F.nfix; ++f) {
@@ -590,11 +583,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
     extern __shared__ __align__(128) unsigned char smem_raw[];
     rq_cplx* sm = reinterpret_cast<rq_cplx*>(smem_raw);
     __shared__ __align__(8) uint64_t bar_storage;
-#ifdef RQ_NO_GFAC
-    rq_cplx* gfac = nullptr;
-#else
     __shared__ __align__(16) rq_cplx gfac[RQ_MAX_DIAGP];        // per-tile factors of the RQ_OP_DIAGP ops
-#endif
 
     const uint32_t tid = threadIdx.x;
     const uint32_t T = prog.hdr.T, n = prog.hdr.n, rowbits = prog.hdr.rowbits;
@@ -626,12 +615,10 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
         for (uint32_t i = 0; i < T - rowbits; ++i) goff |= (uint64_t)((r >> i) & 1u) << prog.hdr.res[rowbits + i];
         bulk_g2s(smem_u32(sm) + r * rowbytes, gtile + goff, rowbytes, bar);
     }
-#ifndef RQ_NO_GFAC
     if (prog.hdr.ndiagp) {                                       // while the tile is in flight
         diagp_tile_factors(prog, gfac, tid, outer);
         __syncthreads();
     }
-#endif
     mbar_wait(bar, 0);
     swizzle_pass<SWZ>(sm, T, tid);
 

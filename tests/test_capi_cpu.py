@@ -79,3 +79,25 @@ def test_exchange_plan_validation():
     assert lib.rocsvxDistPlanExchange(4, 2, 0, capi.uarr([4]), capi.uarr([4]), 1, None, 0, C.byref(n)) == capi.INVALID_VALUE
     assert lib.rocsvxDistPlanExchange(4, 2, 0, capi.uarr([3]), capi.uarr([4]), 1, None, 0, C.byref(n)) == capi.SUCCESS
     assert n.value == 1
+
+
+def test_product_never_touches_the_oracle_or_the_test_interpreter():
+    """oracle/ and tests/hostemu are test infrastructure: nothing under rocquantum_b200/ or include/ imports, includes or
+    loads them (comments may cite them), and the engine libraries depend on CUDA + libc only."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    py = re.compile(r"^\s*(from|import)\s+(oracle|tests)\b", re.M)
+    cc = re.compile(r"#\s*include\s*[<\"][^>\"]*(oracle|hostemu)|dlopen\([^)]*(oracle|emul)", re.M)
+    for base in ("rocquantum_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(root, base)):
+            if "_obj" in dirpath or "__pycache__" in dirpath:
+                continue
+            for f in files:
+                txt = open(os.path.join(dirpath, f), errors="ignore").read() if f.endswith((".py", ".h", ".cuh", ".cu", ".cpp")) else ""
+                assert not (f.endswith(".py") and py.search(txt)), f
+                assert not (not f.endswith(".py") and cc.search(txt)), f
+    for prec in ("c64", "c128"):
+        out = subprocess.run(["ldd", capi.lib_path(prec)], capture_output=True, text=True).stdout
+        assert "oracle" not in out and "emul" not in out
+        assert "libcudart" in out

@@ -310,7 +310,10 @@ def run_engine(args):
         exchange = {"per_step": st.exchanges / args.steps, "ms_per_step": st.exchangeMs / args.steps,
                     "sent_bytes_per_rank_per_step": st.exchangeBytes / args.steps,
                     "send_GBps_per_rank": (st.exchangeBytes / 1e9) / (st.exchangeMs * 1e-3) if st.exchangeMs > 0 else None,
-                    "what": "k rank bits <-> top-k local bits, ncclSend/ncclRecv per peer + staging->slice copy; rank 0's figures"}
+                    "mover": "p2p" if os.environ.get("ROCQ_EXCHANGE", "")[:1] in ("p", "P") else "nccl",
+                    "planner": "program order" if os.environ.get("ROCQ_DIST_INORDER", "0") not in ("", "0") else "deferring",
+                    "what": "k rank bits <-> top-k local bits; mover nccl = ncclSend/ncclRecv per peer + staging->slice copy, "
+                            "p2p = in-place half-swap kernel over IPC-mapped peer slices between two stream barriers; rank 0's figures"}
     sweep_ms = max(0.0, dev_ms - st.exchangeMs) if ngpus > 1 else dev_ms
     avg_sweep_ms = sweep_ms / max(1, st.sweeps)
     achieved = sweep_bytes / (avg_sweep_ms * 1e-3) / 1e9 if avg_sweep_ms > 0 else 0.0

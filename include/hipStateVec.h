@@ -249,6 +249,12 @@ typedef struct { int32_t peer; uint64_t sendOffset; uint64_t recvOffset; uint64_
 rocqStatus_t rocsvxDistPlanExchange(unsigned numLocalQubits, int numRanks, int rank,
                                     const unsigned* localBits, const unsigned* globalBits, unsigned numPairs,
                                     rocsvxExchangeSeg* segs, size_t maxSegs, size_t* numSegs);
+/* The same exchange as the engine moves it with ROCQ_EXCHANGE=p2p (peer slices mapped through CUDA IPC): in-place swaps
+ * own[sendOffset + i] <-> peer's slice[recvOffset + i], i < count.  The two ranks of a pair split every run -- the lower
+ * rank swaps its first half, the higher rank the rest -- so each amplitude is moved by exactly one rank, nothing is staged. */
+rocqStatus_t rocsvxDistPlanPeerSwap(unsigned numLocalQubits, int numRanks, int rank,
+                                    const unsigned* localBits, const unsigned* globalBits, unsigned numPairs,
+                                    rocsvxExchangeSeg* segs, size_t maxSegs, size_t* numSegs);
 
 /* Host-only plan of a whole distributed circuit (no GPU, no NCCL): the steps the engine would execute on numRanks
  * ranks -- "R" blocks of ops in PHYSICAL qubit positions (positions >= numLocalQubits are rank bits) and "X g.."

@@ -101,6 +101,7 @@ PROTOTYPES = {
     "rocsvxDistGetInfo": [_h, C.POINTER(C.c_int), C.POINTER(C.c_int), _up, C.POINTER(_p)],
     "rocsvxDistPlanCircuit": [_u, C.c_int, C.POINTER(GateOp), _sz, C.c_int, C.c_int, _up, C.c_char_p, _sz],
     "rocsvxDistPlanExchange": [_u, C.c_int, C.c_int, _up, _up, _u, C.POINTER(ExchangeSeg), _sz, C.POINTER(_sz)],
+    "rocsvxDistPlanPeerSwap": [_u, C.c_int, C.c_int, _up, _up, _u, C.POINTER(ExchangeSeg), _sz, C.POINTER(_sz)],
 }
 SYMBOLS = sorted(PROTOTYPES)
 REFERENCE_SYMBOLS = sorted(s for s in PROTOTYPES if not s.startswith("rocsvx"))   # the 42 of the reference header

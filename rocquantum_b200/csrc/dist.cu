@@ -10,6 +10,8 @@
 //     the preceding fused sweep), chosen by farthest-next-use when a whole circuit is known;
 //   * controls and diagonal gates on rank bits need no communication (the tile base carries the rank);
 //   * scalars (probability masses, expectation values) are exact all-gathers / fp64 all-reduces.
+// Two data movers for the exchange: NCCL send/recv into a staging buffer + copy (default), and -- behind
+// ROCQ_EXCHANGE=p2p -- an in-place swap kernel over IPC-mapped peer slices (peer_swap_kernel below).
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -107,6 +109,72 @@ size_t plan_exchange(unsigned n_local, int nranks, int rank, const unsigned* loc
     return count;
 }
 
+// Peer-memory form of the same exchange.  Every segment of plan_exchange is one half of an in-place swap between this
+// rank's run and the peer's matching run.  The two ranks split each swap -- the lower rank moves the first half of the run,
+// the higher rank the rest -- so every element is read and written by exactly one of them and nothing is staged.  Output
+// segment: {peer, sendOffset = offset in OWN slice, recvOffset = offset in the PEER's slice, count}; empty halves are
+// dropped.  Pure host code (tests/test_dist_cpu.py re-plays it on numpy shards).
+size_t plan_peer_swap(unsigned n_local, int nranks, int rank, const unsigned* local_bits, const unsigned* global_bits,
+                      unsigned npairs, rocsvxExchangeSeg* out, size_t maxsegs) {
+    const size_t ns = plan_exchange(n_local, nranks, rank, local_bits, global_bits, npairs, nullptr, 0);
+    std::vector<rocsvxExchangeSeg> mine(ns), theirs(ns);
+    plan_exchange(n_local, nranks, rank, local_bits, global_bits, npairs, mine.data(), ns);
+    std::vector<char> done(ns, 0);
+    size_t count = 0;
+    for (size_t i = 0; i < ns; ++i) {
+        if (done[i]) continue;
+        const int peer = mine[i].peer;
+        plan_exchange(n_local, nranks, peer, local_bits, global_bits, npairs, theirs.data(), ns);   // same segment count on every rank
+        size_t j = 0;
+        for (size_t m = i; m < ns; ++m) {                      // the m-th run towards `peer` pairs with the peer's m-th run towards us
+            if (mine[m].peer != peer) continue;
+            while (j < ns && theirs[j].peer != rank) ++j;
+            if (j == ns) return 0;                              // plans disagree: cannot happen for valid bit lists
+            done[m] = 1;
+            const uint64_t half = mine[m].count / 2;
+            const bool low = rank < peer;
+            const uint64_t skip = low ? 0 : half, len = low ? half : mine[m].count - half;
+            if (len) {
+                if (out && count < maxsegs) out[count] = rocsvxExchangeSeg{peer, mine[m].sendOffset + skip, theirs[j].sendOffset + skip, len};
+                ++count;
+            }
+            ++j;
+        }
+    }
+    return count;
+}
+
+// swap local[i] <-> peer[i]: 16-byte (or one-amplitude) elements, U independent loads of each side in flight per thread
+#define RQ_PEER_MAXSEG 15
+struct PeerSwapArgs {
+    void* local[RQ_PEER_MAXSEG];
+    void* peer[RQ_PEER_MAXSEG];
+    uint64_t count[RQ_PEER_MAXSEG];          // elements of type V
+};
+template <typename V>
+__global__ void __launch_bounds__(256) peer_swap_kernel(const PeerSwapArgs a) {
+    constexpr int U = 4;
+    V* __restrict__ L = static_cast<V*>(a.local[blockIdx.y]);
+    V* __restrict__ P = static_cast<V*>(a.peer[blockIdx.y]);
+    const uint64_t n = a.count[blockIdx.y];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        V p[U], l[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) p[u] = P[i + u * stride];          // remote reads first: the long-latency side
+#pragma unroll
+        for (int u = 0; u < U; ++u) l[u] = L[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { P[i + u * stride] = l[u]; L[i + u * stride] = p[u]; }
+    }
+    for (; i < n; i += stride) {
+        const V p = P[i], l = L[i];
+        P[i] = l;
+        L[i] = p;
+    }
+}
+
 // ---- lifecycle -------------------------------------------------------------------------------------------
 rocqStatus_t Dist::init(rocsvInternalHandle* h, int rank_, int nranks_, const void* id128) {
     (void)h;
@@ -129,7 +197,58 @@ rocqStatus_t Dist::init(rocsvInternalHandle* h, int rank_, int nranks_, const vo
     return ROCQ_STATUS_SUCCESS;
 }
 
-void Dist::shutdown() {
+// ---- peer slices through CUDA IPC (ROCQ_EXCHANGE=p2p) ------------------------------------------------------------------
+static bool want_p2p() {
+    const char* e = getenv("ROCQ_EXCHANGE");
+    return e && (e[0] == 'p' || e[0] == 'P');
+}
+// stream-ordered barrier over all ranks: nobody's stream passes it before everybody's stream has reached it
+static rocqStatus_t stream_barrier(rocsvInternalHandle* h, Dist& d) {
+    int* flag = reinterpret_cast<int*>(d.d_gather + 40);               // a word neither the all-gathers nor allreduce_sum use
+    RQ_NCCL(g_nccl.AllReduce(flag, flag, 1, ncclInt, ncclMax, (ncclComm_t)d.comm, h->stream));
+    return ROCQ_STATUS_SUCCESS;
+}
+static void close_peers(rocsvInternalHandle* h, Dist& d) {
+    if (d.peer_state.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < d.nranks; ++r)
+        if (r != d.rank && d.peer_state[r]) cudaIpcCloseMemHandle(d.peer_state[r]);
+    d.peer_state.clear();
+    if (d.comm && stream_barrier(h, d) == ROCQ_STATUS_SUCCESS) cudaStreamSynchronize(h->stream);   // owners free only after every importer closed
+}
+// map every rank's slice; all ranks agree on the outcome (one rank without peer access sends everybody back to NCCL)
+static rocqStatus_t open_peers(rocsvInternalHandle* h, Dist& d) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t mine;
+    int ok = cudaIpcGetMemHandle(&mine, h->d_state) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof mine); }
+    uint64_t* send = d.d_gather;
+    uint64_t* recv = d.d_gather + 64;                                  // 8 * nranks words = 64 bytes per rank
+    RQ_CU(cudaMemcpyAsync(send, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    RQ_NCCL(g_nccl.AllGather(send, recv, sizeof mine, ncclChar, (ncclComm_t)d.comm, h->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)d.nranks);
+    RQ_OK(rq_engine_fetch(h, recv, all.data(), all.size() * sizeof mine));
+    std::vector<void*> ptrs((size_t)d.nranks, nullptr);
+    ptrs[d.rank] = h->d_state;
+    for (int r = 0; r < d.nranks && ok; ++r) {
+        if (r == d.rank) continue;
+        if (cudaIpcOpenMemHandle(&ptrs[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ptrs[r] = nullptr; ok = 0; }
+    }
+    double agree = ok ? 0.0 : 1.0;                                      // number of ranks that failed
+    RQ_OK(d.allreduce_sum(h, &agree, 1));
+    if (agree != 0.0) {
+        for (int r = 0; r < d.nranks; ++r) if (r != d.rank && ptrs[r]) cudaIpcCloseMemHandle(ptrs[r]);
+        if (d.rank == 0) fprintf(stderr, "hipStateVec(B200): ROCQ_EXCHANGE=p2p: peer slices cannot be mapped on %d rank(s); using NCCL send/recv\n", (int)agree);
+        return ROCQ_STATUS_SUCCESS;
+    }
+    d.peer_state.swap(ptrs);
+    return ROCQ_STATUS_SUCCESS;
+}
+
+void Dist::shutdown(rocsvInternalHandle* h) {
+    close_peers(h, *this);
+    for (auto& ev : timed) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    timed.clear();
     if (staging) { cudaFree(staging); staging = nullptr; }
     if (d_gather) { cudaFree(d_gather); d_gather = nullptr; }
     if (comm) { g_nccl.CommDestroy((ncclComm_t)comm); comm = nullptr; }
@@ -143,6 +262,7 @@ rocqStatus_t Dist::allocate(rocsvInternalHandle* h, unsigned total_qubits) {
     while ((1 << M) < nranks) ++M;
     if (total_qubits < M || total_qubits > 60) return ROCQ_STATUS_INVALID_VALUE;
     n_total = 0;                                                      // inactive while (re)allocating
+    close_peers(h, *this);                                            // importers unmap before any owner frees its slice
     const rocqStatus_t s = rocsvAllocateState(h, total_qubits - M, nullptr, 1);
     if (s != ROCQ_STATUS_SUCCESS) return s;
     n_global = M;
@@ -154,6 +274,7 @@ rocqStatus_t Dist::allocate(rocsvInternalHandle* h, unsigned total_qubits) {
         const uint64_t slice = 1ull << n_local;
         staging_amps = std::min<uint64_t>(slice, 1ull << 25) * (uint64_t)(nranks - 1);     // <= 256 MiB (c64) per peer
         if (cudaMalloc(&staging, staging_amps * sizeof(rq_cplx)) != cudaSuccess) { cudaGetLastError(); return ROCQ_STATUS_ALLOCATION_FAILED; }
+        if (want_p2p()) RQ_OK(open_peers(h, *this));
     }
     return ROCQ_STATUS_SUCCESS;
 }
@@ -169,6 +290,19 @@ rocqStatus_t Dist::initialize(rocsvInternalHandle* h) {
 }
 
 // ---- the exchange -------------------------------------------------------------------------------------------
+// Event pairs wait for rocsvxGetStats; a caller that never asks for stats must not accumulate them without bound.
+static void note_exchange(rocsvInternalHandle* h, Dist& d, cudaEvent_t e0, cudaEvent_t e1) {
+    if (d.timed.size() >= 256) {                       // the oldest pair finished long ago: fold it in now
+        const auto ev = d.timed.front();
+        float ms = 0.f;
+        cudaEventSynchronize(ev.second);
+        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) h->stats.exchangeMs += (double)ms;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+        d.timed.erase(d.timed.begin());
+    }
+    d.timed.push_back({e0, e1});                       // resolved (and destroyed) by rocsvxGetStats
+}
 // move the data of one EXCHANGE step: the k rank bits gpos[] trade places with the top-k local bits
 static rocqStatus_t exchange_data(rocsvInternalHandle* h, Dist& d, const std::vector<unsigned>& gpos) {
     const unsigned k = (unsigned)gpos.size();
@@ -197,7 +331,7 @@ static rocqStatus_t exchange_data(rocsvInternalHandle* h, Dist& d, const std::ve
                                   cudaMemcpyDeviceToDevice, h->stream));
     }
     RQ_CU(cudaEventRecord(e1, h->stream));
-    d.timed.push_back({e0, e1});                       // resolved (and destroyed) by rocsvxGetStats
+    note_exchange(h, d, e0, e1);
     d.exchanges++;
     d.exchanged_amps += run * ns;
     h->stats.exchanges++;
@@ -205,10 +339,59 @@ static rocqStatus_t exchange_data(rocsvInternalHandle* h, Dist& d, const std::ve
     return ROCQ_STATUS_SUCCESS;
 }
 
+// The same EXCHANGE step over peer memory: after a stream-ordered barrier (every rank has finished the sweeps before the
+// exchange) each rank swaps its halves of the runs in place against the peers' slices -- reads and writes cross NVLink in
+// both directions at once, no staging pass -- and a second barrier keeps the next sweep behind the peers' writes.
+static rocqStatus_t exchange_data_p2p(rocsvInternalHandle* h, Dist& d, const std::vector<unsigned>& gpos) {
+    const unsigned k = (unsigned)gpos.size();
+    std::vector<unsigned> lpos(k);
+    for (unsigned i = 0; i < k; ++i) lpos[i] = d.n_local - k + i;
+    std::vector<rocsvxExchangeSeg> segs((size_t)(1u << k));
+    const size_t ns = plan_peer_swap(d.n_local, d.nranks, d.rank, lpos.data(), gpos.data(), k, segs.data(), segs.size());
+    const uint64_t run = 1ull << (d.n_local - k);
+    PeerSwapArgs a{};
+    const uint64_t per16 = 16 / sizeof(rq_cplx);                       // amplitudes per 16-byte element
+    const bool vec = (run / 2) % per16 == 0 && (run - run / 2) % per16 == 0;   // both halves start and end on 16-byte boundaries
+    const uint64_t per = vec ? per16 : 1;
+    uint64_t longest = 0;
+    for (size_t i = 0; i < ns; ++i) {
+        a.local[i] = h->d_state + segs[i].sendOffset;
+        a.peer[i] = static_cast<rq_cplx*>(d.peer_state[segs[i].peer]) + segs[i].recvOffset;
+        a.count[i] = segs[i].count / per;
+        longest = std::max(longest, a.count[i]);
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    RQ_CU(cudaEventCreate(&e0));
+    RQ_CU(cudaEventCreate(&e1));
+    RQ_CU(cudaEventRecord(e0, h->stream));
+    RQ_OK(stream_barrier(h, d));
+    if (ns) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const uint64_t want = (longest + 256 * 4 - 1) / (256 * 4);      // one pass of the unrolled loop per thread at least
+        const unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)(4 * sms + ns - 1) / ns));
+        const dim3 grid(gx, (unsigned)ns);
+        if (vec) peer_swap_kernel<uint4><<<grid, 256, 0, h->stream>>>(a);
+        else peer_swap_kernel<rq_cplx><<<grid, 256, 0, h->stream>>>(a);
+        RQ_CU(cudaGetLastError());
+        h->stats.kernelLaunches++;
+    }
+    RQ_OK(stream_barrier(h, d));
+    RQ_CU(cudaEventRecord(e1, h->stream));
+    note_exchange(h, d, e0, e1);
+    d.exchanges++;
+    d.exchanged_amps += run * ((1ull << k) - 1);
+    h->stats.exchanges++;
+    h->stats.exchangeBytes += run * ((1ull << k) - 1) * sizeof(rq_cplx);     // amplitudes that leave this slice, as in the NCCL path
+    return ROCQ_STATUS_SUCCESS;
+}
+
 // execute and clear the planner's steps
 static rocqStatus_t execute_steps(rocsvInternalHandle* h, Dist& d) {
     for (DistStep& st : d.plan.steps) {
         if (st.kind == DistStep::RUN) RQ_OK(rq_engine_run(h, h->d_state, d.n_local, st.ops, true));
+        else if (!d.peer_state.empty() && st.gpos.size() <= 4 && !st.gpos.empty()) RQ_OK(exchange_data_p2p(h, d, st.gpos));
         else RQ_OK(exchange_data(h, d, st.gpos));
     }
     d.plan.steps.clear();
@@ -463,6 +646,16 @@ rocqStatus_t rocsvxDistPlanExchange(unsigned numLocalQubits, int numRanks, int r
         seenG |= 1ull << globalBits[i];
     }
     const size_t c = rq::plan_exchange(numLocalQubits, numRanks, rank, localBits, globalBits, numPairs, segs, maxSegs);
+    if (numSegs) *numSegs = c;
+    return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t rocsvxDistPlanPeerSwap(unsigned numLocalQubits, int numRanks, int rank, const unsigned* localBits,
+                                    const unsigned* globalBits, unsigned numPairs, rocsvxExchangeSeg* segs, size_t maxSegs,
+                                    size_t* numSegs) {
+    size_t c = 0;
+    const rocqStatus_t s = rocsvxDistPlanExchange(numLocalQubits, numRanks, rank, localBits, globalBits, numPairs, nullptr, 0, &c);   // argument checks
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    c = rq::plan_peer_swap(numLocalQubits, numRanks, rank, localBits, globalBits, numPairs, segs, maxSegs);
     if (numSegs) *numSegs = c;
     return ROCQ_STATUS_SUCCESS;
 }

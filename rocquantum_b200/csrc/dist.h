@@ -30,6 +30,7 @@ struct Dist {
     uint64_t exchanges = 0;          // statistics
     uint64_t exchanged_amps = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;   // event pairs around exchanges not yet folded into stats
+    std::vector<void*> peer_state;   // ROCQ_EXCHANGE=p2p: every rank's slice mapped through CUDA IPC ([rank] = own pointer); else empty
 
     bool active() const { return inited && n_total > 0; }
     unsigned num_local() const { return n_local; }
@@ -40,7 +41,7 @@ struct Dist {
     rocqStatus_t init(rocsvInternalHandle* h, int rank_, int nranks_, const void* id128);
     rocqStatus_t allocate(rocsvInternalHandle* h, unsigned total_qubits);
     rocqStatus_t initialize(rocsvInternalHandle* h);
-    void shutdown();
+    void shutdown(rocsvInternalHandle* h);
 
     // rewrite op from logical to physical positions, exchanging slices first if a non-diagonal target is global
     rocqStatus_t localize(rocsvInternalHandle* h, HostOp& op);
@@ -56,5 +57,8 @@ struct Dist {
 // pure host: segments of a global<->local index-bit exchange (see include/hipStateVec.h)
 size_t plan_exchange(unsigned n_local, int nranks, int rank, const unsigned* local_bits, const unsigned* global_bits,
                      unsigned npairs, rocsvxExchangeSeg* segs, size_t maxsegs);
+// the same exchange as in-place half-swaps against peer memory (recvOffset = offset in the peer's slice)
+size_t plan_peer_swap(unsigned n_local, int nranks, int rank, const unsigned* local_bits, const unsigned* global_bits,
+                      unsigned npairs, rocsvxExchangeSeg* segs, size_t maxsegs);
 
 }  // namespace rq

@@ -536,7 +536,7 @@ rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
 rocqStatus_t rocsvDestroy(rocsvHandle_t h) {
     if (!h) return ROCQ_STATUS_SUCCESS;                   // hipStateVec.cpp:203-210
     if (h->stream) { flush(h); cudaStreamSynchronize(h->stream); }
-    h->dist.shutdown();
+    h->dist.shutdown(h);
     rocsvFreeState(h);
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->d_upartials) cudaFree(h->d_upartials);

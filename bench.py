@@ -90,11 +90,53 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms use every host core they may run on and
+    report how many that is."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        gomp = C.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(int(n))
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return int(os.environ.get("OMP_NUM_THREADS", n))
+
+
+def compiled_reference_sample(n_run, n, q1, q2, n1, n2, repeats=2):
+    """The reference's OWN code (hipStateVec.cpp + *_kernels.hip compiled unmodified under the host HIP shim,
+    oracle/_ref) on the host cores.  It defines no arbitrary-matrix entry point, so the workload's Haar gates
+    cannot run on it; every one-qubit gate of the reference goes through the same generic 2x2 kernel
+    (hipStateVec.cpp:100-140), so rocsvApplyRy stands for a Haar one-qubit gate at equal cost, and rocsvApplyCNOT --
+    the cheapest two-qubit pass it has -- stands for a Haar two-qubit gate (a lower bound on its time)."""
+    from oracle import sv_oracle as so
+    if not so.ref_available("c64"):
+        return None
+    r = so.RefLib("c64")
+    try:
+        r.allocate(n_run)
+        r.gate("ry", q1, 0.3); r.gate("cnot", q2[0], q2[1])           # warm-up: page in the state
+        t1 = t2 = 0.0
+        for _ in range(repeats):
+            t = time.perf_counter(); assert r.gate("ry", q1, 0.7) == 0; t1 += time.perf_counter() - t
+            t = time.perf_counter(); assert r.gate("cnot", q2[0], q2[1]) == 0; t2 += time.perf_counter() - t
+    finally:
+        r.close()
+    scale = 2.0 ** (n - n_run) / repeats
+    t1, t2 = t1 * scale, t2 * scale
+    return {"value": (n1 + n2) / (n1 * t1 + n2 * t2) * 2.0 ** (n - 30), "unit": unit_for(n), "kind": "reference",
+            "s_per_1q_gate": t1, "s_per_2q_gate": t2,
+            "sample": (f"oracle/_ref (the reference's sources under the host HIP shim, OpenMP): rocsvApplyRy on qubit {q1} and "
+                       f"rocsvApplyCNOT on qubits {list(q2)} at {n_run} qubits, {repeats} timed calls each"
+                       + ("" if n_run == n else f", extrapolated x2^{n - n_run} to {n} qubits")
+                       + "; stand-ins of equal (1q) / lower (2q) cost for the workload's Haar gates, which the reference cannot apply")}
+
+
 def cpu_sample(n, gates, prec="c64", repeats=1):
     """Time the oracle port (one full pass per gate, like the reference's one-kernel-per-gate path) on a few
     gates of the workload.  Returns (seconds per 1q gate, seconds per 2q gate, cores)."""
     from oracle import sv_oracle as so
     from tests import util
+    cores = use_all_host_threads()
     o = so.Oracle(n, prec)
     one = [g for g in gates if len(g[1]) == 1][:3]
     two = [g for g in gates if len(g[1]) == 2][:2]
@@ -103,7 +145,7 @@ def cpu_sample(n, gates, prec="c64", repeats=1):
     for _ in range(repeats):
         t = time.perf_counter(); util.run_on_oracle(o, one); t1 += (time.perf_counter() - t) / len(one)
         t = time.perf_counter(); util.run_on_oracle(o, two); t2 += (time.perf_counter() - t) / len(two)
-    return t1 / repeats, t2 / repeats, os.cpu_count()
+    return t1 / repeats, t2 / repeats, cores
 
 
 def host_ram_gb():
@@ -141,6 +183,7 @@ def run_reference(args):
         return
     from oracle import sv_oracle as so
     so.build(ref=False)
+    cores = use_all_host_threads()
     n, gates, wl = workload_for(args.gpus)
     n_run = n
     need_gb = (1 << n) * 8 / 1e9 * 1.3
@@ -166,12 +209,17 @@ def run_reference(args):
     t2 = statistics.mean(x[1] for x in times) * 2.0 ** (n - n_run)
     circuit_s = n1 * t1 + n2 * t2
     value = len(gates) / circuit_s * 2.0 ** (n - 30)
+    del o
+    compiled = compiled_reference_sample(n_run, n, one[0][1][0], tuple(two[0][1]), n1, n2)
+    if compiled:
+        compiled["cores"] = cores
     sample = (f"1 one-qubit + 1 two-qubit Haar gate of the workload per step at {n_run} qubits"
               + ("" if n_run == n else f", extrapolated x2^{n - n_run} to {n} qubits") + "; one full pass per gate (no fusion), OpenMP")
     line = {"impl": "reference", "metric": "gates_per_sec", "value": value, "unit": unit_for(n), "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": circuit_s * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "c64", "data": "synthetic", "config": {"workload": wl},
-            "cpu_baseline": {"value": value, "unit": unit_for(n), "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": unit_for(n), "cores": cores, "kind": "port", "sample": sample,
+                             "compiled_reference": compiled},
             "e2e": {"value": value, "unit": unit_for(n), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -360,6 +408,10 @@ def run_engine(args):
                    "sample": f"3 one-qubit + 2 two-qubit Haar gates of the same circuit at {n_cpu} qubits"
                              + ("" if n_cpu == n else f" (extrapolated x2^{n - n_cpu})") + ", one full pass per gate, OpenMP over all cores; "
                              "'port' because the reference never defines rocsvApplyMatrix (SURVEY.md section 0.1)"}
+            two = [g for g in gates if len(g[1]) == 2][0]
+            cpu["compiled_reference"] = compiled_reference_sample(n_cpu, n, 0, tuple(two[1]), n1, ngates - n1, repeats=1)
+            if cpu["compiled_reference"]:
+                cpu["compiled_reference"]["cores"] = cores
         except Exception as ex:                      # the baseline must not take the bench down
             cpu = {"value": None, "unit": "gates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 

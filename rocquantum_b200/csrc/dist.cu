@@ -580,14 +580,10 @@ rocqStatus_t Dist::sample(rocsvInternalHandle* h, const unsigned* measured, unsi
     std::vector<uint64_t> idx(shots);
     RQ_CU(cudaMemcpyAsync(idx.data(), d_idx, (size_t)shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
     RQ_CU(cudaStreamSynchronize(h->stream));
-    for (unsigned s = 0; s < shots; ++s) {
-        uint64_t bits = 0;
-        if (idx[s] != ~0ull) {
-            const uint64_t phys = ((uint64_t)rank << n_local) | idx[s];
-            for (unsigned j = 0; j < nm; ++j) bits |= ((phys >> plan.map[measured[j]]) & 1ull) << j;
-        }
-        idx[s] = bits;
-    }
+    std::vector<unsigned> where(nm);                                        // physical position of every measured qubit
+    for (unsigned j = 0; j < nm; ++j) where[j] = plan.map[measured[j]];
+    const BitGather gather(where.data(), nm);
+    for (unsigned s = 0; s < shots; ++s) idx[s] = idx[s] != ~0ull ? gather(((uint64_t)rank << n_local) | idx[s]) : 0ull;
     if (nranks > 1) {                                                       // exactly one rank owns each shot: sum = gather
         RQ_CU(cudaMemcpyAsync(d_idx, idx.data(), (size_t)shots * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
         RQ_NCCL(g_nccl.AllReduce(d_idx, d_idx, shots, ncclUint64, ncclSum, (ncclComm_t)comm, h->stream));

@@ -940,11 +940,8 @@ rocqStatus_t rocsvSample(rocsvHandle_t h, rocComplex* d, unsigned n, const unsig
     RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
     cudaFreeAsync(d_hi, h->stream);
     cudaFreeAsync(d_idx, h->stream);
-    for (unsigned sidx = 0; sidx < numShots; ++sidx) {
-        uint64_t bits = 0;
-        for (unsigned j = 0; j < nm; ++j) bits |= ((idx[sidx] >> measured[j]) & 1ull) << j;
-        h_results[sidx] = bits;
-    }
+    const rq::BitGather gather(measured, nm);
+    for (unsigned sidx = 0; sidx < numShots; ++sidx) h_results[sidx] = gather(idx[sidx]);
     return ROCQ_STATUS_SUCCESS;
 }
 

@@ -1140,4 +1140,26 @@ inline std::string dump_plan(const std::vector<SweepPlan>& plans, const std::vec
     return s;
 }
 
+// ---- sampled basis indices -> result words ---------------------------------------------------------------------------
+// Bit j of a result word is bit measured[j] of the sampled basis index (hipStateVec.h:427-445).  Maximal runs
+// measured[j + 1] == measured[j] + 1 move as ONE shifted field, so the usual request "every qubit, in order" costs a single
+// mask per shot instead of one step per bit (a million 28-bit shots: 28 M steps on the host otherwise).
+struct BitGather {
+    struct Field { unsigned src, dst; uint64_t mask; };
+    std::vector<Field> fields;
+    BitGather(const unsigned* measured, unsigned nm) {
+        for (unsigned j = 0; j < nm;) {
+            unsigned len = 1;
+            while (j + len < nm && measured[j + len] == measured[j] + len) ++len;
+            fields.push_back(Field{measured[j], j, len >= 64 ? ~0ull : ((1ull << len) - 1ull)});
+            j += len;
+        }
+    }
+    uint64_t operator()(uint64_t idx) const {
+        uint64_t bits = 0;
+        for (const Field& f : fields) bits |= ((idx >> f.src) & f.mask) << f.dst;
+        return bits;
+    }
+};
+
 }  // namespace rq

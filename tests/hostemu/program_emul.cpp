@@ -343,4 +343,10 @@ int hostemu_run_circuit(unsigned n, unsigned tileBits, const rocsvxGateOp* ops, 
     return 0;
 }
 
+// rq::BitGather (host_ops.h) as rocsvSample uses it: out[s] bit j = bit measured[j] of idx[s]
+void hostemu_gather_bits(const uint64_t* idx, size_t shots, const unsigned* measured, unsigned nm, uint64_t* out) {
+    const rq::BitGather gather(measured, nm);
+    for (size_t s = 0; s < shots; ++s) out[s] = gather(idx[s]);
+}
+
 }  // extern "C"

@@ -205,3 +205,30 @@ def test_mixed_plan_with_blocks_on_rank_slices(rb):
         out, launches, nblocks = run_emu("c64", n, gates, sl, 0, rank_bits=rb, rank=rank, flags=2 | 4)
         assert nblocks >= 3
         assert util.rel_err(out, want[rank << nl:(rank + 1) << nl]) < 2e-6
+
+
+def test_shot_bit_gather_matches_the_per_bit_definition():
+    """rocsvSample's index -> result-word mapping (rq::BitGather, host_ops.h): bit j = bit measured[j] of the index
+    (hipStateVec.h:427-445), whatever runs the measured list happens to contain."""
+    lib = emu("c64")
+    lib.hostemu_gather_bits.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint), C.c_uint, C.c_void_p]
+    lib.hostemu_gather_bits.restype = None
+    rng = np.random.default_rng(7)
+    idx = rng.integers(0, 1 << 63, size=4096, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=4096, dtype=np.uint64)
+    idx[:4] = [0, 2**64 - 1, 1, 1 << 63]
+    cases = [[], [0], [63], list(range(28)), list(range(64)), list(range(63, -1, -1)), [5, 6, 7, 2, 3, 40, 41, 42, 43, 0],
+             [3, 3, 4, 4], [1, 0, 1, 2, 3], list(range(10, 40)) + list(range(0, 10)), [62, 63, 0, 1]]
+    for _ in range(40):
+        nm = int(rng.integers(1, 65))
+        cases.append([int(q) for q in rng.integers(0, 64, size=nm)])                    # arbitrary, duplicates allowed
+        start = int(rng.integers(0, 64 - nm + 1))
+        perm = list(range(start, start + nm))
+        cut = int(rng.integers(0, nm))
+        cases.append(perm[cut:] + perm[:cut])                                            # two long runs
+    for measured in cases:
+        out = np.zeros(idx.size, dtype=np.uint64)
+        lib.hostemu_gather_bits(idx.ctypes.data, idx.size, capi.uarr(measured) if measured else None, len(measured), out.ctypes.data)
+        want = np.zeros(idx.size, dtype=np.uint64)
+        for j, q in enumerate(measured):
+            want |= ((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(j)
+        assert np.array_equal(out, want), measured

@@ -35,6 +35,22 @@ enum hipMemcpyKind { hipMemcpyHostToHost, hipMemcpyHostToDevice, hipMemcpyDevice
 
 extern thread_local dim3 blockIdx, threadIdx, blockDim, gridDim;
 
+// measurement_kernels.hip (compiled for oracle/hip_shim/spec_driver.cpp only; the reference launches none of it) uses
+// block-shared scratch, barriers and shared-memory atomics.  With ONE thread per block -- the only geometry this shim
+// ever runs -- a block's shared memory is that thread's own, a barrier has nobody to wait for, an atomic has no rival.
+#define __shared__ thread_local
+// (spec_driver.cpp also runs ONE kernel -- local_bit_swap_permutation_kernel, which has no shared memory -- as a real block
+// of OpenMP threads; only then is the flag set and the barrier real.)
+extern bool shim_block_is_a_team;
+static inline void __syncthreads() {
+    if (shim_block_is_a_team) {
+        _Pragma("omp barrier")
+    }
+}
+template <typename T, typename V> static inline T atomicAdd(T* p, V v) { const T old = *p; *p = old + (T)v; return old; }
+// swap_kernels.hip's packing kernels (never run here: their cursor order is nondeterministic by design) need the name
+template <typename T, typename V> static inline T hipAtomicAdd(T* p, V v) { return atomicAdd(p, v); }
+
 template <typename T> static inline hipError_t hipMalloc(T** p, size_t bytes) {
     void* q = nullptr;
     if (posix_memalign(&q, 64, bytes ? bytes : 64) != 0) { *p = nullptr; return hipErrorOutOfMemory; }

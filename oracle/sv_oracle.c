@@ -10,9 +10,19 @@
  *     CRX/CRY/CRZ, MCX, CSWAP, readback) are pinned against the reference's own sources compiled
  *     unmodified under a host HIP shim (oracle/_ref, built by oracle/Makefile) -- tests/test_oracle_vs_ref.py --
  *     and against the golden vectors of the reference's tests (tests/golden/).
- *   - the 17 entry points the reference only DECLARES (ApplyMatrix, ControlledMatrix, Measure, Sample,
- *     expectations, SwapIndexBits, ...) have no executable reference: "parity unpinned" beyond the
- *     analytic known-answer vectors the reference's tests/examples state (Bell, GHZ expectations, ...).
+ *   - the 17 entry points the reference only DECLARES have no callable reference, but for four of them the
+ *     reference ships the KERNELS they were meant to launch; those are compiled unmodified into oracle/_ref and
+ *     launched by oracle/hip_shim/spec_driver.cpp (tests/test_oracle.py, "..._spec_kernel" / "..._kernels"):
+ *       ApplyMatrix (k <= 4; and through it ControlledMatrix / FusedSingleQubitMatrix)  bit-exact vs
+ *           apply_multi_qubit_generic_matrix_kernel, multi_qubit_kernels.hip:37-115
+ *       Measure (probability, collapse, renormalisation for the outcome drawn)           to summation order vs
+ *           calculate_prob0 / collapse_state / sum_sq_magnitudes / renormalize_state, measurement_kernels.hip:12-99
+ *       Z / Z-product expectations                                                        to summation order vs
+ *           calculate_multi_z_probabilities_kernel + reduction, measurement_kernels.hip:283-387
+ *       SwapIndexBits, local<->local                                                      bit-exact vs
+ *           local_bit_swap_permutation_kernel, swap_kernels.hip:95-114
+ *     Still "parity unpinned" beyond the analytic known-answer vectors of the reference's tests/examples (Bell, GHZ
+ *     expectations, ...): ApplyMatrix for k >= 5, X/Y factors of Pauli expectations, Sample, the distributed calls.
  *   - the RNG stream is ours (Philox4x32-10, checked against the Random123 known-answer vectors): the
  *     reference specifies none (simulator.cpp:174 seeds mt19937 from random_device).
  */

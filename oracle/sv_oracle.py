@@ -225,6 +225,41 @@ class RefLib:
             raise ValueError(name)
         return st
 
+    def spec_apply_matrix(self, targets, M):
+        """The reference's own (never launched) ApplyMatrix kernel, multi_qubit_kernels.hip:37-115, driven by
+        oracle/hip_shim/spec_driver.cpp: 1 <= len(targets) <= 4, batch 1.  M[i, j] = row i, column j; it is handed over
+        column-major as hipStateVec.h:145-148 specifies."""
+        assert self.batch == 1
+        k = len(targets)
+        buf = np.ascontiguousarray(np.asarray(M, dtype=self.dtype).reshape(1 << k, 1 << k).T).reshape(-1)
+        st = self.lib.refspec_apply_matrix(self.d, C.c_uint(self.n), _uarr(targets), C.c_uint(k), buf.ctypes.data_as(C.c_void_p))
+        assert st == 0, st
+
+    def spec_measure_with_outcome(self, q, outcome):
+        """prob0 -> collapse -> sum of squares -> renormalise by the reference's own measurement kernels
+        (measurement_kernels.hip:12-99) for a given outcome; returns prob0 as the kernel summed it."""
+        assert self.batch == 1
+        p0 = C.c_double()
+        st = self.lib.refspec_measure_with_outcome(self.d, C.c_uint(self.n), C.c_uint(q), C.c_int(outcome), C.byref(p0))
+        assert st == 0, st
+        return p0.value
+
+    def spec_multi_z_probabilities(self, qubits):
+        """Joint Z-basis outcome probabilities of up to 8 qubits (bin bit j <-> qubits[j]) by
+        calculate_multi_z_probabilities_kernel + its reduction (measurement_kernels.hip:283-387)."""
+        assert self.batch == 1
+        probs = np.zeros(1 << len(qubits), dtype=np.float64)
+        st = self.lib.refspec_multi_z_probabilities(self.d, C.c_uint(self.n), _uarr(qubits), C.c_uint(len(qubits)),
+                                                    probs.ctypes.data_as(C.c_void_p))
+        assert st == 0, st
+        return probs
+
+    def spec_local_bit_swap(self, q1, q2):
+        """local_bit_swap_permutation_kernel (swap_kernels.hip:95-114) run as one real block of 2^n threads (n <= 8)."""
+        assert self.batch == 1
+        st = self.lib.refspec_local_bit_swap(self.d, C.c_uint(self.n), C.c_uint(q1), C.c_uint(q2))
+        assert st == 0, st
+
     def state(self):
         out = np.empty(self.batch << self.n, dtype=self.dtype)
         assert self.lib.rocsvGetStateVectorFull(self.h, self.d, out.ctypes.data_as(C.c_void_p)) == 0

@@ -6,9 +6,11 @@
  *
  * Every function cites the reference file:line whose behaviour it restates
  * (paths relative to /root/reference).  Entry points the reference declares but
- * never defines are restated from the header contract and are
- * marked "parity unpinned" -- they are pinned only by the analytic known-answer
- * vectors in tests/golden/.
+ * never defines are restated from the header contract; where the
+ * reference ships the kernel such a call was meant to launch (ApplyMatrix k <= 4, Measure,
+ * Z-product probabilities, the local bit swap) the restatement is pinned against that kernel
+ * run through oracle/hip_shim/spec_driver.cpp; the rest is marked "parity unpinned" -- pinned
+ * only by the analytic known-answer vectors in tests/golden/ (see the list in sv_oracle.c).
  */
 
 typedef struct { REAL x, y; } SFX(cplx);

@@ -19,10 +19,12 @@
  *           calculate_prob0 / collapse_state / sum_sq_magnitudes / renormalize_state, measurement_kernels.hip:12-99
  *       Z / Z-product expectations                                                        to summation order vs
  *           calculate_multi_z_probabilities_kernel + reduction, measurement_kernels.hip:283-387
+ *       Pauli strings with X / Y factors                                                  to summation order vs
+ *           the recipe of rocquantum/utils/hamiltonian.py:35-59 run with the compiled Sdg / H kernels + the kernel above
  *       SwapIndexBits, local<->local                                                      bit-exact vs
  *           local_bit_swap_permutation_kernel, swap_kernels.hip:95-114
  *     Still "parity unpinned" beyond the analytic known-answer vectors of the reference's tests/examples (Bell, GHZ
- *     expectations, ...): ApplyMatrix for k >= 5, X/Y factors of Pauli expectations, Sample, the distributed calls.
+ *     expectations, ...): ApplyMatrix for k >= 5, Sample, the distributed calls.
  *   - the RNG stream is ours (Philox4x32-10, checked against the Random123 known-answer vectors): the
  *     reference specifies none (simulator.cpp:174 seeds mt19937 from random_device).
  */

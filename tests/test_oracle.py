@@ -260,3 +260,35 @@ def test_swap_index_bits_matches_the_references_local_permutation_kernel(prec):
         assert np.array_equal(o.state, want), (a, b)
         if a != b:
             assert not np.array_equal(want, v)
+
+
+@pytest.mark.parametrize("prec,tol", [("c64", 2e-5), ("c128", 1e-12)])
+def test_pauli_string_expectation_matches_the_references_basis_change_recipe(prec, tol):
+    """rocsvGetExpectationPauliString (declared only) against reference code end to end: the reference's own recipe
+    (rocquantum/utils/hamiltonian.py:35-59: Sdg then H on the Y qubits, H on the X qubits, then the Z product over all
+    non-identity qubits), carried out with the reference's compiled gate kernels (rocsvApplySdg / rocsvApplyH) and its
+    outcome-probability kernel (measurement_kernels.hip:283-387).  Also checks that the oracle leaves the state alone."""
+    if not so.ref_available(prec):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    n = 9
+    v = util.random_state(n, seed=88).astype(so.DT[prec])
+    o = so.Oracle(n, prec); o.set_state(v)
+    for paulis, qubits in [("X", [0]), ("Y", [8]), ("XY", [3, 5]), ("YX", [0, 8]), ("XYZ", [1, 2, 3]), ("ZYXI", [7, 0, 4, 2]),
+                           ("YYYY", [8, 6, 1, 3]), ("XZXZXZ", [0, 1, 2, 3, 4, 5]), ("IXI", [2, 6, 7])]:
+        r = so.RefLib(prec); r.allocate(n); r.set_state(v)
+        for p, q in zip(paulis, qubits):
+            if p == "Y":
+                assert r.gate("sdg", q) == 0
+        for p, q in zip(paulis, qubits):
+            if p == "X":
+                assert r.gate("h", q) == 0
+        for p, q in zip(paulis, qubits):
+            if p == "Y":
+                assert r.gate("h", q) == 0
+        zq = [q for p, q in zip(paulis, qubits) if p != "I"]
+        probs = r.spec_multi_z_probabilities(zq)
+        r.close()
+        want = float(sum((-1) ** bin(b).count("1") * pb for b, pb in enumerate(probs)))
+        got = o.expect_pauli(paulis, qubits)
+        assert abs(got - want) < tol * 20, (paulis, qubits, got, want)
+        assert np.array_equal(o.state, v)                           # non-destructive (hipStateVec.h:402-423)

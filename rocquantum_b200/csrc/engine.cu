@@ -914,7 +914,11 @@ rocqStatus_t rocsvSample(rocsvHandle_t h, rocComplex* d, unsigned n, const unsig
     if (s != ROCQ_STATUS_SUCCESS) return s;
     if (h->dist.active()) return h->dist.sample(h, measured, nm, numShots, h_results);
 
-    const unsigned cb = n < 10 ? n : (n > 30 ? n - 20 : 10);              // chunk of 2^cb amplitudes, <= 2^20 chunks
+    unsigned cb = n < 10 ? n : (n > 30 ? n - 20 : 10);                    // chunk of 2^cb amplitudes, <= 2^20 chunks
+    // Masses are exact integers, so the sampled indices do not depend on the chunking: ROCQ_SAMPLE_CHUNK_BITS trades the
+    // host scan (2^(n-cb) chunk masses there and back) against the in-chunk walk per shot (2^cb amplitudes) -- tuning only.
+    static const int cb_env = getenv("ROCQ_SAMPLE_CHUNK_BITS") ? atoi(getenv("ROCQ_SAMPLE_CHUNK_BITS")) : -1;
+    if (cb_env >= 0) cb = std::min<unsigned>(n, std::max<unsigned>((unsigned)cb_env, n > 30 ? n - 20 : 0u));
     const uint64_t nchunks = 1ull << (n - cb);
     uint64_t *d_hi = nullptr, *d_idx = nullptr;
     RQ_CUDA(cudaMallocAsync(&d_hi, 2 * nchunks * sizeof(uint64_t), h->stream), "chunk scratch");

@@ -93,3 +93,23 @@ def test_block_plan_large_brick_circuit_block_occupancy():
     nb, ns, steps = util.plan_blocks(30, gates)
     in_blocks = sum(len(s["ops"]) for s in steps if "blk" in s)
     assert nb <= 90 and in_blocks / nb >= 6.5              # blocks stay full (a brick diamond holds 9 two-qubit matrices)
+
+
+def test_block_plan_starts_a_brick_circuit_with_disjoint_blocks():
+    """configs[1]: greedy absorption alone starts as a staircase of overlapping blocks (0-5, 4-9, 8-13, ...: 7 matrices
+    each) and needs 70 passes; the planner also tries disjoint first blocks on untouched qubits and keeps the shorter plan:
+    the second row already consists of full 9-matrix diamonds (plan_mixed, host_ops.h)."""
+    gates = workloads.c2_random_unitary(30, 40, seed=30)
+    nb, ns, steps = util.plan_blocks(30, gates)
+    assert nb + ns <= 64                                   # one pass over the state per step; the diamond bound is 580 / 9 = 64.4 blocks
+    first_row = [st["blk"] for st in steps[:5]]
+    assert first_row == [list(range(6 * i, 6 * i + 6)) for i in range(5)]
+    assert [len(st["ops"]) for st in steps[5:9]] == [9, 9, 9, 9]
+    assert sum(len(st["ops"]) for st in steps) == 20 * 15 + 20 * 14      # every two-qubit matrix of the circuit, once
+
+
+@pytest.mark.parametrize("n,depth", [(14, 12), (17, 9), (19, 7)])
+def test_block_plan_with_spread_first_row_is_equivalent(n, depth):
+    gates = workloads.c2_random_unitary(n, depth, seed=n)
+    nb, ns, steps = _check_blocks(n, gates)
+    assert nb >= 2

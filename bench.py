@@ -210,9 +210,12 @@ def run_reference(args):
     circuit_s = n1 * t1 + n2 * t2
     value = len(gates) / circuit_s * 2.0 ** (n - 30)
     del o
-    compiled = compiled_reference_sample(n_run, n, one[0][1][0], tuple(two[0][1]), n1, n2)
-    if compiled:
-        compiled["cores"] = cores
+    try:
+        compiled = compiled_reference_sample(n_run, n, one[0][1][0], tuple(two[0][1]), n1, n2)
+        if compiled:
+            compiled["cores"] = cores
+    except Exception as ex:                          # the extra datum must not take the reference line down
+        compiled = {"error": str(ex)[:200]}
     sample = (f"1 one-qubit + 1 two-qubit Haar gate of the workload per step at {n_run} qubits"
               + ("" if n_run == n else f", extrapolated x2^{n - n_run} to {n} qubits") + "; one full pass per gate (no fusion), OpenMP")
     line = {"impl": "reference", "metric": "gates_per_sec", "value": value, "unit": unit_for(n), "n_gpus": args.gpus,

@@ -219,6 +219,7 @@ static void close_peers(rocsvInternalHandle* h, Dist& d) {
 // map every rank's slice; all ranks agree on the outcome (one rank without peer access sends everybody back to NCCL)
 static rocqStatus_t open_peers(rocsvInternalHandle* h, Dist& d) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    if (d.nranks > 64) return ROCQ_STATUS_SUCCESS;                     // the gathered handles travel through the 4 KB pinned scratch
     cudaIpcMemHandle_t mine;
     int ok = cudaIpcGetMemHandle(&mine, h->d_state) == cudaSuccess;
     if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof mine); }

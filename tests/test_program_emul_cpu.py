@@ -232,3 +232,15 @@ def test_shot_bit_gather_matches_the_per_bit_definition():
         for j, q in enumerate(measured):
             want |= ((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(j)
         assert np.array_equal(out, want), measured
+
+
+@pytest.mark.parametrize("n,depth", [(13, 8), (15, 10)])
+def test_mixed_plan_of_a_brick_circuit_through_the_interpreter(n, depth):
+    """configs[1] in miniature under the two-policy block planner: blocks (as 64x64 products) and whatever ordinary sweeps
+    remain, interpreted from the emitted programs, equal the oracle."""
+    gates = workloads.c2_random_unitary(n, depth, seed=n)
+    v = util.random_state(n, seed=n)
+    want = oracle_run(n, gates, v)
+    out, launches, nblocks = run_emu("c64", n, gates, v, 0, flags=4)
+    assert nblocks >= 2
+    assert util.rel_err(out, want) < 2e-6

@@ -1,7 +1,8 @@
 """Generate tests/golden/*.npy from the REFERENCE ITSELF: its hipStateVec.cpp + kernels compiled unmodified
 under the host HIP shim (make -C oracle ref; needs /root/reference).  Run from the repo root:
     python tests/golden/make_golden.py
-The fixtures are small (2^10 amplitudes) and committed; the GPU box never needs /root/reference."""
+The fixtures are small (2^10 amplitudes) and committed (c1 / mixed: the reference's rocsv* entry points; c2: its ApplyMatrix
+spec kernel driven by oracle/hip_shim/spec_driver.cpp); the GPU box never needs /root/reference."""
 import os
 import sys
 
@@ -24,5 +25,14 @@ for prec in ("c64", "c128"):
     r.allocate(10, 1)
     util.run_on_ref(r, util.random_gates(10, 200, seed=4242, allow_matrix=False))
     np.save(os.path.join(HERE, f"mixed_n10_{prec}.npy"), r.state())
+    r.close()
+    # configs[1] in miniature: Haar one- and two-qubit gates.  The reference defines no entry point for them, but it ships
+    # the kernel rocsvApplyMatrix was meant to launch (multi_qubit_kernels.hip:37-115); oracle/hip_shim/spec_driver.cpp
+    # launches it, gate by gate.
+    r = so.RefLib(prec)
+    r.allocate(10, 1)
+    for g in workloads.c2_random_unitary(10, 6, seed=30):
+        r.spec_apply_matrix(list(g[1]), g[4])
+    np.save(os.path.join(HERE, f"c2_n10_{prec}.npy"), r.state())
     r.close()
 print("golden fixtures written to", HERE)

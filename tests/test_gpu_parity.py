@@ -63,10 +63,12 @@ def test_golden_vectors_through_the_c_abi(prec):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("name", ["c1_n10", "mixed_n10"])
+@pytest.mark.parametrize("name", ["c1_n10", "mixed_n10", "c2_n10"])
 def test_compiled_reference_fixtures(prec, name):
     want = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}_{prec}.npy"))
-    gates = workloads.c1_ghz_random_layers(10, 6, seed=20) if name == "c1_n10" else util.random_gates(10, 200, seed=4242, allow_matrix=False)
+    gates = {"c1_n10": lambda: workloads.c1_ghz_random_layers(10, 6, seed=20),
+             "mixed_n10": lambda: util.random_gates(10, 200, seed=4242, allow_matrix=False),
+             "c2_n10": lambda: workloads.c2_random_unitary(10, 6, seed=30)}[name]()      # c2: the reference's ApplyMatrix spec kernel
     for fusion in (False, True):
         g = StateVector(10, prec, fusion=fusion)
         util.run_per_gate(g, gates)

@@ -99,6 +99,24 @@ def test_golden_fixture_c1(prec):
     assert np.array_equal(o.state, want)
 
 
+@pytest.mark.parametrize("prec", ["c64", "c128"])
+def test_golden_fixture_c2(prec):
+    """tests/golden/c2_n10_*.npy: configs[1] in miniature, produced by the reference's own ApplyMatrix spec kernel gate by
+    gate (tests/golden/make_golden.py).  The generic restatement reproduces it bit for bit; the route the GPU tests take
+    (one-qubit gates through the reference's 2x2 kernel arithmetic) to rounding."""
+    import os
+    from rocquantum_b200 import workloads
+    want = np.load(os.path.join(os.path.dirname(__file__), "golden", f"c2_n10_{prec}.npy"))
+    gates = workloads.c2_random_unitary(10, 6, seed=30)
+    o = so.Oracle(10, prec)
+    for g in gates:
+        o.apply_matrix(list(g[1]), g[4])
+    assert np.array_equal(o.state, want)
+    o2 = so.Oracle(10, prec)
+    util.run_on_oracle(o2, gates)
+    assert util.rel_err(o2.state, want) < (2e-6 if prec == "c64" else 1e-14)
+
+
 def test_init_state_only_first_batch_member():
     # hipStateVec.cpp:260-268: (1,0) is written at absolute index 0 only
     o = so.Oracle(3, "c64", batch=2)

@@ -250,15 +250,13 @@ void build_block_terms(const std::vector<cd>& U, std::vector<uint16_t>& out) {
 bool build_block_tensor_map(const rq_cplx* state, const rq::BlockLayout& L, CUtensorMap* tm) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static encode_fn encode = nullptr;
-    static bool looked = false;
-    if (!looked) {
-        looked = true;
+    static const encode_fn encode = []() -> encode_fn {       // looked up once; initialisation of a local static is thread-safe
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            encode = reinterpret_cast<encode_fn>(fn);
-    }
+            return reinterpret_cast<encode_fn>(fn);
+        return nullptr;
+    }();
     if (!encode) return false;
     cuuint64_t dims[5], strides[5];
     cuuint32_t box[5], estr[5];

@@ -548,7 +548,7 @@ inline unsigned pool_need(const HostOp& o, unsigned T = RQ_MAX_TILE_BITS) {
 // with it on a qubit (diagonal/control action on a shared qubit commutes, so only non-diagonal overlap
 // blocks) and (b) its non-diagonal targets fit in the resident set.  Diagonal factors and controls never
 // need residency: the kernel resolves them from the tile base.
-inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L) {
+inline std::vector<SweepPlan> plan_sweeps_forward(const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L) {
     std::vector<SweepPlan> plans;
     const unsigned T = std::min(n, L.tile_bits);
     std::vector<char> done(ops.size(), 0);
@@ -605,6 +605,58 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
         plans.push_back(std::move(sp));
     }
     return plans;
+}
+
+// The greedy partition depends on the direction it reads the circuit in: residents are granted to the ops that come first.
+// A QFT ends in swaps (i, n-1-i); read forwards, every sweep has spent its resident slots on Hadamards long before the
+// swaps are seen, and they need sweeps of their own; read BACKWARDS the swaps come first, each sweep seats both partners
+// of a few swaps and then the Hadamards of exactly those qubits -- QFT-33: 5 sweeps instead of 6, and no sweep that only
+// permutes.  Reversal is sound because the rule that lets an op overtake a deferred one (they commute) is symmetric: a
+// valid sweep schedule of the reversed list, executed back to front, is a valid schedule of the list.  Both directions
+// are planned; the backward plan is used only when it is strictly shorter.
+// Within a run of consecutive ops on pairwise DISJOINT qubits any order is the same circuit.  The greedy planner seats ops
+// in list order, so such a run is put in the order in which the ops that follow it need its qubits (stable): the ops a
+// sweep seats first are then the ones whose successors can join them in the same sweep.
+inline void order_disjoint_runs_by_next_use(std::vector<HostOp>& ops, std::vector<int>& orig) {
+    const size_t N = ops.size();
+    for (size_t i = 0; i < N;) {
+        uint64_t mask = ops[i].qubits();
+        size_t j = i + 1;
+        while (j < N && !(ops[j].qubits() & mask)) { mask |= ops[j].qubits(); ++j; }
+        if (j - i >= 2) {
+            std::vector<std::pair<size_t, size_t>> key;                 // (next use, position in the run)
+            for (size_t r = i; r < j; ++r) {
+                size_t next = N;
+                const uint64_t Q = ops[r].qubits();
+                for (size_t k = j; k < N && k < j + 4096; ++k) if (ops[k].qubits() & Q) { next = k; break; }
+                key.push_back({next, r});
+            }
+            std::stable_sort(key.begin(), key.end(), [](const std::pair<size_t, size_t>& a, const std::pair<size_t, size_t>& b) { return a.first < b.first; });
+            std::vector<HostOp> run;
+            std::vector<int> run_orig;
+            for (const auto& kv : key) { run.push_back(std::move(ops[kv.second])); run_orig.push_back(orig[kv.second]); }
+            for (size_t r = i; r < j; ++r) { ops[r] = std::move(run[r - i]); orig[r] = run_orig[r - i]; }
+        }
+        i = j;
+    }
+}
+
+inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L) {
+    std::vector<SweepPlan> fwd = plan_sweeps_forward(ops, n, L);
+    if (fwd.size() < 3) return fwd;
+    for (const HostOp& o : ops) if (o.ext || o.defer) return fwd;
+    std::vector<HostOp> rev(ops.rbegin(), ops.rend());
+    std::vector<int> orig(ops.size());
+    for (size_t k = 0; k < ops.size(); ++k) orig[k] = (int)(ops.size() - 1 - k);
+    order_disjoint_runs_by_next_use(rev, orig);
+    std::vector<SweepPlan> bwd = plan_sweeps_forward(rev, n, L);
+    if (bwd.size() >= fwd.size()) return fwd;
+    std::reverse(bwd.begin(), bwd.end());
+    for (SweepPlan& sp : bwd) {
+        for (int& k : sp.ops) k = orig[k];
+        std::sort(sp.ops.begin(), sp.ops.end());                        // program order inside a sweep
+    }
+    return bwd;
 }
 
 // ---- tile geometry of the tensor-core block sweep (block_sweep.cu) -------------------------------------------------------
@@ -707,7 +759,6 @@ struct MixedStep {
     SweepPlan sweep;                 // otherwise
 };
 
-inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L);
 
 // policy 0: the candidate set that absorbs the most arithmetic, always.
 // policy 1: the same, except while the oldest op sits on qubits NO earlier step has touched (the start of a circuit, or of
@@ -827,7 +878,7 @@ inline std::vector<MixedStep> plan_mixed_policy(const std::vector<HostOp>& ops, 
                 rest.back().defer = keep_for_blocks && ops[i].kind == HostOp::DENSE && eligible(ops[i]);
                 back.push_back((int)i);
             }
-        std::vector<SweepPlan> plans = plan_sweeps(rest, n, L);
+        std::vector<SweepPlan> plans = plan_sweeps_forward(rest, n, L);   // only the first sweep is used: forward order
         MixedStep st;
         st.sweep = std::move(plans[0]);
         for (int& k : st.sweep.ops) { k = back[k]; done[k] = 1; --remaining; touched |= ops[k].qubits(); }

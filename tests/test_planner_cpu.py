@@ -113,3 +113,31 @@ def test_block_plan_with_spread_first_row_is_equivalent(n, depth):
     gates = workloads.c2_random_unitary(n, depth, seed=n)
     nb, ns, steps = _check_blocks(n, gates)
     assert nb >= 2
+
+
+def test_qft33_plan_reads_the_circuit_backwards():
+    """configs[2]: read forwards, the greedy partition has handed every resident slot to Hadamards before it meets the
+    final swaps (6 sweeps, two of them pure permutations); read backwards the swaps seat both partners first and the
+    Hadamards of those qubits join them (plan_sweeps, host_ops.h): 5 sweeps, none without arithmetic."""
+    n = 33
+    gates = workloads.c3_qft(n, seed=33)
+    nsw, sweeps = util.plan(n, gates, 0, prec="c128")
+    assert nsw == 5
+    kinds = [sorted({op["kind"] for op in sw["ops"]}) for sw in sweeps]
+    assert all(1 in k for k in kinds)                                   # every sweep carries Hadamards (DENSE), not only swaps
+    hs = [sum(1 for op in sw["ops"] if op["kind"] == 1) for sw in sweeps]
+    assert n - 2 <= sum(hs) <= n                                        # the Hadamards (algebraic fusion may pair the last ones)
+    assert sum(len(sw["ops"]) for sw in sweeps) == 79                   # nothing lost, nothing doubled
+
+
+@pytest.mark.parametrize("n,T,expect", [(14, 8, 3), (18, 9, 5), (17, 7, 6)])
+def test_backward_qft_plans_are_equivalent(n, T, expect):
+    """Small QFTs whose backward plan is one sweep shorter than the forward one (4 / 6 / 7 forwards, complex128 limits):
+    the plan the engine would follow, replayed sweep by sweep on the oracle, is the circuit."""
+    gates = workloads.c3_qft(n, seed=33)
+    nsw, sweeps = util.plan(n, gates, T, prec="c128")
+    assert nsw == expect
+    v = util.random_state(n, seed=n)
+    a = so.Oracle(n, "c128"); a.set_state(v); util.run_on_oracle(a, gates)
+    b = so.Oracle(n, "c128"); b.set_state(v); util.simulate_plan(b, sweeps)
+    assert util.rel_err(b.state, a.state) < 1e-11

@@ -244,3 +244,15 @@ def test_mixed_plan_of_a_brick_circuit_through_the_interpreter(n, depth):
     out, launches, nblocks = run_emu("c64", n, gates, v, 0, flags=4)
     assert nblocks >= 2
     assert util.rel_err(out, want) < 2e-6
+
+
+@pytest.mark.parametrize("n,tile_bits,expect", [(14, 8, 3), (18, 9, 5), (17, 7, 6)])
+def test_backward_planned_qft_through_the_interpreter(n, tile_bits, expect):
+    """QFTs for which plan_sweeps keeps the backward-read plan (swaps, Hadamards and merged ladders in the same sweeps):
+    the emitted complex128 programs, interpreted, equal the oracle."""
+    gates = workloads.c3_qft(n, seed=33)
+    v = util.random_state(n, seed=n)
+    want = oracle_run(n, gates, v)
+    out, nsw, nmerged = run_emu("c128", n, gates, v, tile_bits=tile_bits)
+    assert nsw == expect and nmerged >= n - 4
+    assert util.rel_err(out, want) < 1e-12

@@ -15,3 +15,8 @@ timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-qft > gpurun_out/ncu_bench.log 2>&1
 python tools/launch_summary.py gpurun_out/launches_bench.csv > gpurun_out/launches_bench_summary.md 2>&1; head -12 gpurun_out/launches_bench_summary.md
+# QFT-33 complex128 with the two-direction sweep planner (5 sweeps expected): time first, then the launch list
+timeout 600 python tools/config_bench.py --only c3 --reps 2 > gpurun_out/config_bench_c3.log 2>&1; cut -c1-400 gpurun_out/config_bench_c3.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_qft33_c128.csv \
+    python tools/config_bench.py --only c3 --reps 1 > gpurun_out/ncu_qft33.log 2>&1
+python tools/launch_summary.py gpurun_out/launches_qft33_c128.csv > gpurun_out/launches_qft33_c128_summary.md 2>&1; head -14 gpurun_out/launches_qft33_c128_summary.md

@@ -892,7 +892,13 @@ inline std::vector<MixedStep> plan_mixed(const std::vector<HostOp>& ops, unsigne
     std::vector<MixedStep> greedy = plan_mixed_policy(ops, n, L, BL, 0);
     bool any_block = false;
     for (const MixedStep& st : greedy) any_block = any_block || st.block;
-    if (!any_block) return greedy;                             // nothing a different first row could change
+    if (!any_block) {                                          // no block formed: the plan is a plain sweep partition, so the
+        std::vector<SweepPlan> plans = plan_sweeps(ops, n, L);  // two-direction sweep planner may know a shorter one
+        if (plans.size() >= greedy.size()) return greedy;
+        std::vector<MixedStep> steps(plans.size());
+        for (size_t i = 0; i < plans.size(); ++i) steps[i].sweep = std::move(plans[i]);
+        return steps;
+    }
     std::vector<MixedStep> spread = plan_mixed_policy(ops, n, L, BL, 1);
     return spread.size() < greedy.size() ? spread : greedy;
 }

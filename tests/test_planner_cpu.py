@@ -141,3 +141,12 @@ def test_backward_qft_plans_are_equivalent(n, T, expect):
     a = so.Oracle(n, "c128"); a.set_state(v); util.run_on_oracle(a, gates)
     b = so.Oracle(n, "c128"); b.set_state(v); util.simulate_plan(b, sweeps)
     assert util.rel_err(b.state, a.state) < 1e-11
+
+
+def test_blockless_mixed_plan_uses_the_two_direction_sweep_planner():
+    """complex64 from 24 qubits plans through plan_mixed; a circuit that forms no block (a QFT: one-qubit gates, wide
+    diagonals, swaps) must still get the shorter of the forward / backward sweep partitions."""
+    nb, ns, steps = util.plan_blocks(30, workloads.c3_qft(30, seed=33))
+    assert nb == 0 and ns == 5
+    _check_blocks(16, workloads.c3_qft(16, seed=33))
+    _check_blocks(19, workloads.c3_qft(19, seed=33))

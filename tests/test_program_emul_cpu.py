@@ -256,3 +256,29 @@ def test_backward_planned_qft_through_the_interpreter(n, tile_bits, expect):
     out, nsw, nmerged = run_emu("c128", n, gates, v, tile_bits=tile_bits)
     assert nsw == expect and nmerged >= n - 4
     assert util.rel_err(out, want) < 1e-12
+
+
+def test_random_circuits_through_both_planners():
+    """A seeded mix of circuit families, sizes and tile widths through the interpreter: ordinary sweeps (forward or
+    backward partition, whichever the planner kept) in both precisions, and the mixed block plan in complex64."""
+    rng = np.random.default_rng(2024)
+    for trial in range(16):
+        n = int(rng.integers(8, 17)); tb = int(rng.integers(6, min(n, 10) + 1)); seed = int(rng.integers(1 << 30))
+        g = [lambda: util.random_gates(n, 150, seed=seed, maxk=min(4, n)),
+             lambda: diag_heavy_gates(n, 120, seed) + workloads.c3_qft(n, seed=seed),
+             lambda: workloads.c3_qft(n, seed=seed) + util.random_gates(n, 60, seed=seed, maxk=2),
+             lambda: workloads.c1_ghz_random_layers(n, 6, seed=seed) + workloads.c3_qft(n, seed=seed)[::-1]][trial % 4]()
+        v = util.random_state(n, seed=seed % 1000)
+        want = oracle_run(n, g, v)
+        for prec, tol in (("c128", 1e-11), ("c64", 2e-5)):
+            out, nsw, nm = run_emu(prec, n, g, v, tile_bits=tb)
+            assert util.rel_err(out, want) < tol, (trial, n, tb, seed, prec)
+    for trial in range(8):
+        n = int(rng.integers(13, 18)); seed = int(rng.integers(1 << 30)); depth = int(rng.integers(2, 9))
+        g = [lambda: workloads.c2_random_unitary(n, depth, seed=seed),
+             lambda: workloads.c2_random_unitary(n, depth, seed=seed) + util.random_gates(n, 60, seed=seed, maxk=3),
+             lambda: workloads.c4_global_layers(n, depth, seed=seed, top=3) + workloads.c2_random_unitary(n, 3, seed=seed),
+             lambda: util.random_gates(n, 80, seed=seed, maxk=2) + workloads.c2_random_unitary(n, depth, seed=seed)[::-1]][trial % 4]()
+        v = util.random_state(n, seed=seed % 1000)
+        out, nsw, nb = run_emu("c64", n, g, v, 0, flags=4)
+        assert util.rel_err(out, oracle_run(n, g, v)) < 2e-5, (trial, n, seed)

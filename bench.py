@@ -418,6 +418,39 @@ def run_engine(args):
         except Exception as ex:                      # the baseline must not take the bench down
             cpu = {"value": None, "unit": "gates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 
+    # ---- configs[0], the reference's own CPU-runnable case: the SAME 20-qubit circuit (named gates only) on the reference's
+    #      compiled sources (oracle/_ref, all host cores) and on the engine, in this run, states compared -----------------
+    c1 = None
+    if ngpus == 1 and not args.no_cpu:
+        try:
+            from oracle import sv_oracle as so
+            from rocquantum_b200 import workloads as wl1
+            from tests import util
+            if so.ref_available("c64"):
+                cores1 = use_all_host_threads()
+                g1 = wl1.c1_ghz_random_layers(20, 20, seed=20)
+                r = so.RefLib("c64"); r.allocate(20); util.run_on_ref(r, g1[:60]); r.close()       # warm-up: threads, pages
+                r = so.RefLib("c64"); r.allocate(20)
+                t1 = time.perf_counter(); util.run_on_ref(r, g1); ref_s = time.perf_counter() - t1
+                want = r.state(); r.close()
+                e = StateVector(20, "c64")
+                arr1, keep1 = capi.make_ops(g1)
+                for _ in range(3):
+                    e.init(); assert lib.rocsvxApplyCircuit(e.h, e.d, 20, arr1, len(g1)) == 0
+                e.init(); e.sync(); e.timer_start()
+                assert lib.rocsvxApplyCircuit(e.h, e.d, 20, arr1, len(g1)) == 0
+                dev1 = e.timer_stop()
+                err1 = util.rel_err(e.state(), want)
+                e.close()
+                c1 = {"workload": "C1: 20-qubit GHZ + 20 random 1q/2q layers, complex64, %d gates" % len(g1),
+                      "reference_ms": ref_s * 1e3, "reference_gates_per_s": len(g1) / ref_s, "kind": "reference", "cores": cores1,
+                      "engine_device_ms": dev1, "engine_gates_per_s": len(g1) / (dev1 * 1e-3),
+                      "max_rel_err_vs_reference": err1, "tolerance": 1e-5,
+                      "note": "reference = its hipStateVec.cpp + kernels compiled unmodified under the host HIP shim, one pass per gate; "
+                              "engine = rocsvxApplyCircuit, state resident; the 8 MB state sits in L2 on the GPU"}
+        except Exception as ex:                                  # never take the bench line down
+            c1 = {"error": str(ex)[:200]}
+
     # ---- second headline of BASELINE.json's metric: HBM GB/s per sweep on the 33-qubit complex128 QFT (configs[2]) ------
     qft = None
     if ngpus == 1 and not args.no_qft:
@@ -459,6 +492,8 @@ def run_engine(args):
             "gpu_launches": int(st.kernelLaunches), "roofline": roofline, "cpu_baseline": cpu}
     if exchange:
         line["exchange"] = exchange
+    if c1:
+        line["c1_reference"] = c1
     if qft:
         line["qft33_c128"] = qft
     print(json.dumps(line), flush=True)

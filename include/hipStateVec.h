@@ -196,12 +196,19 @@ rocqStatus_t rocsvxSetMergeDiagonals(rocsvHandle_t handle, int enabled);
 /* ||psi||^2 of batch member 0 (one read sweep). */
 rocqStatus_t rocsvxGetNorm(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits, double* result);
 
-/* Batched Pauli-string expectation: numTerms strings in one call.  paulis = concatenated characters,
- * qubits = concatenated qubit indices, offsets[t]..offsets[t+1] delimit term t (offsets has
- * numTerms+1 entries).  results[t] = <psi|P_t|psi>. */
+/* Batched Pauli-string expectation: numTerms strings in one call (what python/rocq/api.py:520-643 get_expval / grad and
+ * rocquantum/solvers/vqe_solver.py:120-136 evaluate one term and one full-state pass at a time).  paulis = concatenated
+ * characters, qubits = concatenated qubit indices, offsets[t]..offsets[t+1] delimit term t (offsets has numTerms+1
+ * entries).  results[t] = <psi|P_t|psi> of batch member 0.  Terms are grouped by the set of qubits carrying X or Y: every
+ * group is ONE read sweep over the state (all terms made of I and Z only: one sweep in total), and all results return in
+ * one device->host copy.  ...AllStates evaluates every state of the handle's batch (parameter-shift batches prepared
+ * through batchSize): results[state * numTerms + t]. */
 rocqStatus_t rocsvxGetExpectationPauliBatch(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits,
                                             const char* paulis, const unsigned* qubits, const unsigned* offsets,
                                             unsigned numTerms, double* results);
+rocqStatus_t rocsvxGetExpectationPauliBatchAllStates(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits,
+                                                     const char* paulis, const unsigned* qubits, const unsigned* offsets,
+                                                     unsigned numTerms, double* results);
 
 /* Counters since rocsvCreate / the last reset: what the engine actually launched. */
 typedef struct {
@@ -216,6 +223,7 @@ typedef struct {
     double   exchangeMs;       /* multi-process: device time of those exchanges (CUDA events around each) */
     uint64_t blockSweeps;      /* launches of the tensor-core block-sweep kernel (counted in `sweeps` too) */
     uint64_t planCacheHits;    /* rocsvxApplyCircuit calls that replayed the recorded launches of an identical earlier call */
+    uint64_t expectationSweeps; /* read sweeps launched by the batched expectation calls (one per x-mask group) */
 } rocsvxStats;
 rocqStatus_t rocsvxGetStats(rocsvHandle_t handle, rocsvxStats* stats, int reset);
 

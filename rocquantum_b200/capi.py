@@ -31,7 +31,7 @@ class Stats(C.Structure):
     _fields_ = [("kernelLaunches", C.c_uint64), ("sweeps", C.c_uint64), ("gatesSubmitted", C.c_uint64),
                 ("opsExecuted", C.c_uint64), ("h2dBytes", C.c_uint64), ("lastSweepMs", C.c_double),
                 ("exchanges", C.c_uint64), ("exchangeBytes", C.c_uint64), ("exchangeMs", C.c_double), ("blockSweeps", C.c_uint64),
-                ("planCacheHits", C.c_uint64)]
+                ("planCacheHits", C.c_uint64), ("expectationSweeps", C.c_uint64)]
 
 
 class ExchangeSeg(C.Structure):
@@ -91,6 +91,7 @@ PROTOTYPES = {
     "rocsvxSetMergeDiagonals": [_h, C.c_int],
     "rocsvxGetNorm": [_h, _p, _u, C.POINTER(_d)],
     "rocsvxGetExpectationPauliBatch": [_h, _p, _u, C.c_char_p, _up, _up, _u, C.POINTER(_d)],
+    "rocsvxGetExpectationPauliBatchAllStates": [_h, _p, _u, C.c_char_p, _up, _up, _u, C.POINTER(_d)],
     "rocsvxGetStats": [_h, C.POINTER(Stats), C.c_int],
     "rocsvxTimerStart": [_h],
     "rocsvxTimerStop": [_h, C.POINTER(_d)],

@@ -9,9 +9,11 @@
 //   * tile = 64 block values x 128 columns.  D[column][out] = sum_k X'[column][k] * A'[out][k], k over (re|im, block
 //     value): tcgen05.mma.cta_group::1.kind::f16, M = 128 (tile columns), N = 128, K = 16 per instruction, operands in
 //     shared memory (K-major, no swizzle, 8x16B core matrices), accumulator in TMEM (128 lanes x 128 fp32 columns).
-//   * fp32-class accuracy from fp16 tensor-core inputs: amplitudes are scaled by a power of two (|amp| <= 1 -> the fp16
-//     normal range), then both operands are split in two fp16 terms (hi + lo = 22 mantissa bits) and the three products
-//     of order <= 1 are accumulated in fp32: 24 MMAs per tile (the lo*lo product is 2^-22 relative and dropped).
+//   * fp32-class accuracy from fp16 tensor-core inputs: every tile COLUMN (the 64 amplitudes one block matrix mixes) is
+//     scaled by its own power of two so that its largest component lands in [2^14, 2^15) -- whatever the magnitude of the
+//     state there, peaked or unnormalised -- then both operands are split in two fp16 terms (hi + lo = 22 mantissa
+//     bits) and the three products of order <= 1 are accumulated in fp32: 48 MMAs per tile (lo*lo is 2^-22 relative and
+//     dropped).  Components more than 2^-39 below their column's maximum are lost, which is beyond fp32 resolution anyway.
 //   * the tensor core truncates when it adds a K = 16 partial sum into the accumulator; the correction products are
 //     therefore accumulated first and the dominant hi*hi product last, and for a unitary block the epilogue restores the
 //     norm of every tile column (which the block preserves exactly).
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
     __shared__ __align__(8) uint64_t bar_u, bar_mma[2], bar_x[2], bar_full[3];
     __shared__ uint32_t tmem_slot;
     __shared__ float2 red[2][16];      // per-warp (|in|^2, |out|^2) of a tile, double-buffered
+    __shared__ uint8_t cexp[2][4][128]; // biased exponent of max |component| per (tile parity, quarter of the block values, column)
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
@@ -232,7 +235,6 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
         const uint32_t lbase = lcol | ((qt & 1u) << P.lp_blk[4]) | ((qt >> 1) << P.lp_blk[5]);
         const uint32_t sbase = (lbase ^ (((lbase >> 4) & 7u) << 1)) * 8u;                      // bytes, swizzled
         const uint32_t s0 = 8u << P.lp_blk[0], s1 = 8u << P.lp_blk[1], s2 = 8u << P.lp_blk[2], s3 = 8u << P.lp_blk[3];   // byte strides of value bits 0..3
-        const float scale = P.scale, inv_scale = 1.f / P.scale;
         const uint32_t tlane = tmem_d + (((warp & 3u) * 32u) << 16);            // this warp's TMEM lane quarter
 
         // phase timers (ROCQ_BLOCK_DEBUG & 16): threads 0 and 64 of CTA 0 accumulate clock deltas between marks
@@ -283,9 +285,10 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
         // ---- epilogue of tile i from pipeline buffer B: TMEM lane = column; re at column t, im at column 64 + t.  The
         //      thread overwrites exactly the amplitudes it read, so the tile is transformed in place without a barrier. ----
         float my_in = 0.f;                                                     // |.|^2 of this thread's inputs of the tile in flight
-        float fcorr = inv_scale;                                               // output factor: 1/scale times the norm correction
+        float my_inv = 1.f;                                                    // 1 / (scale of this thread's column) of the tile in flight
+        float fcorr = 1.f;                                                     // norm correction (unitary blocks)
         float acc_in = 0.f, acc_out = 0.f;                                     // |in|^2, |scaled out|^2 over the CTA's finished tiles
-        auto epilogue = [&](auto BC, uint64_t i, float in2) {
+        auto epilogue = [&](auto BC, uint64_t i, float in2, float inv_scale) {
             constexpr uint32_t B = decltype(BC)::value;
             mark(4);
             if (!(dbg & 1u)) mbar_wait(smem_u32(&bar_mma[B]), (uint32_t)(i >> 1) & 1u);
@@ -314,10 +317,10 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                 acc_out += v.y;
                 if (acc_in > 0.f && acc_out > 0.f) {
                     const float r = sqrtf(acc_in / acc_out);
-                    if (fabsf(r * scale - 1.f) < 1e-4f) fcorr = r;
+                    if (fabsf(r - 1.f) < 1e-4f) fcorr = r;
                 }
             }
-            const float f = fcorr;
+            const float f = fcorr * inv_scale;
             unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES;
             float out2 = 0.f;
 #pragma unroll
@@ -327,6 +330,7 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                 *reinterpret_cast<float2*>(S + (sbase ^ vaddr(j))) = make_float2(a * f, b * f);
             }
             if (P.renorm) {
+                out2 *= inv_scale * inv_scale;                                 // back to the state's own units (columns differ in scale)
 #pragma unroll
                 for (int m = 16; m >= 1; m >>= 1) {
                     in2 += __shfl_xor_sync(0xffffffffu, in2, m);
@@ -349,14 +353,50 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             mark(0);
             const unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES;
             float in2 = 0.f;
+#ifndef RQ_BS_SCALE
+#define RQ_BS_SCALE 1            // tuning A/B only: 0 global scale (round 1), 1 per-column scale, 2 same but re-reading shared memory, 3 no exchange (wrong)
+#endif
+#if RQ_BS_SCALE == 1
+            float2 a[16];
+#define RQ_BS_A(j) a[j]
+#else
+#define RQ_BS_A(j) (*reinterpret_cast<const float2*>(S + (sbase ^ vaddr(j))))
+#endif
+            float mx = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float2 v = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(j)));
+#if RQ_BS_SCALE == 1
+                a[j] = v;
+#endif
+                in2 = fmaf(v.x, v.x, fmaf(v.y, v.y, in2));
+#if RQ_BS_SCALE != 0
+                mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
+#endif
+            }
+#if RQ_BS_SCALE == 0
+            const float scale = P.scale, cur_inv = 1.f / P.scale;
+            (void)mx;
+#else
+            // the column's scale: the four threads that hold a column (one per quarter, same lane, warps w, w+4, w+8, w+12)
+            // exchange the exponents of their maxima through shared memory behind a 128-thread named barrier
+            uint32_t e = __float_as_uint(mx) >> 23;
+#if RQ_BS_SCALE != 3
+            cexp[i & 1u][qt][ncol] = (uint8_t)e;
+            asm volatile("bar.sync %0, 128;" ::"r"(2u + (warp & 3u)) : "memory");
+            e = max(max((uint32_t)cexp[i & 1u][0][ncol], (uint32_t)cexp[i & 1u][1][ncol]),
+                    max((uint32_t)cexp[i & 1u][2][ncol], (uint32_t)cexp[i & 1u][3][ncol]));
+#endif
+            e = min(max(e, 20u), 254u);                                        // empty / denormal columns and inf / nan: any finite scale
+            const float scale = __uint_as_float((268u - e) << 23);             // column maximum -> [2^14, 2^15)
+            const float cur_inv = __uint_as_float((e - 14u) << 23);
+#endif
 #pragma unroll
             for (int c = 0; c < 2; ++c) {                                      // 8 block values -> 4 packed words per (term, re|im)
                 uint32_t hr[4], lr[4], hi[4], li[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float2 a0 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j)));
-                    const float2 a1 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j + 1)));
-                    in2 = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, in2))));
+                    const float2 a0 = RQ_BS_A(8 * c + 2 * j), a1 = RQ_BS_A(8 * c + 2 * j + 1);
                     split2(a0.x * scale, a1.x * scale, hr[j], lr[j]);
                     split2(a0.y * scale, a1.y * scale, hi[j], li[j]);
                 }
@@ -381,9 +421,10 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                 load_rows(i + 1);
             }
             mark(2);
-            const float prev_in = my_in;
+            const float prev_in = my_in, prev_inv = my_inv;
             my_in = in2;
-            if (i >= 1) epilogue(std::integral_constant<uint32_t, B ^ 1u>{}, i - 1, prev_in);
+            my_inv = cur_inv;
+            if (i >= 1) epilogue(std::integral_constant<uint32_t, B ^ 1u>{}, i - 1, prev_in, prev_inv);
             mark(3);
         };
 
@@ -395,8 +436,8 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             if (i + 1 < cnt) step(std::integral_constant<uint32_t, 1u>{}, i + 1);
         }
         if (cnt > 0) {
-            if ((cnt - 1) & 1u) epilogue(std::integral_constant<uint32_t, 1u>{}, cnt - 1, my_in);
-            else epilogue(std::integral_constant<uint32_t, 0u>{}, cnt - 1, my_in);
+            if ((cnt - 1) & 1u) epilogue(std::integral_constant<uint32_t, 1u>{}, cnt - 1, my_in, my_inv);
+            else epilogue(std::integral_constant<uint32_t, 0u>{}, cnt - 1, my_in, my_inv);
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last stores must be complete before the CTA exits
         if (timed) {

@@ -25,6 +25,7 @@
 
 #include "dist_plan.h"
 #include "engine.h"
+#include "group.h"
 
 namespace rq {
 
@@ -197,18 +198,49 @@ rocqStatus_t Dist::init(rocsvInternalHandle* h, int rank_, int nranks_, const vo
     return ROCQ_STATUS_SUCCESS;
 }
 
+rocqStatus_t Dist::init_in_group(rocsvInternalHandle* h, int rank_, rocsvGroup* g) {
+    (void)h;
+    if (inited || !g || rank_ < 0 || rank_ >= g->P) return ROCQ_STATUS_INVALID_VALUE;
+    rank = rank_;
+    nranks = g->P;
+    group = g;
+    RQ_CU(cudaMalloc(&d_gather, (size_t)(64 + 8 * nranks) * sizeof(uint64_t)));
+    RQ_CU(cudaEventCreateWithFlags(&g->ev[rank], cudaEventDisableTiming));
+    inited = true;
+    return ROCQ_STATUS_SUCCESS;
+}
+
 // ---- peer slices through CUDA IPC (ROCQ_EXCHANGE=p2p) ------------------------------------------------------------------
+// default mover: the peer-memory swap kernel (measured on 2 B200s: 688 GB/s per direction against 303 GB/s for
+// ncclSend/ncclRecv + staging copy, profiles/r02_bench_n2_*.log); ROCQ_EXCHANGE=nccl keeps the NCCL mover
 static bool want_p2p() {
     const char* e = getenv("ROCQ_EXCHANGE");
-    return e && (e[0] == 'p' || e[0] == 'P');
+    return !(e && (e[0] == 'n' || e[0] == 'N'));
 }
 // stream-ordered barrier over all ranks: nobody's stream passes it before everybody's stream has reached it
 static rocqStatus_t stream_barrier(rocsvInternalHandle* h, Dist& d) {
+    if (d.group) {
+        // one process: every rank records an event, and every stream waits for all the others' events.  The host barriers
+        // only order the host calls (record before wait, wait before the next record); the streams never block the host.
+        rocsvGroup* g = d.group;
+        RQ_CU(cudaEventRecord(g->ev[d.rank], h->stream));
+        g->barrier();
+        for (int r = 0; r < d.nranks; ++r) if (r != d.rank) RQ_CU(cudaStreamWaitEvent(h->stream, g->ev[r], 0));
+        g->barrier();
+        return ROCQ_STATUS_SUCCESS;
+    }
     int* flag = reinterpret_cast<int*>(d.d_gather + 40);               // a word neither the all-gathers nor allreduce_sum use
     RQ_NCCL(g_nccl.AllReduce(flag, flag, 1, ncclInt, ncclMax, (ncclComm_t)d.comm, h->stream));
     return ROCQ_STATUS_SUCCESS;
 }
 static void close_peers(rocsvInternalHandle* h, Dist& d) {
+    if (d.group) {                                                     // plain pointers of one address space: nothing to unmap,
+        if (d.peer_state.empty()) return;                              // but nobody may free its slice while a peer's kernel uses it
+        cudaStreamSynchronize(h->stream);
+        d.peer_state.clear();
+        d.group->barrier();
+        return;
+    }
     if (d.peer_state.empty()) return;
     cudaStreamSynchronize(h->stream);
     for (int r = 0; r < d.nranks; ++r)
@@ -218,6 +250,29 @@ static void close_peers(rocsvInternalHandle* h, Dist& d) {
 }
 // map every rank's slice; all ranks agree on the outcome (one rank without peer access sends everybody back to NCCL)
 static rocqStatus_t open_peers(rocsvInternalHandle* h, Dist& d) {
+    if (d.group) {
+        rocsvGroup* g = d.group;
+        g->slice[d.rank] = h->d_state;
+        g->barrier();
+        int ok = 1;
+        for (int r = 0; r < d.nranks && ok; ++r) {
+            if (g->device[r] == g->device[d.rank]) continue;           // same device: directly addressable
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, g->device[d.rank], g->device[r]) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(g->device[r], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+            cudaGetLastError();
+        }
+        std::vector<void*> ptrs(g->slice);
+        double fail = ok ? 0.0 : 1.0;
+        RQ_OK(d.allreduce_sum(h, &fail, 1));                           // (ends with a barrier: g->slice may be rewritten afterwards)
+        if (fail != 0.0) {
+            if (d.rank == 0) fprintf(stderr, "hipStateVec(B200): single-process multi-GPU needs peer access between the devices (%d rank(s) without)\n", (int)fail);
+            return ROCQ_STATUS_NOT_IMPLEMENTED;
+        }
+        d.peer_state.swap(ptrs);
+        return ROCQ_STATUS_SUCCESS;
+    }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
     if (d.nranks > 64) return ROCQ_STATUS_SUCCESS;                     // the gathered handles travel through the 4 KB pinned scratch
     cudaIpcMemHandle_t mine;
@@ -246,6 +301,8 @@ static rocqStatus_t open_peers(rocsvInternalHandle* h, Dist& d) {
     return ROCQ_STATUS_SUCCESS;
 }
 
+static rocqStatus_t allgather_u64(rocsvInternalHandle* h, Dist& d, const uint64_t* mine, unsigned count, std::vector<uint64_t>& out);
+
 void Dist::shutdown(rocsvInternalHandle* h) {
     close_peers(h, *this);
     for (auto& ev : timed) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -253,6 +310,8 @@ void Dist::shutdown(rocsvInternalHandle* h) {
     if (staging) { cudaFree(staging); staging = nullptr; }
     if (d_gather) { cudaFree(d_gather); d_gather = nullptr; }
     if (comm) { g_nccl.CommDestroy((ncclComm_t)comm); comm = nullptr; }
+    if (group && group->ev[rank]) { cudaEventDestroy(group->ev[rank]); group->ev[rank] = nullptr; }
+    group = nullptr;
     inited = false;
     n_total = 0;
 }
@@ -272,10 +331,20 @@ rocqStatus_t Dist::allocate(rocsvInternalHandle* h, unsigned total_qubits) {
     plan.reset(n_total, n_local);
     if (staging) { cudaFree(staging); staging = nullptr; }
     if (nranks > 1) {
-        const uint64_t slice = 1ull << n_local;
-        staging_amps = std::min<uint64_t>(slice, 1ull << 25) * (uint64_t)(nranks - 1);     // <= 256 MiB (c64) per peer
-        if (cudaMalloc(&staging, staging_amps * sizeof(rq_cplx)) != cudaSuccess) { cudaGetLastError(); return ROCQ_STATUS_ALLOCATION_FAILED; }
-        if (want_p2p()) RQ_OK(open_peers(h, *this));
+        if (group) {
+            RQ_OK(open_peers(h, *this));                  // one process: the exchange always goes through peer memory
+        } else {
+            const uint64_t slice = 1ull << n_local;
+            staging_amps = std::min<uint64_t>(slice, 1ull << 25) * (uint64_t)(nranks - 1);     // <= 256 MiB (c64) per peer
+            if (cudaMalloc(&staging, staging_amps * sizeof(rq_cplx)) != cudaSuccess) { cudaGetLastError(); return ROCQ_STATUS_ALLOCATION_FAILED; }
+            if (want_p2p()) RQ_OK(open_peers(h, *this));
+        }
+        // every rank evaluates the same Philox stream (measure / sample): all ranks continue rank 0's
+        std::vector<uint64_t> all;
+        const uint64_t mine[2] = {h->seed, h->draws};
+        RQ_OK(allgather_u64(h, *this, mine, 2, all));
+        h->seed = all[0];
+        h->draws = all[1];
     }
     return ROCQ_STATUS_SUCCESS;
 }
@@ -308,6 +377,7 @@ static void note_exchange(rocsvInternalHandle* h, Dist& d, cudaEvent_t e0, cudaE
 static rocqStatus_t exchange_data(rocsvInternalHandle* h, Dist& d, const std::vector<unsigned>& gpos) {
     const unsigned k = (unsigned)gpos.size();
     if (k == 0) return ROCQ_STATUS_SUCCESS;
+    if (!d.comm) return ROCQ_STATUS_NOT_IMPLEMENTED;                   // (single-process groups always have peer slices)
     std::vector<unsigned> lpos(k);
     for (unsigned i = 0; i < k; ++i) lpos[i] = d.n_local - k + i;
     std::vector<rocsvxExchangeSeg> segs((size_t)(1u << k));
@@ -439,6 +509,7 @@ rocqStatus_t Dist::swap_index_bits(rocsvInternalHandle* h, unsigned q1, unsigned
     // Physically relabelling two index bits equals a SWAP gate on the two logical qubits (hipStateVec.h:123-137).
     // local<->local: a PERM sweep; local<->global: one exchange; global<->global: through local slots
     // (the reference leaves this case NOT_IMPLEMENTED, MULTI_GPU_GUIDE.md:50).
+    RQ_OK(rq_engine_flush(h));                        // gates still queued (fusion mode) come before the relabelling
     HostOp op = make_swap(q1, q2);
     RQ_OK(localize(h, op));
     std::vector<HostOp> one{op};
@@ -458,6 +529,17 @@ rocqStatus_t Dist::canonicalize(rocsvInternalHandle* h) {
 rocqStatus_t Dist::allreduce_sum(rocsvInternalHandle* h, double* v, unsigned count) {
     if (nranks == 1) return ROCQ_STATUS_SUCCESS;
     if (count > 32) return ROCQ_STATUS_INVALID_VALUE;
+    if (group) {                                                       // threads of one process: through host memory, rank order
+        for (unsigned i = 0; i < count; ++i) group->dvals[(size_t)rank * 32 + i] = v[i];
+        group->barrier();
+        for (unsigned i = 0; i < count; ++i) {
+            double s = 0.0;
+            for (int r = 0; r < nranks; ++r) s += group->dvals[(size_t)r * 32 + i];
+            v[i] = s;
+        }
+        group->barrier();
+        return ROCQ_STATUS_SUCCESS;
+    }
     double* dbuf = reinterpret_cast<double*>(d_gather);
     RQ_CU(cudaMemcpyAsync(dbuf, v, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     RQ_NCCL(g_nccl.AllReduce(dbuf, dbuf, count, ncclDouble, ncclSum, (ncclComm_t)comm, h->stream));
@@ -469,6 +551,14 @@ static rocqStatus_t allgather_u64(rocsvInternalHandle* h, Dist& d, const uint64_
     out.assign((size_t)count * d.nranks, 0);
     if (d.nranks == 1) { for (unsigned i = 0; i < count; ++i) out[i] = mine[i]; return ROCQ_STATUS_SUCCESS; }
     if (count > 8) return ROCQ_STATUS_INVALID_VALUE;
+    if (d.group) {
+        for (unsigned i = 0; i < count; ++i) d.group->uvals[(size_t)d.rank * 8 + i] = mine[i];
+        d.group->barrier();
+        for (int r = 0; r < d.nranks; ++r)
+            for (unsigned i = 0; i < count; ++i) out[(size_t)r * count + i] = d.group->uvals[(size_t)r * 8 + i];
+        d.group->barrier();
+        return ROCQ_STATUS_SUCCESS;
+    }
     uint64_t* send = d.d_gather;
     uint64_t* recv = d.d_gather + 64;
     RQ_CU(cudaMemcpyAsync(send, mine, count * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
@@ -542,57 +632,62 @@ rocqStatus_t Dist::measure(rocsvInternalHandle* h, unsigned q, int* outcome, dou
 }
 
 rocqStatus_t Dist::sample(rocsvInternalHandle* h, const unsigned* measured, unsigned nm, unsigned shots, uint64_t* out) {
+    // Everything stays on the devices: chunk masses -> exact scan -> (all-gather of the slice totals) -> one warp per shot.
+    // Exactly one rank owns each shot and writes its result word; the others leave 0, so a sum over ranks gathers.
     const unsigned n = n_local;
     const unsigned cb = n < 10 ? n : (n > 30 ? n - 20 : 10);
     const uint64_t nchunks = 1ull << (n - cb);
-    uint64_t* d_hi = nullptr;
-    RQ_CU(cudaMallocAsync(&d_hi, (2 * nchunks + shots) * sizeof(uint64_t), h->stream));
-    uint64_t* d_lo = d_hi + nchunks;
-    uint64_t* d_idx = d_hi + 2 * nchunks;
+    StreamBuf scratch(h->stream);
+    RQ_CU(scratch.alloc((2 * nchunks + 2 * RQ_SCAN_MAXSEG + 4 + (size_t)shots) * sizeof(uint64_t)));
+    uint64_t* d_hi = scratch.as<uint64_t>();
+    uint64_t *d_lo = d_hi + nchunks, *d_btot = d_lo + nchunks, *d_tot = d_btot + 2 * RQ_SCAN_MAXSEG, *d_idx = d_tot + 4;
     if (rq_launch_chunk_masses(h->d_state, n, cb, d_hi, d_lo, h->stream) != 0) return ROCQ_STATUS_HIP_ERROR;
-    std::vector<uint64_t> hv(2 * nchunks);
-    RQ_CU(cudaMemcpyAsync(hv.data(), d_hi, 2 * nchunks * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
-    RQ_CU(cudaStreamSynchronize(h->stream));
-    u128 acc = 0;
-    for (uint64_t c = 0; c < nchunks; ++c) {
-        acc += ((u128)hv[c] << 64) | hv[nchunks + c];
-        hv[c] = (uint64_t)(acc >> 64);
-        hv[nchunks + c] = (uint64_t)acc;
+    if (rq_launch_scan_masses(d_hi, d_lo, nchunks, d_btot, d_tot, h->stream) != 0) return ROCQ_STATUS_HIP_ERROR;
+    std::vector<uint64_t> all((size_t)2 * nranks, 0);
+    if (nranks == 1 || group) {
+        uint64_t mine[2];
+        RQ_OK(rq_engine_fetch(h, d_tot, mine, sizeof mine));
+        RQ_OK(allgather_u64(h, *this, mine, 2, all));
+    } else {
+        uint64_t* recv = d_gather + 64;
+        RQ_NCCL(g_nccl.AllGather(d_tot, recv, 2, ncclUint64, (ncclComm_t)comm, h->stream));
+        RQ_OK(rq_engine_fetch(h, recv, all.data(), all.size() * sizeof(uint64_t)));
     }
-    RQ_CU(cudaMemcpyAsync(d_hi, hv.data(), 2 * nchunks * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
-    const uint64_t mine[2] = {(uint64_t)(acc >> 64), (uint64_t)acc};
-    std::vector<uint64_t> all;
-    RQ_OK(allgather_u64(h, *this, mine, 2, all));
     u128 total = 0, win = 0;
     for (int r = 0; r < nranks; ++r) {
         const u128 m = ((u128)all[2 * r] << 64) | all[2 * r + 1];
         if (r < rank) win += m;
         total += m;
     }
-    if (total == 0) { cudaFreeAsync(d_hi, h->stream); return ROCQ_STATUS_FAILURE; }
-    if (acc == 0) {
-        RQ_CU(cudaMemsetAsync(d_idx, 0xFF, (size_t)shots * sizeof(uint64_t), h->stream));
-    } else if (rq_launch_sample(h->d_state, n, cb, d_hi, d_lo, nchunks, (uint64_t)(total >> 64), (uint64_t)total, (uint64_t)(win >> 64),
-                                (uint64_t)win, h->seed, h->draws, shots, 0, d_idx, h->stream) != 0) {
+    if (total == 0) return ROCQ_STATUS_FAILURE;
+    const uint64_t tot4[4] = {(uint64_t)(total >> 64), (uint64_t)total, (uint64_t)(win >> 64), (uint64_t)win};
+    RQ_CU(cudaMemcpyAsync(d_tot, tot4, sizeof tot4, cudaMemcpyHostToDevice, h->stream));     // pageable source: staged before the call returns
+    rq_shot_map map{};
+    map.high_base = (uint64_t)rank << n_local;
+    map.miss = 0;
+    map.nm = nm;
+    for (unsigned j = 0; j < nm; ++j) map.pos[j] = (uint8_t)plan.map[measured[j]];           // physical position of every measured qubit
+    if (rq_launch_sample(h->d_state, n, cb, d_hi, d_lo, nchunks, d_tot, h->seed, h->draws, shots, 0, &map, d_idx, h->stream) != 0)
         return ROCQ_STATUS_HIP_ERROR;
-    }
     h->draws++;
-    h->stats.kernelLaunches += 2;
-    std::vector<uint64_t> idx(shots);
-    RQ_CU(cudaMemcpyAsync(idx.data(), d_idx, (size_t)shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
-    RQ_CU(cudaStreamSynchronize(h->stream));
-    std::vector<unsigned> where(nm);                                        // physical position of every measured qubit
-    for (unsigned j = 0; j < nm; ++j) where[j] = plan.map[measured[j]];
-    const BitGather gather(where.data(), nm);
-    for (unsigned s = 0; s < shots; ++s) idx[s] = idx[s] != ~0ull ? gather(((uint64_t)rank << n_local) | idx[s]) : 0ull;
-    if (nranks > 1) {                                                       // exactly one rank owns each shot: sum = gather
-        RQ_CU(cudaMemcpyAsync(d_idx, idx.data(), (size_t)shots * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
-        RQ_NCCL(g_nccl.AllReduce(d_idx, d_idx, shots, ncclUint64, ncclSum, (ncclComm_t)comm, h->stream));
-        RQ_CU(cudaMemcpyAsync(idx.data(), d_idx, (size_t)shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    h->stats.kernelLaunches += nchunks > 256 ? 5 : 4;
+    if (group) {                                                       // one process: the ranks' words meet in host memory
+        std::vector<uint64_t>& mine = group->shots[rank];
+        mine.resize(shots);
+        RQ_CU(cudaMemcpyAsync(mine.data(), d_idx, (size_t)shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
         RQ_CU(cudaStreamSynchronize(h->stream));
+        group->barrier();
+        for (unsigned s = 0; s < shots; ++s) {
+            uint64_t v = 0;
+            for (int r = 0; r < nranks; ++r) v |= group->shots[r][s];
+            out[s] = v;
+        }
+        group->barrier();
+        return ROCQ_STATUS_SUCCESS;
     }
-    cudaFreeAsync(d_hi, h->stream);
-    memcpy(out, idx.data(), (size_t)shots * sizeof(uint64_t));
+    if (nranks > 1) RQ_NCCL(g_nccl.AllReduce(d_idx, d_idx, shots, ncclUint64, ncclSum, (ncclComm_t)comm, h->stream));
+    RQ_CU(cudaMemcpyAsync(out, d_idx, (size_t)shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    RQ_CU(cudaStreamSynchronize(h->stream));
     return ROCQ_STATUS_SUCCESS;
 }
 

@@ -14,6 +14,7 @@
 #include "host_ops.h"
 
 struct rocsvInternalHandle;
+struct rocsvGroup;
 
 namespace rq {
 
@@ -22,7 +23,8 @@ struct Dist {
     int rank = 0, nranks = 1;
     unsigned n_total = 0, n_local = 0, n_global = 0;
     DistPlanner plan;                // logical->physical map + step planner (dist_plan.h)
-    void* comm = nullptr;            // ncclComm_t
+    rocsvGroup* group = nullptr;     // single-process mode (group.h): the ranks are threads of this process and meet through the group, not NCCL
+    void* comm = nullptr;            // ncclComm_t (multi-process mode)
     void* nccl = nullptr;            // dlopen handle
     rq_cplx* staging = nullptr;      // exchange staging (device)
     size_t staging_amps = 0;
@@ -36,9 +38,11 @@ struct Dist {
     unsigned num_local() const { return n_local; }
     unsigned num_total() const { return n_total; }
     uint64_t global_mask() const { return n_global ? (((1ull << n_global) - 1ull) << n_local) : 0ull; }
+    void reset_layout() { plan.reset(n_total, n_local); }     // identity logical->physical map (fresh data in canonical order)
     uint64_t high_base() const { return active() ? ((uint64_t)rank << n_local) : 0ull; }
 
     rocqStatus_t init(rocsvInternalHandle* h, int rank_, int nranks_, const void* id128);
+    rocqStatus_t init_in_group(rocsvInternalHandle* h, int rank_, rocsvGroup* g);
     rocqStatus_t allocate(rocsvInternalHandle* h, unsigned total_qubits);
     rocqStatus_t initialize(rocsvInternalHandle* h);
     void shutdown(rocsvInternalHandle* h);

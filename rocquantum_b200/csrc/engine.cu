@@ -14,7 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hipStateVec.h"
@@ -199,17 +201,17 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
             if (k > 10) return ROCQ_STATUS_NOT_IMPLEMENTED;
             h->recordingValid = false;                   // the gather kernel's matrix upload is not replayable
             const rq_cplx* dm = reinterpret_cast<const rq_cplx*>(o.ext);
-            rq_cplx* tmp = nullptr;
+            rq::StreamBuf tmp(h->stream);     // freed (stream-ordered) on every path out of this scope
             if (!dm) {                        // host matrix (or diagonal): upload, stream-ordered
                 const size_t D = (size_t)1 << k;
                 std::vector<rq_cplx> hm(D * D, rq_cplx{0, 0});
                 if (o.kind == HostOp::DIAG) for (size_t d = 0; d < D; ++d) { hm[d + d * D].x = (rq_real)o.data[d].real(); hm[d + d * D].y = (rq_real)o.data[d].imag(); }
                 else for (size_t e = 0; e < D * D; ++e) { hm[e].x = (rq_real)o.data[e].real(); hm[e].y = (rq_real)o.data[e].imag(); }
-                RQ_CUDA(cudaMallocAsync(&tmp, D * D * sizeof(rq_cplx), h->stream), "cudaMallocAsync");
-                RQ_CUDA(cudaMemcpyAsync(tmp, hm.data(), D * D * sizeof(rq_cplx), cudaMemcpyHostToDevice, h->stream), "matrix upload");
+                RQ_CUDA(tmp.alloc(D * D * sizeof(rq_cplx)), "cudaMallocAsync");
+                RQ_CUDA(cudaMemcpyAsync(tmp.p, hm.data(), D * D * sizeof(rq_cplx), cudaMemcpyHostToDevice, h->stream), "matrix upload");
                 RQ_CUDA(cudaStreamSynchronize(h->stream), "sync");     // hm goes out of scope
                 h->stats.h2dBytes += D * D * sizeof(rq_cplx);
-                dm = tmp;
+                dm = tmp.as<rq_cplx>();
             }
             // controls on rank bits of a distributed state select whole slices: resolve them here
             const uint64_t lmask = n >= 64 ? ~0ull : ((1ull << n) - 1ull), gctl = o.cmask & ~lmask;
@@ -218,7 +220,6 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
                 h->stats.kernelLaunches++;
             }
             h->stats.opsExecuted++;
-            if (tmp) RQ_CUDA(cudaFreeAsync(tmp, h->stream), "cudaFreeAsync");
             ++i;
         }
     }
@@ -299,8 +300,13 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     if (keep) RQ_CUDA(cudaMalloc(&d_terms, RQ_BLOCK_UBYTES + 256), "block terms alloc (cached)");
     else RQ_CUDA(cudaMallocAsync(&d_terms, RQ_BLOCK_UBYTES + 256, h->stream), "block terms alloc");   // + debug timers
     // pageable source: cudaMemcpyAsync stages it before returning, so `terms` may go out of scope
+    struct TermsGuard {                                     // an early return must not leak the operand buffer
+        void*& p; bool cached; cudaStream_t s; bool armed = true;
+        ~TermsGuard() { if (armed && p) { if (cached) cudaFree(p); else cudaFreeAsync(p, s); p = nullptr; } }
+    } guard{d_terms, keep, h->stream};
     RQ_CUDA(cudaMemcpyAsync(d_terms, terms.data(), RQ_BLOCK_UBYTES, cudaMemcpyHostToDevice, h->stream), "block terms upload");
     RQ_CUDA(rq_launch_block_sweep(state, &P, d_terms, &tm, h->stream), "block sweep launch");
+    guard.armed = false;
     if (P.pad & 16u) {                                   // ROCQ_BLOCK_DEBUG & 16: per-phase clock totals of CTA 0, threads 0 and 64
         long long t[32];
         cudaMemcpyAsync(t, (char*)d_terms + RQ_BLOCK_UBYTES, sizeof t, cudaMemcpyDeviceToHost, h->stream);
@@ -400,6 +406,86 @@ rocqStatus_t flush(H* h) {
     cudaEventRecord(h->ev1, h->stream);
     h->stats.lastSweepMs = -1.0;         // resolved lazily in rocsvxGetStats
     return s;
+}
+
+#define RQ_OK(call) do { const rocqStatus_t _s = (call); if (_s != ROCQ_STATUS_SUCCESS) return _s; } while (0)
+
+// a call that overwrites `state`: gates queued for THIS buffer are dead and dropped, gates queued for another buffer run first
+rocqStatus_t discard_or_flush_queue(H* h, const rq_cplx* state) {
+    if (h->queue.empty()) return ROCQ_STATUS_SUCCESS;
+    if (h->queue_state == state) { h->queue.clear(); return ROCQ_STATUS_SUCCESS; }
+    return flush(h);
+}
+
+// ---- state import / export through page-locked staging (the reference: one synchronous hipMemcpy into
+//      pageable memory, hipStateVec.cpp:691-706) ------------------------------------------------------------------------
+// A pageable destination cannot be DMA'd into, so a plain cudaMemcpy stages it through small driver buffers on one host
+// thread.  Here the transfer is cut into STAGE_BYTES chunks that alternate between two page-locked buffers of the handle: the
+// DMA of chunk c runs while the host (several threads) drains chunk c-1 into the caller's memory.  A destination that is
+// already page-locked (cudaHostAlloc / cudaHostRegister, e.g. the handle's own rocsvEnsurePinnedBuffer) is one DMA.
+constexpr size_t STAGE_BYTES = (size_t)64 << 20;
+void parallel_copy(void* dst, const void* src, size_t bytes) {
+    static const unsigned T = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    if (T == 1 || bytes < ((size_t)4 << 20)) { memcpy(dst, src, bytes); return; }
+    const size_t per = ((bytes / T) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) {
+        const size_t b = std::min(bytes, per * t), e = std::min(bytes, per * (t + 1));
+        if (e > b) th.emplace_back([=] { memcpy((char*)dst + b, (const char*)src + b, e - b); });
+    }
+    memcpy(dst, src, std::min(bytes, per));
+    for (std::thread& x : th) x.join();
+}
+bool is_page_locked(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+rocqStatus_t ensure_stage(H* h) {
+    for (int b = 0; b < 2; ++b) {
+        if (!h->stage[b]) RQ_CUDA(cudaHostAlloc(&h->stage[b], STAGE_BYTES, cudaHostAllocDefault), "staging buffer");
+        if (!h->stageEv[b]) RQ_CUDA(cudaEventCreateWithFlags(&h->stageEv[b], cudaEventDisableTiming), "staging event");
+    }
+    return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t staged_d2h(H* h, void* dst, const void* src, size_t bytes) {
+    if (bytes <= ((size_t)8 << 20) || is_page_locked(dst)) {
+        RQ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream), "state D2H");
+        RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
+        return ROCQ_STATUS_SUCCESS;
+    }
+    RQ_OK(ensure_stage(h));
+    const size_t nchunks = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+    auto len = [&](size_t c) { return std::min(STAGE_BYTES, bytes - c * STAGE_BYTES); };
+    for (size_t c = 0; c <= nchunks; ++c) {
+        if (c < nchunks) {                                   // buffer c&1 was drained two iterations ago
+            RQ_CUDA(cudaMemcpyAsync(h->stage[c & 1], (const char*)src + c * STAGE_BYTES, len(c), cudaMemcpyDeviceToHost, h->stream), "state D2H chunk");
+            RQ_CUDA(cudaEventRecord(h->stageEv[c & 1], h->stream), "staging event");
+        }
+        if (c >= 1) {
+            RQ_CUDA(cudaEventSynchronize(h->stageEv[(c - 1) & 1]), "staging wait");
+            parallel_copy((char*)dst + (c - 1) * STAGE_BYTES, h->stage[(c - 1) & 1], len(c - 1));
+        }
+    }
+    return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t staged_h2d(H* h, void* dst, const void* src, size_t bytes) {
+    if (bytes <= ((size_t)8 << 20) || is_page_locked(src)) {
+        RQ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream), "state H2D");
+        RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
+        return ROCQ_STATUS_SUCCESS;
+    }
+    RQ_OK(ensure_stage(h));
+    const size_t nchunks = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+    for (size_t c = 0; c < nchunks; ++c) {
+        const size_t len = std::min(STAGE_BYTES, bytes - c * STAGE_BYTES);
+        if (c >= 2) RQ_CUDA(cudaEventSynchronize(h->stageEv[c & 1]), "staging wait");     // the DMA that last read this buffer
+        parallel_copy(h->stage[c & 1], (const char*)src + c * STAGE_BYTES, len);
+        RQ_CUDA(cudaMemcpyAsync((char*)dst + c * STAGE_BYTES, h->stage[c & 1], len, cudaMemcpyHostToDevice, h->stream), "state H2D chunk");
+        RQ_CUDA(cudaEventRecord(h->stageEv[c & 1], h->stream), "staging event");
+    }
+    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
+    return ROCQ_STATUS_SUCCESS;
 }
 
 // validate-and-dispatch for one gate: reference order of checks (hipStateVec.cpp:280-282, 108-110)
@@ -520,6 +606,10 @@ rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
         rocsvDestroy(h);
         return ROCQ_STATUS_HIP_ERROR;
     }
+    // like the reference's QuantumSimulator (simulator.cpp:174: std::random_device): every handle draws its own measurement /
+    // sampling stream unless a seed is set (rocsvxSetSeed, or ROCQ_SEED for whole runs)
+    if (const char* e = getenv("ROCQ_SEED")) h->seed = strtoull(e, nullptr, 0);
+    else { std::random_device rd; h->seed = ((uint64_t)rd() << 32) | (uint64_t)rd(); }
     if (const char* e = getenv("ROCQ_FUSION")) h->fusion = atoi(e) != 0;
     if (const char* e = getenv("ROCQ_TILE_BITS")) { const int t = atoi(e); if (t >= 6 && t <= RQ_MAX_TILE_BITS) h->tileBits = (unsigned)t; }
     if (const char* e = getenv("ROCQ_TC")) h->tcBlocks = (e[0] == 'a' || e[0] == '-') ? -1 : (atoi(e) != 0 && sizeof(rq_real) == 4) ? 1 : 0;
@@ -540,6 +630,7 @@ rocqStatus_t rocsvDestroy(rocsvHandle_t h) {
     if (h->d_upartials) cudaFree(h->d_upartials);
     if (h->h_scratch) cudaFreeHost(h->h_scratch);
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (int b = 0; b < 2; ++b) { if (h->stage[b]) cudaFreeHost(h->stage[b]); if (h->stageEv[b]) cudaEventDestroy(h->stageEv[b]); }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->tm0) cudaEventDestroy(h->tm0);
@@ -583,7 +674,9 @@ rocqStatus_t rocsvInitializeState(rocsvHandle_t h, rocComplex* d_state, unsigned
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     rq_cplx* state = resolve(h, d_state);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
-    h->queue.clear();                                      // anything queued is overwritten by the reset
+    // a distributed handle has one state, its slices: the reset is the distributed one (it also resets the qubit map)
+    if (h->dist.active() && state == h->d_state) return h->dist.initialize(h);
+    RQ_OK(discard_or_flush_queue(h, state));
     const size_t total = h->batchSize * ((size_t)1 << numQubits);
     RQ_CUDA(rq_launch_init_state(state, total, 1, h->stream), "initialize state");
     h->stats.kernelLaunches++;
@@ -727,9 +820,7 @@ rocqStatus_t rocsvGetStateVectorFull(rocsvHandle_t h, rocComplex* d_state, rocCo
     if (s != ROCQ_STATUS_SUCCESS) return s;
     if (h->dist.active()) { s = h->dist.canonicalize(h); if (s != ROCQ_STATUS_SUCCESS) return s; }
     const size_t total = h->batchSize * ((size_t)1 << h->numQubits);
-    RQ_CUDA(cudaMemcpyAsync(h_state, state, total * sizeof(rq_cplx), cudaMemcpyDeviceToHost, h->stream), "state D2H");
-    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
-    return ROCQ_STATUS_SUCCESS;
+    return staged_d2h(h, h_state, state, total * sizeof(rq_cplx));
 }
 rocqStatus_t rocsvGetStateVectorSlice(rocsvHandle_t h, rocComplex* d_state, rocComplex* h_state, unsigned batch_index) {
     if (!h || !h_state) return ROCQ_STATUS_INVALID_VALUE;
@@ -740,9 +831,7 @@ rocqStatus_t rocsvGetStateVectorSlice(rocsvHandle_t h, rocComplex* d_state, rocC
     if (s != ROCQ_STATUS_SUCCESS) return s;
     if (h->dist.active()) { s = h->dist.canonicalize(h); if (s != ROCQ_STATUS_SUCCESS) return s; }
     const size_t N = (size_t)1 << h->numQubits;
-    RQ_CUDA(cudaMemcpyAsync(h_state, state + batch_index * N, N * sizeof(rq_cplx), cudaMemcpyDeviceToHost, h->stream), "slice D2H");
-    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
-    return ROCQ_STATUS_SUCCESS;
+    return staged_d2h(h, h_state, state + batch_index * N, N * sizeof(rq_cplx));
 }
 
 // ---- pinned buffer (hipStateVec.h:307-324) ---------------------------------------------------------------
@@ -765,13 +854,11 @@ rocqStatus_t rocsvFreePinnedBuffer(rocsvHandle_t h) {
 }
 
 // ---- expectation values (hipStateVec.h:340-423) ---------------------------------------------------------------
-static rocqStatus_t expect_string(H* h, rocComplex* d, unsigned n, const char* paulis, const unsigned* qubits, unsigned k, double* result) {
-    if (!h || !result) return ROCQ_STATUS_INVALID_VALUE;
-    rq_cplx* state = resolve(h, d);
-    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+static rocqStatus_t parse_pauli(unsigned n, const char* paulis, const unsigned* qubits, unsigned k, uint64_t& xm, uint64_t& zm, unsigned& ny) {
     if (k > 0 && (!paulis || !qubits)) return ROCQ_STATUS_INVALID_VALUE;
-    uint64_t xm = 0, zm = 0, seen = 0;
-    unsigned ny = 0;
+    xm = zm = 0;
+    ny = 0;
+    uint64_t seen = 0;
     for (unsigned j = 0; j < k; ++j) {
         if (!valid_q(qubits[j], n) || ((seen >> qubits[j]) & 1ull)) return ROCQ_STATUS_INVALID_VALUE;
         seen |= 1ull << qubits[j];
@@ -784,7 +871,17 @@ static rocqStatus_t expect_string(H* h, rocComplex* d, unsigned n, const char* p
             default: return ROCQ_STATUS_INVALID_VALUE;
         }
     }
-    rocqStatus_t s = flush(h);
+    return ROCQ_STATUS_SUCCESS;
+}
+static rocqStatus_t expect_string(H* h, rocComplex* d, unsigned n, const char* paulis, const unsigned* qubits, unsigned k, double* result) {
+    if (!h || !result) return ROCQ_STATUS_INVALID_VALUE;
+    rq_cplx* state = resolve(h, d);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    uint64_t xm = 0, zm = 0;
+    unsigned ny = 0;
+    rocqStatus_t s = parse_pauli(n, paulis, qubits, k, xm, zm, ny);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    s = flush(h);
     if (s != ROCQ_STATUS_SUCCESS) return s;
     if (h->dist.active()) return h->dist.pauli_expect(h, xm, zm, ny, result);
     return pauli_expect(h, state, n, xm, zm, ny, result);
@@ -803,16 +900,61 @@ rocqStatus_t rocsvGetExpectationPauliString(rocsvHandle_t h, rocComplex* d, unsi
     if (paulis && strlen(paulis) != k) return ROCQ_STATUS_INVALID_VALUE;       // hipStateVec.h:413
     return expect_string(h, d, n, paulis, qs, k, r);
 }
-rocqStatus_t rocsvxGetExpectationPauliBatch(rocsvHandle_t h, rocComplex* d, unsigned n, const char* paulis, const unsigned* qubits,
-                                            const unsigned* offsets, unsigned numTerms, double* results) {
+// Batched form (callers python/rocq/api.py:520-643 get_expval / grad, solvers/vqe_solver.py:120-136): terms
+// are grouped by x-mask, every group is ONE read sweep that accumulates all its sign patterns (all-Z terms: one sweep in
+// total), and the results come back in one copy.  allStates: evaluate every state of the batch (parameter-shift batches
+// through batchSize), results[state * numTerms + term]; otherwise state 0 only, like the single-term calls.
+static rocqStatus_t expect_batch(H* h, rocComplex* d, unsigned n, const char* paulis, const unsigned* qubits, const unsigned* offsets,
+                                 unsigned numTerms, double* results, bool allStates) {
     if (!h || !results || !offsets) return ROCQ_STATUS_INVALID_VALUE;
+    rq_cplx* state = resolve(h, d);
+    if (!state) return ROCQ_STATUS_INVALID_VALUE;
+    if (numTerms == 0) return ROCQ_STATUS_SUCCESS;
+    struct Term { uint64_t xm, zm; unsigned ny; };
+    std::vector<Term> terms(numTerms);
     for (unsigned t = 0; t < numTerms; ++t) {
         const unsigned b = offsets[t], e = offsets[t + 1];
         if (e < b) return ROCQ_STATUS_INVALID_VALUE;
-        const rocqStatus_t s = expect_string(h, d, n, paulis + b, qubits + b, e - b, results + t);
+        const rocqStatus_t s = parse_pauli(n, paulis + b, qubits + b, e - b, terms[t].xm, terms[t].zm, terms[t].ny);
         if (s != ROCQ_STATUS_SUCCESS) return s;
     }
+    RQ_OK(flush(h));
+    if (h->dist.active()) {                                // slices: one term at a time (X/Y qubits may need an exchange first)
+        for (unsigned t = 0; t < numTerms; ++t) RQ_OK(h->dist.pauli_expect(h, terms[t].xm, terms[t].zm, terms[t].ny, results + t));
+        return ROCQ_STATUS_SUCCESS;
+    }
+    const unsigned nstates = allStates ? (unsigned)h->batchSize : 1u;
+    std::vector<rq_pauli_group> groups;                    // first-appearance order of the x-masks, <= RQ_PAULI_GROUP_MAX terms each
+    for (unsigned t = 0; t < numTerms; ++t) {
+        rq_pauli_group* g = nullptr;
+        for (rq_pauli_group& c : groups) if (c.xmask == terms[t].xm && c.nterms < RQ_PAULI_GROUP_MAX) { g = &c; break; }
+        if (!g) { groups.emplace_back(); g = &groups.back(); memset(g, 0, sizeof *g); g->xmask = terms[t].xm; }
+        g->zmask[g->nterms] = terms[t].zm;
+        g->ny[g->nterms] = (uint8_t)(terms[t].ny & 0xffu);          // only ny mod 4 matters
+        g->index[g->nterms] = t;
+        g->nterms++;
+    }
+    rq::StreamBuf buf(h->stream);
+    const size_t npart = (size_t)rq_reduce_blocks() * RQ_PAULI_GROUP_MAX * nstates, nres = (size_t)numTerms * nstates;
+    RQ_CUDA(buf.alloc((npart + nres) * sizeof(double)), "expectation scratch");
+    double* d_part = buf.as<double>();
+    double* d_res = d_part + npart;
+    for (const rq_pauli_group& g : groups) {
+        RQ_CUDA(rq_launch_pauli_group(state, n, nstates, &g, numTerms, d_part, d_res, h->stream), "expectation group launch");
+        h->stats.kernelLaunches += 2;
+    }
+    h->stats.expectationSweeps += groups.size();
+    RQ_CUDA(cudaMemcpyAsync(results, d_res, nres * sizeof(double), cudaMemcpyDeviceToHost, h->stream), "expectation D2H");
+    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
     return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t rocsvxGetExpectationPauliBatch(rocsvHandle_t h, rocComplex* d, unsigned n, const char* paulis, const unsigned* qubits,
+                                            const unsigned* offsets, unsigned numTerms, double* results) {
+    return expect_batch(h, d, n, paulis, qubits, offsets, numTerms, results, false);
+}
+rocqStatus_t rocsvxGetExpectationPauliBatchAllStates(rocsvHandle_t h, rocComplex* d, unsigned n, const char* paulis, const unsigned* qubits,
+                                                     const unsigned* offsets, unsigned numTerms, double* results) {
+    return expect_batch(h, d, n, paulis, qubits, offsets, numTerms, results, true);
 }
 rocqStatus_t rocsvxSetTensorCoreBlocks(rocsvHandle_t h, int enabled) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
@@ -914,36 +1056,29 @@ rocqStatus_t rocsvSample(rocsvHandle_t h, rocComplex* d, unsigned n, const unsig
 
     unsigned cb = n < 10 ? n : (n > 30 ? n - 20 : 10);                    // chunk of 2^cb amplitudes, <= 2^20 chunks
     // Masses are exact integers, so the sampled indices do not depend on the chunking: ROCQ_SAMPLE_CHUNK_BITS trades the
-    // host scan (2^(n-cb) chunk masses there and back) against the in-chunk walk per shot (2^cb amplitudes) -- tuning only.
+    // scan (2^(n-cb) chunk masses) against the in-chunk walk per shot (2^cb amplitudes) -- tuning only.
     static const int cb_env = getenv("ROCQ_SAMPLE_CHUNK_BITS") ? atoi(getenv("ROCQ_SAMPLE_CHUNK_BITS")) : -1;
     if (cb_env >= 0) cb = std::min<unsigned>(n, std::max<unsigned>((unsigned)cb_env, n > 30 ? n - 20 : 0u));
     const uint64_t nchunks = 1ull << (n - cb);
-    uint64_t *d_hi = nullptr, *d_idx = nullptr;
-    RQ_CUDA(cudaMallocAsync(&d_hi, 2 * nchunks * sizeof(uint64_t), h->stream), "chunk scratch");
-    uint64_t* d_lo = d_hi + nchunks;
+    // everything stays on the device: chunk masses -> exact scan -> one warp per shot -> result words (bit j = measured
+    // qubit j); the host sees one copy of the results and the total mass
+    rq::StreamBuf scratch(h->stream);
+    RQ_CUDA(scratch.alloc((2 * nchunks + 2 * RQ_SCAN_MAXSEG + 4 + (size_t)numShots) * sizeof(uint64_t)), "sampling scratch");
+    uint64_t* d_hi = scratch.as<uint64_t>();
+    uint64_t *d_lo = d_hi + nchunks, *d_btot = d_lo + nchunks, *d_tot = d_btot + 2 * RQ_SCAN_MAXSEG, *d_idx = d_tot + 4;
     RQ_CUDA(rq_launch_chunk_masses(state, n, cb, d_hi, d_lo, h->stream), "chunk masses");
-    std::vector<uint64_t> hv(2 * nchunks);
-    RQ_CUDA(cudaMemcpyAsync(hv.data(), d_hi, 2 * nchunks * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream), "chunk D2H");
-    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
-    u128 acc = 0;                                                          // exact inclusive scan
-    for (uint64_t c = 0; c < nchunks; ++c) {
-        acc += ((u128)hv[c] << 64) | hv[nchunks + c];
-        hv[c] = (uint64_t)(acc >> 64);
-        hv[nchunks + c] = (uint64_t)acc;
-    }
-    if (acc == 0) { cudaFreeAsync(d_hi, h->stream); return ROCQ_STATUS_FAILURE; }
-    RQ_CUDA(cudaMemcpyAsync(d_hi, hv.data(), 2 * nchunks * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream), "scan H2D");
-    RQ_CUDA(cudaMallocAsync(&d_idx, (size_t)numShots * sizeof(uint64_t), h->stream), "shot scratch");
-    RQ_CUDA(rq_launch_sample(state, n, cb, d_hi, d_lo, nchunks, (uint64_t)(acc >> 64), (uint64_t)acc, 0, 0, h->seed, h->draws++, numShots, 0,
-                             d_idx, h->stream), "sample");
-    h->stats.kernelLaunches += 2;
-    std::vector<uint64_t> idx(numShots);
-    RQ_CUDA(cudaMemcpyAsync(idx.data(), d_idx, (size_t)numShots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream), "shots D2H");
-    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
-    cudaFreeAsync(d_hi, h->stream);
-    cudaFreeAsync(d_idx, h->stream);
-    const rq::BitGather gather(measured, nm);
-    for (unsigned sidx = 0; sidx < numShots; ++sidx) h_results[sidx] = gather(idx[sidx]);
+    RQ_CUDA(cudaMemsetAsync(d_tot, 0, 4 * sizeof(uint64_t), h->stream), "totals clear");      // win = 0: one rank holds everything
+    RQ_CUDA(rq_launch_scan_masses(d_hi, d_lo, nchunks, d_btot, d_tot, h->stream), "mass scan");
+    rq_shot_map map{};
+    map.nm = nm;
+    for (unsigned j = 0; j < nm; ++j) map.pos[j] = (uint8_t)measured[j];
+    RQ_CUDA(rq_launch_sample(state, n, cb, d_hi, d_lo, nchunks, d_tot, h->seed, h->draws++, numShots, 0, &map, d_idx, h->stream), "sample");
+    h->stats.kernelLaunches += nchunks > 256 ? 5 : 4;
+    RQ_CUDA(cudaMemcpyAsync(h_results, d_idx, (size_t)numShots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream), "shots D2H");
+    uint64_t tot[2];
+    s = fetch(h, d_tot, tot, sizeof tot);
+    if (s != ROCQ_STATUS_SUCCESS) return s;
+    if (tot[0] == 0 && tot[1] == 0) return ROCQ_STATUS_FAILURE;           // an all-zero state has no distribution to draw from
     return ROCQ_STATUS_SUCCESS;
 }
 
@@ -953,17 +1088,18 @@ rocqStatus_t rocsvxSetSeed(rocsvHandle_t h, uint64_t seed) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     h->seed = seed;
     h->draws = 0;
+    h->seedExplicit = true;
     return ROCQ_STATUS_SUCCESS;
 }
 rocqStatus_t rocsvxSetStateVector(rocsvHandle_t h, rocComplex* d_state, const rocComplex* h_state) {
     if (!h || !h_state) return ROCQ_STATUS_INVALID_VALUE;
     rq_cplx* state = resolve(h, d_state);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
-    h->queue.clear();
+    RQ_OK(discard_or_flush_queue(h, state));
+    // the host slice of a distributed state is in canonical layout: the loaded data starts from the identity qubit map
+    if (h->dist.active() && state == h->d_state) h->dist.reset_layout();
     const size_t total = h->batchSize * ((size_t)1 << h->numQubits);
-    RQ_CUDA(cudaMemcpyAsync(state, h_state, total * sizeof(rq_cplx), cudaMemcpyHostToDevice, h->stream), "state H2D");
-    RQ_CUDA(cudaStreamSynchronize(h->stream), "stream sync");
-    return ROCQ_STATUS_SUCCESS;
+    return staged_h2d(h, state, h_state, total * sizeof(rq_cplx));
 }
 rocqStatus_t rocsvxSynchronize(rocsvHandle_t h) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;

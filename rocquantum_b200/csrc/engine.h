@@ -9,6 +9,20 @@
 #include "host_ops.h"
 #include "sv_internal.h"
 
+namespace rq {
+// stream-ordered scratch that is released on every path out of its scope (early error returns included)
+struct StreamBuf {
+    void* p = nullptr;
+    cudaStream_t s;
+    explicit StreamBuf(cudaStream_t st) : s(st) {}
+    StreamBuf(const StreamBuf&) = delete;
+    StreamBuf& operator=(const StreamBuf&) = delete;
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, s); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+    ~StreamBuf() { if (p) cudaFreeAsync(p, s); }
+};
+}  // namespace rq
+
 // One launch of a planned circuit, kept so that resubmitting the identical circuit skips fusion, planning and the host-side
 // matrix products (rocsvxApplyCircuit's plan cache): a block sweep (parameters, tensor map, its operand terms in a device
 // buffer the entry owns) or a tile sweep (the program that travels in the kernel parameters).
@@ -40,13 +54,16 @@ struct rocsvInternalHandle {
     rq_cplx* queue_state = nullptr;
     unsigned queue_n = 0;
     // RNG
-    uint64_t seed = 0, draws = 0;
+    uint64_t seed = 0, draws = 0;       // seed: std::random_device at rocsvCreate unless ROCQ_SEED / rocsvxSetSeed
+    bool seedExplicit = false;
     // scratch
     double* d_partials = nullptr;       // RBLOCKS doubles + 8 results
     uint64_t* d_upartials = nullptr;    // 4*RBLOCKS + 4
     void* h_scratch = nullptr;          // pinned, 4 KB
     void* pinned = nullptr;             // user-visible pinned buffer (rocsvEnsurePinnedBuffer)
     size_t pinnedSize = 0;
+    void* stage[2] = {nullptr, nullptr};   // page-locked staging of state import / export (two halves in flight)
+    cudaEvent_t stageEv[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     // tuning
     int tcBlocks = -1;                  // 6-qubit tensor-core blocks in rocsvxApplyCircuit / fused flushes: 0 off, 1 on, -1 auto (on from RQ_BLOCK_AUTO_QUBITS qubits)

@@ -148,6 +148,28 @@ struct rq_block_params {
 #define RQ_BLOCK_AUTO_QUBITS 24        // 'auto': tensor-core blocks from this many qubits (state beyond L2; below, launch overheads dominate)
 #define RQ_BLOCK_UBYTES 32768        // Re U and Im U of the 64x64 block, two fp16 terms each, in UMMA K-major core-matrix order
 
+// rocsvSample: result bit j of a shot = bit pos[j] of (high_base | sampled local index); nm = RQ_SHOT_RAW keeps the index itself.
+// miss = what a shot owned by another rank of a distributed state leaves behind (0, so that a sum over ranks gathers).
+#define RQ_SHOT_RAW 255u
+#define RQ_SCAN_MAXSEG 1024
+struct rq_shot_map {
+    uint64_t high_base;
+    uint64_t miss;
+    uint32_t nm;
+    uint8_t pos[64];
+};
+
+// One group of Pauli terms that share the x-mask (rocsvxGetExpectationPauliBatch): evaluated by one read sweep.
+#define RQ_PAULI_GROUP_MAX 32
+struct rq_pauli_group {
+    uint64_t xmask;
+    uint32_t nterms;
+    uint32_t pad;
+    uint64_t zmask[RQ_PAULI_GROUP_MAX];
+    uint32_t index[RQ_PAULI_GROUP_MAX];   // position of the term in the caller's list
+    uint8_t ny[RQ_PAULI_GROUP_MAX];       // number of Y factors
+};
+
 // ---- thin C ABI to the launchers (all return a cudaError_t as int; stream is a cudaStream_t) --------
 extern "C" {
 int rq_launch_sweep_small(rq_cplx* state, const rq_program_small* prog, void* stream);
@@ -163,15 +185,21 @@ int rq_launch_init_state(rq_cplx* state, size_t total_amps, int write_one, void*
 // reductions: results land in d_out (device doubles / uint64), caller copies them back
 int rq_launch_pauli_expect(const rq_cplx* state, unsigned n, uint64_t xmask, uint64_t zmask, unsigned ny,
                            double* d_partials, unsigned nblocks, double* d_out, void* stream);
+// d_partials: RBLOCKS * RQ_PAULI_GROUP_MAX * nstates doubles; results[state * num_terms_total + G->index[t]]
+int rq_launch_pauli_group(const rq_cplx* state, unsigned n, unsigned nstates, const rq_pauli_group* G, unsigned num_terms_total,
+                          double* d_partials, double* d_results, void* stream);
 int rq_launch_fixed_masses(const rq_cplx* state, unsigned n, unsigned q, uint64_t* d_partials, unsigned nblocks,
                            uint64_t* d_out4, void* stream);
 int rq_launch_collapse(rq_cplx* state, unsigned n, unsigned q, int outcome, double scale, void* stream);
 int rq_launch_chunk_masses(const rq_cplx* state, unsigned n, unsigned chunk_bits, uint64_t* d_chunk_hi,
                            uint64_t* d_chunk_lo, void* stream);
+// exact inclusive scan of count 128-bit masses (hi[], lo[]) in place; d_btot: 2 * RQ_SCAN_MAXSEG words of scratch; the grand
+// total lands in d_total2[0..1]
+int rq_launch_scan_masses(uint64_t* d_hi, uint64_t* d_lo, uint64_t count, uint64_t* d_btot, uint64_t* d_total2, void* stream);
+// d_totals4 = {total.hi, total.lo, win.hi, win.lo} in device memory; map: how a sampled basis index becomes a result word
 int rq_launch_sample(const rq_cplx* state, unsigned n, unsigned chunk_bits, const uint64_t* d_incl_hi,
-                     const uint64_t* d_incl_lo, uint64_t nchunks, uint64_t total_hi, uint64_t total_lo,
-                     uint64_t win_hi, uint64_t win_lo, uint64_t seed, uint64_t call, unsigned shots,
-                     uint64_t shot_offset, uint64_t* d_indices, void* stream);
+                     const uint64_t* d_incl_lo, uint64_t nchunks, const uint64_t* d_totals4, uint64_t seed, uint64_t call,
+                     unsigned shots, uint64_t shot_offset, const rq_shot_map* map, uint64_t* d_indices, void* stream);
 unsigned rq_reduce_blocks(void);
 int rq_block_configure(void);
 // d_uterms: RQ_BLOCK_UBYTES device bytes (+ 256 bytes of debug counters)

@@ -193,6 +193,78 @@ __global__ void __launch_bounds__(RT) sum_partials_kernel(const double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Batched expectation: every term of a group shares the x-mask, so ONE read sweep serves them all -- the pair product
+// conj(a_j) a_i is formed once and each term only adds its sign (-1)^{popcount(i & zmask_t)} and picks Re or Im by the
+// parity of its Y count.  All-Z Hamiltonian terms are one group (xmask = 0): one sweep however many there are.
+// grid = (blocks, states of the batch); partials[(state * blocks + block) * TT + t].
+// ---------------------------------------------------------------------------------------------------
+template <int TT>
+__global__ void __launch_bounds__(RT) pauli_group_kernel(const rq_cplx* __restrict__ state_all, unsigned n,
+                                                         const __grid_constant__ rq_pauli_group G, double* __restrict__ partials) {
+    const uint64_t N = 1ull << n;
+    const rq_cplx* __restrict__ state = state_all + (uint64_t)blockIdx.y * N;
+    const uint64_t stride = (uint64_t)gridDim.x * RT;
+    double acc[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) acc[t] = 0.0;
+    if (G.xmask == 0) {
+        for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < N; i += stride) {
+            const double p = prob(state[i]);
+#pragma unroll
+            for (int t = 0; t < TT; ++t) acc[t] += (__popcll(i & G.zmask[t]) & 1) ? -p : p;
+        }
+    } else {
+        const unsigned pv = 63u - (unsigned)__clzll((long long)G.xmask);
+        const uint64_t low = (1ull << pv) - 1ull;
+        for (uint64_t h = (uint64_t)blockIdx.x * RT + threadIdx.x; h < (N >> 1); h += stride) {
+            const uint64_t i = ((h & ~low) << 1) | (h & low), j = i ^ G.xmask;
+            const rq_cplx a = state[i], b = state[j];
+            const double tr = (double)b.x * a.x + (double)b.y * a.y;
+            const double ti = (double)b.x * a.y - (double)b.y * a.x;
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                const double v = (G.ny[t] & 1u) ? ti : tr;
+                acc[t] += (__popcll(i & G.zmask[t]) & 1) ? -v : v;
+            }
+        }
+    }
+    __shared__ double wsum[RT / 32][TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+        const double v = warp_sum(acc[t]);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < TT) {
+        double sum = 0.0;
+        for (int w = 0; w < RT / 32; ++w) sum += wsum[w][threadIdx.x];
+        partials[((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * TT + threadIdx.x] = sum;
+    }
+}
+// grid = (terms of the group, states): deterministic second stage, the i^ny coefficient, and the scatter to
+// results[state * num_terms_total + G.index[t]]
+__global__ void __launch_bounds__(RT) pauli_group_finish_kernel(const double* __restrict__ partials, unsigned nblocks, unsigned TT,
+                                                                const __grid_constant__ rq_pauli_group G, unsigned num_terms_total,
+                                                                double* __restrict__ results) {
+    const unsigned t = blockIdx.x, st = blockIdx.y;
+    __shared__ double wsum[RT / 32];
+    double acc = 0.0;
+    for (unsigned b = threadIdx.x; b < nblocks; b += RT) acc += partials[((uint64_t)st * nblocks + b) * TT + t];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < RT / 32; ++w) sum += wsum[w];
+        if (G.xmask != 0) {
+            const unsigned ny = G.ny[t];
+            sum *= ((ny & 3u) == 0u || (ny & 3u) == 3u) ? 2.0 : -2.0;
+        }
+        results[(uint64_t)st * num_terms_total + G.index[t]] = sum;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // exact probability masses of "bit q = 0" and "bit q = 1" (q >= n: everything counts as 0)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RT) fixed_masses_kernel(const rq_cplx* __restrict__ state, unsigned n, unsigned q,
@@ -248,18 +320,110 @@ __global__ void __launch_bounds__(RT) collapse_kernel(rq_cplx* __restrict__ stat
     }
 }
 
-// one warp per chunk of 2^chunk_bits amplitudes: exact mass of the chunk
+// one warp per chunk of 2^chunk_bits amplitudes: exact mass of the chunk.  A lane moves 16 bytes per load (two complex64 / one
+// complex128 amplitude) with four loads in flight, i.e. 2 KB per warp iteration: 64 resident warps keep 128 KB per SM in flight,
+// enough to cover the HBM latency (the one-amplitude-per-load version ran at 0.43 of the copy peak).
+struct __align__(16) amp16 { rq_cplx a[16 / sizeof(rq_cplx)]; };
+__device__ __forceinline__ void add_amp16(u128& acc, const amp16& v) {
+#pragma unroll
+    for (unsigned e = 0; e < 16 / sizeof(rq_cplx); ++e) add128(acc, fix88(prob(v.a[e])));
+}
 __global__ void __launch_bounds__(RT) chunk_masses_kernel(const rq_cplx* __restrict__ state, unsigned n, unsigned chunk_bits,
                                                           uint64_t* __restrict__ hi, uint64_t* __restrict__ lo) {
+    constexpr unsigned PER = 16 / sizeof(rq_cplx);                  // amplitudes per 16-byte element
     const uint64_t nchunks = 1ull << (n - chunk_bits);
     const unsigned lane = threadIdx.x & 31;
     const uint64_t warps = (uint64_t)gridDim.x * (RT / 32);
+    const uint64_t len = 1ull << chunk_bits;
     for (uint64_t c = (uint64_t)blockIdx.x * (RT / 32) + (threadIdx.x >> 5); c < nchunks; c += warps) {
         const rq_cplx* p = state + (c << chunk_bits);
         u128 acc = {0, 0};
-        for (uint64_t i = lane; i < (1ull << chunk_bits); i += 32) add128(acc, fix88(prob(p[i])));
+        if (len >= 128 * PER) {                                     // whole unrolled iterations only (chunks are powers of two)
+            const amp16* v = reinterpret_cast<const amp16*>(p);
+            const uint64_t nv = len / PER;
+            for (uint64_t i = lane; i < nv; i += 128) {
+                const amp16 v0 = v[i], v1 = v[i + 32], v2 = v[i + 64], v3 = v[i + 96];
+                add_amp16(acc, v0); add_amp16(acc, v1); add_amp16(acc, v2); add_amp16(acc, v3);
+            }
+        } else {
+            for (uint64_t i = lane; i < len; i += 32) add128(acc, fix88(prob(p[i])));
+        }
         acc = warp_sum128(acc);
         if (lane == 0) { hi[c] = acc.hi; lo[c] = acc.lo; }
+    }
+}
+
+// ---- exact inclusive scan of the chunk masses, on the device (128-bit integers: the result is order-independent) ----
+// pass 1: block b scans its segment [b*seg, (b+1)*seg) in place and leaves the segment total in btot[b]
+// pass 2: one block turns btot[] into exclusive offsets and writes the grand total to total2[0..1]
+// pass 3: block b adds its offset to its segment
+constexpr int ST = 256;
+__device__ __forceinline__ u128 warp_incl_scan128(u128 v, unsigned lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u128 o;
+        o.hi = __shfl_up_sync(0xffffffffu, v.hi, d);
+        o.lo = __shfl_up_sync(0xffffffffu, v.lo, d);
+        if ((int)lane >= d) add128(v, o);
+    }
+    return v;
+}
+// exclusive prefix of `mine` over the block's threads (in thread order); *block_total (optional) = sum over the block
+__device__ __forceinline__ u128 block_excl_scan128(u128 mine, u128* block_total) {
+    __shared__ uint64_t wt[ST / 32][2];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u128 incl = warp_incl_scan128(mine, lane);
+    if (lane == 31) { wt[w][0] = incl.hi; wt[w][1] = incl.lo; }
+    __syncthreads();
+    u128 before = {0, 0}, all = {0, 0};
+    for (unsigned k = 0; k < ST / 32; ++k) {
+        const u128 t = {wt[k][0], wt[k][1]};
+        if (k < w) add128(before, t);
+        add128(all, t);
+    }
+    __syncthreads();
+    if (block_total) *block_total = all;
+    add128(before, sub128(incl, mine));
+    return before;
+}
+__global__ void __launch_bounds__(ST) scan_segments_kernel(uint64_t* __restrict__ hi, uint64_t* __restrict__ lo, uint64_t count, uint64_t seg,
+                                                           uint64_t* __restrict__ btot) {
+    const uint64_t begin = (uint64_t)blockIdx.x * seg, end = begin + seg < count ? begin + seg : count;
+    const uint64_t per = (seg + ST - 1) / ST;                       // consecutive items per thread
+    const uint64_t b0 = begin + (uint64_t)threadIdx.x * per, b1 = b0 + per < end ? b0 + per : end;
+    u128 mine = {0, 0};
+    for (uint64_t i = b0; i < b1; ++i) add128(mine, u128{hi[i], lo[i]});
+    u128 total;
+    u128 run = block_excl_scan128(mine, &total);
+    for (uint64_t i = b0; i < b1; ++i) {
+        add128(run, u128{hi[i], lo[i]});
+        hi[i] = run.hi; lo[i] = run.lo;
+    }
+    if (threadIdx.x == 0) { btot[2 * blockIdx.x] = total.hi; btot[2 * blockIdx.x + 1] = total.lo; }
+}
+__global__ void __launch_bounds__(ST) scan_totals_kernel(uint64_t* __restrict__ btot, unsigned nseg, uint64_t* __restrict__ total2) {
+    const unsigned per = (nseg + ST - 1) / ST;
+    const unsigned b0 = threadIdx.x * per, b1 = b0 + per < nseg ? b0 + per : nseg;
+    u128 mine = {0, 0};
+    for (unsigned i = b0; i < b1; ++i) add128(mine, u128{btot[2 * i], btot[2 * i + 1]});
+    u128 total;
+    u128 run = block_excl_scan128(mine, &total);
+    for (unsigned i = b0; i < b1; ++i) {
+        const u128 v = {btot[2 * i], btot[2 * i + 1]};
+        btot[2 * i] = run.hi; btot[2 * i + 1] = run.lo;             // exclusive
+        add128(run, v);
+    }
+    if (threadIdx.x == 0) { total2[0] = total.hi; total2[1] = total.lo; }
+}
+__global__ void __launch_bounds__(ST) scan_add_kernel(uint64_t* __restrict__ hi, uint64_t* __restrict__ lo, uint64_t count, uint64_t seg,
+                                                      const uint64_t* __restrict__ btot) {
+    if (blockIdx.x == 0) return;
+    const u128 off = {btot[2 * blockIdx.x], btot[2 * blockIdx.x + 1]};
+    const uint64_t begin = (uint64_t)blockIdx.x * seg, end = begin + seg < count ? begin + seg : count;
+    for (uint64_t i = begin + threadIdx.x; i < end; i += ST) {
+        u128 v = {hi[i], lo[i]};
+        add128(v, off);
+        hi[i] = v.hi; lo[i] = v.lo;
     }
 }
 
@@ -293,13 +457,14 @@ __device__ __forceinline__ u128 mul_u53(const u128 S, const uint64_t U) {
 // one warp per shot: index = min{ i : r < sum_{j<=i} q_j }, r = floor(U * S / 2^53)
 __global__ void __launch_bounds__(RT) sample_kernel(const rq_cplx* __restrict__ state, unsigned n, unsigned chunk_bits,
                                                     const uint64_t* __restrict__ incl_hi, const uint64_t* __restrict__ incl_lo,
-                                                    uint64_t nchunks, uint64_t total_hi, uint64_t total_lo, uint64_t win_hi,
-                                                    uint64_t win_lo, uint64_t seed, uint64_t call, unsigned shots,
-                                                    uint64_t shot_offset, uint64_t* __restrict__ indices) {
-    // total = mass of the whole (possibly distributed) state; win = mass held by lower ranks.  A shot whose
-    // threshold r falls outside [win, win + local mass) belongs to another rank: sentinel ~0.
+                                                    uint64_t nchunks, const uint64_t* __restrict__ totals4, uint64_t seed, uint64_t call,
+                                                    unsigned shots, uint64_t shot_offset, const __grid_constant__ rq_shot_map map,
+                                                    uint64_t* __restrict__ indices) {
+    // totals4 = {total.hi, total.lo, win.hi, win.lo}: total = mass of the whole (possibly distributed) state; win = mass held
+    // by lower ranks.  A shot whose threshold r falls outside [win, win + local mass) belongs to another rank: map.miss.
     const unsigned lane = threadIdx.x & 31;
     const unsigned warps = gridDim.x * (RT / 32);
+    const uint64_t total_hi = totals4[0], total_lo = totals4[1], win_hi = totals4[2], win_lo = totals4[3];
     for (unsigned s = blockIdx.x * (RT / 32) + (threadIdx.x >> 5); s < shots; s += warps) {
         const uint64_t shot = shot_offset + s;
         uint32_t x0, x1;
@@ -311,7 +476,7 @@ __global__ void __launch_bounds__(RT) sample_kernel(const rq_cplx* __restrict__ 
         const u128 local_total = {incl_hi[nchunks - 1], incl_lo[nchunks - 1]};
         bool mine = !lt128(r, win);
         if (mine) { r = sub128(r, win); mine = lt128(r, local_total); }
-        if (!mine) { if (lane == 0) indices[s] = ~0ull; continue; }
+        if (!mine) { if (lane == 0) indices[s] = map.miss; continue; }
         uint64_t lo = 0, hi = nchunks - 1;                          // first chunk with r < incl[c]
         while (lo < hi) {
             const uint64_t mid = lo + ((hi - lo) >> 1);
@@ -341,7 +506,15 @@ __global__ void __launch_bounds__(RT) sample_kernel(const rq_cplx* __restrict__ 
             run.hi = __shfl_sync(0xffffffffu, v.hi, 31);
             run.lo = __shfl_sync(0xffffffffu, v.lo, 31);
         }
-        if (lane == 0) indices[s] = (c << chunk_bits) + found;
+        if (lane == 0) {
+            const uint64_t idx = map.high_base | ((c << chunk_bits) + found);
+            uint64_t out = idx;
+            if (map.nm != RQ_SHOT_RAW) {                            // result bit j = index bit pos[j] (hipStateVec.h:439-445)
+                out = 0;
+                for (unsigned j = 0; j < map.nm; ++j) out |= ((idx >> map.pos[j]) & 1ull) << j;
+            }
+            indices[s] = out;
+        }
     }
 }
 
@@ -383,6 +556,30 @@ extern "C" int rq_launch_pauli_expect(const rq_cplx* state, unsigned n, uint64_t
     return (int)cudaGetLastError();
 }
 
+extern "C" int rq_launch_pauli_group(const rq_cplx* state, unsigned n, unsigned nstates, const rq_pauli_group* G, unsigned num_terms_total,
+                                     double* d_partials, double* d_results, void* stream) {
+    unsigned TT = 1;
+    while (TT < G->nterms) TT <<= 1;
+    if (TT > RQ_PAULI_GROUP_MAX || G->nterms == 0 || nstates == 0) return (int)cudaErrorInvalidValue;
+    // small states: no more blocks than there is work for (the second stage reads nblocks partials per term)
+    const uint64_t items = G->xmask ? ((1ull << n) >> 1) : (1ull << n);
+    unsigned nb = (unsigned)((items + RT - 1) / RT);
+    if (nb > RBLOCKS) nb = RBLOCKS;
+    if (nb == 0) nb = 1;
+    const dim3 grid(nb, nstates);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (TT) {
+        case 1: pauli_group_kernel<1><<<grid, RT, 0, st>>>(state, n, *G, d_partials); break;
+        case 2: pauli_group_kernel<2><<<grid, RT, 0, st>>>(state, n, *G, d_partials); break;
+        case 4: pauli_group_kernel<4><<<grid, RT, 0, st>>>(state, n, *G, d_partials); break;
+        case 8: pauli_group_kernel<8><<<grid, RT, 0, st>>>(state, n, *G, d_partials); break;
+        case 16: pauli_group_kernel<16><<<grid, RT, 0, st>>>(state, n, *G, d_partials); break;
+        default: pauli_group_kernel<32><<<grid, RT, 0, st>>>(state, n, *G, d_partials); break;
+    }
+    pauli_group_finish_kernel<<<dim3(G->nterms, nstates), RT, 0, st>>>(d_partials, nb, TT, *G, num_terms_total, d_results);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int rq_launch_fixed_masses(const rq_cplx* state, unsigned n, unsigned q, uint64_t* d_partials, unsigned nblocks,
                                       uint64_t* d_out4, void* stream) {
     fixed_masses_kernel<<<nblocks, RT, 0, (cudaStream_t)stream>>>(state, n, q, d_partials);
@@ -401,14 +598,24 @@ extern "C" int rq_launch_chunk_masses(const rq_cplx* state, unsigned n, unsigned
     return (int)cudaGetLastError();
 }
 
+extern "C" int rq_launch_scan_masses(uint64_t* d_hi, uint64_t* d_lo, uint64_t count, uint64_t* d_btot, uint64_t* d_total2, void* stream) {
+    // <= RQ_SCAN_MAXSEG segments of at least ST items
+    uint64_t seg = (count + RQ_SCAN_MAXSEG - 1) / RQ_SCAN_MAXSEG;
+    if (seg < (uint64_t)ST) seg = ST;
+    const unsigned nseg = (unsigned)((count + seg - 1) / seg);
+    scan_segments_kernel<<<nseg, ST, 0, (cudaStream_t)stream>>>(d_hi, d_lo, count, seg, d_btot);
+    scan_totals_kernel<<<1, ST, 0, (cudaStream_t)stream>>>(d_btot, nseg, d_total2);
+    if (nseg > 1) scan_add_kernel<<<nseg, ST, 0, (cudaStream_t)stream>>>(d_hi, d_lo, count, seg, d_btot);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int rq_launch_sample(const rq_cplx* state, unsigned n, unsigned chunk_bits, const uint64_t* d_incl_hi,
-                                const uint64_t* d_incl_lo, uint64_t nchunks, uint64_t total_hi, uint64_t total_lo, uint64_t win_hi,
-                                uint64_t win_lo, uint64_t seed, uint64_t call, unsigned shots, uint64_t shot_offset,
-                                uint64_t* d_indices, void* stream) {
+                                const uint64_t* d_incl_lo, uint64_t nchunks, const uint64_t* d_totals4, uint64_t seed, uint64_t call,
+                                unsigned shots, uint64_t shot_offset, const rq_shot_map* map, uint64_t* d_indices, void* stream) {
     unsigned blocks = (shots + (RT / 32) - 1) / (RT / 32);
     if (blocks > RBLOCKS) blocks = RBLOCKS;
     if (blocks == 0) blocks = 1;
-    sample_kernel<<<blocks, RT, 0, (cudaStream_t)stream>>>(state, n, chunk_bits, d_incl_hi, d_incl_lo, nchunks, total_hi, total_lo,
-                                                           win_hi, win_lo, seed, call, shots, shot_offset, d_indices);
+    sample_kernel<<<blocks, RT, 0, (cudaStream_t)stream>>>(state, n, chunk_bits, d_incl_hi, d_incl_lo, nchunks, d_totals4, seed, call,
+                                                           shots, shot_offset, *map, d_indices);
     return (int)cudaGetLastError();
 }

@@ -36,8 +36,7 @@ class DistStateVector:
         nl = C.c_uint()
         self.lib.rocsvxDistGetInfo(self.h, None, None, C.byref(nl), None)
         self.n_local = nl.value
-        if seed:
-            self._ck("rocsvxSetSeed", self.lib.rocsvxSetSeed(self.h, seed))
+        self._ck("rocsvxSetSeed", self.lib.rocsvxSetSeed(self.h, seed))     # fixed stream (handles seed from std::random_device)
 
     @staticmethod
     def _ck(fn, st):

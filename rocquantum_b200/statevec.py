@@ -30,8 +30,7 @@ class StateVector:
         self._ck("rocsvInitializeState", self.lib.rocsvInitializeState(self.h, self.d, n))
         if fusion:
             self.set_fusion(True)
-        if seed:
-            self.set_seed(seed)
+        self.set_seed(seed)           # handles seed themselves from std::random_device; tests and benches want a fixed stream
 
     @staticmethod
     def _ck(fn, st):
@@ -197,6 +196,30 @@ class StateVector:
         o, p = C.c_int(), C.c_double()
         self._ck("rocsvMeasure", self.lib.rocsvMeasure(self.h, self.d, self.n, q, C.byref(o), C.byref(p)))
         return o.value, p.value
+
+    def apply_matrix_and_measure(self, targets, M, q):
+        """rocsvApplyMatrixAndMeasure (hipStateVec.h:487-494): the matrix on `targets`, then a projective measurement of q."""
+        k = len(targets)
+        t = self._device_matrix(M, k)
+        o = C.c_int()
+        st = self.lib.rocsvApplyMatrixAndMeasure(self.h, self.d, self.n, capi.uarr(targets), k, C.c_void_p(t.data_ptr()), q, C.byref(o))
+        self.sync()
+        self._ck("rocsvApplyMatrixAndMeasure", st)
+        return o.value
+
+    def expect_batch(self, terms, all_states=False) -> np.ndarray:
+        """terms: [(pauli string, qubits)] -> rocsvxGetExpectationPauliBatch[AllStates]; shape (terms,) or (batch, terms)."""
+        paulis = "".join(t[0] for t in terms).encode()
+        qubits = capi.uarr([q for t in terms for q in t[1]])
+        offs, acc = [0], 0
+        for t in terms:
+            acc += len(t[0]); offs.append(acc)
+        ns = self.batch if all_states else 1
+        res = (C.c_double * max(1, len(terms) * ns))()
+        fn = self.lib.rocsvxGetExpectationPauliBatchAllStates if all_states else self.lib.rocsvxGetExpectationPauliBatch
+        self._ck("rocsvxGetExpectationPauliBatch", fn(self.h, self.d, self.n, paulis, qubits, capi.uarr(offs), len(terms), res))
+        out = np.array(res[:len(terms) * ns])
+        return out.reshape(ns, len(terms)) if all_states else out
 
     def sample(self, qubits, shots) -> np.ndarray:
         out = np.zeros(max(1, shots), dtype=np.uint64)

@@ -106,3 +106,37 @@ def test_rocq_api_style_flow():
     from oracle import sv_oracle as so
     o = so.Oracle(n, "c64"); o.gate("h", 0); o.gate("cnot", 0, 1); o.gate("ry", 2, 0.3); o.gate("cnot", 1, 2); o.gate("rz", 0, 0.5)
     assert np.abs(got - o.state).max() < 1e-6
+
+
+@pytest.mark.parametrize("prec", ["c64", "c128"])
+def test_hipstatevec_backend_cpp_client(prec, tmp_path):
+    """rocq::HipStateVecBackend (rocqCompiler/HipStateVecBackend.cpp:65-253) compiled as the reference's own C++ client would
+    be -- our header, our library, no other change -- and driven by gate NAME through every alias family: initialize ->
+    apply_gate("ccx") -> apply_parametrized_gate("crz") -> get_state_vector -> destroy, against the oracle."""
+    import subprocess
+    from oracle import sv_oracle as so
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / f"backend_driver_{prec}")
+    libname = "libhipStateVec.so" if prec == "c64" else "libhipStateVec_f64.so"
+    cmd = ["g++", "-O1", "-std=c++17", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+           os.path.join(root, "tests", "cpp", "backend_driver.cpp"), os.path.join(root, "rocquantum_b200", "csrc", "facade", "HipStateVecBackend.cpp"),
+           "-o", exe, "-L", LIB, f"-l:{libname}", f"-Wl,-rpath,{LIB}", "-L", "/usr/local/cuda/lib64", "-lcudart"]
+    if prec == "c128":
+        cmd.insert(1, "-DROCQ_PRECISION_DOUBLE")
+    subprocess.run(cmd, check=True)
+    n = 6
+    script = [f"n {n}", "g H 0", "g h 3", "g PauliX 1", "g x 2", "g CX 0 4", "g cnot 3 5", "g ccx 1 2 5", "g Toffoli 0 3 1", "g mcx 0 1 2 4",
+              "p rx 0.3 2", "p RY 1.1 4", "p rz -0.7 0", "p crz 0.9 3 2", "p CRX 0.4 0 5", "p cry 2.2 4 1", "g s 0", "g Sdag 3", "g sdg 4", "g t 5",
+              "g cz 0 5", "g swap 1 4", "g cswap 3 0 2", "g Fredkin 5 1 3", "g y 2", "g PauliZ 4", "g pauliy 0",
+              "e nosuchgate 0", "e h 0 1", "e ccx 1"]
+    out = subprocess.run([exe], input="\n".join(script) + "\n", capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0] == "threw runtime_error" and out[1] == "threw invalid_argument" and out[2] == "threw invalid_argument"
+    assert out[3] == f"state {1 << n}" and out[-1] == "threw runtime_error"      # after destroy(): "Backend not initialized."
+    got = np.array([complex(*map(float, l.split())) for l in out[4:4 + (1 << n)]])
+    o = so.Oracle(n, prec)
+    for g, a in (("h", (0,)), ("h", (3,)), ("x", (1,)), ("x", (2,)), ("cnot", (0, 4)), ("cnot", (3, 5)), ("mcx", ([1, 2], 5)), ("mcx", ([0, 3], 1)),
+                 ("mcx", ([0, 1, 2], 4)), ("rx", (2, 0.3)), ("ry", (4, 1.1)), ("rz", (0, -0.7)), ("crz", (3, 2, 0.9)), ("crx", (0, 5, 0.4)),
+                 ("cry", (4, 1, 2.2)), ("s", (0,)), ("sdg", (3,)), ("sdg", (4,)), ("t", (5,)), ("cz", (0, 5)), ("swap", (1, 4)), ("cswap", (3, 0, 2)),
+                 ("cswap", (5, 1, 3)), ("y", (2,)), ("z", (4,)), ("y", (0,))):
+        o.gate(g, *a)
+    assert np.abs(got - o.state).max() < (1e-6 if prec == "c64" else 1e-13)

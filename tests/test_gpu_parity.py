@@ -101,7 +101,7 @@ def test_every_named_gate_on_every_target(prec, n):
                 continue
             o.gate("mcx", [a, b], c); g.gate("mcx", [a, b], c)
             o.gate("cswap", a, b, c); g.gate("cswap", a, b, c)
-    assert util.rel_err(g.state(), o.state) < TOL[prec] * 10      # ~1e3 gates accumulate rounding
+    assert util.rel_err(g.state(), o.state) < TOL[prec]           # north_star's tolerance, no slack (~1e3 gates)
 
 
 @pytest.mark.parametrize("prec", PRECS)
@@ -111,11 +111,11 @@ def test_mixed_bag_eager_and_fused(prec, n, batch):
     v = util.random_state(n, batch, seed=n)
     o = so.Oracle(n, prec, batch=batch); o.set_state(v); util.run_on_oracle(o, gates)
     e = StateVector(n, prec, batch=batch); e.set_state(v); util.run_per_gate(e, gates)
-    assert util.rel_err(e.state(), o.state) < TOL[prec] * 4
+    assert util.rel_err(e.state(), o.state) < TOL[prec]
     f = StateVector(n, prec, batch=batch); f.set_state(v); f.apply_circuit(gates)
-    assert util.rel_err(f.state(), o.state) < TOL[prec] * 4
+    assert util.rel_err(f.state(), o.state) < TOL[prec]
     d = StateVector(n, prec, batch=batch, fusion=True); d.set_state(v); util.run_per_gate(d, gates)
-    assert util.rel_err(d.state(), o.state) < TOL[prec] * 4
+    assert util.rel_err(d.state(), o.state) < TOL[prec]
     assert d.stats().sweeps < e.stats().sweeps
 
 
@@ -130,7 +130,7 @@ def test_apply_matrix_k_qubits_with_controls(prec, k):
         nc = trial
         U = workloads.haar_unitary(rng, 1 << k)
         o.apply_matrix(q[:k], U, q[k:k + nc]); g.apply_matrix(q[:k], U, q[k:k + nc])
-    assert util.rel_err(g.state(), o.state) < TOL[prec] * 4
+    assert util.rel_err(g.state(), o.state) < TOL[prec]
 
 
 @pytest.mark.parametrize("prec", PRECS)
@@ -141,7 +141,7 @@ def test_c1_config_full_state(prec):
     o = so.Oracle(n, prec); util.run_on_oracle(o, gates)
     g = StateVector(n, prec); g.apply_circuit(gates)
     st = g.state()
-    assert util.rel_err(st, o.state) < TOL[prec] * 10
+    assert util.rel_err(st, o.state) < TOL[prec]
     assert abs(g.norm2() - 1) < (1e-4 if prec == "c64" else 1e-11)
     assert g.stats().sweeps < len(gates) // 5
 
@@ -152,7 +152,7 @@ def test_c2_and_qft_configs_reduced(prec):
     for gates in (workloads.c2_random_unitary(n, 6, seed=30), workloads.c3_qft(n, seed=33)):
         o = so.Oracle(n, prec); util.run_on_oracle(o, gates)
         g = StateVector(n, prec); g.apply_circuit(gates)
-        assert util.rel_err(g.state(), o.state) < TOL[prec] * 10
+        assert util.rel_err(g.state(), o.state) < TOL[prec]
 
 
 @pytest.mark.parametrize("prec", PRECS)
@@ -165,16 +165,16 @@ def test_merged_controlled_phase_ladders(prec, n, batch, seed):
     v = util.random_state(n, batch, seed=seed)
     o = so.Oracle(n, prec, batch=batch); o.set_state(v); util.run_on_oracle(o, gates)
     m = StateVector(n, prec, batch=batch); m.set_state(v); m.apply_circuit(gates)
-    assert util.rel_err(m.state(), o.state) < TOL[prec] * 4
+    assert util.rel_err(m.state(), o.state) < TOL[prec]
     p = StateVector(n, prec, batch=batch); p.set_merge_diagonals(False); p.set_state(v); p.apply_circuit(gates)
-    assert util.rel_err(p.state(), o.state) < TOL[prec] * 4
+    assert util.rel_err(p.state(), o.state) < TOL[prec]
     assert m.stats().opsExecuted < p.stats().opsExecuted
     # deferred rocsvApply* calls (named gates only: a device-matrix call flushes the queue)
     named = diag_heavy_gates(n, 200, seed, named_only=True)
     o = so.Oracle(n, prec, batch=batch); o.set_state(v); util.run_on_oracle(o, named)
     d = StateVector(n, prec, batch=batch, fusion=True); d.set_state(v); util.run_per_gate(d, named)
     q = StateVector(n, prec, batch=batch, fusion=True); q.set_merge_diagonals(False); q.set_state(v); util.run_per_gate(q, named)
-    assert util.rel_err(d.state(), o.state) < TOL[prec] * 4 and util.rel_err(q.state(), o.state) < TOL[prec] * 4
+    assert util.rel_err(d.state(), o.state) < TOL[prec] and util.rel_err(q.state(), o.state) < TOL[prec]
     assert d.stats().opsExecuted < q.stats().opsExecuted
 
 
@@ -414,3 +414,193 @@ def test_plan_cache_replays_identical_circuits_only(n):
     d = StateVector(12, "c128"); q = workloads.c3_qft(12, seed=33)
     d.apply_circuit(q); a = d.state(); d.init(); d.apply_circuit(q)
     assert d.stats().planCacheHits == 1 and np.array_equal(d.state(), a)
+
+
+# ---- round 2 -------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECS)
+def test_apply_matrix_and_measure(prec):
+    """rocsvApplyMatrixAndMeasure (hipStateVec.h:487-494) = ApplyMatrix then Measure on the shared Philox stream: outcome
+    and post-measurement state against the oracle's two halves, for 1-, 2- and 3-qubit matrices, eager and deferred."""
+    n = 12
+    rng = np.random.default_rng(77)
+    for fusion in (False, True):
+        v = util.random_state(n, 1, seed=9)
+        o = so.Oracle(n, prec, seed=31); o.set_state(v)
+        g = StateVector(n, prec, fusion=fusion, seed=31); g.set_state(v)
+        for k, q in ((1, 0), (2, 7), (3, 11), (2, 3)):
+            t = [int(x) for x in rng.permutation(n)[:k]]
+            U = workloads.haar_unitary(rng, 1 << k)
+            o.apply_matrix(t, U)
+            want, _ = o.measure(q)
+            got = g.apply_matrix_and_measure(t, U, q)
+            assert got == want
+            assert util.rel_err(g.state(), o.state) < TOL[prec]
+    g = StateVector(3, prec)
+    out = C.c_int()
+    assert g.lib.rocsvApplyMatrixAndMeasure(g.h, g.d, 3, capi.uarr([0]), 1, None, 0, C.byref(out)) == capi.INVALID_VALUE
+    assert g.lib.rocsvApplyMatrixAndMeasure(g.h, g.d, 3, capi.uarr([0]), 1, C.c_void_p(g.d.value), 5, C.byref(out)) == capi.INVALID_VALUE
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_batched_expectation_groups_by_x_mask(prec):
+    """rocsvxGetExpectationPauliBatch: one read sweep per x-mask group, every result against oracle.expect_pauli."""
+    n = 14
+    o, g = _pair(n, prec, seed=21)
+    gates = workloads.c5_vqe_ansatz(n, seed=5)
+    util.run_on_oracle(o, gates); g.apply_circuit(gates)
+    tol = 1e-5 if prec == "c64" else 1e-12
+    zterms = [("Z" * len(q), q) for q in ([0], [3], [0, 3], [1, 2, 13], [5, 6, 7, 8], list(range(n)))]
+    xy = [("XX", [2, 3]), ("YY", [2, 3]), ("XY", [2, 3]), ("YX", [3, 2]), ("XZX", [2, 9, 3]), ("YZZY", [3, 0, 13, 2])]     # one x-mask {2,3}
+    rnd = workloads.random_pauli_strings(n, 40, 6, seed=8)
+    terms = zterms + xy + rnd + [("", []), ("I", [4])]
+    g.stats(reset=True)
+    got = g.expect_batch(terms)
+    for r, t in zip(got, terms):
+        assert abs(r - o.expect_pauli(*t)) < tol, t
+    masks = {frozenset(q for p, q in zip(*t) if p in "XY") for t in terms}
+    assert g.stats().expectationSweeps == len(masks) < len(terms)
+    assert util.rel_err(g.state(), o.state) < TOL[prec]              # non-destructive
+    # more terms in one group than a launch carries (32): 70 Z-strings -> 3 sweeps
+    many = [("Z" * 3, [int(a), int(b), int(c)]) for a, b, c in (np.random.default_rng(i).permutation(n)[:3] for i in range(70))]
+    g.stats(reset=True)
+    got = g.expect_batch(many)
+    assert g.stats().expectationSweeps == 3
+    for r, t in zip(got, many):
+        assert abs(r - o.expect_pauli(*t)) < tol
+    # parameter-shift batch: every state of a batch in the same sweeps
+    b = 3
+    v = util.random_state(9, b, seed=5)
+    ob = [so.Oracle(9, prec) for _ in range(b)]
+    for i, x in enumerate(ob):
+        x.set_state(v[i << 9:(i + 1) << 9])
+    gb = StateVector(9, prec, batch=b); gb.set_state(v)
+    terms = [("ZZ", [0, 8]), ("XX", [1, 2]), ("YZ", [3, 4]), ("XY", [1, 2])]
+    got = gb.expect_batch(terms, all_states=True)
+    assert got.shape == (b, len(terms))
+    for i in range(b):
+        for r, t in zip(got[i], terms):
+            assert abs(r - ob[i].expect_pauli(*t)) < tol
+    bad = (C.c_double * 2)()
+    assert g.lib.rocsvxGetExpectationPauliBatch(g.h, g.d, n, b"XQ", capi.uarr([0, 1]), capi.uarr([0, 1, 2]), 2, bad) == capi.INVALID_VALUE
+
+
+def test_state_export_import_through_pinned_staging():
+    """rocsvGetStateVectorFull / rocsvxSetStateVector of a state larger than the staging chunks (2 x 64 MB, double-buffered):
+    bit-exact round trip, into pageable memory and into the handle's own pinned buffer."""
+    n = 25                                                             # 256 MB of complex64: four chunks
+    rng = np.random.default_rng(3)
+    v = (rng.standard_normal(1 << n, dtype=np.float32) + 1j * rng.standard_normal(1 << n, dtype=np.float32)).astype(np.complex64)
+    g = StateVector(n, "c64")
+    g.set_state(v)
+    assert np.array_equal(g.state(), v)
+    assert g.lib.rocsvEnsurePinnedBuffer(g.h, v.nbytes) == capi.SUCCESS
+    ptr = g.lib.rocsvGetPinnedBufferPointer(g.h)
+    pinned = np.ctypeslib.as_array((C.c_float * (2 << n)).from_address(ptr)).view(np.complex64)
+    assert g.lib.rocsvGetStateVectorFull(g.h, g.d, C.c_void_p(ptr)) == capi.SUCCESS
+    assert np.array_equal(pinned, v)
+    odd = StateVector(21, "c128", batch=3)                             # 3 x 32 MB: a chunk boundary inside batch member 1
+    w = util.random_state(21, 3, seed=2)
+    odd.set_state(w)
+    assert np.array_equal(odd.state(), w.astype(np.complex128))
+    assert np.array_equal(odd.state_slice(2), w[2 << 21:])
+
+
+def test_sampling_is_chunking_independent_and_handles_degenerate_states():
+    n = 16
+    gates = workloads.c2_random_unitary(n, 3, seed=3)
+    o = so.Oracle(n, "c64", seed=4); util.run_on_oracle(o, gates)
+    g = StateVector(n, "c64", seed=4); g.set_state(o.state)
+    want = o.sample([0, 15, 7], 4096)
+    assert np.array_equal(g.sample([0, 15, 7], 4096), want)
+    # basis state: every shot the same index; duplicates and an empty qubit list are legal requests
+    b = StateVector(n, "c64", seed=1); b.gate("x", 3); b.gate("x", 15)
+    assert set(np.unique(b.sample(list(range(n)), 100))) == {(1 << 3) | (1 << 15)}
+    assert set(np.unique(b.sample([3, 3, 0, 15], 10))) == {0b1011}
+    assert not b.sample([], 5).any()
+    z = StateVector(6, "c64"); z.set_state(np.zeros(64, dtype=np.complex64))
+    out = (C.c_uint64 * 4)()
+    assert z.lib.rocsvSample(z.h, z.d, 6, capi.uarr([0]), 1, 4, out) == capi.FAILURE       # nothing to draw from
+
+
+def test_block_path_keeps_small_amplitudes_of_a_peaked_state():
+    """Per-amplitude RELATIVE accuracy on a peaked state through the tensor-core block path.  RX(small) on every qubit gives
+    a product state whose amplitudes span 1 ... eps^n; a 6-qubit block acting on it mixes only amplitudes of one column, so
+    a correct fp32-class kernel keeps every amplitude accurate relative to its COLUMN's magnitude."""
+    n = 20
+    eps = 2e-2
+    rng = np.random.default_rng(5)
+    pre = [("rx", [q], [], 2 * eps) for q in range(n)]
+    blk = [8, 9, 10, 11, 12, 13]
+    U = workloads.haar_unitary(rng, 64)
+    o = so.Oracle(n, "c128"); util.run_on_oracle(o, pre)
+    g = StateVector(n, "c64"); g.apply_circuit(pre)
+    o.apply_matrix(blk, U); g.apply_block6(blk, U)
+    got, want = g.state().astype(np.complex128), o.state
+    # column = all amplitudes that differ only in the block bits
+    idx = np.arange(1 << n)
+    mask = sum(1 << q for q in blk)
+    col = idx & ~mask
+    colmax = np.zeros(1 << n)
+    np.maximum.at(colmax, col, np.abs(want))
+    rel = np.abs(got - want) / colmax[col]
+    assert rel.max() < 1e-5, rel.max()
+
+
+def test_c2_full_depth_parity_n26():
+    """configs[1] in full depth (40 layers, 63-class plan of stacked fp16-split blocks) on 26 qubits, every amplitude
+    against the oracle, plus 32 Pauli strings."""
+    n = 26
+    gates = workloads.c2_random_unitary(n, 40, seed=30)
+    o = so.Oracle(n, "c64"); util.run_on_oracle(o, gates)
+    g = StateVector(n, "c64"); g.apply_circuit(gates)
+    assert g.stats().blockSweeps > 20
+    assert util.rel_err(g.state(), o.state) < TOL["c64"]
+    terms = workloads.random_pauli_strings(n, 32, 8, seed=6)
+    got = g.expect_batch(terms)
+    for r, t in zip(got, terms):
+        assert abs(r - o.expect_pauli(*t)) < 1e-5
+
+
+def test_c3_qft_parity_n24_c128():
+    n = 24
+    gates = workloads.c3_qft(n, seed=33)
+    o = so.Oracle(n, "c128"); util.run_on_oracle(o, gates)
+    g = StateVector(n, "c128"); g.apply_circuit(gates)
+    assert util.rel_err(g.state(), o.state) < TOL["c128"]
+
+
+def test_c2_at_30_qubits_against_the_c128_library():
+    """BASELINE configs[1] at full size and depth: the complex64 engine (tensor-core blocks on) against the complex128
+    library run of the same circuit on a strided subsample of 2^20 amplitudes and 64 random Pauli strings."""
+    n = 30
+    gates = workloads.c2_random_unitary(n, 40, seed=30)
+    terms = workloads.random_pauli_strings(n, 64, 8, seed=7)
+    stride = 1 << (n - 20)
+    d = StateVector(n, "c128"); d.apply_circuit(gates)
+    want_e = d.expect_batch(terms)
+    want = _strided(d, n, stride, np.complex128)
+    del d
+    import gc; gc.collect()
+    g = StateVector(n, "c64"); g.apply_circuit(gates)
+    assert g.stats().blockSweeps >= 50
+    got = _strided(g, n, stride, np.complex64)
+    ref = np.abs(want).max()
+    assert np.abs(got - want).max() / ref < TOL["c64"]
+    got_e = g.expect_batch(terms)
+    assert np.abs(got_e - want_e).max() < 1e-5
+
+
+def _strided(sv, n, stride, dtype):
+    """every stride-th amplitude, read through torch from the library's device pointer (test plumbing only)"""
+    import torch
+    N = 1 << n
+    sv.sync()
+    out = np.empty(N // stride, dtype=dtype)
+    # a device gather through cudaMemcpy2D: rows of one amplitude, pitch = stride amplitudes
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    esz = out.itemsize
+    rc = rt.cudaMemcpy2D(out.ctypes.data_as(C.c_void_p), C.c_size_t(esz), C.c_void_p(sv.d.value), C.c_size_t(stride * esz),
+                         C.c_size_t(esz), C.c_size_t(N // stride), C.c_int(2))
+    assert rc == 0, rc
+    return out

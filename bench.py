@@ -327,6 +327,9 @@ def run_engine(args):
 
     # ---- end to end through the public call: host gate list in, host result out, every step ----------
     e2e_t, d2h = 0.0, 0
+    # no kept plan here: every step converts, fuses and plans the host gate list again and uploads the block operands
+    assert lib.rocsvxSetPlanCache(sv.h, 0) == 0
+    step(); barrier()                                   # (first uncached step also pays one-time allocator growth)
     sv.stats(reset=True)
     barrier()
     t0 = time.perf_counter()
@@ -348,6 +351,39 @@ def run_engine(args):
         e2e_t = float(t[0])
     e2e_value = ngates * args.steps / e2e_t * norm
 
+    # ---- N > 1: the result of exactly this engine configuration, checked.  The same circuit class on n_par qubits over the
+    #      N ranks (deferring planner, tensor-core blocks, the exchange mover of this run) against a complex128 run of the
+    #      same circuit on rank 0 alone, every amplitude ----------------------------------------------------------------
+    parity = None
+    if world > 1 and not args.no_parity:
+        from rocquantum_b200 import distributed, workloads as wlp
+        sv.close()
+        m_ = ngpus.bit_length() - 1
+        n_par = env_int("ROCQ_BENCH_PARITY_QUBITS", 26 + min(m_, 2))
+        pg = wlp.c4_global_layers(n_par, 20, seed=36)
+        d = distributed.DistStateVector(n_par, "c64")
+        assert d.lib.rocsvxSetTensorCoreBlocks(d.h, 1) == 0          # the slices are below the 'auto' threshold: force the bench's path
+        parr, pkeep = capi.make_ops(pg)
+        d.apply_ops(parr, len(pg))
+        pst = d.stats()
+        sl = torch.from_numpy(d.local_slice().view(np.float32)).cuda()
+        outs = [torch.empty_like(sl) for _ in range(world)] if rank == 0 else None
+        dist.gather(sl, outs, dst=0)
+        d.close()
+        if rank == 0:
+            got = np.concatenate([o.cpu().numpy() for o in outs]).view(np.complex64)
+            del outs
+            ref = StateVector(n_par, "c128")
+            rarr, rkeep = capi.make_ops(pg)
+            assert ref.lib.rocsvxApplyCircuit(ref.h, ref.d, n_par, rarr, len(pg)) == 0
+            want = ref.state()
+            ref.close()
+            err = float(np.abs(got - want).max() / np.abs(want).max())
+            parity = {"n": n_par, "gates": len(pg), "max_rel_err": err, "tolerance": 1e-5, "ok": bool(err < 1e-5),
+                      "exchanges": int(pst.exchanges), "block_sweeps": int(pst.blockSweeps), "sweeps": int(pst.sweeps),
+                      "what": "complex64 over %d ranks (blocks on, this run's exchange mover) vs complex128 on rank 0 alone, all 2^%d amplitudes, "
+                              "error relative to the largest amplitude" % (world, n_par)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -361,7 +397,7 @@ def run_engine(args):
         exchange = {"per_step": st.exchanges / args.steps, "ms_per_step": st.exchangeMs / args.steps,
                     "sent_bytes_per_rank_per_step": st.exchangeBytes / args.steps,
                     "send_GBps_per_rank": (st.exchangeBytes / 1e9) / (st.exchangeMs * 1e-3) if st.exchangeMs > 0 else None,
-                    "mover": "p2p" if os.environ.get("ROCQ_EXCHANGE", "")[:1] in ("p", "P") else "nccl",
+                    "mover": "nccl" if os.environ.get("ROCQ_EXCHANGE", "")[:1] in ("n", "N") else "p2p",
                     "planner": "program order" if os.environ.get("ROCQ_DIST_INORDER", "0") not in ("", "0") else "deferring",
                     "what": "k rank bits <-> top-k local bits; mover nccl = ncclSend/ncclRecv per peer + staging->slice copy, "
                             "p2p = in-place half-swap kernel over IPC-mapped peer slices between two stream barriers; rank 0's figures"}
@@ -479,6 +515,54 @@ def run_engine(args):
         except Exception as ex:                                  # never take the bench line down
             qft = {"error": str(ex)[:200]}
 
+    # ---- BASELINE configs[4]: VQE ansatz + batched Pauli-string expectation + 1M-shot sampling, 28 qubits ---------------
+    vqe = None
+    if ngpus == 1 and not args.no_vqe:
+        try:
+            from rocquantum_b200 import workloads as wv
+            try:
+                sv.close()
+            except Exception:
+                pass
+            nv = env_int("ROCQ_BENCH_VQE_QUBITS", 28)
+            layers = []
+            for rep in range(4):
+                layers += wv.c5_vqe_ansatz(nv, seed=5 + rep)[nv if rep else 0:]
+            v = StateVector(nv, "c64")
+            varr, vkeep = capi.make_ops(layers)
+            for rep in range(3):
+                v.init(); v.sync(); v.stats(reset=True)
+                assert lib.rocsvxApplyCircuit(v.h, v.d, nv, varr, len(layers)) == 0
+                v.sync()
+                vs = v.stats()
+            ans_ms, ans_sweeps = vs.lastSweepMs, int(vs.sweeps)
+            rnd = wv.random_pauli_strings(nv, 64, 8, seed=5)
+            ham = wv.hamiltonian_like_terms(nv, 64, seed=5)
+            out = {}
+            for name, terms in (("random64", rnd), ("hamiltonian64", ham)):
+                v.expect_batch(terms)                            # warm-up
+                v.stats(reset=True); v.sync(); v.timer_start()
+                vals = v.expect_batch(terms)
+                ms = v.timer_stop()
+                groups = int(v.stats().expectationSweeps)
+                out[name] = {"terms": len(terms), "read_sweeps": groups, "device_ms": ms, "ms_per_sweep": ms / max(1, groups),
+                             "GBps_per_sweep": (1 << nv) * 8 / (ms / max(1, groups) * 1e-3) / 1e9, "sum": float(np.sum(vals))}
+            v.sample(list(range(nv)), 1000)
+            t0 = time.perf_counter()
+            shots = v.sample(list(range(nv)), 1_000_000)
+            samp_ms = (time.perf_counter() - t0) * 1e3
+            vqe = {"workload": f"C5: {nv}-qubit hardware-efficient ansatz (examples/vqe_lih.py:74-95 pattern) x4, complex64",
+                   "ansatz": {"gates": len(layers), "device_ms": ans_ms, "sweeps": ans_sweeps,
+                              "GBps_per_sweep": 2.0 * (1 << nv) * 8 * ans_sweeps / (ans_ms * 1e-3) / 1e9},
+                   "expectation_batch": out, "sampling_1M": {"wall_ms": samp_ms, "shots_per_s": 1e6 / (samp_ms * 1e-3),
+                                                              "distinct_in_first_10k": int(len(set(shots[:10000].tolist())))},
+                   "note": "expectation: terms grouped by x-mask, one read sweep (2^n * 8 B) per group, one D2H for all results; "
+                           "random64 = 64 random strings of weight <= 8 (nearly all x-masks distinct), hamiltonian64 = Z / ZZ terms plus "
+                           "XX, YY, XY, YX on shared pairs (a molecular Hamiltonian's structure)"}
+            v.close()
+        except Exception as ex:                                  # never take the bench line down
+            vqe = {"error": str(ex)[:200]}
+
     line = {"metric": "gates_per_sec", "value": value, "unit": unit_for(n),
             "n_gpus": ngpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
@@ -487,11 +571,16 @@ def run_engine(args):
             "clocks": clk, "device_ms_per_step": dev_ms / args.steps,
             "e2e": {"value": e2e_value, "unit": unit_for(n),
                     "h2d_bytes_per_step": st_e2e.h2dBytes // args.steps, "d2h_bytes_per_step": d2h,
-                    "what": "rocsvInitializeState + rocsvxApplyCircuit(host gate list) + <Z0> and 256 sampled bitstrings read back, every step; "
-                            "the gate list reaches the device as sweep programs in kernel parameters"},
+                    "what": "rocsvInitializeState + rocsvxApplyCircuit(host gate list, plan cache OFF: converted, fused, planned and its "
+                            "block operands uploaded every step) + <Z0> and 256 sampled bitstrings read back, every step; h2d = block operand "
+                            "terms + sweep programs travelling as kernel parameters"},
             "gpu_launches": int(st.kernelLaunches), "roofline": roofline, "cpu_baseline": cpu}
     if exchange:
         line["exchange"] = exchange
+    if parity:
+        line["parity"] = parity
+    if vqe:
+        line["vqe_c5"] = vqe
     if c1:
         line["c1_reference"] = c1
     if qft:
@@ -509,6 +598,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-qft", action="store_true", help="skip the 33-qubit complex128 QFT leg (137 GB)")
+    ap.add_argument("--no-vqe", action="store_true", help="skip the configs[4] leg (28-qubit ansatz, expectation batch, 1M shots)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the self-check against the complex128 single-GPU run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

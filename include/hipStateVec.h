@@ -53,6 +53,7 @@ extern "C" {
 /* ---- lifecycle and state (REF:43, 51, 61, 69, 79) ---- */
 rocqStatus_t rocsvCreate(rocsvHandle_t* handle);
 rocqStatus_t rocsvDestroy(rocsvHandle_t handle);
+/* numQubits > 40 (8.8 TB of complex64) is refused with ROCQ_STATUS_ALLOCATION_FAILED before any allocation is tried. */
 rocqStatus_t rocsvAllocateState(rocsvHandle_t handle, unsigned numQubits, rocComplex** d_state, size_t batchSize);
 rocqStatus_t rocsvFreeState(rocsvHandle_t handle);
 rocqStatus_t rocsvInitializeState(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits);
@@ -177,6 +178,7 @@ typedef struct {
  * it off. */
 rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t handle, rocComplex* d_state, unsigned numQubits,
                                 const rocsvxGateOp* ops, size_t numOps);
+rocqStatus_t rocsvxSetPlanCache(rocsvHandle_t handle, int enabled);     /* 0: every rocsvxApplyCircuit call plans afresh (and drops the kept plan) */
 
 /* Tensor-core path (complex64 library only): apply one dense 6-qubit matrix (HOST, column-major 64x64, interleaved
  * (re,im) doubles, index bit b <-> qubits[b], any six distinct qubits) to the whole state in one HBM pass with tcgen05
@@ -249,6 +251,19 @@ rocqStatus_t rocsvxPlanCircuitBlocks(unsigned numQubits, const rocsvxGateOp* ops
 rocqStatus_t rocsvxDistGetUniqueId(void* id128);
 rocqStatus_t rocsvxDistInit(rocsvHandle_t handle, int rank, int numRanks, const void* id128);
 rocqStatus_t rocsvxDistGetInfo(rocsvHandle_t handle, int* rank, int* numRanks, unsigned* numLocalQubits, rocComplex** d_localSlice);
+
+/* ---- single-process distribution: the reference's model (MULTI_GPU_GUIDE.md:11-17, test_hipStateVec_multi_gpu.cpp:109-339,
+ *      python/rocq/api.py:53-57).  rocsvAllocateDistributedState on a handle that is NOT a rank of a multi-process job shards
+ *      the state over the visible devices from this one process: the largest power of two of them, at least two local
+ *      qubits per slice (ROCQ_NUM_GPUS caps it).  Every rocsv* call on the handle then acts on all slices (pass d_state =
+ *      NULL), scalar results are returned once, rocsvGetStateVectorFull / rocsvxSetStateVector move the WHOLE 2^n state
+ *      (slice r at r * 2^numLocalQubits).  The devices must have peer access to each other.
+ *      rocsvxDistSetRanks fixes the number of slices of the next allocation (a power of two; 0 = default).  More slices than
+ *      devices are placed round-robin -- useful only to exercise the distributed engine on one GPU.
+ *      rocsvxDistGetRankSlice: device ordinal and raw device pointer of one slice (what the reference's test reads through
+ *      its test-visible handle, test_hipStateVec_multi_gpu.cpp:43-81). ---- */
+rocqStatus_t rocsvxDistSetRanks(rocsvHandle_t handle, int numRanks);
+rocqStatus_t rocsvxDistGetRankSlice(rocsvHandle_t handle, int rank, int* device, rocComplex** d_slice);
 
 /* Host-only plan of a global<->local index-bit exchange: swapping the k = numPairs global bits
  * globalBits[] with the local bits localBits[] on `rank` of `numRanks`.  Writes up to maxSegs

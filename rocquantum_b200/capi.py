@@ -86,6 +86,7 @@ PROTOTYPES = {
     "rocsvxSetFusion": [_h, C.c_int],
     "rocsvxFlush": [_h],
     "rocsvxApplyCircuit": [_h, _p, _u, C.POINTER(GateOp), _sz],
+    "rocsvxSetPlanCache": [_h, C.c_int],
     "rocsvxApplyBlock6": [_h, _p, _u, _up, C.POINTER(_d)],
     "rocsvxSetTensorCoreBlocks": [_h, C.c_int],
     "rocsvxSetMergeDiagonals": [_h, C.c_int],
@@ -100,6 +101,8 @@ PROTOTYPES = {
     "rocsvxDistGetUniqueId": [_p],
     "rocsvxDistInit": [_h, C.c_int, C.c_int, _p],
     "rocsvxDistGetInfo": [_h, C.POINTER(C.c_int), C.POINTER(C.c_int), _up, C.POINTER(_p)],
+    "rocsvxDistSetRanks": [_h, C.c_int],
+    "rocsvxDistGetRankSlice": [_h, C.c_int, C.POINTER(C.c_int), C.POINTER(_p)],
     "rocsvxDistPlanCircuit": [_u, C.c_int, C.POINTER(GateOp), _sz, C.c_int, C.c_int, _up, C.c_char_p, _sz],
     "rocsvxDistPlanExchange": [_u, C.c_int, C.c_int, _up, _up, _u, C.POINTER(ExchangeSeg), _sz, C.POINTER(_sz)],
     "rocsvxDistPlanPeerSwap": [_u, C.c_int, C.c_int, _up, _up, _u, C.POINTER(ExchangeSeg), _sz, C.POINTER(_sz)],

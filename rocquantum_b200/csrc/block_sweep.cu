@@ -37,7 +37,8 @@
 namespace {
 
 constexpr int NW = 512;                        // worker threads: 4 warps per TMEM lane quarter, 16 block values per thread
-constexpr int BT = NW + 32;                    // + one warp that only issues the MMAs
+constexpr int NC = 128;                        // control threads: one scout per tile column; the first of them also issues the MMAs
+constexpr int BT = NW + NC;
 constexpr uint32_t MAT_BYTES = 8192;           // one fp16 term of a 64 x 64 operand (Re U or Im U)
 constexpr uint32_t TILE_BYTES = 65536;         // 2^13 complex64 amplitudes
 constexpr uint32_t SMEM_U = 0;                                    // Re U hi | Re U lo | Im U hi | Im U lo  (B operands, N = 64)
@@ -164,16 +165,17 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                                                              const __grid_constant__ rq_block_params P,
                                                              const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_u, bar_mma[2], bar_x[2], bar_full[3];
+    __shared__ __align__(8) uint64_t bar_u, bar_mma[2], bar_x[2], bar_full[3], bar_scale[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float2 red[2][16];      // per-warp (|in|^2, |out|^2) of a tile, double-buffered
-    __shared__ uint8_t cexp[2][4][128]; // biased exponent of max |component| per (tile parity, quarter of the block values, column)
+    __shared__ uint8_t cexp[2][128];   // biased exponent of the largest |component| of every column of a tile (by tile parity)
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         mbar_init(smem_u32(&bar_u), 1);
         for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_mma[b]), 1); mbar_init(smem_u32(&bar_x[b]), NW / 32); }
         for (int b = 0; b < 3; ++b) mbar_init(smem_u32(&bar_full[b]), 1);
+        for (int b = 0; b < 2; ++b) mbar_init(smem_u32(&bar_scale[b]), NC / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {                                         // all 512 columns: two buffers x (D | X' hi | X' lo)
@@ -189,14 +191,44 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
     const uint64_t first = blockIdx.x, stride = gridDim.x;
     const uint64_t cnt = P.ntiles > first ? (P.ntiles - first + stride - 1) / stride : 0;     // tiles of this CTA
 
-    if (warp == NW / 32) {
-        // ================================ the MMA warp ================================
-        if (lane == 0) {
+    if (warp >= NW / 32) {
+        // ================================ the control group: 4 warps ================================
+        // Every thread is the SCOUT of one tile column: as soon as a tile has landed it reads the column's 64 amplitudes and
+        // publishes the exponent of the largest component, from which the workers derive the column's power-of-two scale.
+        // The scouts run a tile ahead of the split, so the workers never wait for each other to agree on a scale (an
+        // exchange between the four workers of a column costs 14 % of the pass: profiles/r02_block_scale_variants.md).
+        // The first scout also issues the MMAs of the tile once the workers have split it into tensor memory.
+        const uint32_t scol = tid - NW;
+        uint32_t lcol = 0;
+        for (uint32_t b = 0; b < 7; ++b) lcol |= ((scol >> b) & 1u) << P.lp_col[b];
+        const uint32_t cbase = (lcol ^ (((lcol >> 4) & 7u) << 1)) * 8u;                       // bytes, swizzled (block bits never sit on local bits 4-6)
+        uint32_t voff[6];
+        for (uint32_t b = 0; b < 6; ++b) voff[b] = 8u << P.lp_blk[b];
+        const bool issuer = tid == NW;
+        uint32_t urh = 0, url = 0, uih = 0, uil = 0;
+        if (issuer) {
             mbar_expect_tx(smem_u32(&bar_u), 4 * MAT_BYTES);          // the block matrix stays resident for all tiles
             bulk_g2s(smem_u32(smem + SMEM_U), uterms, 4 * MAT_BYTES, smem_u32(&bar_u));
             mbar_wait(smem_u32(&bar_u), 0);
-            const uint32_t urh = smem_u32(smem + SMEM_U), url = urh + MAT_BYTES, uih = urh + 2 * MAT_BYTES, uil = urh + 3 * MAT_BYTES;
-            for (uint64_t i = 0; i < cnt && !(dbg & 1u); ++i) {
+            urh = smem_u32(smem + SMEM_U); url = urh + MAT_BYTES; uih = urh + 2 * MAT_BYTES; uil = urh + 3 * MAT_BYTES;
+        }
+        for (uint64_t i = 0; i < cnt; ++i) {
+            mbar_wait(smem_u32(&bar_full[i % 3u]), (uint32_t)(i / 3u) & 1u);
+            const unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES + cbase;
+            float mx = 0.f;
+#pragma unroll 16
+            for (uint32_t v = 0; v < 64; ++v) {
+                const uint32_t off = ((v & 1u) ? voff[0] : 0u) ^ ((v & 2u) ? voff[1] : 0u) ^ ((v & 4u) ? voff[2] : 0u) ^ ((v & 8u) ? voff[3] : 0u) ^
+                                     ((v & 16u) ? voff[4] : 0u) ^ ((v & 32u) ? voff[5] : 0u);
+                // (cbase's swizzle bits and the value offsets are disjoint: the XOR commutes with the base)
+                const float2 a = *reinterpret_cast<const float2*>(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES + (cbase ^ off));
+                mx = fmaxf(mx, fmaxf(fabsf(a.x), fabsf(a.y)));
+            }
+            (void)S;
+            cexp[i & 1u][scol] = (uint8_t)(__float_as_uint(mx) >> 23);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_scale[i & 1u]));   // release: the exponents are visible to whoever sees the phase flip
+            if (issuer && !(dbg & 1u)) {
                 const uint32_t b = (uint32_t)i & 1u;
                 mbar_wait(smem_u32(&bar_x[b]), (uint32_t)(i >> 1) & 1u);       // X' of tile i is in tensor memory
                 tc_fence_after();
@@ -220,6 +252,7 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                 product(xrh, xih, urh, uih, false);
                 umma_commit(smem_u32(&bar_mma[b]));
             }
+            __syncwarp();
         }
     } else {
         // ================================ 16 worker warps ================================
@@ -353,50 +386,20 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             mark(0);
             const unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES;
             float in2 = 0.f;
-#ifndef RQ_BS_SCALE
-#define RQ_BS_SCALE 1            // tuning A/B only: 0 global scale (round 1), 1 per-column scale, 2 same but re-reading shared memory, 3 no exchange (wrong)
-#endif
-#if RQ_BS_SCALE == 1
-            float2 a[16];
-#define RQ_BS_A(j) a[j]
-#else
-#define RQ_BS_A(j) (*reinterpret_cast<const float2*>(S + (sbase ^ vaddr(j))))
-#endif
-            float mx = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 v = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(j)));
-#if RQ_BS_SCALE == 1
-                a[j] = v;
-#endif
-                in2 = fmaf(v.x, v.x, fmaf(v.y, v.y, in2));
-#if RQ_BS_SCALE != 0
-                mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
-#endif
-            }
-#if RQ_BS_SCALE == 0
-            const float scale = P.scale, cur_inv = 1.f / P.scale;
-            (void)mx;
-#else
-            // the column's scale: the four threads that hold a column (one per quarter, same lane, warps w, w+4, w+8, w+12)
-            // exchange the exponents of their maxima through shared memory behind a 128-thread named barrier
-            uint32_t e = __float_as_uint(mx) >> 23;
-#if RQ_BS_SCALE != 3
-            cexp[i & 1u][qt][ncol] = (uint8_t)e;
-            asm volatile("bar.sync %0, 128;" ::"r"(2u + (warp & 3u)) : "memory");
-            e = max(max((uint32_t)cexp[i & 1u][0][ncol], (uint32_t)cexp[i & 1u][1][ncol]),
-                    max((uint32_t)cexp[i & 1u][2][ncol], (uint32_t)cexp[i & 1u][3][ncol]));
-#endif
+            // the column's scale, found by its scout while the previous tile was being processed
+            mbar_wait(smem_u32(&bar_scale[i & 1u]), (uint32_t)(i >> 1) & 1u);
+            uint32_t e = cexp[i & 1u][ncol];
             e = min(max(e, 20u), 254u);                                        // empty / denormal columns and inf / nan: any finite scale
             const float scale = __uint_as_float((268u - e) << 23);             // column maximum -> [2^14, 2^15)
             const float cur_inv = __uint_as_float((e - 14u) << 23);
-#endif
 #pragma unroll
             for (int c = 0; c < 2; ++c) {                                      // 8 block values -> 4 packed words per (term, re|im)
                 uint32_t hr[4], lr[4], hi[4], li[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float2 a0 = RQ_BS_A(8 * c + 2 * j), a1 = RQ_BS_A(8 * c + 2 * j + 1);
+                    const float2 a0 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j)));
+                    const float2 a1 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j + 1)));
+                    in2 = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, in2))));
                     split2(a0.x * scale, a1.x * scale, hr[j], lr[j]);
                     split2(a0.y * scale, a1.y * scale, hi[j], li[j]);
                 }

@@ -695,13 +695,52 @@ rocqStatus_t Dist::sample(rocsvInternalHandle* h, const unsigned* measured, unsi
 
 extern "C" {
 
+// hipStateVec.h:84-104.  A handle that is a rank of a multi-process job (rocsvxDistInit) allocates its slice.  Any other
+// handle follows the reference's model -- one process, one handle, all GPUs (MULTI_GPU_GUIDE.md:11-17): the state is sharded
+// over the visible devices (the largest power of two of them; rocsvxDistSetRanks / ROCQ_NUM_GPUS choose otherwise) and the
+// handle becomes the front of a group of per-device ranks (group.h).  With one device it is a plain single-slice state.
 rocqStatus_t rocsvAllocateDistributedState(rocsvHandle_t h, unsigned totalNumQubits) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (totalNumQubits > 60) return ROCQ_STATUS_INVALID_VALUE;
+    if (!h->dist.inited || h->group) {
+        int want = h->wantRanks;
+        if (want <= 0) if (const char* e = getenv("ROCQ_NUM_GPUS")) want = atoi(e);
+        if (want <= 0) { if (cudaGetDeviceCount(&want) != cudaSuccess) { cudaGetLastError(); want = 1; } }
+        int P = 1;
+        while (2 * P <= want) P *= 2;
+        while (P > 1 && (1u << (totalNumQubits > 2 ? totalNumQubits - 2 : 0)) < (unsigned)P) P /= 2;    // keep >= 2 local qubits per slice
+        if (h->group && h->group->P != P) rq_group_destroy(h);
+        if (P > 1 && !h->group) {
+            rocsvFreeState(h);                                 // the front handle holds no state of its own
+            const rocqStatus_t s = rq_group_create(h, P);
+            if (s != ROCQ_STATUS_SUCCESS) return s;
+        }
+        if (h->group) return h->group->run([&](rocsvInternalHandle* c, int) { return c->dist.allocate(c, totalNumQubits); });
+    }
     return h->dist.allocate(h, totalNumQubits);
 }
 rocqStatus_t rocsvInitializeDistributedState(rocsvHandle_t h) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->group) return h->group->run([&](rocsvInternalHandle* c, int) { return c->dist.initialize(c); });
     return h->dist.initialize(h);
+}
+rocqStatus_t rocsvxDistSetRanks(rocsvHandle_t h, int numRanks) {
+    if (!h || numRanks < 0 || (numRanks & (numRanks - 1))) return ROCQ_STATUS_INVALID_VALUE;
+    h->wantRanks = numRanks;
+    return ROCQ_STATUS_SUCCESS;
+}
+rocqStatus_t rocsvxDistGetRankSlice(rocsvHandle_t h, int rank, int* device, rocComplex** d_slice) {
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (!h->group) {
+        if (rank != 0) return ROCQ_STATUS_INVALID_VALUE;
+        if (device) cudaGetDevice(device);
+        if (d_slice) *d_slice = reinterpret_cast<rocComplex*>(h->d_state);
+        return ROCQ_STATUS_SUCCESS;
+    }
+    if (rank < 0 || rank >= h->group->P || !h->group->child[(size_t)rank]) return ROCQ_STATUS_INVALID_VALUE;
+    if (device) *device = h->group->device[(size_t)rank];
+    if (d_slice) *d_slice = reinterpret_cast<rocComplex*>(h->group->child[(size_t)rank]->d_state);
+    return ROCQ_STATUS_SUCCESS;
 }
 rocqStatus_t rocsvxDistGetUniqueId(void* id128) {
     if (!id128) return ROCQ_STATUS_INVALID_VALUE;
@@ -712,11 +751,16 @@ rocqStatus_t rocsvxDistGetUniqueId(void* id128) {
     return ROCQ_STATUS_SUCCESS;
 }
 rocqStatus_t rocsvxDistInit(rocsvHandle_t h, int rank, int numRanks, const void* id128) {
-    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (!h || h->group) return ROCQ_STATUS_INVALID_VALUE;
     return h->dist.init(h, rank, numRanks, id128);
 }
 rocqStatus_t rocsvxDistGetInfo(rocsvHandle_t h, int* rank, int* numRanks, unsigned* numLocalQubits, rocComplex** d_localSlice) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->group && h->group->child[0]) {                          // the front of a single-process group answers for rank 0
+        const rocqStatus_t s = rocsvxDistGetInfo(h->group->child[0], rank, numRanks, numLocalQubits, d_localSlice);
+        if (rank) *rank = 0;
+        return s;
+    }
     if (rank) *rank = h->dist.rank;
     if (numRanks) *numRanks = h->dist.nranks;
     if (numLocalQubits) *numLocalQubits = h->dist.n_local;

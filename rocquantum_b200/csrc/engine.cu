@@ -37,6 +37,23 @@ namespace {
 
 typedef rocsvInternalHandle H;
 
+// Single-process multi-GPU (group.h): a call on the front handle of a group runs on every rank's own handle at once.
+// `c` = the rank's handle, `r` = its rank.  d_state arguments are dropped: a distributed state is always the handle's own
+// (MULTI_GPU_GUIDE.md: "multi-GPU always NULL").
+#define RQ_FWD(h, expr)                                                                                        \
+    do {                                                                                                       \
+        if ((h) && (h)->group)                                                                                 \
+            return (h)->group->run([&](rocsvInternalHandle* c, int r) -> rocqStatus_t { (void)r; (void)c; return (expr); }); \
+    } while (0)
+// an output every rank computes identically: rank 0 writes the caller's memory, the others a scratch of their own
+template <typename T>
+struct PerRank {
+    T* user;
+    std::vector<std::vector<T>> scratch;
+    PerRank(T* u, int ranks, size_t count = 1) : user(u), scratch((size_t)ranks, std::vector<T>(u ? count : 0)) {}
+    T* at(int r) { return (r == 0 || !user) ? user : scratch[(size_t)r].data(); }
+};
+
 inline rocqStatus_t cuda_status(int e, const char* what) {
     if (e == (int)cudaSuccess) return ROCQ_STATUS_SUCCESS;
     fprintf(stderr, "hipStateVec(B200): %s failed: %s\n", what, cudaGetErrorString((cudaError_t)e));
@@ -575,6 +592,34 @@ uint64_t uniform53(uint64_t seed, uint64_t call, uint64_t shot) {
 
 }  // namespace
 
+// ---- single-process multi-GPU group (group.h) ----------------------------------------------------------------------
+void rq_group_destroy(rocsvInternalHandle* h) {
+    if (!h || !h->group) return;
+    rocsvGroup* g = h->group;
+    h->group = nullptr;
+    g->run([&](H* c, int r) { const rocqStatus_t s = c ? rocsvDestroy(c) : ROCQ_STATUS_SUCCESS; g->child[(size_t)r] = nullptr; return s; });
+    delete g;
+}
+// one worker thread + one ordinary handle per slice; the ranks inherit the front handle's settings
+rocqStatus_t rq_group_create(rocsvInternalHandle* h, int ranks) {
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1) { cudaGetLastError(); return ROCQ_STATUS_HIP_ERROR; }
+    rocsvGroup* g = new rocsvGroup(ranks, visible);
+    const rocqStatus_t s = g->run([&](H*, int r) -> rocqStatus_t {
+        rocsvHandle_t c = nullptr;
+        const rocqStatus_t cs = rocsvCreate(&c);
+        if (cs != ROCQ_STATUS_SUCCESS) return cs;
+        g->child[(size_t)r] = c;
+        c->fusion = h->fusion; c->tcBlocks = h->tcBlocks; c->mergeDiagonals = h->mergeDiagonals; c->planCache = h->planCache;
+        c->blockMinCost = h->blockMinCost; c->budget = h->budget; c->tileBits = h->tileBits;
+        c->seed = h->seed; c->draws = h->draws; c->seedExplicit = true;      // one Philox stream for all ranks
+        return c->dist.init_in_group(c, r, g);
+    });
+    h->group = g;
+    if (s != ROCQ_STATUS_SUCCESS) rq_group_destroy(h);
+    return s;
+}
+
 // hooks for dist.cu
 rocqStatus_t rq_engine_flush(rocsvInternalHandle* h) { return flush(h); }
 rocqStatus_t rq_engine_run(rocsvInternalHandle* h, rq_cplx* state, unsigned n, const std::vector<HostOp>& ops, bool fused) {
@@ -623,6 +668,7 @@ rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
 
 rocqStatus_t rocsvDestroy(rocsvHandle_t h) {
     if (!h) return ROCQ_STATUS_SUCCESS;                   // hipStateVec.cpp:203-210
+    rq_group_destroy(h);
     if (h->stream) { flush(h); cudaStreamSynchronize(h->stream); }
     h->dist.shutdown(h);
     rocsvFreeState(h);
@@ -642,6 +688,7 @@ rocqStatus_t rocsvDestroy(rocsvHandle_t h) {
 
 rocqStatus_t rocsvAllocateState(rocsvHandle_t h, unsigned numQubits, rocComplex** d_state, size_t batchSize) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    rq_group_destroy(h);                                  // a plain state replaces a distributed one
     if (numQubits > 40) return ROCQ_STATUS_ALLOCATION_FAILED;
     flush(h);
     cudaStreamSynchronize(h->stream);
@@ -661,6 +708,7 @@ rocqStatus_t rocsvAllocateState(rocsvHandle_t h, unsigned numQubits, rocComplex*
 
 rocqStatus_t rocsvFreeState(rocsvHandle_t h) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    rq_group_destroy(h);
     if (h->stream) { flush(h); cudaStreamSynchronize(h->stream); }
     drop_cache(h);
     if (h->d_state && h->ownsState) cudaFree(h->d_state);
@@ -672,6 +720,7 @@ rocqStatus_t rocsvFreeState(rocsvHandle_t h) {
 
 rocqStatus_t rocsvInitializeState(rocsvHandle_t h, rocComplex* d_state, unsigned numQubits) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    RQ_FWD(h, rocsvInitializeDistributedState(c));
     rq_cplx* state = resolve(h, d_state);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
     // a distributed handle has one state, its slices: the reset is the distributed one (it also resets the qubit map)
@@ -686,51 +735,79 @@ rocqStatus_t rocsvInitializeState(rocsvHandle_t h, rocComplex* d_state, unsigned
 
 // ---- named gates (hipStateVec.cpp:276-427) ---------------------------------------------------------------
 rocqStatus_t rocsvApplyH(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) {
+    RQ_FWD(h, rocsvApplyH(c, nullptr, n, t));
     const double s = 1.0 / std::sqrt(2.0);
     return single(h, d, n, t, rq::make_dense1(t, s, s, s, -s));
 }
-rocqStatus_t rocsvApplyX(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) { return single(h, d, n, t, rq::make_x(t)); }
+rocqStatus_t rocsvApplyX(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) {
+    RQ_FWD(h, rocsvApplyX(c, nullptr, n, t));
+    return single(h, d, n, t, rq::make_x(t)); }
 rocqStatus_t rocsvApplyY(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) {
+    RQ_FWD(h, rocsvApplyY(c, nullptr, n, t));
     return single(h, d, n, t, rq::make_dense1(t, 0.0, -I1, I1, 0.0));
 }
-rocqStatus_t rocsvApplyZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) { return single(h, d, n, t, rq::make_phase(1ull << t, -1.0)); }
-rocqStatus_t rocsvApplyS(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) { return single(h, d, n, t, rq::make_phase(1ull << t, I1)); }
-rocqStatus_t rocsvApplySdg(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) { return single(h, d, n, t, rq::make_phase(1ull << t, -I1)); }
+rocqStatus_t rocsvApplyZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) {
+    RQ_FWD(h, rocsvApplyZ(c, nullptr, n, t));
+    return single(h, d, n, t, rq::make_phase(1ull << t, -1.0)); }
+rocqStatus_t rocsvApplyS(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) {
+    RQ_FWD(h, rocsvApplyS(c, nullptr, n, t));
+    return single(h, d, n, t, rq::make_phase(1ull << t, I1)); }
+rocqStatus_t rocsvApplySdg(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) {
+    RQ_FWD(h, rocsvApplySdg(c, nullptr, n, t));
+    return single(h, d, n, t, rq::make_phase(1ull << t, -I1)); }
 rocqStatus_t rocsvApplyT(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t) {
+    RQ_FWD(h, rocsvApplyT(c, nullptr, n, t));
     const double ph = 3.14159265358979323846 / 4.0;
     return single(h, d, n, t, rq::make_phase(1ull << t, cd(std::cos(ph), std::sin(ph))));
 }
 rocqStatus_t rocsvApplyRx(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double theta) {
+    RQ_FWD(h, rocsvApplyRx(c, nullptr, n, t, theta));
     const double c = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
     return single(h, d, n, t, rq::make_dense1(t, c, cd(0.0, -s), cd(0.0, -s), c));
 }
 rocqStatus_t rocsvApplyRy(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double theta) {
+    RQ_FWD(h, rocsvApplyRy(c, nullptr, n, t, theta));
     const double c = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
     return single(h, d, n, t, rq::make_dense1(t, c, -s, s, c));
 }
 rocqStatus_t rocsvApplyRz(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double theta) {
+    RQ_FWD(h, rocsvApplyRz(c, nullptr, n, t, theta));
     const double c = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
     return single(h, d, n, t, rq::make_diag1(t, cd(c, -s), cd(c, s)));
 }
 
 // ---- two-qubit and controlled gates (hipStateVec.cpp:431-687) -----------------------------------------------
-rocqStatus_t rocsvApplyCNOT(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned c, unsigned t) { return two(h, d, n, c, t, rq::make_x(t, 1ull << (c & 63))); }
-rocqStatus_t rocsvApplyCZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned a, unsigned b) { return two(h, d, n, a, b, rq::make_phase((1ull << (a & 63)) | (1ull << (b & 63)), -1.0)); }
-rocqStatus_t rocsvApplySWAP(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned a, unsigned b) { return two(h, d, n, a, b, rq::make_swap(a, b)); }
-rocqStatus_t rocsvApplyCRX(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned c, unsigned t, double theta) {
+rocqStatus_t rocsvApplyCNOT(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned ctl_, unsigned t) {
+    RQ_FWD(h, rocsvApplyCNOT(c, nullptr, n, ctl_, t));
+    const unsigned c = ctl_;
+    return two(h, d, n, c, t, rq::make_x(t, 1ull << (c & 63))); }
+rocqStatus_t rocsvApplyCZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned a, unsigned b) {
+    RQ_FWD(h, rocsvApplyCZ(c, nullptr, n, a, b));
+    return two(h, d, n, a, b, rq::make_phase((1ull << (a & 63)) | (1ull << (b & 63)), -1.0)); }
+rocqStatus_t rocsvApplySWAP(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned a, unsigned b) {
+    RQ_FWD(h, rocsvApplySWAP(c, nullptr, n, a, b));
+    return two(h, d, n, a, b, rq::make_swap(a, b)); }
+rocqStatus_t rocsvApplyCRX(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned ctl_, unsigned t, double theta) {
+    RQ_FWD(h, rocsvApplyCRX(c, nullptr, n, ctl_, t, theta));
+    const unsigned c = ctl_;
     const double co = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
     return two(h, d, n, c, t, rq::make_dense1(t, co, cd(0.0, -s), cd(0.0, -s), co, 1ull << (c & 63)));
 }
-rocqStatus_t rocsvApplyCRY(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned c, unsigned t, double theta) {
+rocqStatus_t rocsvApplyCRY(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned ctl_, unsigned t, double theta) {
+    RQ_FWD(h, rocsvApplyCRY(c, nullptr, n, ctl_, t, theta));
+    const unsigned c = ctl_;
     const double co = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
     return two(h, d, n, c, t, rq::make_dense1(t, co, -s, s, co, 1ull << (c & 63)));
 }
-rocqStatus_t rocsvApplyCRZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned c, unsigned t, double theta) {
+rocqStatus_t rocsvApplyCRZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned ctl_, unsigned t, double theta) {
+    RQ_FWD(h, rocsvApplyCRZ(c, nullptr, n, ctl_, t, theta));
+    const unsigned c = ctl_;
     const double co = std::cos(theta / 2.0), s = std::sin(theta / 2.0);
     return two(h, d, n, c, t, rq::make_diag1(t, cd(co, -s), cd(co, s), 1ull << (c & 63)));
 }
 
 rocqStatus_t rocsvApplyMultiControlledX(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* controls, unsigned nc, unsigned t) {
+    RQ_FWD(h, rocsvApplyMultiControlledX(c, nullptr, n, controls, nc, t));
     if (!h || !controls || nc == 0) return ROCQ_STATUS_INVALID_VALUE;          // hipStateVec.cpp:605-607
     if (!resolve(h, d)) return ROCQ_STATUS_INVALID_VALUE;
     if (!valid_q(t, n)) return ROCQ_STATUS_INVALID_VALUE;
@@ -743,7 +820,9 @@ rocqStatus_t rocsvApplyMultiControlledX(rocsvHandle_t h, rocComplex* d, unsigned
     return submit(h, d, n, rq::make_x(t, mask));
 }
 
-rocqStatus_t rocsvApplyCSWAP(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned c, unsigned a, unsigned b) {
+rocqStatus_t rocsvApplyCSWAP(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned ctl_, unsigned a, unsigned b) {
+    RQ_FWD(h, rocsvApplyCSWAP(c, nullptr, n, ctl_, a, b));
+    const unsigned c = ctl_;
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     if (!resolve(h, d)) return ROCQ_STATUS_INVALID_VALUE;
     if (!valid_q(c, n) || !valid_q(a, n) || !valid_q(b, n) || c == a || c == b || a == b) return ROCQ_STATUS_INVALID_VALUE;
@@ -788,20 +867,24 @@ static rocqStatus_t apply_device_matrix(H* h, rocComplex* d, unsigned n, const u
 
 rocqStatus_t rocsvApplyMatrix(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* qubitIndices, unsigned numTargetQubits,
                               const rocComplex* matrixDevice, unsigned matrixDim) {
+    RQ_FWD(h, rocsvApplyMatrix(c, nullptr, n, qubitIndices, numTargetQubits, matrixDevice, matrixDim));
     if (numTargetQubits < 32 && matrixDim != (1u << numTargetQubits)) return ROCQ_STATUS_INVALID_VALUE;
     return apply_device_matrix(h, d, n, nullptr, 0, qubitIndices, numTargetQubits, matrixDevice);
 }
 rocqStatus_t rocsvApplyControlledMatrix(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* controls, unsigned nc,
                                         const unsigned* targets, unsigned nt, const rocComplex* d_matrix) {
+    RQ_FWD(h, rocsvApplyControlledMatrix(c, nullptr, n, controls, nc, targets, nt, d_matrix));
     return apply_device_matrix(h, d, n, controls, nc, targets, nt, d_matrix);
 }
 rocqStatus_t rocsvApplyFusedSingleQubitMatrix(rocsvHandle_t h, unsigned targetQubit, const rocComplex* d_fusedMatrix) {
+    RQ_FWD(h, rocsvApplyFusedSingleQubitMatrix(c, targetQubit, d_fusedMatrix));
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     const unsigned n = h->dist.active() ? h->dist.num_total() : h->numQubits;
     return apply_device_matrix(h, nullptr, n, nullptr, 0, &targetQubit, 1, d_fusedMatrix);
 }
 
 rocqStatus_t rocsvSwapIndexBits(rocsvHandle_t h, unsigned q1, unsigned q2) {
+    RQ_FWD(h, rocsvSwapIndexBits(c, q1, q2));
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     const unsigned n = h->dist.active() ? h->dist.num_total() : h->numQubits;
     if (!h->d_state) return ROCQ_STATUS_INVALID_VALUE;
@@ -814,6 +897,8 @@ rocqStatus_t rocsvSwapIndexBits(rocsvHandle_t h, unsigned q1, unsigned q2) {
 // ---- readback (hipStateVec.cpp:691-730) ---------------------------------------------------------------
 rocqStatus_t rocsvGetStateVectorFull(rocsvHandle_t h, rocComplex* d_state, rocComplex* h_state) {
     if (!h || !h_state) return ROCQ_STATUS_INVALID_VALUE;
+    // one process, all slices: the caller's buffer holds the WHOLE state, slice r at r * 2^n_local (canonical order)
+    RQ_FWD(h, rocsvGetStateVectorFull(c, nullptr, h_state + ((size_t)r << c->dist.num_local())));
     rq_cplx* state = resolve(h, d_state);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
     rocqStatus_t s = flush(h);
@@ -824,6 +909,7 @@ rocqStatus_t rocsvGetStateVectorFull(rocsvHandle_t h, rocComplex* d_state, rocCo
 }
 rocqStatus_t rocsvGetStateVectorSlice(rocsvHandle_t h, rocComplex* d_state, rocComplex* h_state, unsigned batch_index) {
     if (!h || !h_state) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->group) return batch_index == 0 ? rocsvGetStateVectorFull(h, nullptr, h_state) : ROCQ_STATUS_INVALID_VALUE;   // distributed states are not batched
     rq_cplx* state = resolve(h, d_state);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
     if (batch_index >= h->batchSize) return ROCQ_STATUS_INVALID_VALUE;
@@ -875,6 +961,10 @@ static rocqStatus_t parse_pauli(unsigned n, const char* paulis, const unsigned* 
 }
 static rocqStatus_t expect_string(H* h, rocComplex* d, unsigned n, const char* paulis, const unsigned* qubits, unsigned k, double* result) {
     if (!h || !result) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->group) {
+        PerRank<double> out(result, h->group->P);
+        return h->group->run([&](H* c, int r) { return expect_string(c, nullptr, n, paulis, qubits, k, out.at(r)); });
+    }
     rq_cplx* state = resolve(h, d);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
     uint64_t xm = 0, zm = 0;
@@ -886,7 +976,9 @@ static rocqStatus_t expect_string(H* h, rocComplex* d, unsigned n, const char* p
     if (h->dist.active()) return h->dist.pauli_expect(h, xm, zm, ny, result);
     return pauli_expect(h, state, n, xm, zm, ny, result);
 }
-rocqStatus_t rocsvGetExpectationValueSinglePauliZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double* r) { return expect_string(h, d, n, "Z", &t, 1, r); }
+rocqStatus_t rocsvGetExpectationValueSinglePauliZ(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double* r) {
+    return expect_string(h, d, n, "Z", &t, 1, r);
+}
 rocqStatus_t rocsvGetExpectationValueSinglePauliX(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double* r) { return expect_string(h, d, n, "X", &t, 1, r); }
 rocqStatus_t rocsvGetExpectationValueSinglePauliY(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned t, double* r) { return expect_string(h, d, n, "Y", &t, 1, r); }
 rocqStatus_t rocsvGetExpectationValuePauliProductZ(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* qs, unsigned k, double* r) {
@@ -907,6 +999,10 @@ rocqStatus_t rocsvGetExpectationPauliString(rocsvHandle_t h, rocComplex* d, unsi
 static rocqStatus_t expect_batch(H* h, rocComplex* d, unsigned n, const char* paulis, const unsigned* qubits, const unsigned* offsets,
                                  unsigned numTerms, double* results, bool allStates) {
     if (!h || !results || !offsets) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->group) {
+        PerRank<double> out(results, h->group->P, numTerms);
+        return h->group->run([&](H* c, int r) { return expect_batch(c, nullptr, n, paulis, qubits, offsets, numTerms, out.at(r), allStates); });
+    }
     rq_cplx* state = resolve(h, d);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
     if (numTerms == 0) return ROCQ_STATUS_SUCCESS;
@@ -957,13 +1053,26 @@ rocqStatus_t rocsvxGetExpectationPauliBatchAllStates(rocsvHandle_t h, rocComplex
     return expect_batch(h, d, n, paulis, qubits, offsets, numTerms, results, true);
 }
 rocqStatus_t rocsvxSetTensorCoreBlocks(rocsvHandle_t h, int enabled) {
+    if (h && h->group && (enabled <= 0 || sizeof(rq_real) == 4)) h->tcBlocks = enabled > 0 ? 1 : enabled < 0 ? -1 : 0;
+    RQ_FWD(h, rocsvxSetTensorCoreBlocks(c, enabled));
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     if (enabled > 0 && sizeof(rq_real) != 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
     h->tcBlocks = enabled > 0 ? 1 : enabled < 0 ? -1 : 0;
     return ROCQ_STATUS_SUCCESS;
 }
 
+rocqStatus_t rocsvxSetPlanCache(rocsvHandle_t h, int enabled) {
+    if (h && h->group) h->planCache = enabled != 0;
+    RQ_FWD(h, rocsvxSetPlanCache(c, enabled));
+    if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    h->planCache = enabled != 0;
+    if (!enabled) drop_cache(h);
+    return ROCQ_STATUS_SUCCESS;
+}
+
 rocqStatus_t rocsvxSetMergeDiagonals(rocsvHandle_t h, int enabled) {
+    if (h && h->group) h->mergeDiagonals = enabled != 0;
+    RQ_FWD(h, rocsvxSetMergeDiagonals(c, enabled));
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     const rocqStatus_t s = flush(h);                     // queued gates keep the setting they were submitted under
     h->mergeDiagonals = enabled != 0;
@@ -971,6 +1080,7 @@ rocqStatus_t rocsvxSetMergeDiagonals(rocsvHandle_t h, int enabled) {
 }
 
 rocqStatus_t rocsvxApplyBlock6(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* qubits, const double* matrix) {
+    RQ_FWD(h, rocsvxApplyBlock6(c, nullptr, n, qubits, matrix));
     if (!h || !qubits || !matrix) return ROCQ_STATUS_INVALID_VALUE;
     rq_cplx* state = resolve(h, d);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
@@ -1008,6 +1118,11 @@ rocqStatus_t rocsvxGetNorm(rocsvHandle_t h, rocComplex* d, unsigned n, double* r
 // ---- measurement (hipStateVec.h:172-177; algorithm measurement_kernels.hip:37-77, MULTI_GPU_GUIDE.md:61-78) ----
 rocqStatus_t rocsvMeasure(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned q, int* outcome, double* probability) {
     if (!h || !outcome) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->group) {
+        PerRank<int> o(outcome, h->group->P);
+        PerRank<double> p(probability, h->group->P);
+        return h->group->run([&](H* c, int r) { return rocsvMeasure(c, nullptr, n, q, o.at(r), p.at(r)); });
+    }
     rq_cplx* state = resolve(h, d);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
     if (!valid_q(q, n)) return ROCQ_STATUS_INVALID_VALUE;
@@ -1034,6 +1149,10 @@ rocqStatus_t rocsvMeasure(rocsvHandle_t h, rocComplex* d, unsigned n, unsigned q
 
 rocqStatus_t rocsvApplyMatrixAndMeasure(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* targets, unsigned nt,
                                         const rocComplex* d_matrix, unsigned qubitToMeasure, int* outcome) {
+    if (h && h->group && outcome) {
+        PerRank<int> o(outcome, h->group->P);
+        return h->group->run([&](H* c, int r) { return rocsvApplyMatrixAndMeasure(c, nullptr, n, targets, nt, d_matrix, qubitToMeasure, o.at(r)); });
+    }
     const rocqStatus_t s = apply_device_matrix(h, d, n, nullptr, 0, targets, nt, d_matrix);
     if (s != ROCQ_STATUS_SUCCESS) return s;
     double p = 0.0;
@@ -1044,6 +1163,10 @@ rocqStatus_t rocsvApplyMatrixAndMeasure(rocsvHandle_t h, rocComplex* d, unsigned
 rocqStatus_t rocsvSample(rocsvHandle_t h, rocComplex* d, unsigned n, const unsigned* measured, unsigned nm, unsigned numShots,
                          uint64_t* h_results) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->group) {
+        PerRank<uint64_t> out(h_results, h->group->P, numShots);
+        return h->group->run([&](H* c, int r) { return rocsvSample(c, nullptr, n, measured, nm, numShots, out.at(r)); });
+    }
     rq_cplx* state = resolve(h, d);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
     if (nm > 64 || (nm > 0 && !measured)) return ROCQ_STATUS_INVALID_VALUE;
@@ -1085,6 +1208,8 @@ rocqStatus_t rocsvSample(rocsvHandle_t h, rocComplex* d, unsigned n, const unsig
 // ---- extensions ---------------------------------------------------------------
 unsigned rocsvxGetPrecisionBytes(void) { return (unsigned)sizeof(rq_real); }
 rocqStatus_t rocsvxSetSeed(rocsvHandle_t h, uint64_t seed) {
+    if (h && h->group) { h->seed = seed; h->draws = 0; h->seedExplicit = true; }
+    RQ_FWD(h, rocsvxSetSeed(c, seed));
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     h->seed = seed;
     h->draws = 0;
@@ -1093,6 +1218,7 @@ rocqStatus_t rocsvxSetSeed(rocsvHandle_t h, uint64_t seed) {
 }
 rocqStatus_t rocsvxSetStateVector(rocsvHandle_t h, rocComplex* d_state, const rocComplex* h_state) {
     if (!h || !h_state) return ROCQ_STATUS_INVALID_VALUE;
+    RQ_FWD(h, rocsvxSetStateVector(c, nullptr, h_state + ((size_t)r << c->dist.num_local())));
     rq_cplx* state = resolve(h, d_state);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
     RQ_OK(discard_or_flush_queue(h, state));
@@ -1102,6 +1228,7 @@ rocqStatus_t rocsvxSetStateVector(rocsvHandle_t h, rocComplex* d_state, const ro
     return staged_h2d(h, state, h_state, total * sizeof(rq_cplx));
 }
 rocqStatus_t rocsvxSynchronize(rocsvHandle_t h) {
+    RQ_FWD(h, rocsvxSynchronize(c));
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     const rocqStatus_t s = flush(h);
     if (s != ROCQ_STATUS_SUCCESS) return s;
@@ -1109,16 +1236,22 @@ rocqStatus_t rocsvxSynchronize(rocsvHandle_t h) {
     return ROCQ_STATUS_SUCCESS;
 }
 rocqStatus_t rocsvxSetFusion(rocsvHandle_t h, int enabled) {
+    if (h && h->group) h->fusion = enabled != 0;
+    RQ_FWD(h, rocsvxSetFusion(c, enabled));
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     if (!enabled) { const rocqStatus_t s = flush(h); if (s != ROCQ_STATUS_SUCCESS) return s; }
     h->fusion = enabled != 0;
     return ROCQ_STATUS_SUCCESS;
 }
-rocqStatus_t rocsvxFlush(rocsvHandle_t h) { return h ? flush(h) : ROCQ_STATUS_INVALID_VALUE; }
+rocqStatus_t rocsvxFlush(rocsvHandle_t h) {
+    RQ_FWD(h, rocsvxFlush(c));
+    return h ? flush(h) : ROCQ_STATUS_INVALID_VALUE;
+}
 
 using rq::convert_ops;      // gate_convert.h
 
 rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t h, rocComplex* d, unsigned n, const rocsvxGateOp* ops, size_t numOps) {
+    RQ_FWD(h, rocsvxApplyCircuit(c, nullptr, n, ops, numOps));
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     rq_cplx* state = resolve(h, d);
     if (!state) return ROCQ_STATUS_INVALID_VALUE;
@@ -1173,12 +1306,19 @@ rocqStatus_t rocsvxApplyCircuit(rocsvHandle_t h, rocComplex* d, unsigned n, cons
 }
 
 rocqStatus_t rocsvxTimerStart(rocsvHandle_t h) {
+    RQ_FWD(h, rocsvxTimerStart(c));
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
     RQ_CUDA(cudaEventRecord(h->tm0, h->stream), "timer start");
     return ROCQ_STATUS_SUCCESS;
 }
 rocqStatus_t rocsvxTimerStop(rocsvHandle_t h, double* ms) {
     if (!h || !ms) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->group) {                                        // device time of the slowest rank
+        std::vector<double> each((size_t)h->group->P, 0.0);
+        const rocqStatus_t s = h->group->run([&](H* c, int r) { return rocsvxTimerStop(c, &each[(size_t)r]); });
+        *ms = *std::max_element(each.begin(), each.end());
+        return s;
+    }
     RQ_CUDA(cudaEventRecord(h->tm1, h->stream), "timer stop");
     RQ_CUDA(cudaEventSynchronize(h->tm1), "timer sync");
     float f = 0.f;
@@ -1189,6 +1329,10 @@ rocqStatus_t rocsvxTimerStop(rocsvHandle_t h, double* ms) {
 
 rocqStatus_t rocsvxGetStats(rocsvHandle_t h, rocsvxStats* stats, int reset) {
     if (!h) return ROCQ_STATUS_INVALID_VALUE;
+    if (h->group) {                                        // rank 0's counters (every rank launches the same plan)
+        PerRank<rocsvxStats> out(stats, h->group->P);
+        return h->group->run([&](H* c, int r) { return rocsvxGetStats(c, out.at(r), reset); });
+    }
     if (h->stats.lastSweepMs < 0.0) {
         float ms = 0.f;
         cudaEventSynchronize(h->ev1);

@@ -6,6 +6,7 @@
 
 #include "../../include/hipStateVec.h"
 #include "dist.h"
+#include "group.h"
 #include "host_ops.h"
 #include "sv_internal.h"
 
@@ -78,7 +79,12 @@ struct rocsvInternalHandle {
     std::vector<rocsvCachedStep>* recording = nullptr;   // non-null while a circuit is being planned for the cache
     bool recordingValid = true;
     rq::Dist dist;
+    // single-process multi-GPU (group.h): this handle is the front of `group`; its own stream / state stay unused
+    rocsvGroup* group = nullptr;
+    int wantRanks = 0;                  // rocsvxDistSetRanks: slices of the next rocsvAllocateDistributedState (0: one per visible device)
 };
+void rq_group_destroy(rocsvInternalHandle* h);
+rocqStatus_t rq_group_create(rocsvInternalHandle* h, int ranks);
 
 rocqStatus_t rq_engine_flush(rocsvInternalHandle* h);
 rocqStatus_t rq_engine_run(rocsvInternalHandle* h, rq_cplx* state, unsigned n, const std::vector<rq::HostOp>& ops, bool fused);

@@ -20,14 +20,23 @@ class RocsvError(RuntimeError):
 
 
 class StateVector:
-    def __init__(self, n: int, prec: str = "c64", batch: int = 1, fusion: bool = False, seed: int = 0):
+    def __init__(self, n: int, prec: str = "c64", batch: int = 1, fusion: bool = False, seed: int = 0, ranks: int | None = None):
+        """ranks=None: a plain state (rocsvAllocateState).  ranks=P: the reference's single-process multi-GPU flow --
+        rocsvAllocateDistributedState on ONE handle, P slices (0 = one per visible device; more slices than devices are
+        placed round-robin, which is how the 1-GPU test box exercises the distributed engine); d_state is NULL on every call."""
         self.lib = capi.load(prec)
         self.prec, self.dtype, self.n, self.batch = prec, DT[prec], n, batch
         self.h = C.c_void_p()
         self._ck("rocsvCreate", self.lib.rocsvCreate(C.byref(self.h)))
         self.d = C.c_void_p()
-        self._ck("rocsvAllocateState", self.lib.rocsvAllocateState(self.h, n, C.byref(self.d), batch))
-        self._ck("rocsvInitializeState", self.lib.rocsvInitializeState(self.h, self.d, n))
+        if ranks is None:
+            self._ck("rocsvAllocateState", self.lib.rocsvAllocateState(self.h, n, C.byref(self.d), batch))
+            self._ck("rocsvInitializeState", self.lib.rocsvInitializeState(self.h, self.d, n))
+        else:
+            assert batch == 1
+            self._ck("rocsvxDistSetRanks", self.lib.rocsvxDistSetRanks(self.h, ranks))
+            self._ck("rocsvAllocateDistributedState", self.lib.rocsvAllocateDistributedState(self.h, n))
+            self._ck("rocsvInitializeDistributedState", self.lib.rocsvInitializeDistributedState(self.h))
         if fusion:
             self.set_fusion(True)
         self.set_seed(seed)           # handles seed themselves from std::random_device; tests and benches want a fixed stream
@@ -57,6 +66,24 @@ class StateVector:
 
     def set_seed(self, seed: int):
         self._ck("rocsvxSetSeed", self.lib.rocsvxSetSeed(self.h, seed))
+
+    def dist_info(self):
+        """-> (rank, ranks, local qubits) of the handle's distributed state"""
+        r, p, nl = C.c_int(), C.c_int(), C.c_uint()
+        self._ck("rocsvxDistGetInfo", self.lib.rocsvxDistGetInfo(self.h, C.byref(r), C.byref(p), C.byref(nl), None))
+        return r.value, p.value, nl.value
+
+    def rank_slice(self, rank: int) -> np.ndarray:
+        """the raw device slice of one rank, as the reference's multi-GPU test reads it (test_hipStateVec_multi_gpu.cpp:43-81)"""
+        import ctypes
+        dev, ptr = C.c_int(), C.c_void_p()
+        self._ck("rocsvxDistGetRankSlice", self.lib.rocsvxDistGetRankSlice(self.h, rank, C.byref(dev), C.byref(ptr)))
+        self.sync()
+        _, _, nl = self.dist_info()
+        out = np.empty(1 << nl, dtype=self.dtype)
+        rt = ctypes.CDLL("libcudart.so.12")
+        assert rt.cudaMemcpy(out.ctypes.data_as(C.c_void_p), ptr, C.c_size_t(out.nbytes), C.c_int(2)) == 0
+        return out
 
     def sync(self):
         self._ck("rocsvxSynchronize", self.lib.rocsvxSynchronize(self.h))

@@ -104,5 +104,21 @@ def random_pauli_strings(n: int, count: int = 64, max_weight: int = 8, seed: int
     return out
 
 
+def hamiltonian_like_terms(n: int, count: int = 64, seed: int = 5):
+    """Pauli terms with the structure of a molecular Hamiltonian (examples/vqe_lih.py:66-70 scaled up): single-qubit Z,
+    nearest-neighbour ZZ, and for a few qubit pairs the four strings XX, YY, XY, YX (with Z-strings in between) that share one
+    x-mask.  -> [(paulis, qubits)]"""
+    rng = np.random.default_rng(seed)
+    terms = [("Z", [q]) for q in range(min(n, count // 4))]
+    terms += [("ZZ", [q, q + 1]) for q in range(min(n - 1, count // 4))]
+    while len(terms) < count:
+        a, b = sorted(int(x) for x in rng.permutation(n)[:2])
+        mid = [q for q in range(a + 1, b)][:2]
+        for pa, pb in (("X", "X"), ("Y", "Y"), ("X", "Y"), ("Y", "X")):
+            if len(terms) < count:
+                terms.append((pa + "Z" * len(mid) + pb, [a] + mid + [b]))
+    return terms
+
+
 def count_gates(gates) -> int:
     return len(gates)

@@ -37,8 +37,7 @@
 namespace {
 
 constexpr int NW = 512;                        // worker threads: 4 warps per TMEM lane quarter, 16 block values per thread
-constexpr int NC = 128;                        // control threads: one scout per tile column; the first of them also issues the MMAs
-constexpr int BT = NW + NC;
+constexpr int BT = NW + 32;                    // + one warp that only issues the MMAs
 constexpr uint32_t MAT_BYTES = 8192;           // one fp16 term of a 64 x 64 operand (Re U or Im U)
 constexpr uint32_t TILE_BYTES = 65536;         // 2^13 complex64 amplitudes
 constexpr uint32_t SMEM_U = 0;                                    // Re U hi | Re U lo | Im U hi | Im U lo  (B operands, N = 64)
@@ -165,17 +164,17 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                                                              const __grid_constant__ rq_block_params P,
                                                              const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_u, bar_mma[2], bar_x[2], bar_full[3], bar_scale[2];
+    __shared__ __align__(8) uint64_t bar_u, bar_mma[2], bar_x[2], bar_full[3], bar_scale[2][4];
     __shared__ uint32_t tmem_slot;
     __shared__ float2 red[2][16];      // per-warp (|in|^2, |out|^2) of a tile, double-buffered
-    __shared__ uint8_t cexp[2][128];   // biased exponent of the largest |component| of every column of a tile (by tile parity)
+    __shared__ uint8_t cexp[2][4][128]; // biased exponent of max |component| per (tile parity, quarter of the block values, column)
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         mbar_init(smem_u32(&bar_u), 1);
         for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_mma[b]), 1); mbar_init(smem_u32(&bar_x[b]), NW / 32); }
         for (int b = 0; b < 3; ++b) mbar_init(smem_u32(&bar_full[b]), 1);
-        for (int b = 0; b < 2; ++b) mbar_init(smem_u32(&bar_scale[b]), NC / 32);
+        for (int b = 0; b < 8; ++b) mbar_init(smem_u32(&bar_scale[b >> 2][b & 3]), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {                                         // all 512 columns: two buffers x (D | X' hi | X' lo)
@@ -191,44 +190,14 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
     const uint64_t first = blockIdx.x, stride = gridDim.x;
     const uint64_t cnt = P.ntiles > first ? (P.ntiles - first + stride - 1) / stride : 0;     // tiles of this CTA
 
-    if (warp >= NW / 32) {
-        // ================================ the control group: 4 warps ================================
-        // Every thread is the SCOUT of one tile column: as soon as a tile has landed it reads the column's 64 amplitudes and
-        // publishes the exponent of the largest component, from which the workers derive the column's power-of-two scale.
-        // The scouts run a tile ahead of the split, so the workers never wait for each other to agree on a scale (an
-        // exchange between the four workers of a column costs 14 % of the pass: profiles/r02_block_scale_variants.md).
-        // The first scout also issues the MMAs of the tile once the workers have split it into tensor memory.
-        const uint32_t scol = tid - NW;
-        uint32_t lcol = 0;
-        for (uint32_t b = 0; b < 7; ++b) lcol |= ((scol >> b) & 1u) << P.lp_col[b];
-        const uint32_t cbase = (lcol ^ (((lcol >> 4) & 7u) << 1)) * 8u;                       // bytes, swizzled (block bits never sit on local bits 4-6)
-        uint32_t voff[6];
-        for (uint32_t b = 0; b < 6; ++b) voff[b] = 8u << P.lp_blk[b];
-        const bool issuer = tid == NW;
-        uint32_t urh = 0, url = 0, uih = 0, uil = 0;
-        if (issuer) {
+    if (warp == NW / 32) {
+        // ================================ the MMA warp ================================
+        if (lane == 0) {
             mbar_expect_tx(smem_u32(&bar_u), 4 * MAT_BYTES);          // the block matrix stays resident for all tiles
             bulk_g2s(smem_u32(smem + SMEM_U), uterms, 4 * MAT_BYTES, smem_u32(&bar_u));
             mbar_wait(smem_u32(&bar_u), 0);
-            urh = smem_u32(smem + SMEM_U); url = urh + MAT_BYTES; uih = urh + 2 * MAT_BYTES; uil = urh + 3 * MAT_BYTES;
-        }
-        for (uint64_t i = 0; i < cnt; ++i) {
-            mbar_wait(smem_u32(&bar_full[i % 3u]), (uint32_t)(i / 3u) & 1u);
-            const unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES + cbase;
-            float mx = 0.f;
-#pragma unroll 16
-            for (uint32_t v = 0; v < 64; ++v) {
-                const uint32_t off = ((v & 1u) ? voff[0] : 0u) ^ ((v & 2u) ? voff[1] : 0u) ^ ((v & 4u) ? voff[2] : 0u) ^ ((v & 8u) ? voff[3] : 0u) ^
-                                     ((v & 16u) ? voff[4] : 0u) ^ ((v & 32u) ? voff[5] : 0u);
-                // (cbase's swizzle bits and the value offsets are disjoint: the XOR commutes with the base)
-                const float2 a = *reinterpret_cast<const float2*>(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES + (cbase ^ off));
-                mx = fmaxf(mx, fmaxf(fabsf(a.x), fabsf(a.y)));
-            }
-            (void)S;
-            cexp[i & 1u][scol] = (uint8_t)(__float_as_uint(mx) >> 23);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_scale[i & 1u]));   // release: the exponents are visible to whoever sees the phase flip
-            if (issuer && !(dbg & 1u)) {
+            const uint32_t urh = smem_u32(smem + SMEM_U), url = urh + MAT_BYTES, uih = urh + 2 * MAT_BYTES, uil = urh + 3 * MAT_BYTES;
+            for (uint64_t i = 0; i < cnt && !(dbg & 1u); ++i) {
                 const uint32_t b = (uint32_t)i & 1u;
                 mbar_wait(smem_u32(&bar_x[b]), (uint32_t)(i >> 1) & 1u);       // X' of tile i is in tensor memory
                 tc_fence_after();
@@ -252,7 +221,6 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                 product(xrh, xih, urh, uih, false);
                 umma_commit(smem_u32(&bar_mma[b]));
             }
-            __syncwarp();
         }
     } else {
         // ================================ 16 worker warps ================================
@@ -319,6 +287,17 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
         //      thread overwrites exactly the amplitudes it read, so the tile is transformed in place without a barrier. ----
         float my_in = 0.f;                                                     // |.|^2 of this thread's inputs of the tile in flight
         float my_inv = 1.f;                                                    // 1 / (scale of this thread's column) of the tile in flight
+        // Column scales by guess and verify.  Every tile column (the 64 amplitudes one block matrix mixes, held by the four
+        // threads with this lane in warps w, w+4, w+8, w+12) is multiplied by its own power of two before the fp16 split, so
+        // that peaked or unnormalised states keep fp32-class accuracy.  The four threads must agree on it, and agreeing
+        // BEFORE the split costs 14 % of the pass (a barrier between the load and the split puts the SM in lock step:
+        // profiles/r02_block_scale_variants.md).  So the split runs at once with a GUESS -- the scale this column position
+        // wanted in the previous tile, identical in the four threads by induction -- while the exponents of the four threads'
+        // maxima travel through shared memory behind an mbarrier that is only waited for after the split.  If the guess puts
+        // the column's true maximum inside [2^6, 2^15) the tensor memory already holds valid terms (>= 30 bits below the
+        // column maximum are kept); otherwise (first tile of a CTA, magnitude jumps of > 2^3 up or 2^6 down) the warp splits
+        // its tile again with the exact scale.
+        int guess_exp = (int)(__float_as_uint(P.scale) >> 23) - 127;           // log2 of the guess
         float fcorr = 1.f;                                                     // norm correction (unitary blocks)
         float acc_in = 0.f, acc_out = 0.f;                                     // |in|^2, |scaled out|^2 over the CTA's finished tiles
         auto epilogue = [&](auto BC, uint64_t i, float in2, float inv_scale) {
@@ -386,32 +365,50 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             mark(0);
             const unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES;
             float in2 = 0.f;
-            // the column's scale, found by its scout while the previous tile was being processed
-            mbar_wait(smem_u32(&bar_scale[i & 1u]), (uint32_t)(i >> 1) & 1u);
-            uint32_t e = cexp[i & 1u][ncol];
-            e = min(max(e, 20u), 254u);                                        // empty / denormal columns and inf / nan: any finite scale
-            const float scale = __uint_as_float((268u - e) << 23);             // column maximum -> [2^14, 2^15)
-            const float cur_inv = __uint_as_float((e - 14u) << 23);
+            float mx = 0.f;
+            auto split_tile = [&](int sexp, bool measure) {
+                const float scale = __uint_as_float((uint32_t)(sexp + 127) << 23);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {                                      // 8 block values -> 4 packed words per (term, re|im)
-                uint32_t hr[4], lr[4], hi[4], li[4];
+                for (int c = 0; c < 2; ++c) {                                  // 8 block values -> 4 packed words per (term, re|im)
+                    uint32_t hr[4], lr[4], hi[4], li[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 a0 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j)));
-                    const float2 a1 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j + 1)));
-                    in2 = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, in2))));
-                    split2(a0.x * scale, a1.x * scale, hr[j], lr[j]);
-                    split2(a0.y * scale, a1.y * scale, hi[j], li[j]);
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 a0 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j)));
+                        const float2 a1 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j + 1)));
+                        if (measure) {
+                            in2 = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, in2))));
+                            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(a0.x), fabsf(a0.y))), fmaxf(fabsf(a1.x), fabsf(a1.y)));
+                        }
+                        split2(a0.x * scale, a1.x * scale, hr[j], lr[j]);
+                        split2(a0.y * scale, a1.y * scale, hi[j], li[j]);
+                    }
+                    // packed words [8*qt + 4*c, +4) of the re part and of the im part of this thread's TMEM lane
+                    const uint32_t w = 8u * qt + 4u * c, xh = tlane + B * TM_BUF + TM_XH, xl = tlane + B * TM_BUF + TM_XL;
+                    if (!(dbg & 2u)) {
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xh + w), "r"(hr[0]), "r"(hr[1]), "r"(hr[2]), "r"(hr[3]) : "memory");
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xl + w), "r"(lr[0]), "r"(lr[1]), "r"(lr[2]), "r"(lr[3]) : "memory");
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xh + 32u + w), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xl + 32u + w), "r"(li[0]), "r"(li[1]), "r"(li[2]), "r"(li[3]) : "memory");
+                    }
                 }
-                // packed words [8*qt + 4*c, +4) of the re part and of the im part of this thread's TMEM lane
-                const uint32_t w = 8u * qt + 4u * c, xh = tlane + B * TM_BUF + TM_XH, xl = tlane + B * TM_BUF + TM_XL;
-                if (!(dbg & 2u)) {
-                    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xh + w), "r"(hr[0]), "r"(hr[1]), "r"(hr[2]), "r"(hr[3]) : "memory");
-                    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xl + w), "r"(lr[0]), "r"(lr[1]), "r"(lr[2]), "r"(lr[3]) : "memory");
-                    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xh + 32u + w), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-                    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xl + 32u + w), "r"(li[0]), "r"(li[1]), "r"(li[2]), "r"(li[3]) : "memory");
-                }
-            }
+            };
+            split_tile(guess_exp, true);
+            // publish this thread's exponent, then see what the column's four threads found
+            const uint32_t sbar = smem_u32(&bar_scale[i & 1u][warp & 3u]);
+            cexp[i & 1u][qt][ncol] = (uint8_t)(__float_as_uint(mx) >> 23);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sbar);
+            mbar_wait(sbar, (uint32_t)(i >> 1) & 1u);
+            const int ecol = (int)max(max((uint32_t)cexp[i & 1u][0][ncol], (uint32_t)cexp[i & 1u][1][ncol]),
+                                      max((uint32_t)cexp[i & 1u][2][ncol], (uint32_t)cexp[i & 1u][3][ncol])) - 127;   // floor(log2 max)
+            // want the maximum in [2^12, 2^13); keep the guess while it leaves it in [2^6, 2^16).  Columns of zeros or
+            // denormals (ecol = -127) take any scale; inf / nan columns stay what they are.
+            const int want_exp = min(max(12 - ecol, -100), 100);
+            int use_exp = guess_exp;
+            if (ecol > -127 && (ecol + guess_exp < 6 || ecol + guess_exp > 14)) use_exp = want_exp;     // (2^16 itself is past fp16)
+            if (__any_sync(0xffffffffu, use_exp != guess_exp)) split_tile(use_exp, false);
+            guess_exp = ecol > -127 ? want_exp : guess_exp;
+            const float cur_inv = __uint_as_float((uint32_t)(127 - use_exp) << 23);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();

@@ -312,7 +312,6 @@ def run_engine(args):
     # ---- the tensor-core block sweep alone: ten 6-qubit Haar blocks back to back -------------------------------------
     block_alone = None
     if ngpus == 1 and st.blockSweeps > 0:
-        import numpy as np
         from rocquantum_b200 import workloads as wl_
         U = wl_.haar_unitary(np.random.default_rng(5), 64)
         qs = list(range(n // 2 - 3, n // 2 + 3))

@@ -708,7 +708,7 @@ rocqStatus_t rocsvAllocateDistributedState(rocsvHandle_t h, unsigned totalNumQub
         if (want <= 0) { if (cudaGetDeviceCount(&want) != cudaSuccess) { cudaGetLastError(); want = 1; } }
         int P = 1;
         while (2 * P <= want) P *= 2;
-        while (P > 1 && (1u << (totalNumQubits > 2 ? totalNumQubits - 2 : 0)) < (unsigned)P) P /= 2;    // keep >= 2 local qubits per slice
+        while (P > 1 && (1ull << (totalNumQubits > 2 ? totalNumQubits - 2 : 0)) < (uint64_t)P) P /= 2;    // keep >= 2 local qubits per slice
         if (h->group && h->group->P != P) rq_group_destroy(h);
         if (P > 1 && !h->group) {
             rocsvFreeState(h);                                 // the front handle holds no state of its own

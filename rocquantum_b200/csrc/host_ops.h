@@ -1020,6 +1020,26 @@ inline void build_phases(Prog& P, unsigned T) {
                 if (widx[p] >= 0) o.cm_in |= (uint8_t)(1u << widx[p]); else o.cm_out |= 1u << p;
             }
         }
+        // Peephole: an uncontrolled Hadamard directly followed by the merged ladder it feeds (RQ_OP_DIAGP whose only
+        // control is the Hadamard's qubit: every step "H(i); CP(j, i) for j > i" of a QFT) is one radix-2 butterfly --
+        // add, subtract, one complex multiply -- instead of a dense 2x2 (16 FMA per pair) plus a phase pass.
+        // Hadamard-like: real, all four entries +-v with v ~ 1/sqrt(2) and an odd number of minus signs (H, and H with an X
+        // folded into it by push_x_forward).  a0' = m00 (a0 +- a1), a1' = m10 (a0 -+ a1) * phase.
+        for (unsigned j = first; j + 1 < i; ++j) {
+            rq_tile_op& h = P.ops[j];
+            rq_tile_op& d = P.ops[j + 1];
+            if (h.kind != RQ_OP_DENSE || h.k != 1 || h.ext || h.cm_in || h.cm_out || h.gcmask || h.setmask) continue;
+            if (d.kind != RQ_OP_DIAGP || d.cm_out || d.gcmask || d.cm_in != (uint8_t)(1u << h.wt[0])) continue;
+            const rq_cplx* M = P.pool + h.moff;
+            const rq_cplx m00 = M[0], m10 = M[1 * RQ_MSLOTS], m01 = M[2 * RQ_MSLOTS], m11 = M[3 * RQ_MSLOTS];
+            const rq_real v = m00.x < 0 ? -m00.x : m00.x;
+            auto absq = [](rq_real x) { return x < 0 ? -x : x; };
+            if (m00.y != 0 || m10.y != 0 || m01.y != 0 || m11.y != 0) continue;
+            if (absq(m10.x) != v || absq(m01.x) != v || absq(m11.x) != v || absq(v * v - (rq_real)0.5) > (rq_real)1e-6) continue;
+            if (!((m00.x * m01.x > 0) != (m10.x * m11.x > 0))) continue;       // rows must be (+,+)/(+,-) in some order and sign
+            h.fuse = RQ_FUSE_SKIP;
+            d.fuse = RQ_FUSE_BUTTERFLY;
+        }
     }
 }
 

@@ -39,8 +39,12 @@ struct rq_tile_op {                 // 64 bytes
     uint64_t gcmask;                // controls on non-resident positions: op is skipped for tiles whose base lacks a bit
     uint8_t wt[4];                  // register phases: window-bit index (0..V-1) of target b
     uint8_t cm_in;                  // register phases: controls inside the window, in window-bit coordinates
-    uint8_t pad[3];
+    uint8_t fuse;                   // register phases, peephole of build_phases: RQ_FUSE_SKIP = this Hadamard is carried out by the
+                                    // next op; RQ_FUSE_BUTTERFLY = this DIAGP first applies the Hadamard on its hub (window bit cm_in):
+                                    // a0' = r (a0 + a1), a1' = r * phase * (a0 - a1) -- the radix-2 butterfly of a QFT
+    uint8_t pad[2];
 };
+enum : uint8_t { RQ_FUSE_NONE = 0, RQ_FUSE_SKIP = 1, RQ_FUSE_BUTTERFLY = 2 };
 
 // A phase is what happens between two shared-memory round trips of the tile.
 //   kind 0: one op, applied in place in shared memory (any op).
@@ -114,7 +118,7 @@ typedef rq_program<160, 2496> rq_program_large;     // ~31.6 KB
 #endif
 #define RQ_PHASE_MAX_DIAGP RQ_WINDOW_BITS             // RQ_OP_DIAGP ops per register-window phase (their thread factors stay in registers)
 #ifndef RQ_PHASED_MIN_BLOCKS
-#define RQ_PHASED_MIN_BLOCKS 2                       // resident CTAs per SM the phased variant is compiled for
+#define RQ_PHASED_MIN_BLOCKS 3                       // resident CTAs per SM the phased variant is compiled for (3 x 64 KB tiles; measured: QFT-33 c128 740 -> 644 ms vs 2)
 #endif
 #ifdef ROCQ_PRECISION_DOUBLE
 #define RQ_MAX_TILE_BITS 12                          // 2^12 * 16 B = 64 KB

@@ -142,6 +142,9 @@ __device__ __forceinline__ void rmac(ramp& acc, const mel m, const ramp v) {
 }
 __device__ __forceinline__ ramp rmul(const rq_cplx d, const ramp v) { return cmul(d, v); }
 __device__ __forceinline__ ramp rsel(bool on, const ramp r, const ramp a) { return rq_cplx{on ? r.x : a.x, on ? r.y : a.y}; }
+__device__ __forceinline__ ramp radd(const ramp a, const ramp b) { return rq_cplx{a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ ramp rsub(const ramp a, const ramp b) { return rq_cplx{a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ ramp rscale(rq_real r, const ramp a) { return rq_cplx{r * a.x, r * a.y}; }
 #else
 typedef uint64_t ramp;
 struct mel { float re; uint64_t im2; };
@@ -166,6 +169,9 @@ __device__ __forceinline__ ramp rmul(const rq_cplx d, const ramp v) {
     return fma2(pack2(-d.y, d.y), swap2(v), acc);
 }
 __device__ __forceinline__ ramp rsel(bool on, const ramp r, const ramp a) { return on ? r : a; }
+__device__ __forceinline__ ramp radd(const ramp a, const ramp b) { return fma2(pack2(1.f, 1.f), b, a); }
+__device__ __forceinline__ ramp rsub(const ramp a, const ramp b) { return fma2(pack2(-1.f, -1.f), b, a); }
+__device__ __forceinline__ ramp rscale(rq_real r, const ramp a) { return fma2(pack2(r, r), a, 0ull); }
 #endif
 
 // deposit the bits of g around the fixed positions fix[0..nfix) (ascending), leaving zeros there.
@@ -406,6 +412,27 @@ __device__ __forceinline__ void win_swap(ramp (&a)[1 << V], uint32_t cm_in, bool
     }
 }
 
+// Hadamard-like matrix on window bit W (real entries +-v, v = 1/sqrt 2) followed by the phase ladder hanging on that qubit
+// (RQ_FUSE_BUTTERFLY): the radix-2 butterfly of a QFT,
+//   a0' = c0 (a0 +- a1),   a1' = (c1 * phase(j)) (a0 -+ a1),   c0 = m00, c1 = m10,   SWP: a0' takes the difference
+// 14 FP operations per pair instead of 16 (dense 2x2) + 8 (phase) + selects.  fc = c1 * (tile, thread and table factors).
+template <int V, int W, bool SWP>
+__device__ __forceinline__ void win_butterfly(ramp (&a)[1 << V], const rq_cplx* Wt, const rq_cplx fc, rq_real c0) {
+#pragma unroll
+    for (int j = 0; j < (1 << V); ++j) {
+        if (j & (1 << W)) continue;
+        const ramp a0 = a[j], a1 = a[j | (1 << W)];
+        const ramp s = radd(a0, a1), d = rsub(a0, a1);
+        a[j] = rscale(c0, SWP ? d : s);
+        a[j | (1 << W)] = rmul(cmul(Wt[j | (1 << W)], fc), SWP ? s : d);
+    }
+}
+template <int V, int W>
+__device__ __forceinline__ void win_butterfly_sel(ramp (&a)[1 << V], const rq_cplx* Wt, const rq_cplx fc, rq_real c0, bool swp) {
+    if (swp) win_butterfly<V, W, true>(a, Wt, fc, c0);
+    else win_butterfly<V, W, false>(a, Wt, fc, c0);
+}
+
 template <int V>
 __device__ __forceinline__ void win_dispatch1(ramp (&a)[1 << V], const rq_tile_op& o, const rq_cplx* M, bool dense, bool on) {
     const uint32_t w = o.wt[0], ci = o.cm_in;
@@ -452,7 +479,7 @@ __device__ __forceinline__ void win_dispatch2(ramp (&a)[1 << V], const rq_tile_o
 
 template <int V, bool SWZ, typename Prog>
 __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint32_t tid,
-                                                 uint64_t gbase, const rq_cplx* gfac) {
+                                                 uint64_t gbase, const rq_cplx* gfac, rq_cplx (*tfac)[32]) {
     constexpr int D = 1 << V;
     uint32_t stride[V];
 #pragma unroll
@@ -460,16 +487,34 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
     const uint32_t ngroups = 1u << (T - V);
     // RQ_OP_DIAGP ops of the phase: tile factor x thread factor, once per phase (the group loop only adds the table
     // over the group-index bits above the thread's and the table over the window bits)
+    // The factor of the thread's own eight group-index bits is the same product for every tile and costs eight dependent
+    // complex multiply + select steps per op when every thread forms it alone (a third of a QFT phase).  Instead one warp
+    // per op builds two 16-entry tables in shared memory -- low four bits (times the tile factor), high four bits -- and
+    // every thread multiplies its two entries.
     rq_cplx fA[RQ_PHASE_MAX_DIAGP];
 #pragma unroll
     for (int d = 0; d < RQ_PHASE_MAX_DIAGP; ++d) fA[d] = rq_cplx{(rq_real)1, (rq_real)0};
     if (prog.hdr.ndiagp) {
+        bool any = false;
         for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
             const rq_tile_op& o = prog.ops[oi];
             if (o.kind != RQ_OP_DIAGP) continue;
-            const rq_cplx f = diagp_thread_factor(o, prog.pool, tid, gfac);
+            any = true;
+            if ((tid >> 5) != o.t[3]) continue;                  // warp d serves the phase's d-th DIAGP op
+            const rq_cplx* A = prog.pool + o.moff + 1;
+            const uint32_t na = o.t[0], e = tid & 31u, first_bit = (e >> 4) * 4u;
+            rq_cplx f = e < 16u ? gfac[o.t[2]] : rq_cplx{(rq_real)1, (rq_real)0};
 #pragma unroll
-            for (int d = 0; d < RQ_PHASE_MAX_DIAGP; ++d) if (o.t[3] == d) fA[d] = f;
+            for (uint32_t b = 0; b < 4; ++b) {
+                const uint32_t i = first_bit + b;
+                if (i < na && ((e >> b) & 1u)) f = cmul(A[i], f);
+            }
+            tfac[o.t[3]][e] = f;
+        }
+        if (any) {                                               // (uniform: the phase's op list is the same for all threads)
+            __syncthreads();
+#pragma unroll
+            for (int d = 0; d < RQ_PHASE_MAX_DIAGP; ++d) fA[d] = cmul(tfac[d][tid & 15u], tfac[d][16u + (tid >> 4)]);
         }
     }
     // the host only builds window phases for tiles of >= 2^(V+8) amplitudes: a warp-uniform trip count, so that op
@@ -505,6 +550,7 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
 #else
             const bool on = (base & o.cm_out) == o.cm_out;       // per thread: selected, never branched on
 #endif
+            if (o.fuse == RQ_FUSE_SKIP) continue;               // a Hadamard the next op (a butterfly) carries out
             const rq_cplx* M = prog.pool + o.moff;
             if (o.kind == RQ_OP_DIAG) {
                 const uint32_t lc = o.setmask, k = o.k;
@@ -540,6 +586,17 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
 #pragma unroll
                 for (int d = 1; d < RQ_PHASE_MAX_DIAGP; ++d) if (o.t[3] == d) fs = fA[d];
                 const rq_cplx ft = cmul(B[it], fs);              // NT = 2^8: `it` = the group-index bits above the thread's
+                if (o.fuse == RQ_FUSE_BUTTERFLY) {               // (uniform) Hadamard-like op on the hub, then the ladder: one butterfly
+                    const rq_cplx* H = prog.pool + prog.ops[oi - 1].moff;    // the skipped op's matrix, column-major: m00, m10, m01, m11
+                    const rq_real c0 = H[0].x, c1 = H[1 * RQ_MSLOTS].x;
+                    const bool swp = (c0 < 0) != (H[2 * RQ_MSLOTS].x < 0);
+                    const rq_cplx fc = rq_cplx{ft.x * c1, ft.y * c1};
+                    if (ci == 1u) win_butterfly_sel<V, 0>(a, Wt, fc, c0, swp);
+                    else if (ci == 2u) win_butterfly_sel<V, 1>(a, Wt, fc, c0, swp);
+                    else if (ci == 4u) win_butterfly_sel<V, 2>(a, Wt, fc, c0, swp);
+                    else if (V > 3) win_butterfly_sel<V, (V > 3 ? 3 : 0)>(a, Wt, fc, c0, swp);
+                    continue;
+                }
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
                     if ((j & ci) != ci) continue;                // controls inside the window: uniform
@@ -584,6 +641,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
     rq_cplx* sm = reinterpret_cast<rq_cplx*>(smem_raw);
     __shared__ __align__(8) uint64_t bar_storage;
     __shared__ __align__(16) rq_cplx gfac[RQ_MAX_DIAGP];        // per-tile factors of the RQ_OP_DIAGP ops
+    __shared__ __align__(16) rq_cplx tfac[MODE == 2 ? RQ_PHASE_MAX_DIAGP : 1][32];   // window phases: thread-factor tables of the phase's DIAGP ops
 
     const uint32_t tid = threadIdx.x;
     const uint32_t T = prog.hdr.T, n = prog.hdr.n, rowbits = prog.hdr.rowbits;
@@ -630,7 +688,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
         if (MODE == 2) {
             const rq_phase& ph = prog.phases[step];
             if (ph.kind == 1) {
-                run_window_phase<RQ_WINDOW_BITS, SWZ>(sm, prog, ph, T, tid, gbase, gfac);
+                run_window_phase<RQ_WINDOW_BITS, SWZ>(sm, prog, ph, T, tid, gbase, gfac, tfac);
                 __syncthreads();
                 continue;
             }

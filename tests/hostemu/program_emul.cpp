@@ -65,6 +65,10 @@ bool emulate_window_phase(std::vector<cd>& sm, const Prog& prog, const rq_phase&
             const rq_tile_op& o = prog.ops[oi];
             if ((gbase & o.gcmask) != o.gcmask) continue;
             if ((base & o.cm_out) != o.cm_out) continue;
+            if (o.fuse == RQ_FUSE_SKIP) {                             // a Hadamard the next op (a butterfly) carries out
+                if (o.kind != RQ_OP_DENSE || oi + 1 >= (uint32_t)ph.first + ph.count || prog.ops[oi + 1].fuse != RQ_FUSE_BUTTERFLY) return false;
+                continue;
+            }
             const rq_cplx* M = prog.pool + o.moff;
             const uint32_t ci = o.cm_in;
             if (o.kind == RQ_OP_DIAG) {
@@ -83,6 +87,20 @@ bool emulate_window_phase(std::vector<cd>& sm, const Prog& prog, const rq_phase&
                 const rq_cplx* Wt = B + (1u << o.t[1]);
                 if ((g >> 8) >= (1u << o.t[1])) return false;
                 const cd ft = pc(B[g >> 8]) * fA[o.t[3]];
+                if (o.fuse == RQ_FUSE_BUTTERFLY) {                    // as win_butterfly: Hadamard on the hub (window bit ci), then the ladder
+                    if (ci == 0 || (ci & (ci - 1)) || oi == ph.first || prog.ops[oi - 1].fuse != RQ_FUSE_SKIP) return false;
+                    const rq_cplx* H = prog.pool + prog.ops[oi - 1].moff;
+                    const double c0 = H[0].x, c1 = H[1 * RQ_MSLOTS].x;
+                    const bool swp = (c0 < 0) != (H[2 * RQ_MSLOTS].x < 0);
+                    for (uint32_t j = 0; j < D; ++j) {
+                        if (j & ci) continue;
+                        const cd a0 = a[j], a1 = a[j | ci];
+                        const cd sm_ = a0 + a1, df = a0 - a1;
+                        a[j] = c0 * (swp ? df : sm_);
+                        a[j | ci] = (pc(Wt[j | ci]) * (ft * c1)) * (swp ? sm_ : df);
+                    }
+                    continue;
+                }
                 for (uint32_t j = 0; j < D; ++j)
                     if ((j & ci) == ci) a[j] *= pc(Wt[j]) * ft;
             } else if (o.kind == RQ_OP_DENSE) {

@@ -87,6 +87,7 @@ rocqStatus_t launch_plan(H* h, rq_cplx* state, unsigned n, const rq::SweepPlan& 
     int e;
     const void* prog = nullptr;
     size_t prog_bytes = 0;
+    const rq::NvtxRange nvtx("rocq/tile_sweep");
     if (large) {
         static thread_local rq_program_large P;
         if (!rq::build_program(P, sp, seg, n, h->batchSize, h->dist.high_base())) return ROCQ_STATUS_FAILURE;
@@ -216,6 +217,42 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
             const HostOp& o = ops[i];
             const unsigned k = (unsigned)o.targets.size();
             if (k > 10) return ROCQ_STATUS_NOT_IMPLEMENTED;
+            // complex64, at most six qubits in all (targets + controls): ONE tensor-core block sweep, the matrix embedded in a
+            // 64x64 block (a 5-qubit matrix is padded with an idle qubit, controls become block qubits).  HBM-bound like any
+            // block pass instead of the gather kernel's strided scalar loads.
+            if (sizeof(rq_real) == 4 && n >= 13 && o.kind == HostOp::DENSE && h->tcBlocks != 0) {
+                const uint64_t Q = o.qubits();
+                const unsigned nq = (unsigned)__builtin_popcountll(Q);
+                if (nq <= RQ_BLOCK_QUBITS && (n >= 64 || !(Q >> n))) {
+                    uint64_t bm = 0;
+                    if (nq == RQ_BLOCK_QUBITS) {
+                        if (rq::block_supported(Q, n, h->batchSize)) bm = Q;
+                    } else {                                                   // five qubits: any idle sixth one the kernel's tile geometry accepts
+                        for (unsigned q = 0; q < n && !bm; ++q)
+                            if (!((Q >> q) & 1ull) && rq::block_supported(Q | (1ull << q), n, h->batchSize)) bm = Q | (1ull << q);
+                    }
+                    if (bm) {
+                        HostOp host = o;
+                        if (o.ext) {                                          // device matrix of an eager rocsvApplyMatrix call
+                            const size_t D = (size_t)1 << k;
+                            std::vector<rq_cplx> hm(D * D);
+                            RQ_CUDA(cudaMemcpyAsync(hm.data(), o.ext, D * D * sizeof(rq_cplx), cudaMemcpyDeviceToHost, h->stream), "matrix D2H");
+                            RQ_CUDA(cudaStreamSynchronize(h->stream), "sync");
+                            host.ext = nullptr;
+                            host.data.resize(D * D);
+                            for (size_t e = 0; e < D * D; ++e) host.data[e] = cd(hm[e].x, hm[e].y);
+                        }
+                        std::vector<unsigned> blk;
+                        for (unsigned q = 0; q < n; ++q) if ((bm >> q) & 1ull) blk.push_back(q);
+                        const std::vector<cd> U = rq::to_matrix(host, blk);
+                        const rocqStatus_t s = run_block(h, state, n, blk, U, -1);
+                        if (s != ROCQ_STATUS_SUCCESS) return s;
+                        h->stats.opsExecuted++;
+                        ++i;
+                        continue;
+                    }
+                }
+            }
             h->recordingValid = false;                   // the gather kernel's matrix upload is not replayable
             const rq_cplx* dm = reinterpret_cast<const rq_cplx*>(o.ext);
             rq::StreamBuf tmp(h->stream);     // freed (stream-ordered) on every path out of this scope
@@ -289,6 +326,7 @@ bool build_block_tensor_map(const rq_cplx* state, const rq::BlockLayout& L, CUte
 rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsigned>& blk, const std::vector<cd>& U, int unitary) {
     if (sizeof(rq_real) != 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
     if (n < 13 || blk.size() != RQ_BLOCK_QUBITS) return ROCQ_STATUS_INVALID_VALUE;
+    const rq::NvtxRange nvtx("rocq/block_sweep");
     rq_block_params P{};
     P.n = n; P.T = 13; P.ntiles = (uint64_t)h->batchSize << (n - 13);
     uint64_t bm = 0;
@@ -396,6 +434,7 @@ Hash2 circuit_key(const H* h, const rq_cplx* state, unsigned n, const rocsvxGate
     return k;
 }
 rocqStatus_t replay_cache(H* h, rq_cplx* state) {
+    const rq::NvtxRange nvtx("rocq/replay_cached_plan");
     for (const rocsvCachedStep& st : h->cache.steps) {
         if (st.block) {
             RQ_CUDA(rq_launch_block_sweep(state, &st.bp, st.d_terms, st.tmap, h->stream), "block sweep launch (cached)");
@@ -558,6 +597,7 @@ rocqStatus_t fetch(H* h, const void* dsrc, void* hdst, size_t bytes) {
 }
 
 rocqStatus_t pauli_expect(H* h, rq_cplx* state, unsigned n, uint64_t xm, uint64_t zm, unsigned ny, double* result) {
+    const rq::NvtxRange nvtx("rocq/pauli_expectation");
     const unsigned nb = rq_reduce_blocks();
     RQ_CUDA(rq_launch_pauli_expect(state, n, xm, zm, ny, h->d_partials, nb, h->d_partials + nb, h->stream), "expectation launch");
     h->stats.kernelLaunches += 2;
@@ -1019,6 +1059,7 @@ static rocqStatus_t expect_batch(H* h, rocComplex* d, unsigned n, const char* pa
         for (unsigned t = 0; t < numTerms; ++t) RQ_OK(h->dist.pauli_expect(h, terms[t].xm, terms[t].zm, terms[t].ny, results + t));
         return ROCQ_STATUS_SUCCESS;
     }
+    const rq::NvtxRange nvtx("rocq/pauli_expectation_batch");
     const unsigned nstates = allStates ? (unsigned)h->batchSize : 1u;
     std::vector<rq_pauli_group> groups;                    // first-appearance order of the x-masks, <= RQ_PAULI_GROUP_MAX terms each
     for (unsigned t = 0; t < numTerms; ++t) {
@@ -1185,6 +1226,7 @@ rocqStatus_t rocsvSample(rocsvHandle_t h, rocComplex* d, unsigned n, const unsig
     const uint64_t nchunks = 1ull << (n - cb);
     // everything stays on the device: chunk masses -> exact scan -> one warp per shot -> result words (bit j = measured
     // qubit j); the host sees one copy of the results and the total mass
+    const rq::NvtxRange nvtx("rocq/sample");
     rq::StreamBuf scratch(h->stream);
     RQ_CUDA(scratch.alloc((2 * nchunks + 2 * RQ_SCAN_MAXSEG + 4 + (size_t)numShots) * sizeof(uint64_t)), "sampling scratch");
     uint64_t* d_hi = scratch.as<uint64_t>();
@@ -1458,10 +1500,15 @@ rocqStatus_t rocsvxDistPlanCircuit(unsigned n, int numRanks, const rocsvxGateOp*
                 }
                 txt += "R\n";
                 for (const HostOp& o : st.ops) if (o.targets.size() > 4) return ROCQ_STATUS_NOT_IMPLEMENTED;
-                std::vector<HostOp> fused = st.ops.size() > 1 ? rq::fuse_algebraic(rq::merge_diagonals(rq::push_x_forward(st.ops)), n - M, P.global_mask()) : st.ops;
+                // mode bit 4 (16): what ONE rank really executes -- rank = mode >> 8: controls / diagonal factors on rank bits are
+                // resolved first (specialize_for_rank), exactly as the engine does on a slice; mode bit 5 (32): the engine's own
+                // block threshold (ROCQ_TC_MIN_COST or the default) instead of "a block whenever one is possible"
+                const std::vector<HostOp> spec = (mode & 16) ? rq::specialize_for_rank(st.ops, n - M, (uint64_t)((unsigned)mode >> 8) << (n - M)) : st.ops;
+                std::vector<HostOp> fused = spec.size() > 1 ? rq::fuse_algebraic(rq::merge_diagonals(rq::push_x_forward(spec)), n - M, P.global_mask()) : spec;
                 if (mode & 4) {                              // with tensor-core blocks on the local qubits (complex64 engine)
                     rq::BlockLimits BL;
                     BL.min_cost = 0.0;
+                    if (mode & 32) { BL.min_cost = rocsvInternalHandle().blockMinCost; if (const char* e = getenv("ROCQ_TC_MIN_COST")) { const double b = atof(e); if (b > 0) BL.min_cost = b; } }
                     for (const rq::MixedStep& ms : rq::plan_mixed(fused, n - M, L, BL)) {
                         if (ms.block) {
                             txt += "B";

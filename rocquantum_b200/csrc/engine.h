@@ -10,7 +10,17 @@
 #include "host_ops.h"
 #include "sv_internal.h"
 
+#include <nvtx3/nvToolsExt.h>      // header-only (NVTX 3): no link dependency; a no-op unless a profiler injects itself
+
 namespace rq {
+// NVTX range around one launch group of the engine: a sweep, an exchange, a reduction ("tracing").
+// Visible in Nsight Systems / ncu --nvtx as rocq/<what>; costs two empty calls when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* what) { nvtxRangePushA(what); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 // stream-ordered scratch that is released on every path out of its scope (early error returns included)
 struct StreamBuf {
     void* p = nullptr;

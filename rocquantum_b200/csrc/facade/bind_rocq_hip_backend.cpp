@@ -139,6 +139,30 @@ PYBIND11_MODULE(_rocq_hip_backend, m) {
         must(rocsvGetExpectationPauliString(h.get(), d.c(), n, s.c_str(), q.data(), (unsigned)q.size(), &r), "rocsvGetExpectationPauliString");
         return r;
     }, py::arg("handle"), py::arg("d_state"), py::arg("num_qubits"), py::arg("pauli_string"), py::arg("target_qubits"));
+    // The whole Hamiltonian in one call (extension; what python/rocq/api.py:520-643 get_expval / grad and
+    // rocquantum/solvers/vqe_solver.py:120-136 loop over term by term): terms = [(pauli string, [qubits]), ...] ->
+    // ndarray of <psi|P_t|psi>, evaluated by one read sweep per distinct set of X/Y qubits and one device->host copy.
+    // all_states=True evaluates every state of the handle's batch (parameter-shift batches): shape (batch, terms).
+    m.def("get_expectation_pauli_batch", [](H h, D d, unsigned n, const std::vector<std::pair<std::string, std::vector<unsigned>>>& terms,
+                                            bool all_states, size_t batch) {
+        std::string paulis;
+        std::vector<unsigned> qubits, offsets{0u};
+        for (const auto& t : terms) {
+            if (t.first.size() != t.second.size()) throw std::runtime_error("Pauli string length must match the number of target qubits.");
+            paulis += t.first;
+            qubits.insert(qubits.end(), t.second.begin(), t.second.end());
+            offsets.push_back((unsigned)paulis.size());
+        }
+        const size_t states = all_states ? (batch ? batch : 1) : 1;
+        py::array_t<double> out(states * terms.size());
+        if (terms.empty()) return out;
+        if (qubits.empty()) qubits.push_back(0u);
+        must((all_states ? rocsvxGetExpectationPauliBatchAllStates : rocsvxGetExpectationPauliBatch)(
+                 h.get(), d.c(), n, paulis.c_str(), qubits.data(), offsets.data(), (unsigned)terms.size(), out.mutable_data()),
+             "rocsvxGetExpectationPauliBatch");
+        if (all_states) out.resize({states, terms.size()});
+        return out;
+    }, py::arg("handle"), py::arg("d_state"), py::arg("num_qubits"), py::arg("terms"), py::arg("all_states") = false, py::arg("batch_size") = 1);
     m.def("sample", [](H h, D d, unsigned n, const std::vector<unsigned>& q, unsigned shots) {
         py::array_t<uint64_t> out(shots);
         if (shots == 0) return out;

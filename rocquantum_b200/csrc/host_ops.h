@@ -641,7 +641,31 @@ inline void order_disjoint_runs_by_next_use(std::vector<HostOp>& ops, std::vecto
     }
 }
 
-inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L) {
+// Diagonal ops need no residency, so the diagonal ops a sweep BEGINS with can just as well end the sweep before it.  That
+// matters for a ladder whose Hadamard closed the previous sweep: moved back, it meets its hub resident (one butterfly in a
+// register window) instead of gating whole tiles of the next sweep.
+inline void pull_leading_diagonals_back(std::vector<SweepPlan>& plans, const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L) {
+    const unsigned T = std::min(n, L.tile_bits);
+    for (size_t k = 0; k + 1 < plans.size(); ++k) {
+        SweepPlan& a = plans[k];
+        SweepPlan& b = plans[k + 1];
+        unsigned nops = (unsigned)a.ops.size(), pool = 0, ndiagp = 0;
+        for (int i : a.ops) { pool += pool_need(ops[i], T); ndiagp += ops[i].kind == HostOp::DIAGP; if (ops[i].ext) nops = L.max_ops; }
+        size_t moved = 0;
+        while (moved < b.ops.size() && b.ops.size() - moved > 1) {                // never empty a sweep
+            const HostOp& o = ops[b.ops[moved]];
+            if (o.nondiag() || o.ext || o.defer || (o.kind != HostOp::DIAG && o.kind != HostOp::DIAGP)) break;
+            if (o.kind == HostOp::DIAG && o.targets.size() > 4) break;
+            if (nops + 1 > L.max_ops || pool + pool_need(o, T) > L.pool_cplx || (o.kind == HostOp::DIAGP && ndiagp >= RQ_MAX_DIAGP)) break;
+            ++nops; pool += pool_need(o, T); ndiagp += o.kind == HostOp::DIAGP;
+            a.ops.push_back(b.ops[moved]);
+            ++moved;
+        }
+        b.ops.erase(b.ops.begin(), b.ops.begin() + (long)moved);
+    }
+}
+
+inline std::vector<SweepPlan> plan_sweeps_unfixed(const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L) {
     std::vector<SweepPlan> fwd = plan_sweeps_forward(ops, n, L);
     if (fwd.size() < 3) return fwd;
     for (const HostOp& o : ops) if (o.ext || o.defer) return fwd;
@@ -657,6 +681,11 @@ inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsign
         std::sort(sp.ops.begin(), sp.ops.end());                        // program order inside a sweep
     }
     return bwd;
+}
+inline std::vector<SweepPlan> plan_sweeps(const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L) {
+    std::vector<SweepPlan> plans = plan_sweeps_unfixed(ops, n, L);
+    if (L.budget >= 1e29) pull_leading_diagonals_back(plans, ops, n, L);     // (a cost budget per sweep is the caller's to keep)
+    return plans;
 }
 
 // ---- tile geometry of the tensor-core block sweep (block_sweep.cu) -------------------------------------------------------
@@ -858,6 +887,33 @@ inline std::vector<MixedStep> plan_mixed_policy(const std::vector<HostOp>& ops, 
                 } else if (cost > best_cost) { best_cost = cost; best.swap(pick); bestB = B; }
             }
         }
+        // The oldest op's neighbourhood is not worth a block (the sparse tip of a dependency cone, the tail of a distributed
+        // RUN step): before an ordinary sweep swallows everything that is free -- dozens of dense gates at ~0.27 block passes
+        // each -- look for a worthwhile block around the other free ops of the frontier.
+        if (possible && best_cost < BL.min_cost) {
+            uint64_t bAny = 0, bND = 0;
+            unsigned seeds = 0;
+            size_t scanned = 0;
+            for (size_t i = first; i < ops.size() && scanned < 1024 && seeds < 48; ++i) {
+                if (done[i]) continue;
+                ++scanned;
+                const HostOp& o = ops[i];
+                const uint64_t nd = o.nondiag(), dg = o.qubits() & ~nd;
+                const bool free_ = !((nd & (bAny | bND)) || (dg & bAny));
+                bAny |= nd;                                    // (whatever is not taken now blocks what follows it)
+                bND |= dg;
+                if (!free_ || i == first || !eligible(o) || o.kind != HostOp::DENSE) continue;
+                ++seeds;
+                for (int bias = 0; bias < 3; ++bias) {
+                    const uint64_t B = grow(i, bias);
+                    if ((unsigned)__builtin_popcountll(B) != BL.qubits) continue;
+                    if (BL.supported && !BL.supported(B, n, BL.batch)) continue;
+                    std::vector<int> pick;
+                    const double cost = fold(B, pick);
+                    if (cost >= BL.min_cost && cost > best_cost) { best_cost = cost; best.swap(pick); bestB = B; }
+                }
+            }
+        }
         if (best_cost >= BL.min_cost && !best.empty()) {
             MixedStep st;
             st.block = true;
@@ -887,7 +943,21 @@ inline std::vector<MixedStep> plan_mixed_policy(const std::vector<HostOp>& ops, 
     return steps;
 }
 
-// Every step is one pass over the state, whatever it carries: plan under both policies and keep the shorter plan.
+// Estimated duration of a plan in block passes.  A block pass is HBM-bound whatever it carries (1.0); an ordinary sweep is
+// HBM-bound (0.75 of a block pass) until its arithmetic takes over: ~0.9 ms per dense two-qubit matrix at 30 qubits against
+// 3.3 ms per block pass, i.e. 0.015 per unit of HostOp::cost (profiles/r01_ncu_tile_sweep_fused_after.md).
+inline double plan_time(const std::vector<MixedStep>& steps, const std::vector<HostOp>& ops) {
+    double t = 0.0;
+    for (const MixedStep& st : steps) {
+        if (st.block) { t += 1.0; continue; }
+        double c = 0.0;
+        for (int i : st.sweep.ops) c += ops[i].cost();
+        t += std::max(0.75, 0.015 * c);
+    }
+    return t;
+}
+
+// Plan under both policies and keep the plan with the shorter estimated duration.
 inline std::vector<MixedStep> plan_mixed(const std::vector<HostOp>& ops, unsigned n, const PlanLimits& L, const BlockLimits& BL) {
     std::vector<MixedStep> greedy = plan_mixed_policy(ops, n, L, BL, 0);
     bool any_block = false;
@@ -900,7 +970,7 @@ inline std::vector<MixedStep> plan_mixed(const std::vector<HostOp>& ops, unsigne
         return steps;
     }
     std::vector<MixedStep> spread = plan_mixed_policy(ops, n, L, BL, 1);
-    return spread.size() < greedy.size() ? spread : greedy;
+    return plan_time(spread, ops) < plan_time(greedy, ops) ? spread : greedy;
 }
 
 // ---- order of the ops inside one sweep ---------------------------------------------------------------------------
@@ -983,6 +1053,11 @@ inline void build_phases(Prog& P, unsigned T) {
             if (!need_of(P.ops[i], nd)) break;
             if ((unsigned)__builtin_popcount(W | nd) > V) break;
             if (P.ops[i].kind == RQ_OP_DIAGP && ndp >= RQ_PHASE_MAX_DIAGP) break;
+            // a one-qubit dense op directly followed by the ladder hanging on its qubit becomes one butterfly (below) if both
+            // land in the same phase: do not end the phase between them
+            if (P.ops[i].kind == RQ_OP_DENSE && P.ops[i].k == 1 && !P.ops[i].setmask && !P.ops[i].gcmask && i + 1 < nops &&
+                P.ops[i + 1].kind == RQ_OP_DIAGP && !P.ops[i + 1].gcmask && P.ops[i + 1].setmask == (1u << P.ops[i].t[0]) &&
+                ndp >= RQ_PHASE_MAX_DIAGP && i > first) break;
             ndp += P.ops[i].kind == RQ_OP_DIAGP;
             W |= nd;
             ++i;
@@ -1040,6 +1115,9 @@ inline void build_phases(Prog& P, unsigned T) {
             h.fuse = RQ_FUSE_SKIP;
             d.fuse = RQ_FUSE_BUTTERFLY;
         }
+        bool chain = ((i - first) & 1u) == 0;                      // nothing but butterflies: the interpreter-free routine
+        for (unsigned j = first; j < i && chain; j += 2) chain = P.ops[j].fuse == RQ_FUSE_SKIP && P.ops[j + 1].fuse == RQ_FUSE_BUTTERFLY;
+        if (chain) ph.kind = 2;
     }
 }
 
@@ -1176,7 +1254,12 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
         for (unsigned i = 0; i < P.hdr.nphases; ++i)
             if (P.phases[i].first <= pd.op && pd.op < (unsigned)P.phases[i].first + P.phases[i].count) ph = &P.phases[i];
         if (!ph) return false;
-        const bool win = ph->kind == 1;
+        const bool win = ph->kind == 1 || ph->kind == 2;
+        if (win && t.fuse == RQ_FUSE_BUTTERFLY) {                  // no factor on the window bits below the hub?
+            bool up = true;
+            for (unsigned b = 0; b < ph->v && !((t.cm_in >> b) & 1u); ++b) up = up && pd.floc[ph->w[b]] == cd(1.0, 0.0);
+            if (up) t.fuse = RQ_FUSE_BUTTERFLY_UP;
+        }
         uint32_t skip = 0;
         if (win) for (unsigned b = 0; b < ph->v; ++b) skip |= 1u << ph->w[b];
         else for (unsigned f = 0; f < t.nfix; ++f) skip |= 1u << t.fix[f];

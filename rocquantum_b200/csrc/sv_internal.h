@@ -44,13 +44,17 @@ struct rq_tile_op {                 // 64 bytes
                                     // a0' = r (a0 + a1), a1' = r * phase * (a0 - a1) -- the radix-2 butterfly of a QFT
     uint8_t pad[2];
 };
-enum : uint8_t { RQ_FUSE_NONE = 0, RQ_FUSE_SKIP = 1, RQ_FUSE_BUTTERFLY = 2 };
+// RQ_FUSE_BUTTERFLY_UP: a butterfly whose ladder has no factor on the window bits BELOW its hub (every QFT ladder): the
+// window part of the phase then depends only on the window bits above the hub, 2^(V-1-W) distinct values instead of 2^(V-1).
+enum : uint8_t { RQ_FUSE_NONE = 0, RQ_FUSE_SKIP = 1, RQ_FUSE_BUTTERFLY = 2, RQ_FUSE_BUTTERFLY_UP = 3 };
 
 // A phase is what happens between two shared-memory round trips of the tile.
 //   kind 0: one op, applied in place in shared memory (any op).
 //   kind 1: register window -- every thread loads the 2^v amplitudes that differ in the v window bits w[] (local
 //           positions >= 4, so the loads are bank-conflict free), applies ops first..first+count-1 whose non-diagonal
 //           targets all lie in the window entirely in registers, and stores them back once.
+//   kind 2: a register window whose ops are nothing but (Hadamard-like, ladder) pairs fused into butterflies: executed
+//           by a routine without the per-op interpreter (run_chain_phase).
 struct rq_phase {
     uint8_t kind, v, first, count;
     uint8_t w[4];                   // ascending local positions

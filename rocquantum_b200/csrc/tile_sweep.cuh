@@ -416,21 +416,43 @@ __device__ __forceinline__ void win_swap(ramp (&a)[1 << V], uint32_t cm_in, bool
 // (RQ_FUSE_BUTTERFLY): the radix-2 butterfly of a QFT,
 //   a0' = c0 (a0 +- a1),   a1' = (c1 * phase(j)) (a0 -+ a1),   c0 = m00, c1 = m10,   SWP: a0' takes the difference
 // 14 FP operations per pair instead of 16 (dense 2x2) + 8 (phase) + selects.  fc = c1 * (tile, thread and table factors).
-template <int V, int W, bool SWP>
+template <int V, int W, bool SWP, bool UP>
 __device__ __forceinline__ void win_butterfly(ramp (&a)[1 << V], const rq_cplx* Wt, const rq_cplx fc, rq_real c0) {
+    // UP: the ladder has no factor on the window bits below its hub, so the phase of a pair depends only on the window
+    // bits above W: 2^(V-1-W) complex products instead of 2^(V-1)
+    constexpr int NU = UP ? (1 << (V - 1 - W)) : (1 << (V - 1));
+    rq_cplx ph[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        const int j = UP ? ((u << (W + 1)) | (1 << W)) : ((((u >> W) << (W + 1)) | (u & ((1 << W) - 1))) | (1 << W));
+        ph[u] = cmul(Wt[j], fc);
+    }
 #pragma unroll
     for (int j = 0; j < (1 << V); ++j) {
         if (j & (1 << W)) continue;
         const ramp a0 = a[j], a1 = a[j | (1 << W)];
         const ramp s = radd(a0, a1), d = rsub(a0, a1);
         a[j] = rscale(c0, SWP ? d : s);
-        a[j | (1 << W)] = rmul(cmul(Wt[j | (1 << W)], fc), SWP ? s : d);
+        const int u = UP ? (j >> (W + 1)) : (((j >> (W + 1)) << W) | (j & ((1 << W) - 1)));
+        a[j | (1 << W)] = rmul(ph[u], SWP ? s : d);
     }
 }
 template <int V, int W>
-__device__ __forceinline__ void win_butterfly_sel(ramp (&a)[1 << V], const rq_cplx* Wt, const rq_cplx fc, rq_real c0, bool swp) {
-    if (swp) win_butterfly<V, W, true>(a, Wt, fc, c0);
-    else win_butterfly<V, W, false>(a, Wt, fc, c0);
+__device__ __forceinline__ void win_butterfly_sel(ramp (&a)[1 << V], const rq_cplx* Wt, const rq_cplx fc, rq_real c0, bool swp, bool up) {
+    if (up) {
+        if (swp) win_butterfly<V, W, true, true>(a, Wt, fc, c0);
+        else win_butterfly<V, W, false, true>(a, Wt, fc, c0);
+    } else {
+        if (swp) win_butterfly<V, W, true, false>(a, Wt, fc, c0);
+        else win_butterfly<V, W, false, false>(a, Wt, fc, c0);
+    }
+}
+template <int V>
+__device__ __forceinline__ void win_butterfly_any(ramp (&a)[1 << V], uint32_t ci, const rq_cplx* Wt, const rq_cplx fc, rq_real c0, bool swp, bool up) {
+    if (ci == 1u) win_butterfly_sel<V, 0>(a, Wt, fc, c0, swp, up);
+    else if (ci == 2u) win_butterfly_sel<V, 1>(a, Wt, fc, c0, swp, up);
+    else if (ci == 4u) win_butterfly_sel<V, 2>(a, Wt, fc, c0, swp, up);
+    else if (V > 3) win_butterfly_sel<V, (V > 3 ? 3 : 0)>(a, Wt, fc, c0, swp, up);
 }
 
 template <int V>
@@ -477,6 +499,105 @@ __device__ __forceinline__ void win_dispatch2(ramp (&a)[1 << V], const rq_tile_o
 #undef RQ_PAIR
 }
 
+// The factor of the thread's own eight group-index bits is the same product for every tile and costs eight dependent
+// complex multiply + select steps per op when every thread forms it alone (a third of a QFT phase).  Instead one warp
+// per op builds two 16-entry tables in shared memory -- low four bits (times the tile factor), high four bits -- and
+// every thread multiplies its two entries.
+template <typename Prog>
+__device__ __forceinline__ void phase_thread_factors(const Prog& prog, const rq_phase& ph, uint32_t tid, const rq_cplx* gfac,
+                                                     rq_cplx (*tfac)[32], rq_cplx (&fA)[RQ_PHASE_MAX_DIAGP]) {
+#pragma unroll
+    for (int d = 0; d < RQ_PHASE_MAX_DIAGP; ++d) fA[d] = rq_cplx{(rq_real)1, (rq_real)0};
+    if (!prog.hdr.ndiagp) return;
+    bool any = false;
+    for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
+        const rq_tile_op& o = prog.ops[oi];
+        if (o.kind != RQ_OP_DIAGP) continue;
+        any = true;
+        if ((tid >> 5) != o.t[3]) continue;                  // warp d serves the phase's d-th DIAGP op
+        const rq_cplx* A = prog.pool + o.moff + 1;
+        const uint32_t na = o.t[0], e = tid & 31u, first_bit = (e >> 4) * 4u;
+        rq_cplx f = e < 16u ? gfac[o.t[2]] : rq_cplx{(rq_real)1, (rq_real)0};
+#pragma unroll
+        for (uint32_t b = 0; b < 4; ++b) {
+            const uint32_t i = first_bit + b;
+            if (i < na && ((e >> b) & 1u)) f = cmul(A[i], f);
+        }
+        tfac[o.t[3]][e] = f;
+    }
+    if (any) {                                               // (uniform: the phase's op list is the same for all threads)
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < RQ_PHASE_MAX_DIAGP; ++d) fA[d] = cmul(tfac[d][tid & 15u], tfac[d][16u + (tid >> 4)]);
+    }
+}
+
+// ---- butterfly chains (rq_phase kind 2) -----------------------------------------------------------------------------
+// A phase made of nothing but butterflies -- a radix-2^V pass of a QFT over the window bits -- without the per-op
+// interpreter: the parameters of the <= V butterflies are fetched once, the group loop is load, butterflies, store.
+template <int V, bool SWZ, typename Prog>
+__device__ __forceinline__ void run_chain_phase(rq_cplx* sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint32_t tid,
+                                                const rq_cplx* gfac, rq_cplx (*tfac)[32]) {
+    constexpr int D = 1 << V;
+    static_assert(RQ_PHASE_MAX_DIAGP >= V, "a chain holds up to V butterflies");
+    rq_cplx fA[RQ_PHASE_MAX_DIAGP];
+    phase_thread_factors(prog, ph, tid, gfac, tfac, fA);
+    const uint32_t nb = ph.count >> 1;
+    const rq_cplx* Bt[V];
+    const rq_cplx* Wt[V];
+    rq_real c0[V], c1[V];
+    uint32_t ci[V];
+    bool swp[V], up[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const uint32_t kk = (uint32_t)k < nb ? (uint32_t)k : 0u;        // (unused slots repeat the first pair; never executed)
+        const rq_tile_op& h = prog.ops[ph.first + 2u * kk];
+        const rq_tile_op& o = prog.ops[ph.first + 2u * kk + 1u];
+        const rq_cplx* H = prog.pool + h.moff;
+        const rq_cplx* M = prog.pool + o.moff;
+        Bt[k] = M + 1 + o.t[0];
+        Wt[k] = Bt[k] + (1u << o.t[1]);
+        c0[k] = H[0].x; c1[k] = H[1 * RQ_MSLOTS].x;
+        swp[k] = (c0[k] < 0) != (H[2 * RQ_MSLOTS].x < 0);
+        up[k] = o.fuse == RQ_FUSE_BUTTERFLY_UP;
+        ci[k] = o.cm_in;
+    }
+    uint32_t stride[V];
+#pragma unroll
+    for (int b = 0; b < V; ++b) stride[b] = 1u << ph.w[b];
+    const uint32_t ngroups = 1u << (T - V);
+    for (uint32_t g = tid, it = 0; g < ngroups; g += NT, ++it) {
+        uint32_t base = g;
+#pragma unroll
+        for (int b = 0; b < V; ++b) {
+            const uint32_t p = ph.w[b];
+            base = ((base >> p) << (p + 1)) | (base & ((1u << p) - 1u));
+        }
+        ramp a[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            uint32_t idx = base;
+#pragma unroll
+            for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
+            a[j] = ramp_load(sm, sidx<SWZ>(idx));
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if ((uint32_t)k >= nb) break;
+            const rq_cplx ft = cmul(Bt[k][it], fA[k]);          // the phase's k-th DIAGP op has slot k (build_phases numbers them in order)
+            const rq_cplx fc = rq_cplx{ft.x * c1[k], ft.y * c1[k]};
+            win_butterfly_any<V>(a, ci[k], Wt[k], fc, c0[k], swp[k], up[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            uint32_t idx = base;
+#pragma unroll
+            for (int b = 0; b < V; ++b) if (j & (1 << b)) idx |= stride[b];
+            ramp_store(sm, sidx<SWZ>(idx), a[j]);
+        }
+    }
+}
+
 template <int V, bool SWZ, typename Prog>
 __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint32_t tid,
                                                  uint64_t gbase, const rq_cplx* gfac, rq_cplx (*tfac)[32]) {
@@ -487,36 +608,8 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
     const uint32_t ngroups = 1u << (T - V);
     // RQ_OP_DIAGP ops of the phase: tile factor x thread factor, once per phase (the group loop only adds the table
     // over the group-index bits above the thread's and the table over the window bits)
-    // The factor of the thread's own eight group-index bits is the same product for every tile and costs eight dependent
-    // complex multiply + select steps per op when every thread forms it alone (a third of a QFT phase).  Instead one warp
-    // per op builds two 16-entry tables in shared memory -- low four bits (times the tile factor), high four bits -- and
-    // every thread multiplies its two entries.
     rq_cplx fA[RQ_PHASE_MAX_DIAGP];
-#pragma unroll
-    for (int d = 0; d < RQ_PHASE_MAX_DIAGP; ++d) fA[d] = rq_cplx{(rq_real)1, (rq_real)0};
-    if (prog.hdr.ndiagp) {
-        bool any = false;
-        for (uint32_t oi = ph.first; oi < (uint32_t)ph.first + ph.count; ++oi) {
-            const rq_tile_op& o = prog.ops[oi];
-            if (o.kind != RQ_OP_DIAGP) continue;
-            any = true;
-            if ((tid >> 5) != o.t[3]) continue;                  // warp d serves the phase's d-th DIAGP op
-            const rq_cplx* A = prog.pool + o.moff + 1;
-            const uint32_t na = o.t[0], e = tid & 31u, first_bit = (e >> 4) * 4u;
-            rq_cplx f = e < 16u ? gfac[o.t[2]] : rq_cplx{(rq_real)1, (rq_real)0};
-#pragma unroll
-            for (uint32_t b = 0; b < 4; ++b) {
-                const uint32_t i = first_bit + b;
-                if (i < na && ((e >> b) & 1u)) f = cmul(A[i], f);
-            }
-            tfac[o.t[3]][e] = f;
-        }
-        if (any) {                                               // (uniform: the phase's op list is the same for all threads)
-            __syncthreads();
-#pragma unroll
-            for (int d = 0; d < RQ_PHASE_MAX_DIAGP; ++d) fA[d] = cmul(tfac[d][tid & 15u], tfac[d][16u + (tid >> 4)]);
-        }
-    }
+    phase_thread_factors(prog, ph, tid, gfac, tfac, fA);
     // the host only builds window phases for tiles of >= 2^(V+8) amplitudes: a warp-uniform trip count, so that op
     // headers, matrices and tables are fetched through the uniform datapath
 #ifndef RQ_UNIFORM_LOOPS
@@ -586,15 +679,12 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
 #pragma unroll
                 for (int d = 1; d < RQ_PHASE_MAX_DIAGP; ++d) if (o.t[3] == d) fs = fA[d];
                 const rq_cplx ft = cmul(B[it], fs);              // NT = 2^8: `it` = the group-index bits above the thread's
-                if (o.fuse == RQ_FUSE_BUTTERFLY) {               // (uniform) Hadamard-like op on the hub, then the ladder: one butterfly
+                if (o.fuse >= RQ_FUSE_BUTTERFLY) {               // (uniform) Hadamard-like op on the hub, then the ladder: one butterfly
                     const rq_cplx* H = prog.pool + prog.ops[oi - 1].moff;    // the skipped op's matrix, column-major: m00, m10, m01, m11
                     const rq_real c0 = H[0].x, c1 = H[1 * RQ_MSLOTS].x;
                     const bool swp = (c0 < 0) != (H[2 * RQ_MSLOTS].x < 0);
                     const rq_cplx fc = rq_cplx{ft.x * c1, ft.y * c1};
-                    if (ci == 1u) win_butterfly_sel<V, 0>(a, Wt, fc, c0, swp);
-                    else if (ci == 2u) win_butterfly_sel<V, 1>(a, Wt, fc, c0, swp);
-                    else if (ci == 4u) win_butterfly_sel<V, 2>(a, Wt, fc, c0, swp);
-                    else if (V > 3) win_butterfly_sel<V, (V > 3 ? 3 : 0)>(a, Wt, fc, c0, swp);
+                    win_butterfly_any<V>(a, ci, Wt, fc, c0, swp, o.fuse == RQ_FUSE_BUTTERFLY_UP);
                     continue;
                 }
 #pragma unroll
@@ -687,6 +777,11 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
         uint32_t i = step;
         if (MODE == 2) {
             const rq_phase& ph = prog.phases[step];
+            if (ph.kind == 2) {
+                run_chain_phase<RQ_WINDOW_BITS, SWZ>(sm, prog, ph, T, tid, gfac, tfac);
+                __syncthreads();
+                continue;
+            }
             if (ph.kind == 1) {
                 run_window_phase<RQ_WINDOW_BITS, SWZ>(sm, prog, ph, T, tid, gbase, gfac, tfac);
                 __syncthreads();

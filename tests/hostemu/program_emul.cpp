@@ -32,6 +32,29 @@ inline uint32_t spread(uint32_t g, const rq_tile_op& o) {
     return g;
 }
 
+// what run_chain_phase relies on: (skipped Hadamard-like op, butterfly) pairs only, at most V of them, the k-th butterfly's
+// thread-factor slot is k, one window bit as hub, no predicate of any kind, and -- for the UP variant -- a window table
+// that really does not depend on the window bits below the hub
+template <typename Prog>
+bool chain_is_wellformed(const Prog& prog, const rq_phase& ph) {
+    if ((ph.count & 1u) || ph.count > 2u * ph.v) return false;
+    for (uint32_t k = 0; k < ph.count / 2u; ++k) {
+        const rq_tile_op& h = prog.ops[ph.first + 2u * k];
+        const rq_tile_op& o = prog.ops[ph.first + 2u * k + 1u];
+        if (h.kind != RQ_OP_DENSE || h.fuse != RQ_FUSE_SKIP || h.k != 1) return false;
+        if (o.kind != RQ_OP_DIAGP || o.fuse < RQ_FUSE_BUTTERFLY || o.t[3] != k || o.cm_out || o.gcmask) return false;
+        if (o.cm_in == 0 || (o.cm_in & (o.cm_in - 1u)) || o.cm_in != (1u << h.wt[0])) return false;
+        if (o.fuse == RQ_FUSE_BUTTERFLY_UP) {
+            const rq_cplx* Wt = prog.pool + o.moff + 1 + o.t[0] + (1u << o.t[1]);
+            for (uint32_t j = 0; j < (1u << ph.v); ++j) {
+                const uint32_t hi = j & ~(2u * o.cm_in - 1u);              // keep only the window bits above the hub
+                if (pc(Wt[j | o.cm_in]) != pc(Wt[hi | o.cm_in])) return false;
+            }
+        }
+    }
+    return true;
+}
+
 template <typename Prog>
 bool emulate_window_phase(std::vector<cd>& sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint64_t gbase, const cd* gfac, bool swz) {
     const uint32_t V = ph.v, D = 1u << V;
@@ -66,7 +89,7 @@ bool emulate_window_phase(std::vector<cd>& sm, const Prog& prog, const rq_phase&
             if ((gbase & o.gcmask) != o.gcmask) continue;
             if ((base & o.cm_out) != o.cm_out) continue;
             if (o.fuse == RQ_FUSE_SKIP) {                             // a Hadamard the next op (a butterfly) carries out
-                if (o.kind != RQ_OP_DENSE || oi + 1 >= (uint32_t)ph.first + ph.count || prog.ops[oi + 1].fuse != RQ_FUSE_BUTTERFLY) return false;
+                if (o.kind != RQ_OP_DENSE || oi + 1 >= (uint32_t)ph.first + ph.count || prog.ops[oi + 1].fuse < RQ_FUSE_BUTTERFLY) return false;
                 continue;
             }
             const rq_cplx* M = prog.pool + o.moff;
@@ -87,7 +110,7 @@ bool emulate_window_phase(std::vector<cd>& sm, const Prog& prog, const rq_phase&
                 const rq_cplx* Wt = B + (1u << o.t[1]);
                 if ((g >> 8) >= (1u << o.t[1])) return false;
                 const cd ft = pc(B[g >> 8]) * fA[o.t[3]];
-                if (o.fuse == RQ_FUSE_BUTTERFLY) {                    // as win_butterfly: Hadamard on the hub (window bit ci), then the ladder
+                if (o.fuse >= RQ_FUSE_BUTTERFLY) {                    // as win_butterfly: Hadamard on the hub (window bit ci), then the ladder
                     if (ci == 0 || (ci & (ci - 1)) || oi == ph.first || prog.ops[oi - 1].fuse != RQ_FUSE_SKIP) return false;
                     const rq_cplx* H = prog.pool + prog.ops[oi - 1].moff;
                     const double c0 = H[0].x, c1 = H[1 * RQ_MSLOTS].x;
@@ -259,7 +282,8 @@ bool emulate_program(const Prog& prog, cd* state) {
             uint32_t i = step;
             if (phased) {
                 const rq_phase& ph = prog.phases[step];
-                if (ph.kind == 1) {
+                if (ph.kind == 1 || ph.kind == 2) {                    // kind 2 (butterfly chain): the same arithmetic without the op interpreter
+                    if (ph.kind == 2 && !chain_is_wellformed(prog, ph)) return false;
                     if (!emulate_window_phase(sm, prog, ph, T, gbase, gfac, swz)) return false;
                     continue;
                 }

@@ -95,6 +95,12 @@ def test_rocq_api_style_flow():
     assert abs(b.get_state_vector_slice(h, d, n, 1, 0)[5] - 1) < 1e-6
     with pytest.raises(RuntimeError):
         b.get_expectation_pauli_string(h, d, n, "XYZ", [0, 1])
+    # the batched extension: a whole Hamiltonian in one call, equal to the term-by-term calls
+    terms = [("ZZ", [0, 1]), ("XX", [1, 2]), ("YY", [1, 2]), ("Z", [2]), ("XZX", [0, 1, 2])]
+    got = b.get_expectation_pauli_batch(h, d, n, terms)
+    assert got.shape == (len(terms),)
+    for g_, (ps, qs) in zip(got, terms):
+        assert abs(g_ - b.get_expectation_pauli_string(h, d, n, ps, qs)) < 1e-6
     # GateFusion.processQueue: the whole queue in one fused submission
     b.initialize_state(h, d, n)
     q = []

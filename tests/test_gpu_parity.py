@@ -604,3 +604,29 @@ def _strided(sv, n, stride, dtype):
                          C.c_size_t(esz), C.c_size_t(N // stride), C.c_int(2))
     assert rc == 0, rc
     return out
+
+
+def test_eager_wide_matrices_take_the_block_sweep():
+    """rocsvApplyMatrix / rocsvApplyControlledMatrix with five or six qubits in all (complex64, n >= 13): one tensor-core block
+    pass instead of the gather kernel; seven and more still gather.  Same results as the oracle either way."""
+    n = 15
+    rng = np.random.default_rng(44)
+    o, g = _pair(n, "c64", seed=15)
+    # (targets, controls): neighbouring and scattered sets; a set the block kernel's tile geometry cannot move (more than five
+    # tensor-map dimensions) and everything wider than six qubits stays on the gather kernel
+    cases = [([3, 4, 5, 6, 7], []), ([9, 8, 12, 10, 11, 13], []), ([0, 1, 2, 3, 4], [5]), ([14, 2, 7, 11, 5], []), ([1, 3, 5, 7, 9, 11], []),
+             ([2, 3, 4, 5, 6, 7, 8], []), ([6, 7, 8, 9, 10, 11], [0])]
+    blocks = 0
+    for t, c in cases:
+        U = workloads.haar_unitary(rng, 1 << len(t))
+        before = g.stats().blockSweeps
+        o.apply_matrix(t, U, c); g.apply_matrix(t, U, c)
+        used = g.stats().blockSweeps - before
+        assert used <= (1 if len(t) + len(c) <= 6 else 0)
+        blocks += used
+    assert blocks >= 3
+    assert util.rel_err(g.state(), o.state) < TOL["c64"]
+    # a non-unitary 5-qubit matrix keeps its norm change (no renormalisation)
+    M = rng.standard_normal((32, 32)) + 1j * rng.standard_normal((32, 32))
+    o.apply_matrix([3, 9, 1, 14, 6], M); g.apply_matrix([3, 9, 1, 14, 6], M)
+    assert util.rel_err(g.state(), o.state) < TOL["c64"]

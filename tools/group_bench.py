@@ -45,10 +45,16 @@ def main():
         g.init(); assert g.lib.rocsvxApplyCircuit(g.h, None, n, arr, len(gates)) == 0
     g.sync(); g.stats(reset=True)
     g.timer_start(); t0 = time.perf_counter()
+    host = []
     for _ in range(a.steps):
-        g.init(); assert g.lib.rocsvxApplyCircuit(g.h, None, n, arr, len(gates)) == 0
+        ta = time.perf_counter(); g.init(); tb = time.perf_counter()
+        assert g.lib.rocsvxApplyCircuit(g.h, None, n, arr, len(gates)) == 0
+        host.append((round((tb - ta) * 1e3, 1), round((time.perf_counter() - tb) * 1e3, 1)))
+    tc = time.perf_counter()
     ms = g.timer_stop() / a.steps
     wall = (time.perf_counter() - t0) / a.steps * 1e3
+    print(json.dumps(dict(host_ms_per_call=host, what="(init, ApplyCircuit) host time of every step: the calls return when the launches are queued",
+                          timer_stop_wait_ms=round((time.perf_counter() - tc) * 1e3, 1))), flush=True)
     st = g.stats()
     nl = g.dist_info()[2]
     sweeps = st.sweeps / a.steps

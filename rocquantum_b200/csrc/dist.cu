@@ -376,6 +376,7 @@ static void note_exchange(rocsvInternalHandle* h, Dist& d, cudaEvent_t e0, cudaE
 // move the data of one EXCHANGE step: the k rank bits gpos[] trade places with the top-k local bits
 static rocqStatus_t exchange_data(rocsvInternalHandle* h, Dist& d, const std::vector<unsigned>& gpos) {
     const NvtxRange nvtx("rocq/exchange_nccl");
+    const rq_trace_scope trace(h, "exchange_nccl");
     const unsigned k = (unsigned)gpos.size();
     if (k == 0) return ROCQ_STATUS_SUCCESS;
     if (!d.comm) return ROCQ_STATUS_NOT_IMPLEMENTED;                   // (single-process groups always have peer slices)
@@ -416,6 +417,7 @@ static rocqStatus_t exchange_data(rocsvInternalHandle* h, Dist& d, const std::ve
 // both directions at once, no staging pass -- and a second barrier keeps the next sweep behind the peers' writes.
 static rocqStatus_t exchange_data_p2p(rocsvInternalHandle* h, Dist& d, const std::vector<unsigned>& gpos) {
     const NvtxRange nvtx("rocq/exchange_peer");
+    const rq_trace_scope trace(h, "exchange_peer");
     const unsigned k = (unsigned)gpos.size();
     std::vector<unsigned> lpos(k);
     for (unsigned i = 0; i < k; ++i) lpos[i] = d.n_local - k + i;

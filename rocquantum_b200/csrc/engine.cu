@@ -88,6 +88,7 @@ rocqStatus_t launch_plan(H* h, rq_cplx* state, unsigned n, const rq::SweepPlan& 
     const void* prog = nullptr;
     size_t prog_bytes = 0;
     const rq::NvtxRange nvtx("rocq/tile_sweep");
+    const rq_trace_scope trace(h, "tile_sweep", (unsigned)sp.ops.size());
     if (large) {
         static thread_local rq_program_large P;
         if (!rq::build_program(P, sp, seg, n, h->batchSize, h->dist.high_base())) return ROCQ_STATUS_FAILURE;
@@ -360,7 +361,10 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
         ~TermsGuard() { if (armed && p) { if (cached) cudaFree(p); else cudaFreeAsync(p, s); p = nullptr; } }
     } guard{d_terms, keep, h->stream};
     RQ_CUDA(cudaMemcpyAsync(d_terms, terms.data(), RQ_BLOCK_UBYTES, cudaMemcpyHostToDevice, h->stream), "block terms upload");
-    RQ_CUDA(rq_launch_block_sweep(state, &P, d_terms, &tm, h->stream), "block sweep launch");
+    {
+        const rq_trace_scope trace(h, "block_sweep");
+        RQ_CUDA(rq_launch_block_sweep(state, &P, d_terms, &tm, h->stream), "block sweep launch");
+    }
     guard.armed = false;
     if (P.pad & 16u) {                                   // ROCQ_BLOCK_DEBUG & 16: per-phase clock totals of CTA 0, threads 0 and 64
         long long t[32];
@@ -695,6 +699,7 @@ rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
     // sampling stream unless a seed is set (rocsvxSetSeed, or ROCQ_SEED for whole runs)
     if (const char* e = getenv("ROCQ_SEED")) h->seed = strtoull(e, nullptr, 0);
     else { std::random_device rd; h->seed = ((uint64_t)rd() << 32) | (uint64_t)rd(); }
+    if (const char* e = getenv("ROCQ_TRACE_LAUNCHES")) h->traceLaunches = atoi(e) != 0;
     if (const char* e = getenv("ROCQ_FUSION")) h->fusion = atoi(e) != 0;
     if (const char* e = getenv("ROCQ_TILE_BITS")) { const int t = atoi(e); if (t >= 6 && t <= RQ_MAX_TILE_BITS) h->tileBits = (unsigned)t; }
     if (const char* e = getenv("ROCQ_TC")) h->tcBlocks = (e[0] == 'a' || e[0] == '-') ? -1 : (atoi(e) != 0 && sizeof(rq_real) == 4) ? 1 : 0;
@@ -1388,6 +1393,21 @@ rocqStatus_t rocsvxGetStats(rocsvHandle_t h, rocsvxStats* stats, int reset) {
         cudaEventDestroy(ev.second);
     }
     h->dist.timed.clear();
+    if (!h->traced.empty()) {                              // ROCQ_TRACE_LAUNCHES: the launch list since the last call
+        cudaStreamSynchronize(h->stream);
+        double total = 0.0;
+        for (auto& t : h->traced) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+                fprintf(stderr, "[launch] rank %d %s ops %u ms %.3f\n", h->dist.rank, t.what, t.ops, (double)ms);
+                total += ms;
+            }
+            cudaEventDestroy(t.e0);
+            cudaEventDestroy(t.e1);
+        }
+        fprintf(stderr, "[launch] rank %d total of %zu launches: %.3f ms\n", h->dist.rank, h->traced.size(), total);
+        h->traced.clear();
+    }
     if (stats) *stats = h->stats;
     if (reset) h->stats = rocsvxStats{};
     return ROCQ_STATUS_SUCCESS;

@@ -89,6 +89,11 @@ struct rocsvInternalHandle {
     std::vector<rocsvCachedStep>* recording = nullptr;   // non-null while a circuit is being planned for the cache
     bool recordingValid = true;
     rq::Dist dist;
+    // ROCQ_TRACE_LAUNCHES=1: a CUDA event pair around every sweep / exchange launch, dumped (label, ms) to stderr by
+    // rocsvxGetStats -- a launch list that also works where ncu cannot follow (one rank of a multi-process run)
+    bool traceLaunches = false;
+    struct Traced { const char* what; unsigned ops; cudaEvent_t e0, e1; };
+    std::vector<Traced> traced;
     // single-process multi-GPU (group.h): this handle is the front of `group`; its own stream / state stay unused
     rocsvGroup* group = nullptr;
     int wantRanks = 0;                  // rocsvxDistSetRanks: slices of the next rocsvAllocateDistributedState (0: one per visible device)
@@ -96,6 +101,20 @@ struct rocsvInternalHandle {
 void rq_group_destroy(rocsvInternalHandle* h);
 rocqStatus_t rq_group_create(rocsvInternalHandle* h, int ranks);
 
+// trace scope: records the event pair around the launches issued while it lives (no-op unless h->traceLaunches)
+struct rq_trace_scope {
+    rocsvInternalHandle* h;
+    size_t idx = (size_t)-1;
+    rq_trace_scope(rocsvInternalHandle* h_, const char* what, unsigned ops = 0) : h(h_) {
+        if (!h->traceLaunches || h->traced.size() >= 4096) return;
+        rocsvInternalHandle::Traced t{what, ops, nullptr, nullptr};
+        if (cudaEventCreate(&t.e0) != cudaSuccess || cudaEventCreate(&t.e1) != cudaSuccess) return;
+        cudaEventRecord(t.e0, h->stream);
+        idx = h->traced.size();
+        h->traced.push_back(t);
+    }
+    ~rq_trace_scope() { if (idx != (size_t)-1) cudaEventRecord(h->traced[idx].e1, h->stream); }
+};
 rocqStatus_t rq_engine_flush(rocsvInternalHandle* h);
 rocqStatus_t rq_engine_run(rocsvInternalHandle* h, rq_cplx* state, unsigned n, const std::vector<rq::HostOp>& ops, bool fused);
 rocqStatus_t rq_engine_fetch(rocsvInternalHandle* h, const void* dsrc, void* hdst, size_t bytes);

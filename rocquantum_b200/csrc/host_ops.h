@@ -701,21 +701,27 @@ struct BlockLayout {
     uint8_t col[7], lp_col[7], lp_blk[6];
     uint8_t res[13];                 // tile bits, ascending
 };
-inline bool block_layout(uint64_t blockmask, unsigned n, size_t batch, BlockLayout& L) {
-    if (n < 13 || n > 40 || __builtin_popcountll(blockmask) != 6 || (blockmask >> n)) return false;
+// layout for a given choice of the seven column bits (colmask: 7 non-block positions containing every non-block bit of 0-3)
+inline bool block_layout_with_columns(uint64_t blockmask, uint64_t colmask, unsigned n, size_t batch, BlockLayout& L) {
     unsigned blk[6], nb = 0, nc = 0;
-    uint64_t colmask = 0;
     for (unsigned p = 0; p < n; ++p) {
         if ((blockmask >> p) & 1ull) blk[nb++] = p;
-        else if (nc < 7) { L.col[nc++] = (uint8_t)p; colmask |= 1ull << p; }
+        else if ((colmask >> p) & 1ull) L.col[nc++] = (uint8_t)p;
     }
+    if (nb != 6 || nc != 7) return false;
     const uint64_t tile = blockmask | colmask;
+    if ((tile & 0xFull) != 0xFull) return false;                            // a 128-byte row (index bits 0-3) is always inside the tile
     for (unsigned p = 0, r = 0; p < n; ++p) if ((tile >> p) & 1ull) L.res[r++] = (uint8_t)p;
     // shared-memory order of the tile bits
     unsigned order[13], no = 0;
     for (unsigned p = 0; p < 4; ++p) order[no++] = p;                       // bits 0-3 are always in the tile
     for (unsigned c = 0; c < 7; ++c) if (L.col[c] >= 4) order[no++] = L.col[c];
-    for (unsigned b = 0; b < 6; ++b) if (blk[b] >= 4) order[no++] = blk[b];
+    // block bits: the run that continues the last column bit first (it then shares that column run's dimension), the rest
+    // ascending -- the kernel addresses block bits through lp_blk[], so their order in shared memory is free
+    uint64_t placed = 0;
+    if (no > 4)
+        for (unsigned p = order[no - 1] + 1; p < n && ((blockmask >> p) & 1ull); ++p) { order[no++] = p; placed |= 1ull << p; }
+    for (unsigned b = 0; b < 6; ++b) if (blk[b] >= 4 && !((placed >> blk[b]) & 1ull)) order[no++] = blk[b];
     for (unsigned l = 0; l < 13; ++l) {
         const unsigned p = order[l];
         bool is_blk = false;
@@ -760,6 +766,41 @@ inline bool block_layout(uint64_t blockmask, unsigned n, size_t batch, BlockLayo
     for (unsigned d = 0; d < rank; ++d) if (L.dims[d] > 0xffffffffull || L.box[d] > 256) return false;
     L.rank = rank;
     return true;
+}
+// The column bits are free to choose (any seven positions outside the block, as long as index bits 0-3 are in the tile).
+// The lowest seven give the longest contiguous pieces; when the block is two separate runs of index bits (neighbouring
+// logical qubits that an index-bit exchange left far apart in a distributed slice) that choice needs a sixth tensor-map
+// dimension, and columns that extend a block run downwards or upwards instead keep the tile within five.
+inline bool block_layout(uint64_t blockmask, unsigned n, size_t batch, BlockLayout& L) {
+    if (n < 13 || n > 40 || __builtin_popcountll(blockmask) != 6 || (blockmask >> n)) return false;
+    const uint64_t must = 0xFull & ~blockmask;                              // non-block bits of the 128-byte row
+    const unsigned extra = 7u - (unsigned)__builtin_popcountll(must);
+    auto take = [&](unsigned from, int dir, unsigned count, uint64_t have) {   // `count` free positions >= 4 walking from `from` in direction dir
+        uint64_t m = 0;
+        for (int p = (int)from; p >= 4 && p < (int)n && (unsigned)__builtin_popcountll(m) < count; p += dir)
+            if (!((blockmask >> p) & 1ull) && !((have >> p) & 1ull)) m |= 1ull << p;
+        return m;
+    };
+    uint64_t cands[16];
+    unsigned nc = 0;
+    cands[nc++] = must | take(4, +1, extra, 0);                             // the lowest free positions (what round 1 always took)
+    for (unsigned p = 4; p < n; ++p) {                                      // around every run of block bits above the row
+        if (!((blockmask >> p) & 1ull) || (p > 4 && ((blockmask >> (p - 1)) & 1ull))) continue;
+        unsigned q = p;
+        while (q + 1 < n && ((blockmask >> (q + 1)) & 1ull)) ++q;            // run [p, q]
+        if (nc + 3 > 16) break;
+        const uint64_t below = take(p - 1, -1, extra, 0);
+        cands[nc++] = must | below | take(q + 1, +1, extra - (unsigned)__builtin_popcountll(below), below);
+        const uint64_t above = take(q + 1, +1, extra, 0);
+        cands[nc++] = must | above | take(p - 1, -1, extra - (unsigned)__builtin_popcountll(above), above);
+        const uint64_t half = take(p - 1, -1, extra / 2, 0);
+        cands[nc++] = must | half | take(q + 1, +1, extra - (unsigned)__builtin_popcountll(half), half);
+    }
+    for (unsigned c = 0; c < nc; ++c) {
+        if (__builtin_popcountll(cands[c]) != 7) continue;
+        if (block_layout_with_columns(blockmask, cands[c], n, batch, L)) return true;
+    }
+    return false;
 }
 inline bool block_supported(uint64_t blockmask, unsigned n, size_t batch) {
     BlockLayout L;
@@ -922,6 +963,17 @@ inline std::vector<MixedStep> plan_mixed_policy(const std::vector<HostOp>& ops, 
             for (int i : best) { done[i] = 1; --remaining; touched |= ops[i].qubits(); }
             steps.push_back(std::move(st));
             continue;
+        }
+        if (getenv("ROCQ_PLAN_DEBUG")) {
+            unsigned unsupported = 0, tried_n = 0;
+            if (possible && eligible(ops[first]))
+                for (int bias = 0; bias < 5; ++bias) {
+                    const uint64_t B = grow(first, bias);
+                    ++tried_n;
+                    if ((unsigned)__builtin_popcountll(B) == BL.qubits && BL.supported && !BL.supported(B, n, BL.batch)) ++unsupported;
+                }
+            fprintf(stderr, "[plan] sweep fallback: oldest op kind %d qubits %llx eligible %d best_cost %.0f candidates unsupported %u/%u\n", ops[first].kind,
+                    (unsigned long long)ops[first].qubits(), (int)(possible && eligible(ops[first])), best_cost, unsupported, tried_n);
         }
         // One ordinary sweep over what is left.  When blocks are possible it leaves the dense ops a block could take alone
         // (marked `defer` in the copy), unless the oldest op is such an op itself.

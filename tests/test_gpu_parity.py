@@ -630,3 +630,18 @@ def test_eager_wide_matrices_take_the_block_sweep():
     M = rng.standard_normal((32, 32)) + 1j * rng.standard_normal((32, 32))
     o.apply_matrix([3, 9, 1, 14, 6], M); g.apply_matrix([3, 9, 1, 14, 6], M)
     assert util.rel_err(g.state(), o.state) < TOL["c64"]
+
+
+def test_block6_on_two_runs_of_index_bits():
+    """A block made of two separate runs of index bits (what neighbouring logical qubits look like after an index-bit exchange
+    in a distributed slice): the tile's column bits are then chosen next to a block run so that the tile still fits a
+    five-dimensional tensor map -- same kernel, same results."""
+    rng = np.random.default_rng(21)
+    for n, batch, qs, blocks in ((20, 1, [11, 12, 13, 17, 18, 19], 1), (22, 1, [9, 10, 18, 19, 20, 21], 1), (19, 1, [5, 6, 7, 8, 17, 18], 1),
+                                 (24, 1, [4, 5, 21, 22, 23, 6], 1), (21, 1, [10, 20, 19, 18, 17, 16], 1), (20, 2, [8, 9, 10, 11, 15, 16], 1),
+                                 (19, 2, [5, 6, 7, 8, 17, 18], 0)):          # (last: the batch needs a sixth dimension -> generic dense path)
+        U = workloads.haar_unitary(rng, 64)
+        o, g = _pair(n, "c64", batch=batch, seed=n)
+        o.apply_matrix(qs, U); g.apply_block6(qs, U)
+        assert g.stats().blockSweeps == blocks, qs
+        assert util.rel_err(g.state(), o.state) < 2e-6

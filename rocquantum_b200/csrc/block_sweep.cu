@@ -38,6 +38,7 @@ namespace {
 
 constexpr int NW = 512;                        // worker threads: 4 warps per TMEM lane quarter, 16 block values per thread
 constexpr int BT = NW + 32;                    // + one warp that only issues the MMAs
+constexpr uint32_t NORM_EVERY = 4;             // unitary blocks: the norm ratio is measured on every 4th tile of a CTA
 constexpr uint32_t MAT_BYTES = 8192;           // one fp16 term of a 64 x 64 operand (Re U or Im U)
 constexpr uint32_t TILE_BYTES = 65536;         // 2^13 complex64 amplitudes
 constexpr uint32_t SMEM_U = 0;                                    // Re U hi | Re U lo | Im U hi | Im U lo  (B operands, N = 64)
@@ -316,7 +317,9 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             mark(6);
             // A unitary block preserves the norm of the tile.  The tensor core's truncating accumulation shrinks it
             // systematically (~1e-7 per sweep); the ratio measured on the tiles this CTA has finished removes that bias.
-            if (P.renorm && i > 0) {
+            // Only every NORM_EVERY-th tile is measured: the bias is the same everywhere, and the two sums of squares plus
+            // their reductions were ~12 % of the workers' instructions.
+            if (P.renorm && i > 0 && ((i - 1) % NORM_EVERY) == 0) {
                 float2 v = red[(i - 1) & 1u][lane & 15u];
 #pragma unroll
                 for (int m = 8; m >= 1; m >>= 1) {
@@ -335,13 +338,20 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             const float f = fcorr * inv_scale;
             unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES;
             float out2 = 0.f;
+            const bool tracked = P.renorm && (i % NORM_EVERY) == 0;            // (uniform)
+            if (tracked) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float a = __uint_as_float(re[j]), b = __uint_as_float(im[j]);
+                    out2 = fmaf(a, a, fmaf(b, b, out2));
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const float a = __uint_as_float(re[j]), b = __uint_as_float(im[j]);
-                out2 = fmaf(a, a, fmaf(b, b, out2));
                 *reinterpret_cast<float2*>(S + (sbase ^ vaddr(j))) = make_float2(a * f, b * f);
             }
-            if (P.renorm) {
+            if (tracked) {
                 out2 *= inv_scale * inv_scale;                                 // back to the state's own units (columns differ in scale)
 #pragma unroll
                 for (int m = 16; m >= 1; m >>= 1) {
@@ -366,7 +376,7 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             const unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES;
             float in2 = 0.f;
             float mx = 0.f;
-            auto split_tile = [&](int sexp, bool measure) {
+            auto split_tile = [&](int sexp, bool measure, bool first_pass) {
                 const float scale = __uint_as_float((uint32_t)(sexp + 127) << 23);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {                                  // 8 block values -> 4 packed words per (term, re|im)
@@ -375,10 +385,8 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                     for (int j = 0; j < 4; ++j) {
                         const float2 a0 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j)));
                         const float2 a1 = *reinterpret_cast<const float2*>(S + (sbase ^ vaddr(8 * c + 2 * j + 1)));
-                        if (measure) {
-                            in2 = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, in2))));
-                            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(a0.x), fabsf(a0.y))), fmaxf(fabsf(a1.x), fabsf(a1.y)));
-                        }
+                        if (measure) in2 = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, in2))));
+                        if (first_pass) mx = fmaxf(fmaxf(mx, fmaxf(fabsf(a0.x), fabsf(a0.y))), fmaxf(fabsf(a1.x), fabsf(a1.y)));
                         split2(a0.x * scale, a1.x * scale, hr[j], lr[j]);
                         split2(a0.y * scale, a1.y * scale, hi[j], li[j]);
                     }
@@ -392,7 +400,7 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                     }
                 }
             };
-            split_tile(guess_exp, true);
+            split_tile(guess_exp, P.renorm && (i % NORM_EVERY) == 0, true);
             // publish this thread's exponent, then see what the column's four threads found
             const uint32_t sbar = smem_u32(&bar_scale[i & 1u][warp & 3u]);
             cexp[i & 1u][qt][ncol] = (uint8_t)(__float_as_uint(mx) >> 23);
@@ -406,7 +414,7 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             const int want_exp = min(max(12 - ecol, -100), 100);
             int use_exp = guess_exp;
             if (ecol > -127 && (ecol + guess_exp < 6 || ecol + guess_exp > 14)) use_exp = want_exp;     // (2^16 itself is past fp16)
-            if (__any_sync(0xffffffffu, use_exp != guess_exp)) split_tile(use_exp, false);
+            if (__any_sync(0xffffffffu, use_exp != guess_exp)) split_tile(use_exp, false, false);
             guess_exp = ecol > -127 ? want_exp : guess_exp;
             const float cur_inv = __uint_as_float((uint32_t)(127 - use_exp) << 23);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

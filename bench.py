@@ -47,21 +47,69 @@ def measured_peaks():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  Sampled in-process through NVML (nvidia_ml_py) from a small
+    thread, 4 Hz: a polling `nvidia-smi -lms 200` child slowed the N = 2 run it was watching by 23 % (1326 vs 1079 ms per step,
+    profiles/r02_bench_n2_sampler_ab.log) -- every iteration of it re-attaches to the driver.  `nvidia-smi` is only the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index=0):
         self.p = None
         self.gpu = gpu_index
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            nv, h = self._nvml_handle()
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        mask = int(reasons_fn(h))
+                        for bit, name in self.REASONS:
+                            if mask & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    time.sleep(0.25)
+            import threading
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "1000",
                                        "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(1.0)                              # it attaches to the driver before the timed region, not inside it
         except Exception:
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"], "source": "nvml"}
+            busy = [s for s in self.sm if s > 0.5 * max(self.sm)] or self.sm
+            return {"sm_mhz": statistics.median(busy), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.sm),
+                    "source": "nvml, in-process, 4 Hz"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -86,7 +134,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         busy = [s for s in sm if s > 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 1000"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -276,7 +324,7 @@ def run_engine(args):
     barrier()
     sv.stats(reset=True)
     clocks = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("ROCQ_BENCH_NO_CLOCKS"):       # (diagnosis only: is the sampler itself visible in the timing?)
         clocks.start()
     # device time of the K steps: CUDA events on the engine's own stream (rocsvxTimerStart/Stop), no sync inside the region
     sv.timer_start()

@@ -38,6 +38,7 @@ def main():
     sweep_bytes = 2.0 * (1 << n) * amp
     rng = np.random.default_rng(0)
     U2 = workloads.haar_unitary(rng, 4)
+    U5, U6, U7 = workloads.haar_unitary(rng, 32), workloads.haar_unitary(rng, 64), workloads.haar_unitary(rng, 128)
     cases = []
     for t in sorted({0, 1, 3, 4, 5, 8, 12, 13, 20, n - 2, n - 1}):
         if t < n:
@@ -51,6 +52,13 @@ def main():
         ("U4 q3,q4 (circuit)", lambda: sv.apply_circuit([("matrix", [3, 4], [], 0.0, U2)])),
         (f"U4 q{n-2},q{n-1} (circuit)", lambda: sv.apply_circuit([("matrix", [n - 2, n - 1], [], 0.0, U2)])),
         (f"U4 q2,q{n-1} (circuit)", lambda: sv.apply_circuit([("matrix", [2, n - 1], [], 0.0, U2)])),
+        # eager rocsvApplyMatrix with wide matrices: 5 / 6 qubits take the tensor-core block sweep (complex64), 7 the gather kernel
+        ("U32 q8..12 (eager, device matrix)", lambda: sv.apply_matrix([8, 9, 10, 11, 12], U5)),
+        ("U64 q8..13 (eager, device matrix)", lambda: sv.apply_matrix([8, 9, 10, 11, 12, 13], U6)),
+        (f"U32 q{n-5}..{n-1} (eager, device matrix)", lambda: sv.apply_matrix(list(range(n - 5, n)), U5)),
+        ("U128 q8..14 (eager, gather kernel)", lambda: sv.apply_matrix([8, 9, 10, 11, 12, 13, 14], U7)),
+        ("chunk masses + scan + 256 shots (read sweep)", lambda: sv.sample(list(range(min(n, 64))), 256)),
+        ("8 Z-strings in one batch (read sweep)", lambda: sv.expect_batch([("ZZ", [q, q + 1]) for q in range(8)])),
         ("norm (read sweep)", lambda: sv.norm2()),
         ("<X5 Y9 Z20> (read sweep)", lambda: sv.expect_pauli("XYZ", [5, 9, min(20, n - 1)])),
     ]

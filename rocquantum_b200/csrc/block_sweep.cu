@@ -21,8 +21,14 @@
 //     (one 256-byte segment per LDG.64) and the epilogue (tcgen05.ld -> float2 STG) writes them back the same way:
 //     the tile never needs an fp32 staging buffer; shared memory holds the fp16 operand terms only.
 //   * software pipeline in a persistent CTA per SM: operand buffers and accumulators are double-buffered, so that the
-//     MMAs of tile i run while the CUDA cores do the epilogue of tile i-1 and the split of tile i+1; global loads run
-//     two tiles ahead (128 KB in flight per SM).
+//     MMAs of tile i run while the CUDA cores do the epilogue of tile i-1 and the split of tile i+1.
+//   * shared memory = two INPUT tiles + one OUTPUT tile.  The fp32 amplitudes of a tile are dead as soon as their fp16
+//     terms sit in tensor memory, so an input buffer is handed back to the loader right after the split (not after the
+//     epilogue two steps later): one or two tile loads (64-128 KB per SM) are in flight at any time.  A loader thread,
+//     a storer thread and the MMA thread each run their own loop in a warp of their own; the 16 worker warps meet them
+//     -- and each other -- only through mbarriers (full / empty per input buffer, X' / D per pipeline buffer, written /
+//     drained for the output buffer), never through a CTA-wide barrier, so the warps drift apart and their LDS, TMEM and
+//     ALU phases overlap.
 // complex64 only: there is no fp64 tensor path for this (complex128 stays on the CUDA-core sweep).
 #ifndef ROCQ_PRECISION_DOUBLE
 #include <cuda.h>
@@ -37,13 +43,14 @@
 namespace {
 
 constexpr int NW = 512;                        // worker threads: 4 warps per TMEM lane quarter, 16 block values per thread
-constexpr int BT = NW + 32;                    // + one warp that only issues the MMAs
+constexpr int BT = NW + 96;                    // + three single-thread roles in warps of their own: MMA issue, tile loads, tile stores
 constexpr uint32_t NORM_EVERY = 4;             // unitary blocks: the norm ratio is measured on every 4th tile of a CTA
 constexpr uint32_t MAT_BYTES = 8192;           // one fp16 term of a 64 x 64 operand (Re U or Im U)
 constexpr uint32_t TILE_BYTES = 65536;         // 2^13 complex64 amplitudes
 constexpr uint32_t SMEM_U = 0;                                    // Re U hi | Re U lo | Im U hi | Im U lo  (B operands, N = 64)
-constexpr uint32_t SMEM_S = 4 * MAT_BYTES;                        // 3 tiles (fp32 amplitudes): bulk-loaded, transformed in place, bulk-stored
-constexpr uint32_t SMEM_BYTES = SMEM_S + 3 * TILE_BYTES;
+constexpr uint32_t SMEM_IN = 4 * MAT_BYTES;                       // 2 input tiles (fp32 amplitudes), loaded by tensor-map bulk copies
+constexpr uint32_t SMEM_OUT = SMEM_IN + 2 * TILE_BYTES;           // 1 output tile in the same layout, stored by a tensor-map bulk copy
+constexpr uint32_t SMEM_BYTES = SMEM_OUT + TILE_BYTES;
 // TMEM columns, per pipeline buffer b (at 256 * b): [0,64) Re D, [64,128) Im D, then the packed fp16 pairs of X':
 // [128,160) Re hi, [160,192) Im hi, [192,224) Re lo, [224,256) Im lo
 constexpr uint32_t TM_D = 0, TM_XH = 128, TM_XL = 192, TM_BUF = 256;
@@ -122,7 +129,6 @@ __device__ __forceinline__ void tensor_s2g(const CUtensorMap* tm, const int32_t 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory"); }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                  "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
@@ -165,7 +171,9 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                                                              const __grid_constant__ rq_block_params P,
                                                              const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_u, bar_mma[2], bar_x[2], bar_full[3], bar_scale[2][4];
+    // bar_full / bar_empty: input tile buffer loaded / split by all worker warps; bar_x / bar_mma: X' of a pipeline buffer in
+    // tensor memory / its products accumulated; bar_owritten / bar_odrained: output tile written by all worker warps / read by its store
+    __shared__ __align__(8) uint64_t bar_u, bar_mma[2], bar_x[2], bar_full[2], bar_empty[2], bar_owritten, bar_odrained, bar_scale[2][4];
     __shared__ uint32_t tmem_slot;
     __shared__ float2 red[2][16];      // per-warp (|in|^2, |out|^2) of a tile, double-buffered
     __shared__ uint8_t cexp[2][4][128]; // biased exponent of max |component| per (tile parity, quarter of the block values, column)
@@ -173,8 +181,14 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
 
     if (tid == 0) {
         mbar_init(smem_u32(&bar_u), 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_mma[b]), 1); mbar_init(smem_u32(&bar_x[b]), NW / 32); }
-        for (int b = 0; b < 3; ++b) mbar_init(smem_u32(&bar_full[b]), 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&bar_mma[b]), 1);
+            mbar_init(smem_u32(&bar_x[b]), NW / 32);
+            mbar_init(smem_u32(&bar_full[b]), 1);
+            mbar_init(smem_u32(&bar_empty[b]), NW / 32);
+        }
+        mbar_init(smem_u32(&bar_owritten), NW / 32);
+        mbar_init(smem_u32(&bar_odrained), 1);
         for (int b = 0; b < 8; ++b) mbar_init(smem_u32(&bar_scale[b >> 2][b & 3]), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -191,8 +205,21 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
     const uint64_t first = blockIdx.x, stride = gridDim.x;
     const uint64_t cnt = P.ntiles > first ? (P.ntiles - first + stride - 1) / stride : 0;     // tiles of this CTA
 
+    // A tile is one box of a tensor map over the state: one bulk-tensor instruction per tile and direction.
+    const uint32_t trank = P.trank;
+    auto tile_coords = [&](uint64_t i, int32_t (&c)[5]) {
+        uint64_t t = first + i * stride;                                   // tile index: non-resident bits, compacted, member on top
+#pragma unroll
+        for (uint32_t d = 0; d < 5; ++d) {
+            const uint32_t len = P.tbits[d];
+            if (len == 0) c[d] = 0;
+            else if (len == 255u) c[d] = (int32_t)t;
+            else { c[d] = (int32_t)(t & ((1ull << len) - 1ull)); t >>= len; }
+        }
+    };
+
     if (warp == NW / 32) {
-        // ================================ the MMA warp ================================
+        // ================================ the MMA thread ================================
         if (lane == 0) {
             mbar_expect_tx(smem_u32(&bar_u), 4 * MAT_BYTES);          // the block matrix stays resident for all tiles
             bulk_g2s(smem_u32(smem + SMEM_U), uterms, 4 * MAT_BYTES, smem_u32(&bar_u));
@@ -223,6 +250,37 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                 umma_commit(smem_u32(&bar_mma[b]));
             }
         }
+    } else if (warp == NW / 32 + 1) {
+        // ================================ the loader thread ================================
+        // tile i goes to input buffer i & 1 as soon as every worker warp has split tile i - 2 out of it
+        if (lane == 0) {
+            for (uint64_t i = 0; i < cnt; ++i) {
+                const uint32_t b = (uint32_t)i & 1u;
+                if (i >= 2) mbar_wait(smem_u32(&bar_empty[b]), (uint32_t)((i >> 1) - 1u) & 1u);
+                int32_t c[5];
+                tile_coords(i, c);
+                mbar_expect_tx(smem_u32(&bar_full[b]), TILE_BYTES);
+                tensor_g2s(smem_u32(smem + SMEM_IN + b * TILE_BYTES), &tmap, c, trank, smem_u32(&bar_full[b]));
+            }
+        }
+    } else if (warp == NW / 32 + 2) {
+        // ================================ the storer thread ================================
+        // tile j leaves the output buffer once every worker warp has written its part; the buffer is handed back when the
+        // bulk store has READ it (the global writes complete behind)
+        if (lane == 0) {
+            for (uint64_t j = 0; j < cnt; ++j) {
+                mbar_wait(smem_u32(&bar_owritten), (uint32_t)j & 1u);
+                if (!(dbg & 4u)) {
+                    int32_t c[5];
+                    tile_coords(j, c);
+                    tensor_s2g(&tmap, c, trank, smem_u32(smem + SMEM_OUT));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                mbar_arrive(smem_u32(&bar_odrained));
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");              // the last stores must be complete before the CTA exits
+        }
     } else {
         // ================================ 16 worker warps ================================
         // this thread: tile column ncol (= TMEM lane), block values [16*qt, 16*qt+16)
@@ -239,53 +297,12 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
         const uint32_t s0 = 8u << P.lp_blk[0], s1 = 8u << P.lp_blk[1], s2 = 8u << P.lp_blk[2], s3 = 8u << P.lp_blk[3];   // byte strides of value bits 0..3
         const uint32_t tlane = tmem_d + (((warp & 3u) * 32u) << 16);            // this warp's TMEM lane quarter
 
-        // phase timers (ROCQ_BLOCK_DEBUG & 16): threads 0 and 64 of CTA 0 accumulate clock deltas between marks
-        long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
-        const bool timed = (dbg & 16u) && blockIdx.x == 0 && (tid == 0 || tid == 64);
-        auto mark = [&](int k) {
-            if (timed) {
-                const long long t = clock64();
-                tacc[k] += t - tlast;
-                tlast = t;
-            }
-        };
-        if (timed) tlast = clock64();
-
-        // A tile is one box of a tensor map over the state: one bulk-tensor instruction per tile and direction, issued by thread 0.
-        const uint32_t trank = P.trank;
-        auto tile_coords = [&](uint64_t i, int32_t (&c)[5]) {
-            uint64_t t = first + i * stride;                                   // tile index: non-resident bits, compacted, member on top
-#pragma unroll
-            for (uint32_t d = 0; d < 5; ++d) {
-                const uint32_t len = P.tbits[d];
-                if (len == 0) c[d] = 0;
-                else if (len == 255u) c[d] = (int32_t)t;
-                else { c[d] = (int32_t)(t & ((1ull << len) - 1ull)); t >>= len; }
-            }
-        };
-        auto load_rows = [&](uint64_t i) {
-            if (i < cnt && tid == 0) {
-                const uint32_t bar = smem_u32(&bar_full[i % 3u]);
-                int32_t c[5];
-                tile_coords(i, c);
-                mbar_expect_tx(bar, TILE_BYTES);
-                tensor_g2s(smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES), &tmap, c, trank, bar);
-            }
-        };
-        auto store_rows = [&](uint64_t i) {
-            if (tid == 0) {
-                int32_t c[5];
-                tile_coords(i, c);
-                tensor_s2g(&tmap, c, trank, smem_u32(smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES));
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        };
         // shared-memory address of this thread's block value v of a tile
         // (value bits and the thread's own bits are disjoint, and the swizzle is an XOR: offsets combine with XOR)
         auto vaddr = [&](int v) -> uint32_t { return ((v & 1) ? s0 : 0u) ^ ((v & 2) ? s1 : 0u) ^ ((v & 4) ? s2 : 0u) ^ ((v & 8) ? s3 : 0u); };
 
-        // ---- epilogue of tile i from pipeline buffer B: TMEM lane = column; re at column t, im at column 64 + t.  The
-        //      thread overwrites exactly the amplitudes it read, so the tile is transformed in place without a barrier. ----
+        // ---- epilogue of tile i from pipeline buffer B: TMEM lane = column; re at column t, im at column 64 + t.  The thread
+        //      writes, into the output buffer, the positions it read from the input buffer. ----
         float my_in = 0.f;                                                     // |.|^2 of this thread's inputs of the tile in flight
         float my_inv = 1.f;                                                    // 1 / (scale of this thread's column) of the tile in flight
         // Column scales by guess and verify.  Every tile column (the 64 amplitudes one block matrix mixes, held by the four
@@ -303,10 +320,8 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
         float acc_in = 0.f, acc_out = 0.f;                                     // |in|^2, |scaled out|^2 over the CTA's finished tiles
         auto epilogue = [&](auto BC, uint64_t i, float in2, float inv_scale) {
             constexpr uint32_t B = decltype(BC)::value;
-            mark(4);
             if (!(dbg & 1u)) mbar_wait(smem_u32(&bar_mma[B]), (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
-            mark(5);
             // (TMEM reads run at 64 B/clk per SM, so the accumulator is read exactly once)
             const uint32_t taddr = tlane + B * TM_BUF + TM_D + 16u * qt;
             uint32_t re[16], im[16];
@@ -314,7 +329,9 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             tmem_ld16(taddr + 64u, im);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mark(6);
+            // the output buffer is free once the store of tile i-1 has read it.  That store was issued after EVERY worker warp
+            // had finished its epilogue of tile i-1, so what they left in red[] is visible from here on as well.
+            if (i > 0) mbar_wait(smem_u32(&bar_odrained), (uint32_t)(i - 1) & 1u);
             // A unitary block preserves the norm of the tile.  The tensor core's truncating accumulation shrinks it
             // systematically (~1e-7 per sweep); the ratio measured on the tiles this CTA has finished removes that bias.
             // Only every NORM_EVERY-th tile is measured: the bias is the same everywhere, and the two sums of squares plus
@@ -336,7 +353,7 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                 }
             }
             const float f = fcorr * inv_scale;
-            unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES;
+            unsigned char* S = smem + SMEM_OUT;
             float out2 = 0.f;
             const bool tracked = P.renorm && (i % NORM_EVERY) == 0;            // (uniform)
             if (tracked) {
@@ -360,20 +377,17 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
                 }
                 if (lane == 0) red[i & 1u][warp] = make_float2(in2, out2);
             }
-            mark(7);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> visible to the bulk copy engine
-            workers_sync();
-            if (!(dbg & 4u)) store_rows(i);
-            mark(8);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_owritten));               // one arrival per worker warp
         };
 
-        // ---- one pipeline step: split tile i into tensor memory (buffer B), hand it to the MMA warp, refill the tile buffer freed by
-        //      the last store with tile i+1's successor, finish tile i-1 ----
+        // ---- one pipeline step: split tile i into tensor memory (buffer B), hand it to the MMA thread and its input buffer back to
+        //      the loader, finish tile i-1 ----
         auto step = [&](auto BC, uint64_t i) {
-            constexpr uint32_t B = decltype(BC)::value;
-            mbar_wait(smem_u32(&bar_full[i % 3u]), (uint32_t)(i / 3u) & 1u);
-            mark(0);
-            const unsigned char* S = smem + SMEM_S + (uint32_t)(i % 3u) * TILE_BYTES;
+            constexpr uint32_t B = decltype(BC)::value;                        // = i & 1: tensor-memory buffer and input tile buffer
+            mbar_wait(smem_u32(&bar_full[B]), (uint32_t)(i >> 1) & 1u);
+            const unsigned char* S = smem + SMEM_IN + B * TILE_BYTES;
             float in2 = 0.f;
             float mx = 0.f;
             auto split_tile = [&](int sexp, bool measure, bool first_pass) {
@@ -402,13 +416,13 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             };
             split_tile(guess_exp, P.renorm && (i % NORM_EVERY) == 0, true);
             // publish this thread's exponent, then see what the column's four threads found
-            const uint32_t sbar = smem_u32(&bar_scale[i & 1u][warp & 3u]);
-            cexp[i & 1u][qt][ncol] = (uint8_t)(__float_as_uint(mx) >> 23);
+            const uint32_t sbar = smem_u32(&bar_scale[B][warp & 3u]);
+            cexp[B][qt][ncol] = (uint8_t)(__float_as_uint(mx) >> 23);
             __syncwarp();
             if (lane == 0) mbar_arrive(sbar);
             mbar_wait(sbar, (uint32_t)(i >> 1) & 1u);
-            const int ecol = (int)max(max((uint32_t)cexp[i & 1u][0][ncol], (uint32_t)cexp[i & 1u][1][ncol]),
-                                      max((uint32_t)cexp[i & 1u][2][ncol], (uint32_t)cexp[i & 1u][3][ncol])) - 127;   // floor(log2 max)
+            const int ecol = (int)max(max((uint32_t)cexp[B][0][ncol], (uint32_t)cexp[B][1][ncol]),
+                                      max((uint32_t)cexp[B][2][ncol], (uint32_t)cexp[B][3][ncol])) - 127;   // floor(log2 max)
             // want the maximum in [2^12, 2^13); keep the guess while it leaves it in [2^6, 2^16).  Columns of zeros or
             // denormals (ecol = -127) take any scale; inf / nan columns stay what they are.
             const int want_exp = min(max(12 - ecol, -100), 100);
@@ -417,27 +431,20 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
             if (__any_sync(0xffffffffu, use_exp != guess_exp)) split_tile(use_exp, false, false);
             guess_exp = ecol > -127 ? want_exp : guess_exp;
             const float cur_inv = __uint_as_float((uint32_t)(127 - use_exp) << 23);
+            // every tcgen05.st of this warp has taken its registers -- and with them the shared-memory loads that fed them --
+            // before the two hand-overs: X' to the MMA thread, the input buffer back to the loader
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_x[B]));                   // one arrival per worker warp
-            mark(1);
-            // the buffer of tile i-2 (stored during the previous step) is free once the bulk stores have read it: refill it
-            // with tile i+1.  Each warp waits for, and re-uses, its own rows only.
-            if (i >= 1) {
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                load_rows(i + 1);
+            if (lane == 0) {                                                   // one arrival per worker warp on each
+                mbar_arrive(smem_u32(&bar_x[B]));
+                mbar_arrive(smem_u32(&bar_empty[B]));
             }
-            mark(2);
             const float prev_in = my_in, prev_inv = my_inv;
             my_in = in2;
             my_inv = cur_inv;
             if (i >= 1) epilogue(std::integral_constant<uint32_t, B ^ 1u>{}, i - 1, prev_in, prev_inv);
-            mark(3);
         };
-
-        load_rows(0);
-        load_rows(1);
 
         for (uint64_t i = 0; i < cnt; i += 2) {
             step(std::integral_constant<uint32_t, 0u>{}, i);
@@ -446,12 +453,6 @@ __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__
         if (cnt > 0) {
             if ((cnt - 1) & 1u) epilogue(std::integral_constant<uint32_t, 1u>{}, cnt - 1, my_in, my_inv);
             else epilogue(std::integral_constant<uint32_t, 0u>{}, cnt - 1, my_in, my_inv);
-        }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last stores must be complete before the CTA exits
-        if (timed) {
-            long long* out = reinterpret_cast<long long*>(const_cast<unsigned char*>(uterms) + 4 * MAT_BYTES) + (tid ? 16 : 0);
-            for (int k = 0; k < 10; ++k) out[k] = tacc[k];
-            out[10] = (long long)cnt;
         }
     }
 

@@ -353,8 +353,8 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     build_block_terms(U, terms);
     void* d_terms = nullptr;
     const bool keep = h->recording != nullptr && P.pad == 0;                                     // plan cache: the entry owns the buffer
-    if (keep) RQ_CUDA(cudaMalloc(&d_terms, RQ_BLOCK_UBYTES + 256), "block terms alloc (cached)");
-    else RQ_CUDA(cudaMallocAsync(&d_terms, RQ_BLOCK_UBYTES + 256, h->stream), "block terms alloc");   // + debug timers
+    if (keep) RQ_CUDA(cudaMalloc(&d_terms, RQ_BLOCK_UBYTES), "block terms alloc (cached)");
+    else RQ_CUDA(cudaMallocAsync(&d_terms, RQ_BLOCK_UBYTES, h->stream), "block terms alloc");
     // pageable source: cudaMemcpyAsync stages it before returning, so `terms` may go out of scope
     struct TermsGuard {                                     // an early return must not leak the operand buffer
         void*& p; bool cached; cudaStream_t s; bool armed = true;
@@ -366,18 +366,6 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
         RQ_CUDA(rq_launch_block_sweep(state, &P, d_terms, &tm, h->stream), "block sweep launch");
     }
     guard.armed = false;
-    if (P.pad & 16u) {                                   // ROCQ_BLOCK_DEBUG & 16: per-phase clock totals of CTA 0, threads 0 and 64
-        long long t[32];
-        cudaMemcpyAsync(t, (char*)d_terms + RQ_BLOCK_UBYTES, sizeof t, cudaMemcpyDeviceToHost, h->stream);
-        cudaStreamSynchronize(h->stream);
-        static int printed = 0;
-        if (printed++ < 2)
-            for (int w = 0; w < 2; ++w) {
-                fprintf(stderr, "[block timers, thread %d, %lld tiles] clocks per tile:", w ? 64 : 0, t[16 * w + 10]);
-                for (int k = 0; k < 9; ++k) fprintf(stderr, " %d:%.0f", k, (double)t[16 * w + k] / (double)std::max(1ll, t[16 * w + 10]));
-                fprintf(stderr, "\n");
-            }
-    }
     if (keep) {
         rocsvCachedStep st;
         st.block = true;

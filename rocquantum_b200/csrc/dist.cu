@@ -641,7 +641,7 @@ rocqStatus_t Dist::sample(rocsvInternalHandle* h, const unsigned* measured, unsi
     const unsigned n = n_local;
     const unsigned cb = n < 10 ? n : (n > 30 ? n - 20 : 10);
     const uint64_t nchunks = 1ull << (n - cb);
-    StreamBuf scratch(h->stream);
+    StreamBuf scratch(h->stream, h->pool);
     RQ_CU(scratch.alloc((2 * nchunks + 2 * RQ_SCAN_MAXSEG + 4 + (size_t)shots) * sizeof(uint64_t)));
     uint64_t* d_hi = scratch.as<uint64_t>();
     uint64_t *d_lo = d_hi + nchunks, *d_btot = d_lo + nchunks, *d_tot = d_btot + 2 * RQ_SCAN_MAXSEG, *d_idx = d_tot + 4;

@@ -256,7 +256,7 @@ rocqStatus_t run_ops(H* h, rq_cplx* state, unsigned n, const std::vector<HostOp>
             }
             h->recordingValid = false;                   // the gather kernel's matrix upload is not replayable
             const rq_cplx* dm = reinterpret_cast<const rq_cplx*>(o.ext);
-            rq::StreamBuf tmp(h->stream);     // freed (stream-ordered) on every path out of this scope
+            rq::StreamBuf tmp(h->stream, h->pool);     // freed (stream-ordered) on every path out of this scope
             if (!dm) {                        // host matrix (or diagonal): upload, stream-ordered
                 const size_t D = (size_t)1 << k;
                 std::vector<rq_cplx> hm(D * D, rq_cplx{0, 0});
@@ -354,7 +354,7 @@ rocqStatus_t run_block(H* h, rq_cplx* state, unsigned n, const std::vector<unsig
     void* d_terms = nullptr;
     const bool keep = h->recording != nullptr && P.pad == 0;                                     // plan cache: the entry owns the buffer
     if (keep) RQ_CUDA(cudaMalloc(&d_terms, RQ_BLOCK_UBYTES), "block terms alloc (cached)");
-    else RQ_CUDA(cudaMallocAsync(&d_terms, RQ_BLOCK_UBYTES, h->stream), "block terms alloc");
+    else RQ_CUDA(rq::pool_alloc(&d_terms, RQ_BLOCK_UBYTES, h->pool, h->stream), "block terms alloc");
     // pageable source: cudaMemcpyAsync stages it before returning, so `terms` may go out of scope
     struct TermsGuard {                                     // an early return must not leak the operand buffer
         void*& p; bool cached; cudaStream_t s; bool armed = true;
@@ -673,6 +673,22 @@ rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
         delete h;
         return ROCQ_STATUS_HIP_ERROR;
     }
+    {   // the handle's own pool for stream-ordered scratch; it keeps its memory across synchronisations (engine.h, rq::pool_alloc)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&h->pool, &props) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+            h->pool = nullptr;
+        }
+    }
     const unsigned nb = rq_reduce_blocks();
     if (rq_sweep_configure() != 0 || rq_block_configure() != 0 || cudaMalloc(&h->d_partials, (nb + 8) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_upartials, (4 * nb + 4) * sizeof(uint64_t)) != cudaSuccess ||
@@ -715,6 +731,7 @@ rocqStatus_t rocsvDestroy(rocsvHandle_t h) {
     if (h->tm0) cudaEventDestroy(h->tm0);
     if (h->tm1) cudaEventDestroy(h->tm1);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->pool) cudaMemPoolDestroy(h->pool);
     delete h;
     return ROCQ_STATUS_SUCCESS;
 }
@@ -1064,7 +1081,7 @@ static rocqStatus_t expect_batch(H* h, rocComplex* d, unsigned n, const char* pa
         g->index[g->nterms] = t;
         g->nterms++;
     }
-    rq::StreamBuf buf(h->stream);
+    rq::StreamBuf buf(h->stream, h->pool);
     const size_t npart = (size_t)rq_reduce_blocks() * RQ_PAULI_GROUP_MAX * nstates, nres = (size_t)numTerms * nstates;
     RQ_CUDA(buf.alloc((npart + nres) * sizeof(double)), "expectation scratch");
     double* d_part = buf.as<double>();
@@ -1220,7 +1237,7 @@ rocqStatus_t rocsvSample(rocsvHandle_t h, rocComplex* d, unsigned n, const unsig
     // everything stays on the device: chunk masses -> exact scan -> one warp per shot -> result words (bit j = measured
     // qubit j); the host sees one copy of the results and the total mass
     const rq::NvtxRange nvtx("rocq/sample");
-    rq::StreamBuf scratch(h->stream);
+    rq::StreamBuf scratch(h->stream, h->pool);
     RQ_CUDA(scratch.alloc((2 * nchunks + 2 * RQ_SCAN_MAXSEG + 4 + (size_t)numShots) * sizeof(uint64_t)), "sampling scratch");
     uint64_t* d_hi = scratch.as<uint64_t>();
     uint64_t *d_lo = d_hi + nchunks, *d_btot = d_lo + nchunks, *d_tot = d_btot + 2 * RQ_SCAN_MAXSEG, *d_idx = d_tot + 4;

@@ -21,14 +21,22 @@ struct NvtxRange {
     NvtxRange(const NvtxRange&) = delete;
     NvtxRange& operator=(const NvtxRange&) = delete;
 };
+// Stream-ordered allocation from the handle's own memory pool.  The pool keeps what it has been given (release threshold =
+// everything): the device's default pool hands its unused memory back to the OS at every synchronisation, so a loop of
+// circuit + read-back calls re-mapped its scratch each time -- measured as stalls of 30-100 ms per step on a B200
+// (profiles/r02_e2e_profile_before.log).  A handle without a pool (creation failed) falls back to the default pool.
+inline cudaError_t pool_alloc(void** p, size_t bytes, cudaMemPool_t pool, cudaStream_t s) {
+    return pool ? cudaMallocFromPoolAsync(p, bytes, pool, s) : cudaMallocAsync(p, bytes, s);
+}
 // stream-ordered scratch that is released on every path out of its scope (early error returns included)
 struct StreamBuf {
     void* p = nullptr;
     cudaStream_t s;
-    explicit StreamBuf(cudaStream_t st) : s(st) {}
+    cudaMemPool_t pool;
+    StreamBuf(cudaStream_t st, cudaMemPool_t pl) : s(st), pool(pl) {}
     StreamBuf(const StreamBuf&) = delete;
     StreamBuf& operator=(const StreamBuf&) = delete;
-    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, s); }
+    cudaError_t alloc(size_t bytes) { return pool_alloc(&p, bytes, pool, s); }
     template <typename T> T* as() const { return static_cast<T*>(p); }
     ~StreamBuf() { if (p) cudaFreeAsync(p, s); }
 };
@@ -55,6 +63,7 @@ struct rocsvPlanCache {
 // Reference handle: hipStateVec.cpp:62-68 {stream, batchSize, numQubits, d_state, ownsState}.
 struct rocsvInternalHandle {
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;       // stream-ordered scratch of this handle (rq::pool_alloc)
     size_t batchSize = 1;
     unsigned numQubits = 0;
     rq_cplx* d_state = nullptr;

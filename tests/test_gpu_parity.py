@@ -120,9 +120,9 @@ def test_mixed_bag_eager_and_fused(prec, n, batch):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])            # 10 = the widest matrix the API accepts
 def test_apply_matrix_k_qubits_with_controls(prec, k):
-    n = 11
+    n = 11 if k < 8 else 13
     rng = np.random.default_rng(k)
     o, g = _pair(n, prec, seed=k)
     for trial in range(3):

@@ -673,15 +673,12 @@ rocqStatus_t rocsvCreate(rocsvHandle_t* handle) {
         delete h;
         return ROCQ_STATUS_HIP_ERROR;
     }
-    {   // the handle's own pool for stream-ordered scratch; it keeps its memory across synchronisations (engine.h, rq::pool_alloc)
+    {   // stream-ordered scratch comes from the device's default pool, told to keep its memory across synchronisations
+        // (engine.h, rq::pool_alloc).  A pool of the handle's own did the same for the steady state but paid ~90 ms for its
+        // first large allocation (1M-shot sampling, profiles/r02_expect_variants.log).
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaMemPoolProps props{};
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = dev;
-        if (cudaMemPoolCreate(&h->pool, &props) == cudaSuccess) {
+        if (cudaDeviceGetDefaultMemPool(&h->pool, dev) == cudaSuccess) {
             uint64_t keep = ~0ull;
             cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
         } else {
@@ -731,7 +728,6 @@ rocqStatus_t rocsvDestroy(rocsvHandle_t h) {
     if (h->tm0) cudaEventDestroy(h->tm0);
     if (h->tm1) cudaEventDestroy(h->tm1);
     if (h->stream) cudaStreamDestroy(h->stream);
-    if (h->pool) cudaMemPoolDestroy(h->pool);
     delete h;
     return ROCQ_STATUS_SUCCESS;
 }

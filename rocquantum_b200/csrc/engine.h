@@ -21,10 +21,10 @@ struct NvtxRange {
     NvtxRange(const NvtxRange&) = delete;
     NvtxRange& operator=(const NvtxRange&) = delete;
 };
-// Stream-ordered allocation from the handle's own memory pool.  The pool keeps what it has been given (release threshold =
-// everything): the device's default pool hands its unused memory back to the OS at every synchronisation, so a loop of
-// circuit + read-back calls re-mapped its scratch each time -- measured as stalls of 30-100 ms per step on a B200
-// (profiles/r02_e2e_profile_before.log).  A handle without a pool (creation failed) falls back to the default pool.
+// Stream-ordered allocation from the pool the handle uses: the device's default pool with its release threshold raised to
+// "keep everything" at rocsvCreate.  With the default threshold (0) the pool hands its unused memory back to the OS at every
+// synchronisation, so a loop of circuit + read-back calls re-mapped its scratch each time -- measured as stalls of
+// 30-100 ms per step on a B200 (profiles/r02_e2e_profile_before.log).
 inline cudaError_t pool_alloc(void** p, size_t bytes, cudaMemPool_t pool, cudaStream_t s) {
     return pool ? cudaMallocFromPoolAsync(p, bytes, pool, s) : cudaMallocAsync(p, bytes, s);
 }
@@ -63,7 +63,7 @@ struct rocsvPlanCache {
 // Reference handle: hipStateVec.cpp:62-68 {stream, batchSize, numQubits, d_state, ownsState}.
 struct rocsvInternalHandle {
     cudaStream_t stream = nullptr;
-    cudaMemPool_t pool = nullptr;       // stream-ordered scratch of this handle (rq::pool_alloc)
+    cudaMemPool_t pool = nullptr;       // the device's default pool, kept from releasing at every sync (rq::pool_alloc)
     size_t batchSize = 1;
     unsigned numQubits = 0;
     rq_cplx* d_state = nullptr;

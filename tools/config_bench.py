@@ -69,6 +69,15 @@ def main():
         ms = sv.timer_stop()
         print(json.dumps(dict(config="C5 64 Pauli strings (weight<=8)", qubits=n, device_ms=ms, terms=len(terms),
                               gbs=len(terms) * (1 << n) * 8 / (ms * 1e-3) / 1e9, sum=sum(vals))), flush=True)
+        for name, bt in (("random64", terms), ("hamiltonian64", workloads.hamiltonian_like_terms(n, 64, seed=5))):
+            sv.expect_batch(bt)                                   # warm-up
+            sv.stats(reset=True); sv.sync(); sv.timer_start()
+            bv = sv.expect_batch(bt)
+            ms = sv.timer_stop()
+            groups = int(sv.stats().expectationSweeps)
+            print(json.dumps(dict(config=f"C5 batched expectation, {name}", qubits=n, device_ms=ms, terms=len(bt), read_sweeps=groups,
+                                  ms_per_sweep=ms / max(1, groups), sum=float(sum(bv)))), flush=True)
+        sv.sample(list(range(n)), 1000)                           # warm-up (first call sizes the scratch)
         t0 = time.perf_counter()
         s = sv.sample(list(range(n)), 1_000_000)
         dt = time.perf_counter() - t0

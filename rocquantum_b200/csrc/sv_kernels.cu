@@ -203,62 +203,36 @@ __global__ void __launch_bounds__(RT) pauli_group_kernel(const rq_cplx* __restri
                                                          const __grid_constant__ rq_pauli_group G, double* __restrict__ partials) {
     const uint64_t N = 1ull << n;
     const rq_cplx* __restrict__ state = state_all + (uint64_t)blockIdx.y * N;
-    const uint64_t stride = (uint64_t)gridDim.x * RT;       // a power of two (rq_launch_pauli_group)
+    const uint64_t stride = (uint64_t)gridDim.x * RT;
     double acc[TT];
 #pragma unroll
     for (int t = 0; t < TT; ++t) acc[t] = 0.0;
-    // The loop index h (= the basis index i for an all-Z group, i without its pivot bit otherwise) is
-    //   h = mine + it * stride,  mine = this thread's index in the grid < stride,  stride = 2^sb,
-    // and the sign of term t is the parity of popcount(h & z_t), z_t = the term's z-mask in loop-index coordinates.  It
-    // splits into the thread's own part (constant: one word `w`, bit t = term t's parity, TT popcounts per THREAD) and the
-    // part of `it`, which changes by the bits 0..ctz(it+1) when `it` increments: F[b] = bit t <- parity of z_t over loop
-    // bits sb..sb+b, so the update is w ^= F[ctz(it+1)] -- one table read per iteration instead of one POPC (a quarter-rate
-    // instruction) per term and amplitude.  Per term and amplitude there remain a shift, a LOP3 into the double's sign bit
-    // and the DADD.
-    const unsigned pv = G.xmask ? 63u - (unsigned)__clzll((long long)G.xmask) : 0u;
-    const uint64_t low = (1ull << pv) - 1ull;
-    auto zeff = [&](int t) -> uint64_t {
-        const uint64_t z = G.zmask[t];
-        return G.xmask ? ((((z >> pv) >> 1) << pv) | (z & low)) : z;          // (the pivot bit of i is 0: it never contributes)
-    };
-    const unsigned sb = 63u - (unsigned)__clzll((long long)stride);
-    __shared__ uint32_t F[64];
-    if (threadIdx.x < 64) {
-        const unsigned bt = threadIdx.x;
-        const uint64_t m = bt >= 63u ? ~0ull : ((2ull << bt) - 1ull);
-        uint32_t word = 0;
-#pragma unroll
-        for (int t = 0; t < TT; ++t) word |= (uint32_t)(__popcll((zeff(t) >> sb) & m) & 1) << t;
-        F[bt] = word;
-    }
-    const uint64_t mine = (uint64_t)blockIdx.x * RT + threadIdx.x;
-    uint32_t w = 0;
-#pragma unroll
-    for (int t = 0; t < TT; ++t) w |= (uint32_t)(__popcll(mine & zeff(t)) & 1) << t;
-    __syncthreads();
-    auto add_signed = [&](int t, double v) {
-        acc[t] += __hiloint2double(__double2hiint(v) ^ (int)((w << (31 - t)) & 0x80000000u), __double2loint(v));
+    // sign of term t at index i = parity of popcount(i & zmask_t): two 32-bit halves (the high one only for n > 32), and the
+    // sign is applied by flipping the double's sign bit -- 4 integer instructions + 1 DADD per term and amplitude
+    const bool wide = n > 32;
+    auto add_signed = [&](int t, uint32_t il, uint32_t ih, double v) {
+        uint32_t par = (uint32_t)__popc(il & (uint32_t)G.zmask[t]);
+        if (wide) par += (uint32_t)__popc(ih & (uint32_t)(G.zmask[t] >> 32));
+        acc[t] += __hiloint2double(__double2hiint(v) ^ (int)(par << 31), __double2loint(v));
     };
     if (G.xmask == 0) {
-        uint64_t it = 0;
-        for (uint64_t i = mine; i < N; i += stride) {
+        for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < N; i += stride) {
             const double p = prob(state[i]);
+            const uint32_t il = (uint32_t)i, ih = (uint32_t)(i >> 32);
 #pragma unroll
-            for (int t = 0; t < TT; ++t) add_signed(t, p);
-            ++it;
-            w ^= F[__ffsll((long long)it) - 1];
+            for (int t = 0; t < TT; ++t) add_signed(t, il, ih, p);
         }
     } else {
-        uint64_t it = 0;
-        for (uint64_t h = mine; h < (N >> 1); h += stride) {
+        const unsigned pv = 63u - (unsigned)__clzll((long long)G.xmask);
+        const uint64_t low = (1ull << pv) - 1ull;
+        for (uint64_t h = (uint64_t)blockIdx.x * RT + threadIdx.x; h < (N >> 1); h += stride) {
             const uint64_t i = ((h & ~low) << 1) | (h & low), j = i ^ G.xmask;
             const rq_cplx a = state[i], b = state[j];
             const double tr = (double)b.x * a.x + (double)b.y * a.y;
             const double ti = (double)b.x * a.y - (double)b.y * a.x;
+            const uint32_t il = (uint32_t)i, ih = (uint32_t)(i >> 32);
 #pragma unroll
-            for (int t = 0; t < TT; ++t) add_signed(t, (G.ny[t] & 1u) ? ti : tr);
-            ++it;
-            w ^= F[__ffsll((long long)it) - 1];
+            for (int t = 0; t < TT; ++t) add_signed(t, il, ih, (G.ny[t] & 1u) ? ti : tr);
         }
     }
     __shared__ double wsum[RT / 32][TT];
@@ -270,7 +244,7 @@ __global__ void __launch_bounds__(RT) pauli_group_kernel(const rq_cplx* __restri
     __syncthreads();
     if (threadIdx.x < TT) {
         double sum = 0.0;
-        for (int w_ = 0; w_ < RT / 32; ++w_) sum += wsum[w_][threadIdx.x];
+        for (int w = 0; w < RT / 32; ++w) sum += wsum[w][threadIdx.x];
         partials[((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * TT + threadIdx.x] = sum;
     }
 }
@@ -596,10 +570,9 @@ extern "C" int rq_launch_pauli_group(const rq_cplx* state, unsigned n, unsigned 
     if (TT > RQ_PAULI_GROUP_MAX || G->nterms == 0 || nstates == 0) return (int)cudaErrorInvalidValue;
     // small states: no more blocks than there is work for (the second stage reads nblocks partials per term)
     const uint64_t items = G->xmask ? ((1ull << n) >> 1) : (1ull << n);
-    // a power-of-two grid (the kernel splits the loop index into the thread's own bits and the iteration's): 1024 blocks
-    // on a 148-SM B200, all resident at once
-    unsigned nb = 1;
-    while (2ull * nb * RT <= items && 2u * nb <= RBLOCKS) nb *= 2;
+    unsigned nb = (unsigned)((items + RT - 1) / RT);
+    if (nb > RBLOCKS) nb = RBLOCKS;
+    if (nb == 0) nb = 1;
     const dim3 grid(nb, nstates);
     cudaStream_t st = (cudaStream_t)stream;
     switch (TT) {

@@ -1193,7 +1193,41 @@ inline bool build_program(Prog& P, const SweepPlan& sp, const std::vector<HostOp
     struct PendingDiagp { unsigned op; cd C; std::vector<cd> floc, G; std::vector<uint8_t> gbit; };
     std::vector<PendingDiagp> pending;
     const unsigned maxops = (unsigned)(sizeof(P.ops) / sizeof(P.ops[0])), maxpool = (unsigned)(sizeof(P.pool) / sizeof(P.pool[0]));
-    const std::vector<int> order = phase_friendly_order(sp, ops, RQ_WINDOW_BITS);
+    std::vector<int> order = phase_friendly_order(sp, ops, RQ_WINDOW_BITS);
+    // Swaps that nothing after them in the sweep depends on -- the bit reversal at the end of a QFT -- need no pass over the
+    // tile: exchanging two resident bits is exchanging the positions their values are STORED to.  Such swaps (uncontrolled,
+    // both qubits resident above the minimal row) leave the program and become the store map sres[]; rows shrink to the
+    // lowest swapped position if need be.  Every phase saved is one shared-memory round trip of the tile (complex128:
+    // 2 x 64 KB at 128 B/clk per SM, the bound of the swap-heavy QFT sweeps).
+    {
+        unsigned where[16];                                   // local bit j's value is stored to position res[where[j]]
+        for (unsigned j = 0; j < T; ++j) where[j] = j;
+        uint64_t later = 0;                                   // qubits of the ops that stay, from the end backwards
+        std::vector<int> keep, absorbed;
+        unsigned rowbits = P.hdr.rowbits;
+        for (size_t i = order.size(); i-- > 0;) {
+            const HostOp& o = ops[order[i]];
+            bool take = o.kind == HostOp::PERM_SWAP && o.cmask == 0 && o.targets.size() == 2 && !(o.qubits() & later);
+            if (take) {
+                const int la = local[o.targets[0]], lb = local[o.targets[1]];
+                take = la >= 0 && lb >= 0 && (unsigned)std::min(la, lb) >= std::min<unsigned>(RQ_MIN_ROW_BITS, T);
+            }
+            if (take) absorbed.push_back(order[i]);
+            else { keep.push_back(order[i]); later |= o.qubits(); }
+        }
+        if (!absorbed.empty() && !keep.empty()) {             // (a sweep of nothing but swaps keeps its permutation passes: rare, and it is HBM-bound anyway)
+            std::reverse(keep.begin(), keep.end());
+            std::reverse(absorbed.begin(), absorbed.end());   // program order
+            for (int idx : absorbed) {
+                const unsigned la = (unsigned)local[ops[idx].targets[0]], lb = (unsigned)local[ops[idx].targets[1]];
+                for (unsigned j = 0; j < T; ++j) { if (where[j] == la) where[j] = lb; else if (where[j] == lb) where[j] = la; }
+                rowbits = std::min(rowbits, std::min(la, lb));
+            }
+            order.swap(keep);
+            P.hdr.rowbits = rowbits;
+        }
+        for (unsigned j = 0; j < 16; ++j) P.hdr.sres[j] = j < T ? P.hdr.res[where[j]] : 0;
+    }
     for (int idx : order) {
         const HostOp& o = ops[idx];
         if (P.hdr.nops >= maxops) return false;

@@ -73,6 +73,8 @@ struct rq_sweep_hdr {
     uint64_t high_base;             // OR-ed into every tile's base index for predicates (rank << n_local)
     const void* ext_matrix;         // device matrix of an op with ext = 1 (column-major, rq_cplx)
     uint8_t res[16];                // ascending resident global positions
+    uint8_t sres[16];               // where local bit j is STORED: res[j] unless trailing swaps of resident qubits were folded into
+                                    // the store addressing (host_ops.h, build_program); identity on the row bits
     uint8_t ndiagp;                 // RQ_OP_DIAGP ops of the program; their per-tile factors are computed while the tile loads
     uint8_t diagp_op[RQ_MAX_DIAGP]; // op index of slot s
     uint8_t pad2[7];

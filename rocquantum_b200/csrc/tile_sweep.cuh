@@ -819,9 +819,9 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
     swizzle_pass<SWZ>(sm, T, tid);      // back to the linear layout the bulk stores expect
     fence_async_smem();       // generic-proxy writes to smem -> visible to the async (TMA) proxy
     __syncthreads();
-    for (uint32_t r = tid; r < nrows; r += NT) {
+    for (uint32_t r = tid; r < nrows; r += NT) {          // (sres: trailing swaps of resident qubits ride in the store addresses)
         uint64_t goff = 0;
-        for (uint32_t i = 0; i < T - rowbits; ++i) goff |= (uint64_t)((r >> i) & 1u) << prog.hdr.res[rowbits + i];
+        for (uint32_t i = 0; i < T - rowbits; ++i) goff |= (uint64_t)((r >> i) & 1u) << prog.hdr.sres[rowbits + i];
         bulk_s2g(gtile + goff, smem_u32(sm) + r * rowbytes, rowbytes);
     }
     bulk_commit_wait_read();  // smem must stay valid until the TMA engine has read it

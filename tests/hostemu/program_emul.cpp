@@ -240,9 +240,13 @@ bool emulate_op(std::vector<cd>& sm, const Prog& prog, const rq_tile_op& o, uint
     return true;
 }
 
+unsigned g_store_remaps = 0, g_perm_ops = 0;     // programs whose store map differs from the load map / permutation ops executed as passes
+
 template <typename Prog>
 bool emulate_program(const Prog& prog, cd* state) {
     const uint32_t T = prog.hdr.T, n = prog.hdr.n;
+    for (uint32_t j = 0; j < T; ++j) if (prog.hdr.sres[j] != prog.hdr.res[j]) { ++g_store_remaps; break; }
+    for (uint32_t i = 0; i < prog.hdr.nops; ++i) g_perm_ops += prog.ops[i].kind == RQ_OP_PERM;
     const bool swz = prog.hdr.swz != 0;
     // the launcher's choice of kernel variant (tile_sweep.cuh: launch)
     const bool phased = prog.hdr.nphases > 0 && prog.hdr.max_phase_ops >= 2;
@@ -293,7 +297,18 @@ bool emulate_program(const Prog& prog, cd* state) {
             if ((gbase & o.gcmask) != o.gcmask) continue;
             if (!emulate_op(sm, prog, o, T, gbase, gfac, swz)) return false;
         }
-        for (uint32_t l = 0; l < (1u << T); ++l) gtile[goff(l)] = sm[sidx(swz, l)];
+        auto soff = [&](uint32_t l) {                                // the stores' own map (trailing swaps folded into the addresses)
+            uint64_t o = 0;
+            for (uint32_t j = 0; j < T; ++j) o |= (uint64_t)((l >> j) & 1u) << prog.hdr.sres[j];
+            return o;
+        };
+        for (uint32_t j = 0; j < prog.hdr.rowbits; ++j) if (prog.hdr.sres[j] != j) return false;    // rows stay contiguous
+        {   // sres must be a permutation of res
+            uint64_t a = 0, b = 0;
+            for (uint32_t j = 0; j < T; ++j) { a |= 1ull << prog.hdr.res[j]; b |= 1ull << prog.hdr.sres[j]; }
+            if (a != b) return false;
+        }
+        for (uint32_t l = 0; l < (1u << T); ++l) gtile[soff(l)] = sm[sidx(swz, l)];
     }
     return true;
 }
@@ -303,6 +318,13 @@ bool emulate_program(const Prog& prog, cd* state) {
 extern "C" {
 
 unsigned hostemu_precision_bytes(void) { return (unsigned)sizeof(rq_real); }
+// since the last call: programs with swaps folded into their store addresses, permutation ops left in the programs
+void hostemu_take_counters(unsigned* storeRemaps, unsigned* permOps) {
+    if (storeRemaps) *storeRemaps = g_store_remaps;
+    if (permOps) *permOps = g_perm_ops;
+    g_store_remaps = 0;
+    g_perm_ops = 0;
+}
 
 // state: 2 * 2^n doubles (re, im interleaved), updated in place.  rankBits/rank: emulate the slice of one rank of a
 // distributed state (state then holds 2^(n - rankBits) amplitudes and ops may control / act diagonally on rank bits).

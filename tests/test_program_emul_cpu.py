@@ -282,3 +282,41 @@ def test_random_circuits_through_both_planners():
         v = util.random_state(n, seed=seed % 1000)
         out, nsw, nb = run_emu("c64", n, g, v, 0, flags=4)
         assert util.rel_err(out, oracle_run(n, g, v)) < 2e-5, (trial, n, seed)
+
+
+def take_counters(prec):
+    a, b = C.c_uint(), C.c_uint()
+    emu(prec).hostemu_take_counters(C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+@pytest.mark.parametrize("prec,tol", [("c128", 1e-12), ("c64", 2e-6)])
+def test_trailing_swaps_ride_in_the_store_addresses(prec, tol):
+    """Swaps of resident qubits that nothing later in the sweep depends on (a QFT's bit reversal) leave the program and become
+    the store map sres[]; swaps below the minimal row, controlled swaps and swaps something still depends on stay passes."""
+    rng = np.random.default_rng(8)
+    # QFTs whose sweeps end in their swaps
+    for n, tb in ((14, 0), (16, 10), (18, 9), (17, 12)):
+        gates = workloads.c3_qft(n, seed=n)
+        v = util.random_state(n, seed=n)
+        take_counters(prec)
+        out, nsw, nm = run_emu(prec, n, gates, v, tile_bits=tb)
+        remaps, perms = take_counters(prec)
+        assert util.rel_err(out, oracle_run(n, gates, v)) < tol, (n, tb)
+        assert remaps >= 1, (n, tb)
+        assert perms < n // 2, (n, tb, perms)                 # some of the n/2 swaps are gone from the programs
+    # chains of swaps sharing qubits, swaps followed by gates on their qubits (must stay), a controlled swap, low-bit swaps
+    for trial in range(12):
+        n = int(rng.integers(10, 15))
+        g = util.random_gates(n, 40, seed=100 + trial, maxk=2)
+        q = [int(x) for x in rng.permutation(n)]
+        g += [("swap", [q[0], q[1]], [], 0.0), ("swap", [q[1], q[2]], [], 0.0), ("swap", [q[3], q[0]], [], 0.0)]
+        if trial % 3 == 0:
+            g += [("h", [q[1]], [], 0.0)]                     # depends on the swaps before it
+        if trial % 3 == 1:
+            g += [("cswap", [q[4], q[5]], [q[6]], 0.0), ("swap", [q[7], q[8]], [], 0.0)]
+        if trial % 4 == 2:
+            g += [("swap", [0, 1], [], 0.0), ("swap", [2, q[2] if q[2] != 2 else 3], [], 0.0)]
+        v = util.random_state(n, seed=trial)
+        out, nsw, nm = run_emu(prec, n, g, v, tile_bits=int(rng.integers(8, 11)))
+        assert util.rel_err(out, oracle_run(n, g, v)) < tol * 10, trial

@@ -345,5 +345,13 @@ call_ad() {
   cat gpurun_out/window_variants.log
 }
 
-if [ -z "$1" ] || ! declare -F "call_$1" > /dev/null; then echo "usage: bash tools/gpu_calls.sh {a|b|c|d|e|f|g|h|i|j|k|l|m|n|o|p|q|r|s|t|u|v|w|x|y|z|aa|ab|ac|ad}"; exit 2; fi
+# Round 2, call AE (1 GPU): trailing swaps folded into the store addresses (QFT sweeps lose their permutation passes): the
+# tests that run QFTs / swaps / fused bags, then QFT-33 complex128 and its launch list.
+call_ae() {
+  ( timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "qft or ladders or mixed_bag or named_gate or c1_config or golden or fixtures or swap" ) > gpurun_out/pytest_qft.log 2>&1; tail -3 gpurun_out/pytest_qft.log
+  timeout -s KILL 600 python tools/config_bench.py --only c3 --reps 2 2>&1 | cut -c1-400 | tee gpurun_out/config_bench_c3.log
+  ( ROCQ_TRACE_LAUNCHES=1 timeout -s KILL 600 python tools/config_bench.py --only c3 --reps 1 ) 2>&1 | grep "^\[launch\]" | tail -6 | tee gpurun_out/launches_qft33_c128_trace.log
+}
+
+if [ -z "$1" ] || ! declare -F "call_$1" > /dev/null; then echo "usage: bash tools/gpu_calls.sh {a|b|c|d|e|f|g|h|i|j|k|l|m|n|o|p|q|r|s|t|u|v|w|x|y|z|aa|ab|ac|ad|ae}"; exit 2; fi
 "call_$1"

@@ -543,25 +543,10 @@ __device__ __forceinline__ void run_chain_phase(rq_cplx* sm, const Prog& prog, c
     rq_cplx fA[RQ_PHASE_MAX_DIAGP];
     phase_thread_factors(prog, ph, tid, gfac, tfac, fA);
     const uint32_t nb = ph.count >> 1;
-    const rq_cplx* Bt[V];
-    const rq_cplx* Wt[V];
-    rq_real c0[V], c1[V];
-    uint32_t ci[V];
-    bool swp[V], up[V];
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-        const uint32_t kk = (uint32_t)k < nb ? (uint32_t)k : 0u;        // (unused slots repeat the first pair; never executed)
-        const rq_tile_op& h = prog.ops[ph.first + 2u * kk];
-        const rq_tile_op& o = prog.ops[ph.first + 2u * kk + 1u];
-        const rq_cplx* H = prog.pool + h.moff;
-        const rq_cplx* M = prog.pool + o.moff;
-        Bt[k] = M + 1 + o.t[0];
-        Wt[k] = Bt[k] + (1u << o.t[1]);
-        c0[k] = H[0].x; c1[k] = H[1 * RQ_MSLOTS].x;
-        swp[k] = (c0[k] < 0) != (H[2 * RQ_MSLOTS].x < 0);
-        up[k] = o.fuse == RQ_FUSE_BUTTERFLY_UP;
-        ci[k] = o.cm_in;
-    }
+    // The parameters of butterfly k (table pointers, the Hadamard's two real entries, hub, variant) are warp-uniform and are
+    // fetched where they are used, inside the group loop: held across the loop they cost ~33 vector registers, which at
+    // 80 registers per thread (three 64 KB tiles per SM) went to local memory; the loop runs twice per phase, so
+    // re-fetching them through the uniform datapath is cheaper than the spills.
     uint32_t stride[V];
 #pragma unroll
     for (int b = 0; b < V; ++b) stride[b] = 1u << ph.w[b];
@@ -584,9 +569,16 @@ __device__ __forceinline__ void run_chain_phase(rq_cplx* sm, const Prog& prog, c
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             if ((uint32_t)k >= nb) break;
-            const rq_cplx ft = cmul(Bt[k][it], fA[k]);          // the phase's k-th DIAGP op has slot k (build_phases numbers them in order)
-            const rq_cplx fc = rq_cplx{ft.x * c1[k], ft.y * c1[k]};
-            win_butterfly_any<V>(a, ci[k], Wt[k], fc, c0[k], swp[k], up[k]);
+            const rq_tile_op& h = prog.ops[ph.first + 2u * (uint32_t)k];
+            const rq_tile_op& o = prog.ops[ph.first + 2u * (uint32_t)k + 1u];
+            const rq_cplx* H = prog.pool + h.moff;
+            const rq_cplx* Bt = prog.pool + o.moff + 1 + o.t[0];
+            const rq_cplx* Wt = Bt + (1u << o.t[1]);
+            const rq_real c0 = H[0].x, c1 = H[1 * RQ_MSLOTS].x;
+            const bool swp = (c0 < 0) != (H[2 * RQ_MSLOTS].x < 0);
+            const rq_cplx ft = cmul(Bt[it], fA[k]);             // the phase's k-th DIAGP op has slot k (build_phases numbers them in order)
+            const rq_cplx fc = rq_cplx{ft.x * c1, ft.y * c1};
+            win_butterfly_any<V>(a, o.cm_in, Wt, fc, c0, swp, o.fuse == RQ_FUSE_BUTTERFLY_UP);
         }
 #pragma unroll
         for (int j = 0; j < D; ++j) {
@@ -714,13 +706,21 @@ __device__ __forceinline__ void run_window_phase(rq_cplx* sm, const Prog& prog, 
 template <bool SWZ>
 __device__ __forceinline__ void swizzle_pass(rq_cplx* sm, uint32_t T, uint32_t tid) {
     if (!SWZ) return;
-    for (uint32_t idx = tid; idx < (1u << T); idx += NT) {       // an involution inside each aligned group: swap pairs
-        const uint32_t p = sidx<true>(idx);
-        if (idx < p) {
-            const rq_cplx a = sm[idx], b = sm[p];
-            sm[idx] = b;
-            sm[p] = a;
-        }
+    // phys(idx) = idx ^ ((idx >> B) & (2^B - 1)) is an involution inside every aligned group of 2^(2B) amplitudes: with
+    // h = the group's upper B bits and l its lower B bits, (h, l) trades places with (h, l ^ h).  Only the pairs are
+    // enumerated: h = 1 .. 2^B - 1, and of each pair the member whose bit `top set bit of h` is clear -- 2^(B-1) per h.
+    constexpr uint32_t B = RQ_SWZ_BITS, HM = (1u << B) - 1u, PER = HM << (B - 1);     // swaps per group of 2^(2B)
+    if (T < 2 * B) return;
+    const uint32_t total = PER << (T - 2 * B);
+    for (uint32_t k = tid; k < total; k += NT) {
+        const uint32_t grp = k / PER, r = k - grp * PER;
+        const uint32_t h = 1u + (r >> (B - 1)), m = r & ((1u << (B - 1)) - 1u);
+        const uint32_t tb = 31u - (uint32_t)__clz(h);                                    // l has a 0 there: insert it into m
+        const uint32_t l = ((m >> tb) << (tb + 1)) | (m & ((1u << tb) - 1u));
+        const uint32_t i0 = (grp << (2 * B)) | (h << B) | l, i1 = i0 ^ h;
+        const rq_cplx a = sm[i0], b = sm[i1];
+        sm[i0] = b;
+        sm[i1] = a;
     }
     __syncthreads();
 }

@@ -353,5 +353,17 @@ call_ae() {
   ( ROCQ_TRACE_LAUNCHES=1 timeout -s KILL 600 python tools/config_bench.py --only c3 --reps 1 ) 2>&1 | grep "^\[launch\]" | tail -6 | tee gpurun_out/launches_qft33_c128_trace.log
 }
 
-if [ -z "$1" ] || ! declare -F "call_$1" > /dev/null; then echo "usage: bash tools/gpu_calls.sh {a|b|c|d|e|f|g|h|i|j|k|l|m|n|o|p|q|r|s|t|u|v|w|x|y|z|aa|ab|ac|ad|ae}"; exit 2; fi
+# Round 2, call AF (1 GPU): complex128 QFT sweeps -- qprev = before, qa = chain parameters fetched inside the group loop,
+# cur = qa + the swizzle pass that enumerates only the pairs.  Tests first (QFTs, ladders, fused bags: both layouts), then QFT-33 per variant.
+call_af() {
+  ( timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "qft or ladders or mixed_bag or named_gate or c1_config or golden or c2_and" ) > gpurun_out/pytest_qft.log 2>&1; tail -3 gpurun_out/pytest_qft.log
+  for v in qprev qa cur; do
+    if [ $v = cur ]; then unset ROCQ_LIB_DIR; else export ROCQ_LIB_DIR=$PWD/lib_var/$v; fi
+    echo "== variant $v"
+    ( ROCQ_TRACE_LAUNCHES=1 timeout -s KILL 600 python tools/config_bench.py --only c3 --reps 1 ) 2>&1 | grep "^\[launch\]\|device_ms" | tail -7 | cut -c1-200
+  done > gpurun_out/qft_variants2.log 2>&1
+  cat gpurun_out/qft_variants2.log
+}
+
+if [ -z "$1" ] || ! declare -F "call_$1" > /dev/null; then echo "usage: bash tools/gpu_calls.sh {a|b|c|d|e|f|g|h|i|j|k|l|m|n|o|p|q|r|s|t|u|v|w|x|y|z|aa|ab|ac|ad|ae|af}"; exit 2; fi
 "call_$1"

@@ -365,5 +365,12 @@ call_af() {
   cat gpurun_out/qft_variants2.log
 }
 
-if [ -z "$1" ] || ! declare -F "call_$1" > /dev/null; then echo "usage: bash tools/gpu_calls.sh {a|b|c|d|e|f|g|h|i|j|k|l|m|n|o|p|q|r|s|t|u|v|w|x|y|z|aa|ab|ac|ad|ae|af}"; exit 2; fi
+# Round 2, call AG (1 GPU): ncu --set full of two complex64 window-phase sweeps (configs[1] on the CUDA-core path, ROCQ_TC=0).
+call_ag() {
+  ROCQ_TC=0 timeout -s KILL 600 ncu --set full --import-source on --clock-control none -k regex:tile_sweep -s 8 -c 2 -f -o gpurun_out/r02_window_c64 \
+      python tools/config_bench.py --only c2 --reps 1 > gpurun_out/ncu_window_c64.log 2>&1
+  ls -la gpurun_out/r02_window_c64.ncu-rep
+}
+
+if [ -z "$1" ] || ! declare -F "call_$1" > /dev/null; then echo "usage: bash tools/gpu_calls.sh {a|b|c|d|e|f|g|h|i|j|k|l|m|n|o|p|q|r|s|t|u|v|w|x|y|z|aa|ab|ac|ad|ae|af|ag}"; exit 2; fi
 "call_$1"

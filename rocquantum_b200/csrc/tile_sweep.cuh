@@ -279,8 +279,13 @@ __device__ __forceinline__ void op_diag(rq_cplx* sm, const rq_tile_op& o, const 
 // diagp_tile_factors computes them, one warp per op, while the bulk loads of the tile are in flight.  With 2^8 threads the
 // low 8 bits of the group index are the thread's own, so their factors fold into one per-thread constant; the group-index
 // bits above are warp-uniform and read a small host-built table: two complex multiplies per amplitude.
-template <typename Prog>
-__device__ __forceinline__ void diagp_tile_factors(const Prog& prog, rq_cplx* gfac, uint32_t tid, uint64_t outer) {
+// (MODE 2) The same warp goes on to build the op's two 16-entry thread-factor tables -- low four group-index bits (times the
+// tile factor), high four -- for the first RQ_TFAC_SLOTS ops of the sweep: a butterfly-chain phase then needs neither a
+// scan over its ops, a table build nor a barrier of its own before it starts (they were 13 % of the stall samples and most
+// of the barrier stalls of a QFT sweep, profiles/r02_ncu_qft28_c128_final_lines.txt).
+constexpr uint32_t RQ_TFAC_SLOTS = sizeof(rq_real) == 8 ? 12u : 16u;     // 6 KB / 4 KB of shared memory
+template <bool TABLES, typename Prog>
+__device__ __forceinline__ void diagp_tile_factors(const Prog& prog, rq_cplx* gfac, rq_cplx (*tall)[32], uint32_t tid, uint64_t outer) {
     const uint32_t lane = tid & 31u, warp = tid >> 5;
     for (uint32_t s = warp; s < prog.hdr.ndiagp; s += NT / 32) {
         const rq_tile_op& o = prog.ops[prog.hdr.diagp_op[s]];
@@ -298,7 +303,18 @@ __device__ __forceinline__ void diagp_tile_factors(const Prog& prog, rq_cplx* gf
             g.y = __shfl_xor_sync(0xffffffffu, f.y, d);
             f = cmul(g, f);
         }
-        if (lane == 0) gfac[s] = f;
+        if (lane == 0) gfac[s] = f;                          // (after the xor reduction every lane holds the product)
+        if (TABLES && s < RQ_TFAC_SLOTS && o.t[3] != 0xFF) {
+            const rq_cplx* A = P + 1;
+            const uint32_t na = o.t[0], first_bit = (lane >> 4) * 4u;
+            rq_cplx t = lane < 16u ? f : rq_cplx{(rq_real)1, (rq_real)0};
+#pragma unroll
+            for (uint32_t b = 0; b < 4; ++b) {
+                const uint32_t i = first_bit + b;
+                if (i < na && ((lane >> b) & 1u)) t = cmul(A[i], t);
+            }
+            tall[s][lane] = t;
+        }
     }
 }
 
@@ -537,12 +553,27 @@ __device__ __forceinline__ void phase_thread_factors(const Prog& prog, const rq_
 // interpreter: the parameters of the <= V butterflies are fetched once, the group loop is load, butterflies, store.
 template <int V, bool SWZ, typename Prog>
 __device__ __forceinline__ void run_chain_phase(rq_cplx* sm, const Prog& prog, const rq_phase& ph, uint32_t T, uint32_t tid,
-                                                const rq_cplx* gfac, rq_cplx (*tfac)[32]) {
+                                                const rq_cplx* gfac, rq_cplx (*tfac)[32], rq_cplx (*tall)[32]) {
     constexpr int D = 1 << V;
     static_assert(RQ_PHASE_MAX_DIAGP >= V, "a chain holds up to V butterflies");
     rq_cplx fA[RQ_PHASE_MAX_DIAGP];
-    phase_thread_factors(prog, ph, tid, gfac, tfac, fA);
     const uint32_t nb = ph.count >> 1;
+    bool tabled = true;                                      // (uniform) every butterfly's ladder has a per-tile table
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+        if ((uint32_t)k < nb) tabled = tabled && prog.ops[ph.first + 2u * (uint32_t)k + 1u].t[2] < RQ_TFAC_SLOTS;
+    if (tabled) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            fA[k] = rq_cplx{(rq_real)1, (rq_real)0};
+            if ((uint32_t)k < nb) {
+                const uint32_t s = prog.ops[ph.first + 2u * (uint32_t)k + 1u].t[2];
+                fA[k] = cmul(tall[s][tid & 15u], tall[s][16u + (tid >> 4)]);
+            }
+        }
+    } else {
+        phase_thread_factors(prog, ph, tid, gfac, tfac, fA);
+    }
     // The parameters of butterfly k (table pointers, the Hadamard's two real entries, hub, variant) are warp-uniform and are
     // fetched where they are used, inside the group loop: held across the loop they cost ~33 vector registers, which at
     // 80 registers per thread (three 64 KB tiles per SM) went to local memory; the loop runs twice per phase, so
@@ -551,13 +582,18 @@ __device__ __forceinline__ void run_chain_phase(rq_cplx* sm, const Prog& prog, c
 #pragma unroll
     for (int b = 0; b < V; ++b) stride[b] = 1u << ph.w[b];
     const uint32_t ngroups = 1u << (T - V);
-    for (uint32_t g = tid, it = 0; g < ngroups; g += NT, ++it) {
-        uint32_t base = g;
+    // opening zeros at the window positions is bitwise: deposit(tid + 2^8 it) = deposit(tid) | deposit(2^8 it)
+    auto deposit = [&](uint32_t x) {
 #pragma unroll
         for (int b = 0; b < V; ++b) {
             const uint32_t p = ph.w[b];
-            base = ((base >> p) << (p + 1)) | (base & ((1u << p) - 1u));
+            x = ((x >> p) << (p + 1)) | (x & ((1u << p) - 1u));
         }
+        return x;
+    };
+    const uint32_t base_tid = deposit(tid);
+    for (uint32_t g = tid, it = 0; g < ngroups; g += NT, ++it) {
+        const uint32_t base = base_tid | deposit(it << 8);      // (the second term is warp-uniform)
         ramp a[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
@@ -732,6 +768,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
     __shared__ __align__(8) uint64_t bar_storage;
     __shared__ __align__(16) rq_cplx gfac[RQ_MAX_DIAGP];        // per-tile factors of the RQ_OP_DIAGP ops
     __shared__ __align__(16) rq_cplx tfac[MODE == 2 ? RQ_PHASE_MAX_DIAGP : 1][32];   // window phases: thread-factor tables of the phase's DIAGP ops
+    __shared__ __align__(16) rq_cplx tall[MODE == 2 ? RQ_TFAC_SLOTS : 1][32];        // ... built once per tile for the sweep's first ops (butterfly chains)
 
     const uint32_t tid = threadIdx.x;
     const uint32_t T = prog.hdr.T, n = prog.hdr.n, rowbits = prog.hdr.rowbits;
@@ -764,7 +801,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
         bulk_g2s(smem_u32(sm) + r * rowbytes, gtile + goff, rowbytes, bar);
     }
     if (prog.hdr.ndiagp) {                                       // while the tile is in flight
-        diagp_tile_factors(prog, gfac, tid, outer);
+        diagp_tile_factors<MODE == 2>(prog, gfac, tall, tid, outer);
         __syncthreads();
     }
     mbar_wait(bar, 0);
@@ -778,7 +815,7 @@ __global__ void __launch_bounds__(NT, MODE == 0 ? 4 : (MODE == 2 ? RQ_PHASED_MIN
         if (MODE == 2) {
             const rq_phase& ph = prog.phases[step];
             if (ph.kind == 2) {
-                run_chain_phase<RQ_WINDOW_BITS, SWZ>(sm, prog, ph, T, tid, gfac, tfac);
+                run_chain_phase<RQ_WINDOW_BITS, SWZ>(sm, prog, ph, T, tid, gfac, tfac, tall);
                 __syncthreads();
                 continue;
             }

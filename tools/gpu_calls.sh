@@ -372,5 +372,23 @@ call_ag() {
   ls -la gpurun_out/r02_window_c64.ncu-rep
 }
 
-if [ -z "$1" ] || ! declare -F "call_$1" > /dev/null; then echo "usage: bash tools/gpu_calls.sh {a|b|c|d|e|f|g|h|i|j|k|l|m|n|o|p|q|r|s|t|u|v|w|x|y|z|aa|ab|ac|ad|ae|af|ag}"; exit 2; fi
+# Round 2, call AH (1 GPU): ncu --set full of the first two complex128 QFT-28 sweeps after the store map / chain-register / swizzle changes.
+call_ah() {
+  timeout -s KILL 300 ncu --set full --import-source on --clock-control none -k regex:tile_sweep -c 2 -f -o gpurun_out/r02_qft28_c128_final \
+      python tools/config_bench.py --only c3 --c3-qubits 28 --reps 1 > gpurun_out/ncu_qft28.log 2>&1
+  ls -la gpurun_out/r02_qft28_c128_final.ncu-rep
+}
+
+# Round 2, call AI (1 GPU): butterfly chains with per-tile thread-factor tables and the bitwise group base (qb = before).
+call_ai() {
+  ( timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "qft or ladders or mixed_bag or named_gate or c1_config or golden or c2_and" ) > gpurun_out/pytest_qft.log 2>&1; tail -3 gpurun_out/pytest_qft.log
+  for v in qb cur; do
+    if [ $v = cur ]; then unset ROCQ_LIB_DIR; else export ROCQ_LIB_DIR=$PWD/lib_var/$v; fi
+    echo "== variant $v"
+    ( ROCQ_TRACE_LAUNCHES=1 timeout -s KILL 600 python tools/config_bench.py --only c3 --reps 1 ) 2>&1 | grep "^\[launch\]\|device_ms" | tail -7 | cut -c1-200
+  done > gpurun_out/qft_variants3.log 2>&1
+  cat gpurun_out/qft_variants3.log
+}
+
+if [ -z "$1" ] || ! declare -F "call_$1" > /dev/null; then echo "usage: bash tools/gpu_calls.sh {a|b|c|d|e|f|g|h|i|j|k|l|m|n|o|p|q|r|s|t|u|v|w|x|y|z|aa|ab|ac|ad|ae|af|ag|ah|ai}"; exit 2; fi
 "call_$1"

@@ -171,6 +171,7 @@ struct rq_shot_map {
 
 // One group of Pauli terms that share the x-mask (rocsvxGetExpectationPauliBatch): evaluated by one read sweep.
 #define RQ_PAULI_GROUP_MAX 32
+#define RQ_PAULI_GROUP_TERMS 16       // terms the engine puts in one group (one read sweep)
 struct rq_pauli_group {
     uint64_t xmask;
     uint32_t nterms;

@@ -460,13 +460,30 @@ def test_batched_expectation_groups_by_x_mask(prec):
     masks = {frozenset(q for p, q in zip(*t) if p in "XY") for t in terms}
     assert g.stats().expectationSweeps == len(masks) < len(terms)
     assert util.rel_err(g.state(), o.state) < TOL[prec]              # non-destructive
-    # more terms in one group than a launch carries (32): 70 Z-strings -> 3 sweeps
+    # more terms in one group than a sweep carries (16): 70 Z-strings -> 5 sweeps
     many = [("Z" * 3, [int(a), int(b), int(c)]) for a, b, c in (np.random.default_rng(i).permutation(n)[:3] for i in range(70))]
     g.stats(reset=True)
     got = g.expect_batch(many)
-    assert g.stats().expectationSweeps == 3
+    assert g.stats().expectationSweeps == 5
     for r, t in zip(got, many):
         assert abs(r - o.expect_pauli(*t)) < tol
+    # states of >= 2^15 loop indices take the sign-word kernel for groups of >= 4 terms: all-Z groups of 16 / 8 / 5 terms, groups
+    # on one x-mask with mixed Y counts (4 and 7 terms), a pivot in the middle and on the top qubit
+    n2 = 17
+    o2, g2 = _pair(n2, prec, seed=23)
+    gates2 = workloads.c5_vqe_ansatz(n2, seed=7) + workloads.c1_ghz_random_layers(n2, 2, seed=3)
+    util.run_on_oracle(o2, gates2); g2.apply_circuit(gates2)
+    rng = np.random.default_rng(99)
+    big = [("Z" * k, sorted(int(x) for x in rng.permutation(n2)[:k])) for k in rng.integers(1, 7, size=29)]
+    for a, b in ((4, 9), (0, 16)):
+        mid = [q for q in range(a + 1, b)][:3]
+        big += [(pa + "Z" * len(mid) + pb, [a] + mid + [b]) for pa, pb in (("X", "X"), ("Y", "Y"), ("X", "Y"), ("Y", "X"))]
+    big += [("XZZY", [4, 1, 12, 9]), ("YZX", [4, 16, 9]), ("XX", [9, 4])]
+    g2.stats(reset=True)
+    got = g2.expect_batch(big)
+    assert g2.stats().expectationSweeps == 2 + 1 + 1               # 29 Z-strings -> 16 + 13, then the two x-masks
+    for r, t in zip(got, big):
+        assert abs(r - o2.expect_pauli(*t)) < tol, t
     # parameter-shift batch: every state of a batch in the same sweeps
     b = 3
     v = util.random_state(9, b, seed=5)

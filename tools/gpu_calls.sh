@@ -390,5 +390,38 @@ call_ai() {
   cat gpurun_out/qft_variants3.log
 }
 
-if [ -z "$1" ] || ! declare -F "call_$1" > /dev/null; then echo "usage: bash tools/gpu_calls.sh {a|b|c|d|e|f|g|h|i|j|k|l|m|n|o|p|q|r|s|t|u|v|w|x|y|z|aa|ab|ac|ad|ae|af|ag|ah|ai}"; exit 2; fi
+# Round 2, call AJ (8 GPUs): the N = 8 bench line (36 qubits) with the final build of the round -- parity self-check, exchange
+# figures; two timed steps to keep the 8-GPU charge small.
+call_aj() {
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+  ( ROCQ_TRACE_LAUNCHES=1 timeout -s KILL 300 $TR --master-port 29613 bench.py --gpus 8 --steps 2 --warmup 3 ) > gpurun_out/bench_n8_final2.log 2>&1
+  grep -v "^\[launch\]" gpurun_out/bench_n8_final2.log | tail -1 | cut -c1-1300
+  grep -o '"parity": {[^}]*}' gpurun_out/bench_n8_final2.log | cut -c1-250; grep -o '"exchange": {[^}]*}' gpurun_out/bench_n8_final2.log | cut -c1-250
+  grep "^\[launch\] rank 0" gpurun_out/bench_n8_final2.log | tail -45 > gpurun_out/launches_n8_rank0_final2.log; awk '{print $4, $6, $8}' gpurun_out/launches_n8_rank0_final2.log | tail -42 | tr '\n' ';'
+}
+
+# Round 2, call AK (1 GPU): batched expectation with the sign-word kernel for groups of >= 8 terms (qb = POPC per term and amplitude).
+call_ak() {
+  ( timeout -s KILL 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bindings.py tests/test_gpu_group.py -m gpu -x -q -k "expectation or rocq_api or plugin or group_matches" ) > gpurun_out/pytest_expect.log 2>&1; tail -3 gpurun_out/pytest_expect.log
+  for v in qb cur; do
+    if [ $v = cur ]; then unset ROCQ_LIB_DIR; else export ROCQ_LIB_DIR=$PWD/lib_var/$v; fi
+    echo "== variant $v"
+    timeout -s KILL 300 python tools/config_bench.py --only c5 --reps 2 2>&1 | grep "batched" | cut -c1-300
+  done > gpurun_out/expect_variants3.log 2>&1
+  cat gpurun_out/expect_variants3.log
+}
+
+# Round 2, call AL (1 GPU): sign-word expectation kernel from 4 terms, groups capped at 16 terms (qb = POPC per term, groups of 32).
+call_al() {
+  ( timeout -s KILL 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bindings.py tests/test_gpu_group.py -m gpu -x -q -k "expectation or rocq_api or plugin or group_matches" ) > gpurun_out/pytest_expect.log 2>&1; tail -3 gpurun_out/pytest_expect.log
+  for v in qb cur; do
+    if [ $v = cur ]; then unset ROCQ_LIB_DIR; else export ROCQ_LIB_DIR=$PWD/lib_var/$v; fi
+    echo "== variant $v"
+    timeout -s KILL 300 python tools/expect_split.py 2>&1 | cut -c1-200
+    timeout -s KILL 300 python tools/config_bench.py --only c5 --reps 2 2>&1 | grep "batched" | cut -c1-300
+  done > gpurun_out/expect_split2.log 2>&1
+  cat gpurun_out/expect_split2.log
+}
+
+if [ -z "$1" ] || ! declare -F "call_$1" > /dev/null; then echo "usage: bash tools/gpu_calls.sh {a|b|c|d|e|f|g|h|i|j|k|l|m|n|o|p|q|r|s|t|u|v|w|x|y|z|aa|ab|ac|ad|ae|af|ag|ah|ai|aj|ak|al}"; exit 2; fi
 "call_$1"

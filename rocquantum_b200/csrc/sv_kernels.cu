@@ -248,71 +248,47 @@ __global__ void __launch_bounds__(RT) pauli_group_kernel(const rq_cplx* __restri
         partials[((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * TT + threadIdx.x] = sum;
     }
 }
-// The same sum for groups of many terms (all-Z Hamiltonian terms: up to 32 in one sweep), where one POPC -- a quarter-rate
-// instruction -- per term and amplitude is the bound (2.4 ms for 32 terms at 28 qubits against 0.33 ms for the read).  A warp
-// takes chunks of 2^10 consecutive loop indices h = chunk * 2^10 + j * 32 + lane, and the sign word (bit t = parity of
-// popcount(h & z_t)) splits along those fields:  w = L ^ J[j] ^ C  with
+// The same sum for all-Z groups of several terms (the Z / ZZ terms of a Hamiltonian: one sweep for up to 16 of them), where one
+// POPC -- a quarter-rate instruction -- per term and amplitude is the bound (1.46 ms for 16 terms at 28 qubits against 0.33 ms
+// for the read).  A warp takes chunks of 2^10 consecutive indices i = chunk * 2^10 + j * 32 + lane, and the sign word (bit t =
+// parity of popcount(i & z_t)) splits along those fields:  w = L ^ J[j] ^ C  with
 //   L    the lane's part, constant per thread (TT popcounts per THREAD),
 //   J[j] the part of the 32 values of j: a table in shared memory, read with a warp-uniform address that does not depend on
 //        anything computed in the loop,
 //   C    the chunk's part: lane t counts term t's bits once per chunk, one ballot gathers the word.
-// Per term and amplitude there remain a shift, one LOP3 into the double's sign bit and the DADD.
+// Per term and amplitude there remain a shift, one LOP3 into the double's sign bit and the DADD (0.73 ms for 16 terms).
 template <int TT>
 __global__ void __launch_bounds__(RT) pauli_group_wide_kernel(const rq_cplx* __restrict__ state_all, unsigned n,
                                                               const __grid_constant__ rq_pauli_group G, double* __restrict__ partials) {
-    const uint64_t N = 1ull << n;
+    const uint64_t N = 1ull << n, nchunks = N >> 10;          // (the launcher guarantees N >= 2^15 and an all-Z group)
     const rq_cplx* __restrict__ state = state_all + (uint64_t)blockIdx.y * N;
-    const unsigned pv = G.xmask ? 63u - (unsigned)__clzll((long long)G.xmask) : 0u;
-    const uint64_t low = (1ull << pv) - 1ull;
-    auto zeff = [&](int t) -> uint64_t {                     // the term's z-mask in loop-index coordinates (the pivot bit of i is 0)
-        const uint64_t z = G.zmask[t];
-        return G.xmask ? ((((z >> pv) >> 1) << pv) | (z & low)) : z;
-    };
-    const uint64_t items = G.xmask ? (N >> 1) : N, nchunks = items >> 10;       // (the launcher guarantees items >= 2^10)
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     __shared__ uint32_t J[32];
     if (threadIdx.x < 32) {
         uint32_t word = 0;
 #pragma unroll
-        for (int t = 0; t < TT; ++t) word |= (uint32_t)(__popcll(((uint64_t)threadIdx.x << 5) & zeff(t)) & 1) << t;
+        for (int t = 0; t < TT; ++t) word |= (uint32_t)(__popcll(((uint64_t)threadIdx.x << 5) & G.zmask[t]) & 1) << t;
         J[threadIdx.x] = word;
     }
     uint32_t L = 0;
 #pragma unroll
-    for (int t = 0; t < TT; ++t) L |= (uint32_t)(__popcll((uint64_t)lane & zeff(t)) & 1) << t;
-    const uint64_t myz = lane < (unsigned)TT ? zeff((int)lane) : 0ull;          // lane t serves term t in the ballot
-    uint32_t yw = 0;                                                            // bit t: the term takes the imaginary part
-#pragma unroll
-    for (int t = 0; t < TT; ++t) yw |= (uint32_t)(G.ny[t] & 1u) << t;
+    for (int t = 0; t < TT; ++t) L |= (uint32_t)(__popcll((uint64_t)lane & G.zmask[t]) & 1) << t;
+    const uint64_t myz = lane < (unsigned)TT ? G.zmask[lane] : 0ull;            // lane t serves term t in the ballot
     __syncthreads();
     double acc[TT];
 #pragma unroll
     for (int t = 0; t < TT; ++t) acc[t] = 0.0;
     const uint64_t gw = (uint64_t)blockIdx.x * (RT / 32) + warp, nw = (uint64_t)gridDim.x * (RT / 32);
     for (uint64_t c = gw; c < nchunks; c += nw) {
-        const uint32_t C = __ballot_sync(0xffffffffu, __popcll((c << 10) & myz) & 1);
-        const uint32_t LC = L ^ C;
-        const uint64_t h0 = (c << 10) + lane;
+        const uint32_t LC = L ^ __ballot_sync(0xffffffffu, __popcll((c << 10) & myz) & 1);
+        const rq_cplx* src = state + (c << 10) + lane;
 #pragma unroll 4
         for (uint32_t j = 0; j < 32; ++j) {
-            const uint64_t h = h0 + ((uint64_t)j << 5);
             const uint32_t w = LC ^ J[j];
-            if (G.xmask == 0) {
-                const double p = prob(state[h]);
+            const double p = prob(src[j << 5]);
 #pragma unroll
-                for (int t = 0; t < TT; ++t)
-                    acc[t] += __hiloint2double(__double2hiint(p) ^ (int)((w << (31 - t)) & 0x80000000u), __double2loint(p));
-            } else {
-                const uint64_t i = ((h & ~low) << 1) | (h & low), k = i ^ G.xmask;
-                const rq_cplx a = state[i], b = state[k];
-                const double tr = (double)b.x * a.x + (double)b.y * a.y;
-                const double ti = (double)b.x * a.y - (double)b.y * a.x;
-#pragma unroll
-                for (int t = 0; t < TT; ++t) {
-                    const double v = ((yw >> t) & 1u) ? ti : tr;
-                    acc[t] += __hiloint2double(__double2hiint(v) ^ (int)((w << (31 - t)) & 0x80000000u), __double2loint(v));
-                }
-            }
+            for (int t = 0; t < TT; ++t)
+                acc[t] += __hiloint2double(__double2hiint(p) ^ (int)((w << (31 - t)) & 0x80000000u), __double2loint(p));
         }
     }
     __shared__ double wsum[RT / 32][TT];
@@ -663,7 +639,7 @@ extern "C" int rq_launch_pauli_group(const rq_cplx* state, unsigned n, unsigned 
             case 4: pauli_group_wide_kernel<4><<<grid, RT, 0, st>>>(state, n, *G, d_partials); break;
             case 8: pauli_group_wide_kernel<8><<<grid, RT, 0, st>>>(state, n, *G, d_partials); break;
             case 16: pauli_group_wide_kernel<16><<<grid, RT, 0, st>>>(state, n, *G, d_partials); break;
-            default: pauli_group_wide_kernel<32><<<grid, RT, 0, st>>>(state, n, *G, d_partials); break;
+            default: pauli_group_kernel<32><<<grid, RT, 0, st>>>(state, n, *G, d_partials); break;     // (the engine groups <= 16 terms)
         }
     } else
     switch (TT) {

@@ -87,14 +87,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, 
 constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t IDESC_NEGB = IDESC | (1u << 14);
 
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
-        "}" ::"r"(tmem_d), "l"(a), "l"(b), "r"(IDESC), "r"(accumulate), "r"(0u) : "memory");
-}
 // A operand (X') from tensor memory, B operand (A' = block matrix) from shared memory
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -103,9 +95,6 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
         "}" ::"r"(tmem_d), "r"(tmem_a), "l"(b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 // whole-tile copies through a tensor map (rank 2..5; coordinates in elements of 8 bytes, innermost first)
 __device__ __forceinline__ void tensor_g2s(uint32_t dst, const CUtensorMap* tm, const int32_t (&c)[5], uint32_t rank, uint32_t bar) {
@@ -129,10 +118,6 @@ __device__ __forceinline__ void tensor_s2g(const CUtensorMap* tm, const int32_t 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -155,16 +140,6 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
-__device__ __forceinline__ uint64_t tile_base(uint64_t tile, const rq_block_params& P, uint64_t& member) {
-    member = tile >> (P.n - P.T);
-    uint64_t base = tile & ((1ull << (P.n - P.T)) - 1ull);
-    for (uint32_t j = 0; j < P.T; ++j) {
-        const uint32_t p = P.res[j];
-        base = ((base >> p) << (p + 1)) | (base & ((1ull << p) - 1ull));
-    }
-    return base;
 }
 
 __global__ void __launch_bounds__(BT, 1) block_sweep_kernel(float2* __restrict__ state, const unsigned char* __restrict__ uterms,
